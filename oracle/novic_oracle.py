@@ -1,0 +1,377 @@
+"""CPU oracle for the NOVIC object-noun decoder hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch CPU restatement (torch CPU tensors, explicit maths) of the algorithm the
+reference implements in `embedding_decoder.py` / `embedding_noise.py`.  It exists to *check* the CUDA
+product path; only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs
+of `bench.py` may import it.  Nothing under `novic_b200/` imports it and the product path has no CPU
+fallback.
+
+Parity status: PINNED.  `oracle/validate_vs_reference.py` runs this restatement against the reference's own
+classes imported from /root/reference (possible only in the build container) and
+`oracle/make_golden.py` stores outputs of the *reference itself* under `tests/golden/`; the CPU test suite
+checks this oracle against those committed vectors (tests/test_oracle_golden.py).
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+The schedule deliberately mirrors the reference (no KV cache: every decode step re-runs the whole
+prefix+tokens sequence, `embedding_decoder.py:792-798`), so that timing this oracle on host cores is a
+fair "port" of the reference's CPU inference path.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Optional
+
+import torch
+
+NEG_INF = float("-inf")
+
+
+@dataclasses.dataclass(frozen=True)
+class OracleCfg:
+    """Architecture constants (config/train.yaml:224-308 defaults)."""
+    embed_dim: int = 1024      # F
+    hidden_dim: int = 512      # E
+    ffn_dim: int = 128         # K = E * feedfwd_scale (1/4)
+    num_layers: int = 6        # L
+    num_heads: int = 8
+    prefix_len: int = 4        # P = mlp_seq_len
+    vocab_size: int = 6912     # V
+    token_length: int = 16     # Cmax (includes the trailing end token)
+    ln_eps: float = 1e-5
+    num_end_loss: int = 1
+
+    @property
+    def max_seq_len(self) -> int:  # embedding_decoder.py:648
+        return self.prefix_len + self.token_length - 1
+
+    @property
+    def gen_len(self) -> int:  # embedding_decoder.py:782
+        return self.token_length - 1
+
+
+def cfg_from_state_dict(sd: dict, token_length: Optional[int] = None, num_heads: int = 8) -> OracleCfg:
+    E = sd["logits_linear.weight"].shape[1]
+    V = sd["logits_linear.weight"].shape[0]
+    F = sd["embed_mlp.mlp.0.weight"].shape[1]
+    P = sd["embed_mlp.mlp.0.weight"].shape[0] // E
+    L = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
+    K = sd["transformer.layers.0.linear1.weight"].shape[0]
+    S = sd["pos_embedding.embedding.weight"].shape[0]
+    Cmax = S - P + 1 if token_length is None else token_length
+    return OracleCfg(embed_dim=F, hidden_dim=E, ffn_dim=K, num_layers=L, num_heads=num_heads, prefix_len=P,
+                     vocab_size=V, token_length=Cmax)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Building blocks
+# ----------------------------------------------------------------------------------------------------
+
+def _layer_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    # nn.LayerNorm(bias=False): biased variance, eps inside the sqrt (built at embedding_decoder.py:309-327)
+    mu = x.mean(dim=-1, keepdim=True)
+    var = (x - mu).square().mean(dim=-1, keepdim=True)
+    return (x - mu) * torch.rsqrt(var + eps) * w
+
+
+def _gelu_erf(x: torch.Tensor) -> torch.Tensor:
+    # exact GELU (utils.py:107 -> torch.nn.functional.gelu default)
+    return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
+
+
+def attention_bias(cfg: OracleCfg, S: int, dtype: torch.dtype) -> torch.Tensor:
+    """S x S additive mask: causal, except that the P x P prefix block is fully visible
+    (embedding_decoder.py:651-654)."""
+    q = torch.arange(S).unsqueeze(1)
+    k = torch.arange(S).unsqueeze(0)
+    visible = (k <= q) | ((q < cfg.prefix_len) & (k < cfg.prefix_len))
+    bias = torch.zeros(S, S, dtype=dtype)
+    bias.masked_fill_(~visible, NEG_INF)
+    return bias
+
+
+def key_padding_bias(cfg: OracleCfg, padding: torch.Tensor, S: int, dtype: torch.dtype) -> tuple[torch.Tensor, torch.Tensor]:
+    """Restates embedding_decoder.py:696-712.  padding is A x C bool.  Returns (A x S additive key bias,
+    A x C effective target padding)."""
+    A, C = padding.shape
+    expand = cfg.prefix_len + cfg.num_end_loss - 2
+    keep = C - cfg.num_end_loss + 1
+    if expand < 1:
+        seq_pad = padding
+        eff = padding
+    else:
+        if keep <= 1:
+            seq_pad = padding[:, 0:1].expand(-1, S)
+        else:
+            seq_pad = torch.cat((padding[:, 0:1].expand(-1, expand), padding[:, :keep]), dim=1)
+        eff = seq_pad[:, -C:]
+    bias = torch.zeros(A, S, dtype=dtype)
+    if S > 1:
+        bias[:, 1:].masked_fill_(seq_pad[:, 1:], NEG_INF)  # sequence position 0 is never masked (:711-712)
+    return bias, eff
+
+
+def transformer_stack(cfg: OracleCfg, sd: dict, x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Pre-LN encoder stack + final LayerNorm (nn.TransformerEncoder built at embedding_decoder.py:309-327,
+    called at :714).  x: A x S x E, bias: broadcastable to A x 1 x S x S (additive)."""
+    A, S, E = x.shape
+    H = cfg.num_heads
+    d = E // H
+    scale = 1.0 / math.sqrt(d)
+    for l in range(cfg.num_layers):
+        p = f"transformer.layers.{l}."
+        h = _layer_norm(x, sd[p + "norm1.weight"], cfg.ln_eps)
+        qkv = h @ sd[p + "self_attn.in_proj_weight"].t()
+        q, k, v = qkv.split(E, dim=-1)
+        q = q.view(A, S, H, d).transpose(1, 2)
+        k = k.view(A, S, H, d).transpose(1, 2)
+        v = v.view(A, S, H, d).transpose(1, 2)
+        att = (q @ k.transpose(-1, -2)) * scale + bias
+        att = torch.softmax(att, dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(A, S, E)
+        x = x + o @ sd[p + "self_attn.out_proj.weight"].t()
+        h = _layer_norm(x, sd[p + "norm2.weight"], cfg.ln_eps)
+        h = _gelu_erf(h @ sd[p + "linear1.weight"].t())
+        x = x + h @ sd[p + "linear2.weight"].t()
+    return _layer_norm(x, sd["transformer.norm.weight"], cfg.ln_eps)
+
+
+def forward_logits(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: Optional[torch.Tensor],
+                   padding: Optional[torch.Tensor], only_pred: bool) -> tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Restates PrefixedIterDecoder.forward up to the logits (embedding_decoder.py:659-727).
+    embed B x F; target A x C (A = B*M, sequences of one embedding adjacent, i.e. B-before-M) or None;
+    padding A x C bool or None.  Returns (A x T x V logits, A x T effective padding or None)."""
+    dtype = embed.dtype
+    B = embed.shape[0]
+    P, E = cfg.prefix_len, cfg.hidden_dim
+    Wt = sd["logits_linear.weight"]
+    x = torch.nn.functional.normalize(embed, dim=-1) @ sd["embed_mlp.mlp.0.weight"].t()  # :1276
+    x = x.view(B, P, E)
+    if target is not None:
+        A = target.shape[0]
+        if A != B:
+            x = x.repeat_interleave(A // B, dim=0)  # :674
+        if target.shape[1] > 1:
+            x = torch.cat((x, Wt[target[:, :-1]]), dim=1)  # tied token embedding, :692, utils.py:65-68
+    S = x.shape[1]
+    x = x + sd["pos_embedding.embedding.weight"][:S]  # :1297 (dropout is identity in eval)
+    bias = attention_bias(cfg, S, dtype).view(1, 1, S, S)
+    eff_pad = None
+    if padding is not None:
+        kb, eff_pad = key_padding_bias(cfg, padding, S, dtype)
+        bias = bias + kb.view(-1, 1, 1, S)
+    x = transformer_stack(cfg, sd, x, bias)
+    if only_pred:
+        x = x[:, -1:, :]
+        if eff_pad is not None:
+            eff_pad = eff_pad[:, -1:]
+    else:
+        x = x[:, P - 1:, :]
+    return x @ Wt.t(), eff_pad
+
+
+def forward_loss(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: torch.Tensor, padding: Optional[torch.Tensor],
+                 weight: Optional[torch.Tensor], label_smoothing: float = 0.0):
+    """Teacher-forced forward with loss/correct (embedding_decoder.py:729-761), only_pred=False.
+    Returns (logits A x C x V, loss_sum, loss_basis, correct A x C)."""
+    if weight is not None:  # :681-685
+        wpad = (weight == 0).unsqueeze(1)
+        padding = wpad.expand_as(target) if padding is None else (padding | wpad)
+    logits, eff_pad = forward_logits(cfg, sd, embed, target, padding, only_pred=False)
+    A, C, V = logits.shape
+    tgt = target if eff_pad is None else target.masked_fill(eff_pad, -1)
+    logp = torch.log_softmax(logits, dim=-1)
+    valid = tgt >= 0
+    picked = logp.gather(2, tgt.clamp(min=0).unsqueeze(2)).squeeze(2)
+    nll = -picked
+    if label_smoothing != 0.0:
+        nll = (1.0 - label_smoothing) * nll + label_smoothing * (-logp.mean(dim=-1))
+    nll = nll.masked_fill(~valid, 0.0)
+    if weight is None:
+        loss_sum = nll.sum()
+        loss_basis = valid.sum() if eff_pad is not None else torch.tensor(tgt.numel())
+    else:
+        loss_sum = (weight * nll.sum(dim=1)).sum()
+        n = valid.sum(dim=1) if eff_pad is not None else torch.full((A,), C)
+        loss_basis = (weight * n.to(weight.dtype)).sum()
+    correct = (logits.argmax(dim=2) == tgt)
+    return logits, loss_sum, loss_basis, correct
+
+
+# ----------------------------------------------------------------------------------------------------
+# Greedy decode (embedding_decoder.py:779-850, unguided)
+# ----------------------------------------------------------------------------------------------------
+
+def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: float = 1.0, length_alpha: float = 0.0,
+                    sample_weight: Optional[torch.Tensor] = None, early_exit: bool = True):
+    """Returns dict(target B x T int64, padding B x T bool, logits B x T x V, loss_sum, loss_basis, score B)."""
+    B = embed.shape[0]
+    G = cfg.gen_len
+    tok = torch.zeros(B, G, dtype=torch.int64)
+    pad = torch.zeros(B, G, dtype=torch.bool)
+    done = torch.zeros(B, dtype=torch.bool)
+    step_logits = []
+    T = G
+    for c in range(1, G + 1):
+        if c > 1:
+            pad[:, c - 1] = done  # :797 - the EOS itself is not padding, the positions after it are
+        logits, _ = forward_logits(cfg, sd, embed, tok[:, :c], done.unsqueeze(1).expand(-1, c), only_pred=True)
+        logits = logits[:, 0, :]
+        step_logits.append(logits)
+        if c == 1:
+            nxt = logits[:, 1:].argmax(dim=1) + 1  # first token may not be EOS (:804)
+        else:
+            nxt = logits.argmax(dim=1)
+        tok[:, c - 1] = nxt
+        done = done | (nxt == 0)
+        if early_exit and bool(done.all()):  # :817-820
+            T = c
+            break
+    tok = tok[:, :T].clone()
+    pad = pad[:, :T].clone()
+    seq_logits = torch.stack(step_logits, dim=1)
+    tok.masked_fill_(pad, 0)  # :824
+    logp_t = torch.log_softmax(seq_logits / temperature, dim=2)
+    score = logp_t.gather(2, tok.unsqueeze(2)).squeeze(2).masked_fill(pad, 0.0).sum(dim=1)  # :831-834
+    length = (T - pad.sum(dim=1)).to(score.dtype)
+    if length_alpha != 0:
+        score = score * length.clamp(min=1).pow(-length_alpha)  # :836
+    nll = -torch.log_softmax(seq_logits, dim=2).gather(2, tok.unsqueeze(2)).squeeze(2).masked_fill(pad, 0.0)
+    if sample_weight is None:
+        loss_sum = nll.sum()
+        loss_basis = (~pad).sum()
+    else:
+        loss_sum = (sample_weight * nll.sum(dim=1)).sum()
+        loss_basis = (sample_weight * length).sum()
+    return dict(target=tok, padding=pad, logits=seq_logits, loss_sum=loss_sum, loss_basis=loss_basis, score=score)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Beam search (embedding_decoder.py:852-984, unguided, no vocab prior)
+# ----------------------------------------------------------------------------------------------------
+
+def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temperature: float = 1.0,
+                  length_alpha: float = 0.0, early_exit: bool = True):
+    """Returns dict(target B x H x T, padding B x H x T, score B x H sorted descending)."""
+    B, H, G, V = embed.shape[0], topk, cfg.gen_len, cfg.vocab_size
+    dtype = embed.dtype
+    tok = torch.zeros(B, H, G, dtype=torch.int64)
+    pad = torch.ones(B, H, G, dtype=torch.bool)
+    pad[:, 0, 0] = False                                  # one live empty candidate per sample (:862)
+    score = torch.full((B, H), NEG_INF, dtype=dtype)
+    score[:, 0] = 0.0                                     # :864
+    score_normed = score.clone()
+    seq_len = torch.zeros(B, H, dtype=dtype)
+    seq_len[:, 0] = 1.0                                   # :899
+    T = G
+    for c in range(1, G + 1):
+        cur_tok = tok[:, :, :c].reshape(B * H, c)
+        cur_pad = pad[:, :, :c].reshape(B * H, c)
+        logits, lpad = forward_logits(cfg, sd, embed, cur_tok, cur_pad, only_pred=True)
+        logits = logits.view(B, H, V) / temperature
+        finished = lpad.view(B, H, 1)
+        logits[:, :, 1:] = logits[:, :, 1:].masked_fill(finished, NEG_INF)  # finished candidates extend with EOS at zero cost (:913)
+        cand = torch.log_softmax(logits, dim=2) + score.unsqueeze(2)        # :922, :938
+        if c == 1:
+            cand[:, 0, 0] = NEG_INF                                         # :940
+        flat = cand.view(B, H * V)
+        if length_alpha == 0:
+            best, idx = torch.topk(flat, k=H, dim=1, largest=True, sorted=True)  # :946
+            score = best
+        else:
+            scale = seq_len.clamp(min=1).pow(-length_alpha).unsqueeze(2)         # :948
+            best, idx = torch.topk((cand * scale).view(B, H * V), k=H, dim=1, largest=True, sorted=True)  # :950
+            score_normed = best
+            score = flat.gather(1, idx)                                          # :951
+        parent = idx // V                                                        # :953
+        new_tok = idx % V                                                        # :954
+        gather_idx = parent.unsqueeze(2)
+        if c > 1:
+            tok[:, :, :c - 1] = tok[:, :, :c - 1].gather(1, gather_idx.expand(-1, -1, c - 1))  # :957
+        tok[:, :, c - 1] = new_tok                                                # :958
+        pad[:, :, :c] = pad[:, :, :c].gather(1, gather_idx.expand(-1, -1, c))     # :959
+        if c < G:
+            nxt_pad = (new_tok == 0) | pad[:, :, c - 1]                           # :963
+            pad[:, :, c] = nxt_pad
+            if early_exit and bool(nxt_pad.all()):                                # :964-967
+                T = c
+                break
+            if length_alpha != 0:
+                seq_len = seq_len.gather(1, parent) + (~nxt_pad).to(dtype)        # :978
+    tok = tok[:, :, :T].clone()
+    pad = pad[:, :, :T].clone()
+    tok.masked_fill_(pad, 0)                                                      # :980
+    return dict(target=tok, padding=pad, score=score_normed if length_alpha != 0 else score)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Embedding noise (embedding_noise.py).  The random draws are explicit inputs so that the CUDA kernel's
+# "debug" entry point (pre-drawn normals / uniforms) can be compared bit-for-bit-ish against this.
+# ----------------------------------------------------------------------------------------------------
+
+def _unit(x: torch.Tensor) -> torch.Tensor:
+    return x / x.norm(dim=-1, keepdim=True).clamp_min(1e-12)  # F.normalize semantics
+
+
+def noise_gauss_elem(embed: torch.Tensor, normals: torch.Tensor, vec_norm: float) -> torch.Tensor:
+    """embedding_noise.py:72-75: e + (vec_norm/sqrt(F)) * n, renormalised."""
+    sigma = vec_norm / math.sqrt(embed.shape[1])
+    return _unit(embed + sigma * normals)
+
+
+def noise_gauss_vec(embed: torch.Tensor, normals: torch.Tensor, row_normal: torch.Tensor, vec_norm: float) -> torch.Tensor:
+    """embedding_noise.py:90-95: e + vec_norm * g * unit(n) with one scalar g ~ N(0,1) per row."""
+    return _unit(embed + vec_norm * row_normal.view(-1, 1) * _unit(normals))
+
+
+def noise_angle(embed: torch.Tensor, normals: torch.Tensor, angle_rad: torch.Tensor) -> torch.Tensor:
+    """embedding_noise.py:105-112: rotate e by `angle` towards the direction of n orthogonal to e."""
+    d = _unit(normals - embed * (embed * normals).sum(dim=1, keepdim=True))
+    a = angle_rad.view(-1, 1)
+    return _unit(embed * torch.cos(a) + d * torch.sin(a))
+
+
+def gauss_angle(row_normal: torch.Tensor, angle_std_deg: float, angle_max_deg: float) -> torch.Tensor:
+    """embedding_noise.py:131-132."""
+    m = math.radians(angle_max_deg)
+    return (row_normal * math.radians(angle_std_deg)).clamp(min=-m, max=m)
+
+
+def uniform_angle(row_uniform: torch.Tensor, angle_min_deg: float, angle_max_deg: float) -> torch.Tensor:
+    """embedding_noise.py:151-152: U[min, max) from a U[0,1) draw."""
+    lo, hi = math.radians(angle_min_deg), math.radians(angle_max_deg)
+    return lo + (hi - lo) * row_uniform
+
+
+def noise_gauss_elem_uniform_angle(embed: torch.Tensor, normals_angle: torch.Tensor, angle_uniform: torch.Tensor,
+                                   normals_elem: torch.Tensor, mix_uniform: torch.Tensor, vec_norm: float,
+                                   angle_min_deg: float, angle_max_deg: float, mix_ratio: float) -> torch.Tensor:
+    """embedding_noise.py:169-172: per row, angle noise with probability mix_ratio, else element noise."""
+    a = noise_angle(embed, normals_angle, uniform_angle(angle_uniform, angle_min_deg, angle_max_deg))
+    g = noise_gauss_elem(embed, normals_elem, vec_norm)
+    return torch.where((mix_uniform < mix_ratio).view(-1, 1), a, g)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Synthetic-weight helper shared by tests (the product has its own copy in novic_b200/synth.py; the two
+# are compared in tests so neither silently drifts).
+# ----------------------------------------------------------------------------------------------------
+
+def reference_init_stds(cfg: OracleCfg) -> dict:
+    """Standard deviations the reference's 'balanced' init produces for the default architecture
+    (embedding_decoder.py:203-226, :228-278, :329-407; utils.py:84-112)."""
+    E, L, K, P = cfg.hidden_dim, cfg.num_layers, cfg.ffn_dim, cfg.prefix_len
+    f = 1.0 / math.sqrt(E)
+    lf = 1.0 / math.sqrt(2 * L)
+    attn_scale = math.sqrt((1 + (P - 1) / P) / P)
+    return {
+        "embed_mlp": 1.0 / math.sqrt(2.0),
+        "logits": 1.0 / math.sqrt(2.0),
+        "pos": 1.0 / math.sqrt(2.0),
+        "in_proj": f,
+        "out_proj": f / attn_scale * lf,
+        "linear1": f,
+        "linear2": 1.0 / (math.sqrt(K) * 0.6521) * lf,
+        "norm": 1.0,
+        "final_norm": f,
+    }
