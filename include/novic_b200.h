@@ -1,0 +1,140 @@
+/*
+ * novic_b200 - C ABI of the B200-native NOVIC object-noun decoder hot path.
+ *
+ * The reference (pallgeuer/novic) has no FFI: its seam for this path is the Python class contract of
+ * `embedding_decoder.PrefixedIterDecoder` (embedding_decoder.py:617-1079) selected by name at
+ * infer.py:716.  `novic_b200/decoder.py` mirrors that class; its methods call the entry points below through
+ * ctypes.  Each entry point names the reference function it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `novic_last_error()` describes the failure
+ *   - all pointers marked "device" are raw CUDA device pointers owned by the caller (torch tensors) and are
+ *     only borrowed for the duration of the call; work is enqueued on the `stream` argument
+ *     (a cudaStream_t passed as void*), calls that return a host value synchronise that stream
+ *   - a handle is bound to the CUDA device that was current at novic_create(); handles are not thread-safe
+ *   - token ids are int64, masks are 1-byte booleans, scores / logits are fp32 (what the reference returns)
+ *   - there is no CPU fallback: without an sm_100 device every compute entry point fails
+ */
+#ifndef NOVIC_B200_H_
+#define NOVIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOVIC_MAX_LAYERS 16
+#define NOVIC_MAX_BEAMS 16
+
+/* Architecture of the decoder; mirrors the constructor arguments of PrefixedIterDecoder
+ * (embedding_decoder.py:43-75, :633-640) that influence the computation. */
+typedef struct NovicCfg {
+  int32_t embed_dim;       /* F: CLIP embedding size (embedder.embed_dim, embedding_decoder.py:86)            */
+  int32_t hidden_dim;      /* E: must be 512 (kernels are specialised for config/train.yaml:256)              */
+  int32_t ffn_dim;         /* K: hidden_dim * feedfwd_scale, must be 128                                      */
+  int32_t num_layers;      /* L <= NOVIC_MAX_LAYERS                                                           */
+  int32_t num_heads;       /* must be 8 (head dim 64)                                                         */
+  int32_t prefix_len;      /* P = mlp_seq_len                                                                 */
+  int32_t vocab_size;      /* V = target_config.vocab_size (rows of the tied matrix actually used)            */
+  int32_t token_length;    /* Cmax = target_config.token_length                                               */
+  int32_t strictly_causal; /* embedding_decoder.py:652                                                        */
+  int32_t num_end_loss;    /* embedding_decoder.py:700                                                        */
+  float ln_eps;            /* 1e-5                                                                            */
+  float label_smoothing;   /* embedding_decoder.py:738                                                        */
+} NovicCfg;
+
+/* fp32 parameters exactly as the reference's state dict holds them. */
+typedef struct NovicWeights {
+  const float* embed_mlp;                  /* embed_mlp.mlp.0.weight               [P*E, F]   */
+  const float* tok_embed;                  /* logits_linear.weight (tied)          [>=V, E]   */
+  const float* pos_embed;                  /* pos_embedding.embedding.weight       [P+Cmax-1, E] */
+  const float* final_norm;                 /* transformer.norm.weight              [E]        */
+  const float* in_proj[NOVIC_MAX_LAYERS];  /* ...layers.i.self_attn.in_proj_weight [3E, E]    */
+  const float* out_proj[NOVIC_MAX_LAYERS]; /* ...layers.i.self_attn.out_proj.weight [E, E]    */
+  const float* linear1[NOVIC_MAX_LAYERS];  /* ...layers.i.linear1.weight           [K, E]     */
+  const float* linear2[NOVIC_MAX_LAYERS];  /* ...layers.i.linear2.weight           [E, K]     */
+  const float* norm1[NOVIC_MAX_LAYERS];    /* ...layers.i.norm1.weight             [E]        */
+  const float* norm2[NOVIC_MAX_LAYERS];    /* ...layers.i.norm2.weight             [E]        */
+} NovicWeights;
+
+/* Embedding-noise configuration; mirrors EmbeddingNoise.create (embedding_noise.py:17-41). Angles in degrees. */
+typedef struct NovicNoiseCfg {
+  int32_t scheme;     /* 0 GaussElem, 1 GaussVec, 2 GaussAngle, 3 UniformAngle, 4 GaussElemUniformAngle */
+  int32_t embed_dim;
+  float vec_norm, angle_min, angle_max, angle_std, mix_ratio;
+} NovicNoiseCfg;
+
+typedef struct NovicHandle NovicHandle;
+
+const char* novic_last_error(void);
+int novic_version(void);
+
+/* Replaces PrefixedIterDecoder.__init__ (embedding_decoder.py:633-654) for the compute side. */
+int novic_create(const NovicCfg* cfg, NovicHandle** out);
+int novic_destroy(NovicHandle* h);
+
+/* Bytes of device memory novic_set_weights needs for its bf16 / packed copies. */
+size_t novic_weight_bytes(const NovicHandle* h);
+/* Replaces load_state_dict(...) + .to(device) (infer.py:776, :184): converts the fp32 parameters into the
+ * kernels' bf16 operand layout inside `wbuf` (device, caller-owned, must outlive the handle's use). */
+int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t wbuf_bytes, void* stream);
+
+/* Workspace (KV cache pages, activations, selection partials) for a call over `num_embeds` embeddings with
+ * `seqs_per_embed` sequences each (beam width H, or multi-target count M, or 1) and `rows_per_seq` residual
+ * rows per sequence (0 = decode: max(P, 1) rows; else P + C - 1 for teacher forcing). */
+size_t novic_workspace_bytes(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq);
+
+/* Replaces PrefixedIterDecoder.generate (embedding_decoder.py:779-850), unguided.
+ *   embed [B, F] fp32 device.  Outputs (device): tok [B, G] int64, pad [B, G] u8, score [B] fp32,
+ *   nll [B] fp32 (per-sample sum of -log p over unpadded tokens, label smoothing applied), len [B] fp32
+ *   (unpadded tokens per sample), logits [B, G, V] fp32 or NULL.  *T_out (host) = number of columns the
+ *   reference would return (early exit when every sample has emitted the end token). G = Cmax - 1. */
+int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
+                          int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
+                          int32_t* T_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984), unguided, no vocab prior.
+ *   Outputs (device): tok [B, H, G] int64, pad [B, H, G] u8, score [B, H] fp32 sorted descending. */
+int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H, float temperature,
+                        float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* Replaces PrefixedIterDecoder.forward (embedding_decoder.py:659-777) with guide_targets=None.
+ *   embed [B, F]; target [A, C] int64 with A = B * M (sequences of one embedding adjacent, multi_first=False);
+ *   padding [A, C] u8 or NULL; weight [A] fp32 or NULL.  T = 1 if only_pred else C.
+ *   Outputs (device, each may be NULL): logits [A, T, V] fp32, pad_out [A, T] u8 (effective target padding),
+ *   loss [2] fp32 = {loss_sum, loss_basis}, correct [A, T] u8. */
+int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
+                  const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
+                  uint8_t* pad_out, float* loss, uint8_t* correct, void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces EmbeddingNoise.forward (embedding_noise.py:72-75, :90-95, :105-112, :169-172): in place on
+ * embed [B, F] fp32 device; random draws come from Philox (seed, offset). */
+int novic_noise_apply(const NovicNoiseCfg* cfg, float* embed, int64_t B, uint64_t seed, uint64_t offset, void* stream);
+/* Deterministic variant for parity tests: the draws are supplied (device pointers, see kernels.cuh NoiseParams). */
+int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B, const float* normals_a,
+                               const float* normals_b, const float* row_a, const float* row_b, void* stream);
+
+/* Building-block check used by the test-suite: out[M, N] fp32 = A[M, K] (bf16) * W[N, K]^T (bf16) through the
+ * same tcgen05 / TMA kernel the decoder uses.  K % 64 == 0. */
+int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,
+                     int32_t block_n, void* stream);
+
+/* Byte offset of a named workspace buffer (ein, ebf, x, xn, xfin, q, ao, hb, kv, part) for the same arguments as
+ * novic_workspace_bytes; lets tests inspect intermediates. */
+int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq,
+                          const char* name, size_t* offset_out);
+
+/* Kernel launches issued by this process through the library since load (bench.py's gpu_launches). */
+int64_t novic_launch_count(void);
+/* Device-side watchdog word (non-zero after a kernel trapped on a stuck mbarrier). */
+int novic_watchdog(uint32_t* code_out);
+/* 0/1: capture decode loops into CUDA graphs (default 1). */
+int novic_set_use_graphs(NovicHandle* h, int32_t enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOVIC_B200_H_ */

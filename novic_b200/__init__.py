@@ -1,0 +1,17 @@
+"""novic_b200: B200-native (sm_100a) implementation of NOVIC's object-noun decoder hot path.
+
+Public surface (mirrors the reference's classes for this path):
+  PrefixedIterDecoder, EmbeddingDecoder  - embedding_decoder.py
+  EmbeddingNoise and its five schemes     - embedding_noise.py
+  register(module)                        - make `getattr(embedding_decoder, 'PrefixedIterDecoder')` resolve here
+"""
+from .decoder import EmbeddingDecoder, ParamCount, PrefixedIterDecoder
+from .noise import (AngleNoise, EmbeddingNoise, GaussAngleNoise, GaussElemNoise, GaussElemUniformAngleNoise, GaussVecNoise,
+                    UniformAngleNoise)
+from .factory import DEFAULT_DECODER_KWARGS, default_decoder, register
+from . import synth
+
+__all__ = [
+    "EmbeddingDecoder", "ParamCount", "PrefixedIterDecoder", "EmbeddingNoise", "AngleNoise", "GaussAngleNoise", "GaussElemNoise",
+    "GaussElemUniformAngleNoise", "GaussVecNoise", "UniformAngleNoise", "DEFAULT_DECODER_KWARGS", "default_decoder", "register", "synth",
+]

@@ -1,0 +1,768 @@
+// C ABI + host orchestration of the decoder hot path (see include/novic_b200.h).
+// The host side only plans buffers, builds TMA descriptors and enqueues kernels (optionally captured into a
+// CUDA graph per (mode, batch) so the ~500 small launches of a decode replay as one submission).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/novic_b200.h"
+#include "kernels.cuh"
+
+using namespace novic;
+
+namespace {
+
+thread_local std::string g_err;
+int64_t g_launches = 0;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA descriptors
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_driver_entry() {
+  if (g_encode != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// Row-major bf16 matrix [rows, cols]; boxes of [box_rows, 64] elements, 128-byte swizzle (K-major UMMA operand).
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+  if (load_driver_entry()) return 1;
+  if (cols % kBlockK != 0) return fail("TMA operand inner dimension %lld is not a multiple of %d", (long long)cols, kBlockK);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA operand base is not 16-byte aligned");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld box_rows=%d)", (int)r,
+                                     (long long)rows, (long long)cols, box_rows);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GEMM launch
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStagesQKV = 3, kStagesGelu = 3, kStagesRow = 2, kStagesLogits = 3;
+constexpr int kLogitBN = 128;
+
+template <class Epi, int STAGES>
+int set_gemm_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmSmem<Epi::BN>::bytes(STAGES)));
+  return 0;
+}
+
+template <class Epi, int STAGES>
+int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
+                const typename Epi::Params& ep) {
+  dim3 grid(static_cast<unsigned>(ceil_div(N, Epi::BN)), static_cast<unsigned>(ceil_div(M, kBlockM)));
+  gemm_kernel<Epi, STAGES><<<grid, kGemmThreads, GemmSmem<Epi::BN>::bytes(STAGES), s>>>(ta, tb, M, K / kBlockK, ep);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+__global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    for (; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// Key-padding bytes and effective target padding for teacher forcing (embedding_decoder.py:681-712, :734)
+__global__ void tf_mask_kernel(const long long* __restrict__ target, const unsigned char* __restrict__ padding,
+                               const float* __restrict__ weight, int A, int C, int S, int P, int n_end,
+                               int T, int t0, unsigned char* __restrict__ keypad, unsigned char* __restrict__ effpad,
+                               long long* __restrict__ tgt_masked) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A) return;
+  const bool has_pad = padding != nullptr || weight != nullptr;
+  const bool wzero = weight != nullptr && weight[a] == 0.f;
+  auto pad_at = [&](int c) -> bool { return wzero || (padding != nullptr && padding[static_cast<size_t>(a) * C + c] != 0); };
+  const int expand = P + n_end - 2;
+  const int keep = C - n_end + 1;
+  for (int s = 0; s < S; ++s) {
+    bool m = false;
+    if (has_pad) {
+      if (expand < 1) m = pad_at(s);
+      else if (keep <= 1) m = pad_at(0);
+      else m = (s < expand) ? pad_at(0) : pad_at(s - expand);
+    }
+    keypad[static_cast<size_t>(a) * S + s] = (m && s > 0) ? 1 : 0;
+    const int c = s - (S - C);
+    if (c >= t0 && c - t0 < T) {
+      effpad[static_cast<size_t>(a) * T + (c - t0)] = m ? 1 : 0;
+      const long long t = target[static_cast<size_t>(a) * C + c];
+      tgt_masked[static_cast<size_t>(a) * T + (c - t0)] = m ? -1 : t;
+    }
+  }
+}
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// Handle
+// ---------------------------------------------------------------------------------------------------------
+struct WeightPtrs {
+  const __nv_bfloat16 *embed_mlp, *tok;
+  const __nv_bfloat16 *in_proj[NOVIC_MAX_LAYERS], *out_proj[NOVIC_MAX_LAYERS], *linear1[NOVIC_MAX_LAYERS], *linear2[NOVIC_MAX_LAYERS];
+  const float *tok_f32, *pos, *final_norm, *norm1[NOVIC_MAX_LAYERS], *norm2[NOVIC_MAX_LAYERS];
+  CUtensorMap tm_embed_mlp, tm_tok, tm_in_proj[NOVIC_MAX_LAYERS], tm_out_proj[NOVIC_MAX_LAYERS], tm_linear1[NOVIC_MAX_LAYERS],
+      tm_linear2[NOVIC_MAX_LAYERS];
+};
+
+struct Workspace {
+  // sizes
+  int64_t B = 0, nseq = 0, rows = 0, logit_rows = 0;
+  int H = 1, rps = 0, ntiles = 0, hcap = 0;
+  // device pointers
+  float* ein; __nv_bfloat16* ebf; float* x; __nv_bfloat16 *xn, *xfin, *q, *ao, *hb; __nv_bfloat16* kv;
+  LogitPartial* part; float* topv; int* topi;
+  long long* g_tok; unsigned char *g_pad, *g_done; float *g_score, *g_nll, *g_len, *g_score_out; int* flags;
+  long long* b_tok[2]; unsigned char *b_pad[2], *b_anc[2], *b_fin[2]; float *b_score[2], *b_len[2], *b_norm;
+  unsigned char *keypad, *effpad, *correct; long long* tgt_masked; float *nll_rows, *loss;
+  size_t bytes = 0;
+};
+
+struct GraphKey {
+  int mode; int64_t B; int H; float tau, alpha; void* ws;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(mode, B, H, tau, alpha, ws) < std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws);
+  }
+};
+
+struct NovicHandle {
+  NovicCfg cfg;
+  int device = 0;
+  bool weights_set = false;
+  bool use_graphs = true;
+  WeightPtrs w;
+  cudaStream_t capture_stream = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int64_t> graph_nodes;
+  int* h_flags = nullptr;  // pinned
+  int G() const { return cfg.token_length - 1; }
+  int S() const { return cfg.prefix_len + cfg.token_length - 1; }
+};
+
+namespace {
+
+int plan_workspace(const NovicHandle* h, int64_t B, int H, int rps, char* base, Workspace* ws) {
+  const NovicCfg& c = h->cfg;
+  const int P = c.prefix_len, G = h->G(), S = h->S();
+  Workspace w;
+  w.B = B; w.H = H; w.rps = rps;
+  w.nseq = B * H;
+  const bool tf = rps > 0;
+  w.rows = tf ? w.nseq * rps : std::max<int64_t>(B * P, w.nseq);
+  w.logit_rows = tf ? w.nseq * c.token_length : w.nseq;
+  w.ntiles = static_cast<int>(ceil_div(c.vocab_size, kLogitBN));
+  w.hcap = tf ? 0 : (H <= 1 ? 0 : (H <= 4 ? 4 : 16));
+  const int64_t rows32 = ceil_div(w.rows, 32) * 32;
+  Bump b;
+  auto P_ = [&](size_t bytes) { return base + b.take(bytes); };
+  w.ein = reinterpret_cast<float*>(P_(sizeof(float) * B * c.embed_dim));
+  w.ebf = reinterpret_cast<__nv_bfloat16*>(P_(2 * B * c.embed_dim));
+  w.x = reinterpret_cast<float*>(P_(sizeof(float) * rows32 * kE));
+  w.xn = reinterpret_cast<__nv_bfloat16*>(P_(2 * w.rows * kE));
+  w.xfin = reinterpret_cast<__nv_bfloat16*>(P_(2 * w.logit_rows * kE));
+  w.q = reinterpret_cast<__nv_bfloat16*>(P_(2 * w.rows * kE));
+  w.ao = reinterpret_cast<__nv_bfloat16*>(P_(2 * w.rows * kE));
+  w.hb = reinterpret_cast<__nv_bfloat16*>(P_(2 * w.rows * c.ffn_dim));
+  w.kv = reinterpret_cast<__nv_bfloat16*>(P_(static_cast<size_t>(2) * c.num_layers * 2 * w.nseq * S * kE));
+  w.part = reinterpret_cast<LogitPartial*>(P_(sizeof(LogitPartial) * w.logit_rows * w.ntiles));
+  w.topv = reinterpret_cast<float*>(P_(sizeof(float) * w.logit_rows * w.ntiles * std::max(w.hcap, 1)));
+  w.topi = reinterpret_cast<int*>(P_(sizeof(int) * w.logit_rows * w.ntiles * std::max(w.hcap, 1)));
+  w.flags = reinterpret_cast<int*>(P_(sizeof(int) * (G + 2)));
+  if (!tf && H <= 1) {
+    w.g_tok = reinterpret_cast<long long*>(P_(8 * B * G));
+    w.g_pad = reinterpret_cast<unsigned char*>(P_(B * G));
+    w.g_done = reinterpret_cast<unsigned char*>(P_(B));
+    w.g_score = reinterpret_cast<float*>(P_(4 * B));
+    w.g_nll = reinterpret_cast<float*>(P_(4 * B));
+    w.g_len = reinterpret_cast<float*>(P_(4 * B));
+    w.g_score_out = reinterpret_cast<float*>(P_(4 * B));
+  } else if (!tf) {
+    for (int i = 0; i < 2; ++i) {
+      w.b_tok[i] = reinterpret_cast<long long*>(P_(8 * w.nseq * G));
+      w.b_pad[i] = reinterpret_cast<unsigned char*>(P_(w.nseq * G));
+      w.b_anc[i] = reinterpret_cast<unsigned char*>(P_(w.nseq * G));
+      w.b_fin[i] = reinterpret_cast<unsigned char*>(P_(w.nseq));
+      w.b_score[i] = reinterpret_cast<float*>(P_(4 * w.nseq));
+      w.b_len[i] = reinterpret_cast<float*>(P_(4 * w.nseq));
+    }
+    w.b_norm = reinterpret_cast<float*>(P_(4 * w.nseq));
+  } else {
+    w.keypad = reinterpret_cast<unsigned char*>(P_(w.nseq * S));
+    w.effpad = reinterpret_cast<unsigned char*>(P_(w.logit_rows));
+    w.correct = reinterpret_cast<unsigned char*>(P_(w.logit_rows));
+    w.tgt_masked = reinterpret_cast<long long*>(P_(8 * w.logit_rows));
+    w.nll_rows = reinterpret_cast<float*>(P_(4 * w.logit_rows));
+    w.loss = reinterpret_cast<float*>(P_(4 * 2));
+  }
+  w.bytes = b.off;
+  *ws = w;
+  return 0;
+}
+
+// One pass of the L transformer layers over M residual rows whose LayerNorm-ed copy is already in ws.xn.
+struct PassCfg {
+  int M;
+  // sequences / positions
+  int nseq, nq, q0, slot_mul, beams;
+  const unsigned char* keypad; int keypad_ld;
+  const unsigned char* anc; int anc_ld;
+  // xn row remap applied by the last layer's FFN2 epilogue (0 = identity, output stays in ws.xn)
+  int remap_in, remap_skip, remap_out;
+};
+
+int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const int L = c.num_layers, S = h->S(), M = pc.M;
+  CUtensorMap tm_xn, tm_ao, tm_hb;
+  if (make_tmap(&tm_xn, ws.xn, M, kE, kBlockM)) return 1;
+  if (make_tmap(&tm_ao, ws.ao, M, kE, kBlockM)) return 1;
+  if (make_tmap(&tm_hb, ws.hb, M, c.ffn_dim, kBlockM)) return 1;
+  const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
+  for (int l = 0; l < L; ++l) {
+    __nv_bfloat16* kc = ws.kv + (static_cast<size_t>(l) * 2 + 0) * kv_layer;
+    __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
+    EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S};
+    if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq)) return 1;
+    AttnParams pa;
+    pa.q = ws.q; pa.kcache = kc; pa.vcache = vc; pa.out = ws.ao; pa.keypad = pc.keypad; pa.anc = pc.anc;
+    pa.nseq = pc.nseq; pa.nq = pc.nq; pa.q0 = pc.q0; pa.smax = S; pa.P = c.prefix_len; pa.beams = pc.beams;
+    pa.prefix_bidir = c.strictly_causal ? 0 : 1; pa.keypad_ld = pc.keypad_ld; pa.anc_ld = pc.anc_ld;
+    pa.slot_mul = pc.slot_mul;
+    pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+    attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
+    ++g_launches;
+    EpiRow::Params po{};
+    po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
+    if (launch_gemm<EpiRow, kStagesRow>(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1;
+    EpiGelu::Params pg{ws.hb, c.ffn_dim};
+    if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1;
+    EpiRow::Params pf{};
+    pf.x = ws.x; pf.pos = nullptr; pf.eps = c.ln_eps;
+    if (l + 1 < L) {
+      pf.xn = ws.xn; pf.gain = h->w.norm1[l + 1];
+    } else {
+      pf.gain = h->w.final_norm;
+      pf.xn = pc.remap_in > 0 ? ws.xfin : ws.xn;
+      pf.remap_rows_in = pc.remap_in; pf.remap_skip = pc.remap_skip; pf.remap_rows_out = pc.remap_out;
+    }
+    if (launch_gemm<EpiRow, kStagesRow>(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// embed (fp32, ws.ein) -> normalised bf16 -> prefix projection + positions + layer-0 LayerNorm
+int run_prefix(NovicHandle* h, const Workspace& ws, int rep, int rows_per_seq, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const int B = static_cast<int>(ws.B);
+  embed_prep_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(ws.ein, ws.ebf, B, c.embed_dim);
+  ++g_launches;
+  CUtensorMap tm_e;
+  if (make_tmap(&tm_e, ws.ebf, B, c.embed_dim, kBlockM)) return 1;
+  EpiRow::Params pp{};
+  pp.x = ws.x; pp.xn = ws.xn; pp.gain = h->w.norm1[0]; pp.pos = h->w.pos; pp.prefix_rep = rep;
+  pp.prefix_rows_per_seq = rows_per_seq; pp.eps = c.ln_eps;
+  return launch_gemm<EpiRow, kStagesRow>(s, tm_e, h->w.tm_embed_mlp, B, c.prefix_len * kE, c.embed_dim, pp);
+}
+
+template <int HCAP>
+int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
+                  const long long* target, float inv_tau, int ban_eos, cudaStream_t s) {
+  CUtensorMap tm_a;
+  if (make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
+  typename EpiLogits<kLogitBN, HCAP>::Params pl;
+  pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
+  pl.n_valid = h->cfg.vocab_size; pl.ntiles = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
+  return launch_gemm<EpiLogits<kLogitBN, HCAP>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
+}
+
+int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
+               const long long* target, float inv_tau, int ban_eos, cudaStream_t s) {
+  switch (ws.hcap) {
+    case 0: return launch_logits<0>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, s);
+    case 4: return launch_logits<4>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, s);
+    default: return launch_logits<16>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, s);
+  }
+}
+
+int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, float* logits, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const int B = static_cast<int>(ws.B), P = c.prefix_len, G = h->G(), V = c.vocab_size;
+  const float inv_tau = 1.0f / tau;
+  CUDA_TRY(cudaMemsetAsync(ws.g_done, 0, B, s));
+  CUDA_TRY(cudaMemsetAsync(ws.g_score, 0, 4 * B, s));
+  CUDA_TRY(cudaMemsetAsync(ws.g_nll, 0, 4 * B, s));
+  CUDA_TRY(cudaMemsetAsync(ws.g_len, 0, 4 * B, s));
+  CUDA_TRY(cudaMemsetAsync(ws.flags, 1, sizeof(int) * (G + 2), s));  // bytes 0x01 -> non-zero flags
+  if (run_prefix(h, ws, 1, P, s)) return 1;
+  PassCfg pre{B * P, B, P, 0, 1, 1, nullptr, 0, nullptr, 0, P, P - 1, 1};
+  if (run_layers(h, ws, pre, s)) return 1;
+  GreedyState st{ws.g_tok, ws.g_pad, ws.g_done, ws.g_score, ws.g_nll, ws.g_len, ws.flags};
+  for (int step = 1; step <= G; ++step) {
+    const __nv_bfloat16* a = (step == 1) ? ws.xfin : ws.xn;
+    float* lg = logits != nullptr ? logits + static_cast<size_t>(step - 1) * V : nullptr;
+    if (run_logits(h, ws, a, B, lg, static_cast<long long>(G) * V, nullptr, inv_tau, step == 1 ? 1 : 0, s)) return 1;
+    const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
+    select_greedy_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+        ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
+        ws.xn, c.ln_eps);
+    ++g_launches;
+    if (step < G) {
+      PassCfg dec{B, B, 1, P + step - 1, 1, 1, nullptr, 0, nullptr, 0, 0, 0, 0};
+      if (run_layers(h, ws, dec, s)) return 1;
+    }
+  }
+  greedy_finalize_kernel<<<static_cast<unsigned>(ceil_div(B, 256)), 256, 0, s>>>(B, alpha, ws.g_score, ws.g_len, ws.g_score_out);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <int HCAP>
+void launch_select_beam(const Workspace& ws, NovicHandle* h, int step, float inv_tau, float alpha, const BeamState& st,
+                        const float* pos_next, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  select_beam_kernel<HCAP><<<static_cast<unsigned>(ceil_div(ws.B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+      ws.part, ws.topv, ws.topi, ws.ntiles, static_cast<int>(ws.B), ws.H, h->G(), step, c.vocab_size, inv_tau, alpha, st,
+      h->w.tok_f32, pos_next, h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
+  ++g_launches;
+}
+
+int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const int B = static_cast<int>(ws.B), H = ws.H, P = c.prefix_len, G = h->G();
+  const int A = B * H;
+  const float inv_tau = 1.0f / tau;
+  CUDA_TRY(cudaMemsetAsync(ws.flags, 1, sizeof(int) * (G + 2), s));
+  beam_init_kernel<<<static_cast<unsigned>(ceil_div(A, 256)), 256, 0, s>>>(B, H, G, ws.b_tok[0], ws.b_pad[0], ws.b_anc[0],
+                                                                         ws.b_score[0], ws.b_len[0], ws.b_fin[0]);
+  ++g_launches;
+  if (run_prefix(h, ws, 1, P, s)) return 1;
+  PassCfg pre{B * P, B, P, 0, H, H, nullptr, 0, nullptr, 0, P, P - 1, 1};
+  if (run_layers(h, ws, pre, s)) return 1;
+  for (int step = 1; step <= G; ++step) {
+    const int in = (step - 1) & 1, out = step & 1;
+    const __nv_bfloat16* a = (step == 1) ? ws.xfin : ws.xn;
+    if (run_logits(h, ws, a, step == 1 ? B : A, nullptr, 0, nullptr, inv_tau, step == 1 ? 1 : 0, s)) return 1;
+    BeamState st{ws.b_tok[in], ws.b_tok[out], ws.b_pad[in], ws.b_pad[out], ws.b_anc[in], ws.b_anc[out], ws.b_score[in],
+                 ws.b_score[out], ws.b_norm, ws.b_len[in], ws.b_len[out], ws.b_fin[in], ws.b_fin[out], ws.flags};
+    const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
+    if (ws.hcap == 4) launch_select_beam<4>(ws, h, step, inv_tau, alpha, st, pos_next, s);
+    else launch_select_beam<16>(ws, h, step, inv_tau, alpha, st, pos_next, s);
+    if (step < G) {
+      PassCfg dec{A, A, 1, P + step - 1, 1, H, nullptr, 0, ws.b_anc[out], G, 0, 0, 0};
+      if (run_layers(h, ws, dec, s)) return 1;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int check_ready(NovicHandle* h) {
+  if (h == nullptr) return fail("null handle");
+  if (!h->weights_set) return fail("novic_set_weights has not been called");
+  CUDA_TRY(cudaSetDevice(h->device));
+  return 0;
+}
+
+// Run `enqueue` either directly on `stream` or as a cached CUDA graph (captured on the handle's own stream).
+template <class F>
+int run_maybe_graph(NovicHandle* h, const GraphKey& key, bool allow_graph, cudaStream_t stream, F&& enqueue) {
+  if (!h->use_graphs || !allow_graph) return enqueue(stream);
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = g_launches;
+    int rc = enqueue(h->capture_stream);
+    cudaError_t e = cudaStreamEndCapture(h->capture_stream, &graph);
+    g_launches = before;  // capture does not execute anything
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    size_t nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nodes);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    if (h->graphs.size() >= 16) {  // bound the cache
+      for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+      h->graphs.clear();
+      h->graph_nodes.clear();
+    }
+    h->graphs[key] = exec;
+    h->graph_nodes[key] = static_cast<int64_t>(nodes);
+    it = h->graphs.find(key);
+  }
+  CUDA_TRY(cudaGraphLaunch(it->second, stream));
+  g_launches += h->graph_nodes[key];
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* novic_last_error(void) { return g_err.c_str(); }
+int novic_version(void) { return 1; }
+int64_t novic_launch_count(void) { return g_launches; }
+
+int novic_watchdog(uint32_t* code_out) {
+  unsigned int code = 0;
+  CUDA_TRY(cudaMemcpyFromSymbol(&code, g_watchdog_code, sizeof(code)));
+  *code_out = code;
+  return 0;
+}
+
+int novic_create(const NovicCfg* cfg, NovicHandle** out) {
+  if (cfg == nullptr || out == nullptr) return fail("null argument");
+  if (cfg->hidden_dim != kE) return fail("hidden_dim must be %d (got %d)", kE, cfg->hidden_dim);
+  if (cfg->num_heads != kHeads) return fail("num_heads must be %d (got %d)", kHeads, cfg->num_heads);
+  if (cfg->ffn_dim != 128) return fail("ffn_dim must be 128 (got %d)", cfg->ffn_dim);
+  if (cfg->num_layers < 1 || cfg->num_layers > NOVIC_MAX_LAYERS) return fail("num_layers out of range");
+  if (cfg->embed_dim % 128 != 0) return fail("embed_dim must be a multiple of 128 (got %d)", cfg->embed_dim);
+  if (cfg->prefix_len < 1 || cfg->token_length < 2 || cfg->vocab_size < 2) return fail("bad prefix_len / token_length / vocab_size");
+  if (cfg->prefix_len + cfg->token_length - 1 > 255) return fail("sequence too long");
+  int dev = 0, n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return fail("no CUDA device: novic_b200 has no CPU fallback");
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; novic_b200 kernels are sm_100a only", dev, prop.major, prop.minor);
+  if (load_driver_entry()) return 1;
+  if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_gemm_attr<EpiRow, kStagesRow>() ||
+      set_gemm_attr<EpiLogits<kLogitBN, 0>, kStagesLogits>() || set_gemm_attr<EpiLogits<kLogitBN, 4>, kStagesLogits>() ||
+      set_gemm_attr<EpiLogits<kLogitBN, 16>, kStagesLogits>())
+    return 1;
+  NovicHandle* h = new NovicHandle();
+  h->cfg = *cfg;
+  h->device = dev;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMallocHost(&h->h_flags, sizeof(int) * (cfg->token_length + 2)));
+  const char* env = getenv("NOVIC_NO_GRAPHS");
+  if (env != nullptr && env[0] == '1') h->use_graphs = false;
+  *out = h;
+  return 0;
+}
+
+int novic_destroy(NovicHandle* h) {
+  if (h == nullptr) return 0;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  delete h;
+  return 0;
+}
+
+int novic_set_use_graphs(NovicHandle* h, int32_t enable) {
+  if (h == nullptr) return fail("null handle");
+  h->use_graphs = enable != 0;
+  return 0;
+}
+
+size_t novic_weight_bytes(const NovicHandle* h) {
+  const NovicCfg& c = h->cfg;
+  const size_t E = kE, K = c.ffn_dim, F = c.embed_dim, P = c.prefix_len, V = c.vocab_size, L = c.num_layers;
+  const size_t S = c.prefix_len + c.token_length - 1;
+  Bump b;
+  b.take(2 * P * E * F);
+  b.take(2 * V * E);
+  for (size_t l = 0; l < L; ++l) { b.take(2 * 3 * E * E); b.take(2 * E * E); b.take(2 * K * E); b.take(2 * E * K); }
+  b.take(4 * V * E);
+  b.take(4 * S * E);
+  b.take(4 * E);
+  for (size_t l = 0; l < L; ++l) { b.take(4 * E); b.take(4 * E); }
+  return b.off;
+}
+
+int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t wbuf_bytes, void* stream) {
+  if (h == nullptr || w == nullptr || wbuf == nullptr) return fail("null argument");
+  if (wbuf_bytes < novic_weight_bytes(h)) return fail("weight buffer too small: %zu < %zu", wbuf_bytes, novic_weight_bytes(h));
+  if ((reinterpret_cast<uintptr_t>(wbuf) & 255) != 0) return fail("weight buffer must be 256-byte aligned");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const NovicCfg& c = h->cfg;
+  const size_t E = kE, K = c.ffn_dim, F = c.embed_dim, P = c.prefix_len, V = c.vocab_size, L = c.num_layers;
+  const size_t S = c.prefix_len + c.token_length - 1;
+  char* base = static_cast<char*>(wbuf);
+  Bump b;
+  auto cvt = [&](const float* src, size_t n) -> const __nv_bfloat16* {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base + b.take(2 * n));
+    cvt_bf16_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(n), 4 * 256)), 256, 0, s>>>(src, dst, n);
+    ++g_launches;
+    return dst;
+  };
+  auto cpy = [&](const float* src, size_t n) -> const float* {
+    float* dst = reinterpret_cast<float*>(base + b.take(4 * n));
+    cudaMemcpyAsync(dst, src, 4 * n, cudaMemcpyDeviceToDevice, s);
+    return dst;
+  };
+  WeightPtrs& o = h->w;
+  o.embed_mlp = cvt(w->embed_mlp, P * E * F);
+  o.tok = cvt(w->tok_embed, V * E);
+  for (size_t l = 0; l < L; ++l) {
+    o.in_proj[l] = cvt(w->in_proj[l], 3 * E * E);
+    o.out_proj[l] = cvt(w->out_proj[l], E * E);
+    o.linear1[l] = cvt(w->linear1[l], K * E);
+    o.linear2[l] = cvt(w->linear2[l], E * K);
+  }
+  o.tok_f32 = cpy(w->tok_embed, V * E);
+  o.pos = cpy(w->pos_embed, S * E);
+  o.final_norm = cpy(w->final_norm, E);
+  for (size_t l = 0; l < L; ++l) { o.norm1[l] = cpy(w->norm1[l], E); o.norm2[l] = cpy(w->norm2[l], E); }
+  CUDA_TRY(cudaGetLastError());
+  if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, 256)) return 1;
+  if (make_tmap(&o.tm_tok, o.tok, V, E, kLogitBN)) return 1;
+  for (size_t l = 0; l < L; ++l) {
+    if (make_tmap(&o.tm_in_proj[l], o.in_proj[l], 3 * E, E, 128)) return 1;
+    if (make_tmap(&o.tm_out_proj[l], o.out_proj[l], E, E, 256)) return 1;
+    if (make_tmap(&o.tm_linear1[l], o.linear1[l], K, E, 128)) return 1;
+    if (make_tmap(&o.tm_linear2[l], o.linear2[l], E, K, 256)) return 1;
+  }
+  // the weight pointers are baked into captured graphs
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear();
+  h->graph_nodes.clear();
+  h->weights_set = true;
+  return 0;
+}
+
+size_t novic_workspace_bytes(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq) {
+  Workspace ws;
+  plan_workspace(h, num_embeds, seqs_per_embed, rows_per_seq, nullptr, &ws);
+  return ws.bytes;
+}
+
+int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
+                          int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
+                          int32_t* T_out, void* wsbuf, size_t ws_bytes, void* stream) {
+  if (check_ready(h)) return 1;
+  if (B < 1 || B > (1 << 24)) return fail("batch size out of range");
+  if (!(temperature > 0.f)) return fail("temperature must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace ws;
+  plan_workspace(h, B, 1, 0, static_cast<char*>(wsbuf), &ws);
+  if (ws_bytes < ws.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, ws.bytes);
+  const int G = h->G();
+  CUDA_TRY(cudaMemcpyAsync(ws.ein, embed, sizeof(float) * B * h->cfg.embed_dim, cudaMemcpyDeviceToDevice, s));
+  GraphKey key{0, B, 1, temperature, length_alpha, wsbuf};
+  if (run_maybe_graph(h, key, logits == nullptr, s, [&](cudaStream_t cs) { return enqueue_greedy(h, ws, temperature, length_alpha, logits, cs); }))
+    return 1;
+  CUDA_TRY(cudaMemcpyAsync(tok, ws.g_tok, 8 * B * G, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(pad, ws.g_pad, B * G, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(score, ws.g_score_out, 4 * B, cudaMemcpyDeviceToDevice, s));
+  if (nll) CUDA_TRY(cudaMemcpyAsync(nll, ws.g_nll, 4 * B, cudaMemcpyDeviceToDevice, s));
+  if (len) CUDA_TRY(cudaMemcpyAsync(len, ws.g_len, 4 * B, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_flags, ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int T = G;
+  for (int c = 1; c <= G; ++c) if (h->h_flags[c] != 0) { T = c; break; }
+  if (T_out) *T_out = T;
+  return 0;
+}
+
+int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H, float temperature,
+                        float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, void* wsbuf,
+                        size_t ws_bytes, void* stream) {
+  if (check_ready(h)) return 1;
+  if (B < 1 || B * H > (1 << 24)) return fail("batch size out of range");
+  if (H < 2 || H > NOVIC_MAX_BEAMS) return fail("beam width must be in [2, %d] (got %d); use greedy for 1", NOVIC_MAX_BEAMS, H);
+  if (H >= h->cfg.vocab_size) return fail("beam width must be smaller than the vocabulary");
+  if (!(temperature > 0.f)) return fail("temperature must be positive");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace ws;
+  plan_workspace(h, B, H, 0, static_cast<char*>(wsbuf), &ws);
+  if (ws_bytes < ws.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, ws.bytes);
+  const int G = h->G();
+  CUDA_TRY(cudaMemcpyAsync(ws.ein, embed, sizeof(float) * B * h->cfg.embed_dim, cudaMemcpyDeviceToDevice, s));
+  GraphKey key{1, B, H, temperature, length_alpha, wsbuf};
+  if (run_maybe_graph(h, key, true, s, [&](cudaStream_t cs) { return enqueue_beam(h, ws, temperature, length_alpha, cs); })) return 1;
+  const int fin = G & 1;
+  CUDA_TRY(cudaMemcpyAsync(tok, ws.b_tok[fin], 8 * ws.nseq * G, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(pad, ws.b_pad[fin], ws.nseq * G, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(score, length_alpha != 0.f ? ws.b_norm : ws.b_score[fin], 4 * ws.nseq, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_flags, ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  int T = G;
+  for (int c = 1; c < G; ++c) if (h->h_flags[c] != 0) { T = c; break; }
+  if (T_out) *T_out = T;
+  return 0;
+}
+
+int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
+                  const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
+                  uint8_t* pad_out, float* loss, uint8_t* correct, void* wsbuf, size_t ws_bytes, void* stream) {
+  if (check_ready(h)) return 1;
+  const NovicCfg& c = h->cfg;
+  if (B < 1 || M < 1 || C < 1 || C > c.token_length) return fail("bad B / M / C (C must be in [1, token_length])");
+  if (target == nullptr) return fail("target is required (embedding-only forward is not part of the hot path)");
+  const int64_t A = B * M;
+  const int P = c.prefix_len, S = P + C - 1, T = only_pred ? 1 : C, t0 = only_pred ? C - 1 : 0;
+  if (A * S > (1LL << 30)) return fail("too many rows for one call; split the batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace ws;
+  plan_workspace(h, B, M, h->S(), static_cast<char*>(wsbuf), &ws);
+  if (ws_bytes < ws.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, ws.bytes);
+  CUDA_TRY(cudaMemcpyAsync(ws.ein, embed, sizeof(float) * B * c.embed_dim, cudaMemcpyDeviceToDevice, s));
+  tf_mask_kernel<<<static_cast<unsigned>(ceil_div(A, 128)), 128, 0, s>>>(
+      reinterpret_cast<const long long*>(target), padding, weight, static_cast<int>(A), C, S, P, c.num_end_loss, T, t0, ws.keypad,
+      ws.effpad, ws.tgt_masked);
+  ++g_launches;
+  // the KV cache is laid out with smax = P + Cmax - 1 rows per sequence regardless of C
+  if (run_prefix(h, ws, M, S, s)) return 1;
+  if (C > 1) {
+    token_embed_kernel<<<static_cast<unsigned>(ceil_div(A * (C - 1), kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+        reinterpret_cast<const long long*>(target), C, static_cast<int>(A), C - 1, S, P, c.vocab_size, h->w.tok_f32, h->w.pos,
+        h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
+    ++g_launches;
+  }
+  const bool has_pad = padding != nullptr || weight != nullptr;
+  PassCfg pc{static_cast<int>(A * S), static_cast<int>(A), S, 0, 1, 1, has_pad ? ws.keypad : nullptr, S, nullptr, 0,
+             S, only_pred ? S - 1 : P - 1, T};
+  if (run_layers(h, ws, pc, s)) return 1;
+  const bool need_stats = loss != nullptr || correct != nullptr;
+  if (run_logits(h, ws, ws.xfin, static_cast<int>(A * T), logits, c.vocab_size, need_stats ? ws.tgt_masked : nullptr, 1.0f, 0, s)) return 1;
+  if (need_stats) {
+    loss_rows_kernel<<<static_cast<unsigned>(ceil_div(A * T, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+        ws.part, ws.ntiles, static_cast<int>(A * T), c.vocab_size, c.label_smoothing, ws.tgt_masked, ws.nll_rows, ws.correct);
+    ++g_launches;
+    if (loss != nullptr) {
+      loss_reduce_kernel<<<1, 1024, 0, s>>>(ws.nll_rows, ws.tgt_masked, weight, static_cast<int>(A), T, ws.loss);
+      ++g_launches;
+      CUDA_TRY(cudaMemcpyAsync(loss, ws.loss, 8, cudaMemcpyDeviceToDevice, s));
+    }
+    if (correct != nullptr) CUDA_TRY(cudaMemcpyAsync(correct, ws.correct, A * T, cudaMemcpyDeviceToDevice, s));
+  }
+  if (pad_out != nullptr) CUDA_TRY(cudaMemcpyAsync(pad_out, ws.effpad, A * T, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int noise_launch(const NovicNoiseCfg* cfg, float* embed, int64_t B, const float* na, const float* nb, const float* ra,
+                        const float* rb, uint64_t seed, uint64_t offset, cudaStream_t s) {
+  if (cfg == nullptr || embed == nullptr) return fail("null argument");
+  if (cfg->scheme < 0 || cfg->scheme > 4) return fail("unsupported embedding noise scheme %d", cfg->scheme);
+  if (cfg->embed_dim % 128 != 0 || cfg->embed_dim > 2048) return fail("embed_dim must be a multiple of 128 and <= 2048");
+  const float d2r = 0.017453292519943295f;
+  NoiseParams p;
+  p.scheme = cfg->scheme; p.F = cfg->embed_dim; p.vec_norm = cfg->vec_norm;
+  p.angle_min_rad = cfg->angle_min * d2r; p.angle_max_rad = cfg->angle_max * d2r; p.angle_std_rad = cfg->angle_std * d2r;
+  p.mix_ratio = cfg->mix_ratio;
+  p.pre_normals_a = na; p.pre_normals_b = nb; p.pre_row_a = ra; p.pre_row_b = rb;
+  const unsigned grid = static_cast<unsigned>(ceil_div(B, kWarpsPerBlock));
+  if (cfg->embed_dim <= 1024) noise_kernel<32><<<grid, kWarpsPerBlock * 32, 0, s>>>(embed, static_cast<int>(B), p, seed, offset);
+  else noise_kernel<64><<<grid, kWarpsPerBlock * 32, 0, s>>>(embed, static_cast<int>(B), p, seed, offset);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int novic_noise_apply(const NovicNoiseCfg* cfg, float* embed, int64_t B, uint64_t seed, uint64_t offset, void* stream) {
+  return noise_launch(cfg, embed, B, nullptr, nullptr, nullptr, nullptr, seed, offset, static_cast<cudaStream_t>(stream));
+}
+
+int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B, const float* normals_a,
+                               const float* normals_b, const float* row_a, const float* row_b, void* stream) {
+  if (normals_a == nullptr) return fail("normals_a is required");
+  return noise_launch(cfg, embed, B, normals_a, normals_b, row_a, row_b, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq,
+                          const char* name, size_t* offset_out) {
+  if (h == nullptr || name == nullptr || offset_out == nullptr) return fail("null argument");
+  Workspace ws;
+  plan_workspace(h, num_embeds, seqs_per_embed, rows_per_seq, nullptr, &ws);
+  const std::string n(name);
+  const char* p = nullptr;
+  if (n == "ein") p = reinterpret_cast<const char*>(ws.ein);
+  else if (n == "ebf") p = reinterpret_cast<const char*>(ws.ebf);
+  else if (n == "x") p = reinterpret_cast<const char*>(ws.x);
+  else if (n == "xn") p = reinterpret_cast<const char*>(ws.xn);
+  else if (n == "xfin") p = reinterpret_cast<const char*>(ws.xfin);
+  else if (n == "q") p = reinterpret_cast<const char*>(ws.q);
+  else if (n == "ao") p = reinterpret_cast<const char*>(ws.ao);
+  else if (n == "hb") p = reinterpret_cast<const char*>(ws.hb);
+  else if (n == "kv") p = reinterpret_cast<const char*>(ws.kv);
+  else if (n == "part") p = reinterpret_cast<const char*>(ws.part);
+  else return fail("unknown workspace buffer '%s'", name);
+  *offset_out = static_cast<size_t>(p - static_cast<const char*>(nullptr));
+  return 0;
+}
+
+int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,
+                     int32_t block_n, void* stream) {
+  if (M < 1 || N < 1 || K < 64 || K % 64 != 0) return fail("bad GEMM shape");
+  if (block_n != 128) return fail("debug GEMM supports block_n = 128");
+  if (set_gemm_attr<EpiLogits<128, 0>, kStagesLogits>()) return 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tb;
+  if (make_tmap(&ta, a_bf16, M, K, kBlockM)) return 1;
+  if (make_tmap(&tb, w_bf16, N, K, 128)) return 1;
+  const int ntiles = static_cast<int>(ceil_div(N, 128));
+  LogitPartial* part = nullptr;
+  CUDA_TRY(cudaMallocAsync(&part, sizeof(LogitPartial) * static_cast<size_t>(M) * ntiles, s));
+  EpiLogits<128, 0>::Params pl;
+  pl.logits = out; pl.ld_logits = N; pl.part = part; pl.topv = nullptr; pl.topi = nullptr; pl.target = nullptr;
+  pl.n_valid = N; pl.ntiles = ntiles; pl.inv_tau = 1.0f; pl.ban_eos = 0;
+  int rc = launch_gemm<EpiLogits<128, 0>, kStagesLogits>(s, ta, tb, M, N, K, pl);
+  CUDA_TRY(cudaFreeAsync(part, s));
+  return rc;
+}
+
+}  // extern "C"

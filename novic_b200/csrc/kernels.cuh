@@ -1,0 +1,615 @@
+// Non-GEMM kernels of the decoder hot path: embedding normalisation, token-embedding gather + LayerNorm,
+// KV-cache attention (decode / prefill / teacher-forced), greedy and beam selection over the vocabulary
+// partials written by the logits epilogue, loss reduction, and the fused embedding-noise kernel.
+// All of them are HBM/L2-bound byte shuffling: warp-per-row, 128-bit coalesced accesses, shuffles for the
+// reductions, no shared-memory staging needed.
+#pragma once
+
+#include <curand_kernel.h>
+
+#include "gemm.cuh"
+
+namespace novic {
+
+constexpr int kHeads = 8;
+constexpr int kHeadDim = 64;
+constexpr int kWarpsPerBlock = 4;
+
+// ---------------------------------------------------------------------------------------------------------
+// F.normalize(embed) -> bf16 (embedding_decoder.py:1276), warp per row
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+embed_prep_kernel(const float* __restrict__ embed, __nv_bfloat16* __restrict__ out, int B, int F) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = lane_id();
+  const float4* src = reinterpret_cast<const float4*>(embed + static_cast<size_t>(row) * F);
+  float ss = 0.f;
+  for (int i = lane; i < F / 4; i += 32) {
+    const float4 v = __ldg(src + i);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  uint2* dst = reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * F);
+  for (int i = lane; i < F / 4; i += 32) {
+    const float4 v = __ldg(src + i);
+    dst[i] = make_uint2(pack_bf16x2(v.x * inv, v.y * inv), pack_bf16x2(v.z * inv, v.w * inv));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One residual-stream row from a token id: x = W_tied[tok] + pos[p]; xn = LayerNorm(x) * gain -> bf16.
+// Executed by a full warp; lane owns columns [16*lane, 16*lane + 16).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void embed_token_row(const float* __restrict__ wtok, const float* __restrict__ pos_row,
+                                                const float* __restrict__ gain, long long tok, int out_row,
+                                                float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps) {
+  const int lane = lane_id();
+  const float4* w4 = reinterpret_cast<const float4*>(wtok + static_cast<size_t>(tok) * kE) + lane * 4;
+  const float4* p4 = reinterpret_cast<const float4*>(pos_row) + lane * 4;
+  float v[16];
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 a = __ldg(w4 + q);
+    const float4 b = __ldg(p4 + q);
+    v[q * 4 + 0] = a.x + b.x; v[q * 4 + 1] = a.y + b.y; v[q * 4 + 2] = a.z + b.z; v[q * 4 + 3] = a.w + b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { sum += v[i]; sumsq += v[i] * v[i]; }
+  sum = warp_sum(sum);
+  sumsq = warp_sum(sumsq);
+  const float mean = sum * (1.0f / kE);
+  const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + eps);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<float4*>(x + xblk_off(out_row, lane * 4 + q)) =
+        make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+  const float4* g4 = reinterpret_cast<const float4*>(gain) + lane * 4;
+  uint32_t o[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 g = __ldg(g4 + q);
+    o[q * 2 + 0] = pack_bf16x2((v[q * 4 + 0] - mean) * rstd * g.x, (v[q * 4 + 1] - mean) * rstd * g.y);
+    o[q * 2 + 1] = pack_bf16x2((v[q * 4 + 2] - mean) * rstd * g.z, (v[q * 4 + 3] - mean) * rstd * g.w);
+  }
+  uint4* d = reinterpret_cast<uint4*>(xn + static_cast<size_t>(out_row) * kE) + lane * 2;
+  d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// Teacher-forced token rows (embedding_decoder.py:692-693): sequence a, token index i -> row a*S + P + i.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+token_embed_kernel(const long long* __restrict__ target, int ld_target, int nseq, int ntok, int S, int P, int V,
+                   const float* __restrict__ wtok, const float* __restrict__ pos, const float* __restrict__ gain,
+                   float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps) {
+  const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (w >= nseq * ntok) return;
+  const int a = w / ntok, i = w - a * ntok;
+  long long tok = target[static_cast<size_t>(a) * ld_target + i];
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  embed_token_row(wtok, pos + static_cast<size_t>(P + i) * kE, gain, tok, a * S + P + i, x, xn, eps);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Attention over the KV cache.  One warp per (sequence, query position); lane owns 16 contiguous channels
+// (head = lane / 4), K/V rows are read as 2 x 128-bit per lane (1 KB per row per warp, fully coalesced),
+// scores are reduced over the 4 lanes of a head with shuffles, softmax is online in fp32.
+// Visibility (embedding_decoder.py:651-654, :696-712): key j is visible to query s iff j <= s, or both are
+// prefix positions (unless strictly causal); a key-padding byte masks key j > 0.
+// KV pages: prefix positions live in the page of the first beam of the sequence's group; token position j
+// lives in the page named by the ancestry table (beam search reorders by rewriting this table, never by
+// moving K/V); the query's own position is always in the sequence's own page.
+// ---------------------------------------------------------------------------------------------------------
+struct AttnParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* kcache;
+  const __nv_bfloat16* vcache;
+  __nv_bfloat16* out;
+  const unsigned char* keypad;  // optional [nseq, keypad_ld]
+  const unsigned char* anc;     // optional [nseq, anc_ld]
+  int nseq, nq, q0, smax, P, beams, slot_mul, prefix_bidir, keypad_ld, anc_ld;
+  float scale_log2e;            // (1/sqrt(head_dim)) * log2(e)
+};
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float* f) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) attention_kernel(const AttnParams p) {
+  const int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (w >= p.nseq * p.nq) return;
+  const int lane = lane_id();
+  const int a = w / p.nq;
+  const int qpos = p.q0 + (w - a * p.nq);
+  const int nkeys = (p.prefix_bidir && qpos < p.P) ? p.P : qpos + 1;
+  const int own_slot = a * p.slot_mul;
+  const int group0 = (own_slot / p.beams) * p.beams;
+
+  float qf[16];
+  {
+    const uint4* q4 = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(w) * kE) + lane * 2;
+    const uint4 u0 = __ldg(q4), u1 = __ldg(q4 + 1);
+    bf16x8_to_f32(u0, qf);
+    bf16x8_to_f32(u1, qf + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) qf[i] *= p.scale_log2e;
+  }
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+
+  constexpr int UNR = 4;
+  for (int j0 = 0; j0 < nkeys; j0 += UNR) {
+    uint4 kr[UNR][2], vr[UNR][2];
+    bool valid[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u;
+      valid[u] = j < nkeys;
+      if (valid[u] && p.keypad != nullptr && j > 0 && p.keypad[static_cast<size_t>(a) * p.keypad_ld + j]) valid[u] = false;
+      if (valid[u]) {
+        int slot;
+        if (j < p.P) slot = group0;
+        else if (p.anc != nullptr && j < qpos) slot = group0 + p.anc[static_cast<size_t>(a) * p.anc_ld + (j - p.P)];
+        else slot = own_slot;
+        const size_t off = (static_cast<size_t>(slot) * p.smax + j) * kE;
+        const uint4* k4 = reinterpret_cast<const uint4*>(p.kcache + off) + lane * 2;
+        const uint4* v4 = reinterpret_cast<const uint4*>(p.vcache + off) + lane * 2;
+        kr[u][0] = k4[0]; kr[u][1] = k4[1];
+        vr[u][0] = v4[0]; vr[u][1] = v4[1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (!valid[u]) continue;  // warp-uniform
+      float kf[16];
+      bf16x8_to_f32(kr[u][0], kf);
+      bf16x8_to_f32(kr[u][1], kf + 8);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s = fmaf(qf[i], kf[i], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const float m_new = fmaxf(m, s);
+      const float corr = exp2f(m - m_new);
+      const float pj = exp2f(s - m_new);
+      l = l * corr + pj;
+      float vf[16];
+      bf16x8_to_f32(vr[u][0], vf);
+      bf16x8_to_f32(vr[u][1], vf + 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], corr, pj * vf[i]);
+      m = m_new;
+    }
+  }
+  const float inv = 1.0f / l;
+  uint32_t o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+  uint4* d = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(w) * kE) + lane * 2;
+  d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Merging the per-tile logits statistics of one row (executed by a full warp)
+// ---------------------------------------------------------------------------------------------------------
+struct RowStats {
+  float max_all;   // natural-unit max over the vocabulary
+  float lse_tau;   // log sum exp(x / tau)
+  float lse_one;   // log sum exp(x)
+  float sum_x;
+  float best_val;
+  int best_idx;
+  float tgt_logit;
+};
+
+__device__ __forceinline__ RowStats merge_partials(const LogitPartial* __restrict__ part, int ntiles, float inv_tau) {
+  const int lane = lane_id();
+  float mx = -INFINITY, best = -INFINITY, sum_x = 0.f, tgt = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int t = lane; t < ntiles; t += 32) {
+    const LogitPartial q = part[t];
+    mx = fmaxf(mx, q.max_all);
+    sum_x += q.sum_x;
+    tgt = fmaxf(tgt, q.tgt_logit);
+    if (q.best_val > best || (q.best_val == best && q.best_idx < best_i)) { best = q.best_val; best_i = q.best_idx; }
+  }
+  mx = warp_max(mx);
+  float s_tau = 0.f, s_one = 0.f;
+  for (int t = lane; t < ntiles; t += 32) {
+    const LogitPartial q = part[t];
+    s_one += q.sumexp_one * __expf(q.max_all - mx);
+    s_tau += q.sumexp_tau * __expf((q.max_all - mx) * inv_tau);
+  }
+  s_one = warp_sum(s_one);
+  s_tau = warp_sum(s_tau);
+  sum_x = warp_sum(sum_x);
+  tgt = warp_max(tgt);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+  }
+  RowStats r;
+  r.max_all = mx;
+  r.lse_one = mx + __logf(s_one);
+  r.lse_tau = mx * inv_tau + __logf(s_tau);
+  r.sum_x = sum_x;
+  r.best_val = best;
+  r.best_idx = best_i;
+  r.tgt_logit = tgt;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Greedy step (embedding_decoder.py:802-817): pick the arg-max token, update padding / done / score / loss
+// accumulators and emit the next step's input row (token embedding + position + layer-0 LayerNorm).
+// ---------------------------------------------------------------------------------------------------------
+struct GreedyState {
+  long long* tok;        // [B, G]
+  unsigned char* pad;    // [B, G]
+  unsigned char* done;   // [B]
+  float* score;          // [B]  sum of log p_tau(token)
+  float* nll;            // [B]  sum of -log p_1(token)  (+ label smoothing term)
+  float* len;            // [B]  number of unpadded tokens
+  int* alldone;          // [G + 1] per-step "every row finished" flags (host resets to 1)
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+select_greedy_kernel(const LogitPartial* __restrict__ part, int ntiles, int B, int G, int step /*1-based*/, int V,
+                     float inv_tau, float label_smoothing, GreedyState st, const float* __restrict__ wtok,
+                     const float* __restrict__ pos_next, const float* __restrict__ gain0, float* __restrict__ x,
+                     __nv_bfloat16* __restrict__ xn, float eps) {
+  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const RowStats r = merge_partials(part + static_cast<size_t>(b) * ntiles, ntiles, inv_tau);
+  const bool was_done = st.done[b] != 0;
+  const long long tok = r.best_idx;
+  if (lane_id() == 0) {
+    st.pad[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 1 : 0;
+    st.tok[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 0 : tok;
+    if (!was_done) {
+      st.score[b] += r.best_val * inv_tau - r.lse_tau;
+      float nll = r.lse_one - r.best_val;
+      if (label_smoothing != 0.f) nll = (1.f - label_smoothing) * nll + label_smoothing * (r.lse_one - r.sum_x / V);
+      st.nll[b] += nll;
+      st.len[b] += 1.f;
+    }
+    const bool now_done = was_done || tok == 0;
+    st.done[b] = now_done ? 1 : 0;
+    if (!now_done) st.alldone[step] = 0;
+  }
+  if (pos_next != nullptr) embed_token_row(wtok, pos_next, gain0, tok, b, x, xn, eps);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Beam step (embedding_decoder.py:911-978, unguided, no vocab prior).  One warp per sample.  Every live
+// candidate row contributes its per-tile top-HCAP logits (the H best continuations of a row are among the
+// union of its tiles' H best); a finished candidate contributes exactly (its score, end token).  The H best
+// totals are drawn in (score descending, flat index ascending) order.
+// ---------------------------------------------------------------------------------------------------------
+struct BeamState {
+  const long long* tok_in;  long long* tok_out;          // [B, H, G]
+  const unsigned char* pad_in; unsigned char* pad_out;   // [B, H, G]
+  const unsigned char* anc_in; unsigned char* anc_out;   // [B, H, G]
+  const float* score_in; float* score_out;               // [B, H] raw sum of log-probs
+  float* score_norm_out;                                 // [B, H] length-normalised score of this step's ranking
+  const float* len_in; float* len_out;                   // [B, H]
+  const unsigned char* fin_in; unsigned char* fin_out;   // [B, H] candidate finished (its next position is padding)
+  int* allfin;                                           // [G + 1]
+};
+
+template <int HCAP>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restrict__ topv, const int* __restrict__ topi,
+                   int ntiles, int B, int H, int G, int step, int V, float inv_tau, float length_alpha, BeamState st,
+                   const float* __restrict__ wtok, const float* __restrict__ pos_next, const float* __restrict__ gain0,
+                   float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps) {
+  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = lane_id();
+  const int nrows = (step == 1) ? 1 : H;                 // logits rows available for this sample
+  const size_t row0 = (step == 1) ? static_cast<size_t>(b) : static_cast<size_t>(b) * H;
+  __shared__ float s_lse[kWarpsPerBlock][16], s_base[kWarpsPerBlock][16], s_scale[kWarpsPerBlock][16];
+  __shared__ unsigned char s_fin[kWarpsPerBlock][16];
+  float* lse = s_lse[threadIdx.x >> 5];
+  float* base = s_base[threadIdx.x >> 5];
+  float* scale = s_scale[threadIdx.x >> 5];
+  unsigned char* fin = s_fin[threadIdx.x >> 5];
+  for (int h = 0; h < H; ++h) {
+    float l = 0.f;
+    if (h < nrows) {
+      const RowStats r = merge_partials(part + (row0 + h) * ntiles, ntiles, inv_tau);
+      l = r.lse_tau;
+    }
+    if (lane == 0) {
+      lse[h] = l;
+      base[h] = st.score_in[static_cast<size_t>(b) * H + h];
+      fin[h] = st.fin_in[static_cast<size_t>(b) * H + h];
+      scale[h] = (length_alpha != 0.f) ? __powf(fmaxf(st.len_in[static_cast<size_t>(b) * H + h], 1.f), -length_alpha) : 1.f;
+    }
+  }
+  __syncwarp();
+  const int per_row = ntiles * HCAP;
+  float prev_v = INFINITY;
+  long long prev_f = -1;
+  for (int k = 0; k < H; ++k) {
+    float bv = -INFINITY, braw = -INFINITY;
+    long long bf = 0x7fffffffffffffffLL;
+    for (int h = 0; h < H; ++h) {
+      if (fin[h] || h >= nrows) {
+        // finished (or not yet existing) candidate: single continuation = end token at zero cost
+        if (lane == 0) {
+          const float raw = base[h];
+          const float v = (length_alpha != 0.f) ? raw * scale[h] : raw;
+          const long long f = static_cast<long long>(h) * V;
+          const bool after_prev = (v < prev_v) || (v == prev_v && f > prev_f);
+          if (after_prev && (v > bv || (v == bv && f < bf))) { bv = v; bf = f; braw = raw; }
+        }
+        continue;
+      }
+      const float* tvp = topv + (row0 + h) * per_row;
+      const int* tip = topi + (row0 + h) * per_row;
+      for (int e = lane; e < per_row; e += 32) {
+        const int idx = tip[e];
+        if (idx >= V) continue;  // unused slot
+        const float raw = base[h] + (tvp[e] * inv_tau - lse[h]);
+        const float v = (length_alpha != 0.f) ? raw * scale[h] : raw;
+        const long long f = static_cast<long long>(h) * V + idx;
+        const bool after_prev = (v < prev_v) || (v == prev_v && f > prev_f);
+        if (after_prev && (v > bv || (v == bv && f < bf))) { bv = v; bf = f; braw = raw; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const float oraw = __shfl_xor_sync(0xffffffffu, braw, o);
+      const long long of = __shfl_xor_sync(0xffffffffu, bf, o);
+      if (ov > bv || (ov == bv && of < bf)) { bv = ov; bf = of; braw = oraw; }
+    }
+    prev_v = bv;
+    prev_f = bf;
+    const int parent = static_cast<int>(bf / V);
+    const long long tok = bf - static_cast<long long>(parent) * V;
+    const size_t o = static_cast<size_t>(b) * H + k;
+    const size_t pi = static_cast<size_t>(b) * H + parent;
+    const bool parent_fin = fin[parent] != 0;
+    const bool nxt_fin = parent_fin || tok == 0;
+    // history: columns [0, step-1) come from the parent, column step-1 is the new token
+    for (int j = lane; j < G; j += 32) {
+      long long t = 0;
+      unsigned char pd = 1, an = 0;
+      if (j < step - 1) {
+        t = st.tok_in[pi * G + j];
+        pd = st.pad_in[pi * G + j];
+        an = st.anc_in[pi * G + j];
+      } else if (j == step - 1) {
+        t = tok;
+        pd = parent_fin ? 1 : 0;
+      } else if (j == step) {
+        pd = nxt_fin ? 1 : 0;
+      }
+      if (step >= 2 && j == step - 2) an = static_cast<unsigned char>(parent);
+      st.tok_out[o * G + j] = pd ? 0 : t;
+      st.pad_out[o * G + j] = pd;
+      st.anc_out[o * G + j] = an;
+    }
+    if (lane == 0) {
+      st.score_out[o] = braw;
+      st.score_norm_out[o] = bv;
+      st.len_out[o] = st.len_in[pi] + (nxt_fin ? 0.f : 1.f);
+      st.fin_out[o] = nxt_fin ? 1 : 0;
+      if (!nxt_fin) st.allfin[step] = 0;
+    }
+    if (pos_next != nullptr) embed_token_row(wtok, pos_next, gain0, tok, static_cast<int>(o), x, xn, eps);
+  }
+}
+
+__global__ void beam_init_kernel(int B, int H, int G, long long* tok, unsigned char* pad, unsigned char* anc, float* score,
+                                 float* len, unsigned char* fin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int h = i % H;
+  for (int j = 0; j < G; ++j) {
+    tok[static_cast<size_t>(i) * G + j] = 0;
+    pad[static_cast<size_t>(i) * G + j] = (h == 0 && j == 0) ? 0 : 1;   // embedding_decoder.py:861-862
+    anc[static_cast<size_t>(i) * G + j] = 0;
+  }
+  score[i] = (h == 0) ? 0.f : -INFINITY;                                // :863-864
+  len[i] = (h == 0) ? 1.f : 0.f;                                        // :898-899
+  fin[i] = (h == 0) ? 0 : 1;
+}
+
+// score * clamp(len, 1)^-alpha (embedding_decoder.py:836)
+__global__ void greedy_finalize_kernel(int B, float length_alpha, const float* __restrict__ score_sum,
+                                       const float* __restrict__ len, float* __restrict__ score_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = score_sum[b];
+  if (length_alpha != 0.f) s *= __powf(fmaxf(len[b], 1.f), -length_alpha);
+  score_out[b] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Teacher-forced loss / correctness per target position (embedding_decoder.py:729-761)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+loss_rows_kernel(const LogitPartial* __restrict__ part, int ntiles, int nrows, int V, float label_smoothing,
+                 const long long* __restrict__ target /*-1 = ignored*/, float* __restrict__ nll_out,
+                 unsigned char* __restrict__ correct_out) {
+  const int r = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= nrows) return;
+  const RowStats s = merge_partials(part + static_cast<size_t>(r) * ntiles, ntiles, 1.0f);
+  if (lane_id() == 0) {
+    const long long t = target[r];
+    float nll = 0.f;
+    if (t >= 0) {
+      nll = s.lse_one - s.tgt_logit;
+      if (label_smoothing != 0.f) nll = (1.f - label_smoothing) * nll + label_smoothing * (s.lse_one - s.sum_x / V);
+    }
+    nll_out[r] = nll;
+    if (correct_out != nullptr) correct_out[r] = (t >= 0 && static_cast<long long>(s.best_idx) == t) ? 1 : 0;
+  }
+}
+
+// Deterministic single-block reduction: loss_sum = sum_a w_a * sum_t nll[a, t]; basis = sum_a w_a * n_valid_a
+__global__ void __launch_bounds__(1024)
+loss_reduce_kernel(const float* __restrict__ nll, const long long* __restrict__ target, const float* __restrict__ weight,
+                   int nseq, int C, float* __restrict__ out /*[2]*/) {
+  __shared__ double s_loss[32], s_basis[32];
+  double loss = 0.0, basis = 0.0;
+  for (int a = threadIdx.x; a < nseq; a += blockDim.x) {
+    float l = 0.f;
+    int n = 0;
+    for (int t = 0; t < C; ++t) {
+      l += nll[static_cast<size_t>(a) * C + t];
+      n += target[static_cast<size_t>(a) * C + t] >= 0;
+    }
+    const float w = weight != nullptr ? weight[a] : 1.f;
+    loss += static_cast<double>(w) * l;
+    basis += static_cast<double>(w) * n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    basis += __shfl_xor_sync(0xffffffffu, basis, o);
+  }
+  if (lane_id() == 0) { s_loss[threadIdx.x >> 5] = loss; s_basis[threadIdx.x >> 5] = basis; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    loss = threadIdx.x < (blockDim.x >> 5) ? s_loss[threadIdx.x] : 0.0;
+    basis = threadIdx.x < (blockDim.x >> 5) ? s_basis[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      basis += __shfl_xor_sync(0xffffffffu, basis, o);
+    }
+    if (threadIdx.x == 0) { out[0] = static_cast<float>(loss); out[1] = static_cast<float>(basis); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Embedding noise (embedding_noise.py), fused draw + perturb + renormalise, in place.  Warp per row.
+// With `pre` pointers given the random draws are read instead of generated (deterministic parity mode).
+// ---------------------------------------------------------------------------------------------------------
+enum NoiseScheme : int { kGaussElem = 0, kGaussVec = 1, kGaussAngle = 2, kUniformAngle = 3, kGaussElemUniformAngle = 4 };
+
+struct NoiseParams {
+  int scheme, F;
+  float vec_norm, angle_min_rad, angle_max_rad, angle_std_rad, mix_ratio;
+  const float* pre_normals_a;  // [B, F] direction normals (angle schemes) or element normals (Gauss schemes)
+  const float* pre_normals_b;  // [B, F] element normals of the mix scheme's Gaussian branch
+  const float* pre_row_a;      // [B] angle draw (uniform [0,1) or standard normal) / GaussVec scalar normal
+  const float* pre_row_b;      // [B] mix uniform
+};
+
+template <int MAXF_PER_LANE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+noise_kernel(float* __restrict__ embed, int B, NoiseParams p, unsigned long long seed, unsigned long long offset) {
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = lane_id();
+  const int F = p.F;
+  const int per = F / 32;  // host guarantees F % 128 == 0 and per <= MAXF_PER_LANE
+  float* e = embed + static_cast<size_t>(row) * F;
+  const bool pre = p.pre_normals_a != nullptr;
+
+  curandStatePhilox4_32_10_t rng;
+  if (!pre) curand_init(seed, static_cast<unsigned long long>(row) * 32 + lane, offset, &rng);
+
+  float row_a = 0.f, row_b = 0.f;
+  if (pre) {
+    row_a = p.pre_row_a != nullptr ? p.pre_row_a[row] : 0.f;
+    row_b = p.pre_row_b != nullptr ? p.pre_row_b[row] : 0.f;
+  } else {
+    // per-row scalars are drawn by lane 0 and broadcast
+    float ua = 0.f, ub = 0.f;
+    if (lane == 0) {
+      const float4 n = curand_normal4(&rng);
+      const float4 u = curand_uniform4(&rng);
+      ua = (p.scheme == kGaussAngle || p.scheme == kGaussVec) ? n.x : (1.0f - u.x);  // curand uniform is (0,1]
+      ub = 1.0f - u.y;
+    } else {
+      (void)curand_normal4(&rng);
+      (void)curand_uniform4(&rng);
+    }
+    row_a = __shfl_sync(0xffffffffu, ua, 0);
+    row_b = __shfl_sync(0xffffffffu, ub, 0);
+  }
+  const bool angle_branch = p.scheme == kGaussAngle || p.scheme == kUniformAngle ||
+                            (p.scheme == kGaussElemUniformAngle && row_b < p.mix_ratio);
+
+  float ev[MAXF_PER_LANE], nv[MAXF_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAXF_PER_LANE; i += 4) {
+    if (i < per) {
+      const int col = (i / 4) * 128 + lane * 4;
+      const float4 v = *reinterpret_cast<const float4*>(e + col);
+      ev[i] = v.x; ev[i + 1] = v.y; ev[i + 2] = v.z; ev[i + 3] = v.w;
+      float4 n;
+      if (pre) {
+        const float* src = (p.scheme == kGaussElemUniformAngle && !angle_branch) ? p.pre_normals_b : p.pre_normals_a;
+        n = *reinterpret_cast<const float4*>(src + static_cast<size_t>(row) * F + col);
+      } else {
+        n = curand_normal4(&rng);
+      }
+      nv[i] = n.x; nv[i + 1] = n.y; nv[i + 2] = n.z; nv[i + 3] = n.w;
+    }
+  }
+  float outv[MAXF_PER_LANE];
+  if (angle_branch) {
+    // d = unit(n - e (e.n)); e' = unit(e cos(a) + d sin(a))       (embedding_noise.py:105-112)
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) dot = fmaf(ev[i], nv[i], dot);
+    dot = warp_sum(dot);
+    float dd = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) { nv[i] = fmaf(-ev[i], dot, nv[i]); dd = fmaf(nv[i], nv[i], dd); }
+    dd = warp_sum(dd);
+    const float dinv = 1.0f / fmaxf(sqrtf(dd), 1e-12f);
+    float ang;
+    if (p.scheme == kGaussAngle) ang = fminf(fmaxf(row_a * p.angle_std_rad, -p.angle_max_rad), p.angle_max_rad);
+    else ang = p.angle_min_rad + (p.angle_max_rad - p.angle_min_rad) * row_a;
+    float sn, cs;
+    sincosf(ang, &sn, &cs);
+#pragma unroll
+    for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) outv[i] = ev[i] * cs + nv[i] * dinv * sn;
+  } else if (p.scheme == kGaussVec) {
+    // e' = unit(e + vec_norm * g * unit(n))                         (embedding_noise.py:90-95)
+    float nn = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) nn = fmaf(nv[i], nv[i], nn);
+    nn = warp_sum(nn);
+    const float k = p.vec_norm * row_a / fmaxf(sqrtf(nn), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) outv[i] = fmaf(k, nv[i], ev[i]);
+  } else {
+    // e' = unit(e + (vec_norm / sqrt(F)) * n)                       (embedding_noise.py:72-75)
+    const float sigma = p.vec_norm * rsqrtf(static_cast<float>(F));
+#pragma unroll
+    for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) outv[i] = fmaf(sigma, nv[i], ev[i]);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXF_PER_LANE; ++i) if (i < per) ss = fmaf(outv[i], outv[i], ss);
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < MAXF_PER_LANE; i += 4) {
+    if (i < per) {
+      const int col = (i / 4) * 128 + lane * 4;
+      *reinterpret_cast<float4*>(e + col) = make_float4(outv[i] * inv, outv[i + 1] * inv, outv[i + 2] * inv, outv[i + 3] * inv);
+    }
+  }
+}
+
+}  // namespace novic
