@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the NOVIC decoder hot path: labels/sec, greedy decode, batch 4096 per GPU (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one greedy decode (prefix prefill + 15 autoregressive steps, KV-cached) of one batch of 4096 synthetic
+unit-norm 1024-d embeddings per GPU through novic_b200.PrefixedIterDecoder (random-init default decoder,
+config/train.yaml:224-308).  Rank 0 prints ONE JSON line (see the keys below).  `--impl reference` times the CPU
+port of the reference's own algorithm (oracle/, re-forward schedule without KV cache) on the host cores instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH_PER_GPU = 4096
+METRIC = "labels/sec (greedy, batch 4096)"
+UNIT = "labels/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="embeddings per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="embeddings in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": "BASELINE configs[1]: random-init default EmbeddingDecoder (E=512, FFN 128, L=6, 8 heads, P=4, V=6912, Cmax=16), "
+                    f"{args.batch} synthetic unit-norm 1024-d embeddings per GPU, greedy decode (15 steps, tau=1, alpha=0), bf16 operands / fp32 accumulate",
+        "batch_per_gpu": args.batch, "global_batch": args.batch * world, "gen_steps": 15, "parallelism": f"dp{world} (batch shards, final id gather)",
+        "l2": "L2 flushed (256 MiB write) between timed iterations; per-step working set (KV cache 0.96 GB) also exceeds L2",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference algorithm (no KV cache, re-forward every step), all host threads
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_greedy_rate(sample: int, repeats: int = 1, warmup: int = 1):
+    from novic_b200 import synth
+    from oracle import novic_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    dims = synth.DecoderDims()
+    sd = synth.synth_state_dict(dims, seed=1)
+    cfg = orc.cfg_from_state_dict(sd)
+    embed = synth.synth_embeddings(sample, seed=1234)
+    times = []
+    with torch.inference_mode():
+        for _ in range(warmup):
+            orc.generate_greedy(cfg, sd, embed[: min(16, sample)], 1.0, 0.0)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            orc.generate_greedy(cfg, sd, embed, 1.0, 0.0)
+            times.append(time.perf_counter() - t0)
+    return times, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    sample = args.cpu_sample
+    times, cores = cpu_greedy_rate(sample, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    ms = statistics.mean(times) * 1e3
+    value = sample / (ms / 1e3)
+    desc = f"greedy decode of {sample} embeddings per step (bounded sample of the 4096-embedding workload), fp32, torch CPU ops, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# algorithmic work per kernel class for one greedy decode of B embeddings
+# ----------------------------------------------------------------------------------------------------------------
+def algorithmic_work(B: int, dims) -> dict:
+    F, E, K, L, P, V, G = dims.embed_dim, dims.hidden_dim, dims.ffn_dim, dims.num_layers, dims.prefix_len, dims.vocab_size, dims.token_length - 1
+    rows = B * (P + G - 1)                       # residual rows that pass through the layers (prefill P + G-1 decode steps)
+    attn_bytes = 0
+    attn_bytes += B * L * (P * 2 * E * 2 + 2 * P * E * 2)                    # prefill: K,V rows once + q in + out
+    for s in range(P, P + G - 1):                                              # decode query at position s sees s+1 keys
+        attn_bytes += B * L * ((s + 1) * 2 * E * 2 + 2 * E * 2)
+    return {
+        "embed_prep": ("hbm", B * F * (4 + 2)),
+        "prefix_gemm": ("tensor", 2 * B * F * P * E),
+        "qkv_gemm": ("tensor", 2 * rows * E * 3 * E * L),
+        "attention": ("hbm", attn_bytes),
+        "outproj_gemm": ("tensor", 2 * rows * E * E * L),
+        "ffn1_gemm": ("tensor", 2 * rows * E * K * L),
+        "ffn2_gemm": ("tensor", 2 * rows * K * E * L),
+        "logits_gemm": ("tensor", 2 * B * G * E * V),
+        "select": ("hbm", B * G * (-(-V // 128) * 32 + E * (4 + 4 + 2))),
+    }
+
+
+def kernel_breakdown(model, embed, steps: int, peaks: dict, dims) -> dict:
+    """Direct-launch (no graph) replay with a CUDA-event pair around every launch, on the launching stream."""
+    import ctypes as C
+    from novic_b200 import _abi
+    lib = _abi.lib()
+    st = model._state(embed.device)
+    _abi.check(lib.novic_set_use_graphs(st["handle"], 0))
+    with torch.inference_mode():
+        model.generate(embed, False, True, 1.0, 0.0, None, None, False)
+        torch.cuda.synchronize()
+        _abi.check(lib.novic_kernel_timing(1))
+        for _ in range(steps):
+            model.generate(embed, False, True, 1.0, 0.0, None, None, False)
+        n = len(_abi.KERNEL_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _abi.check(lib.novic_kernel_times(ms, cnt, n))
+        _abi.check(lib.novic_kernel_timing(0))
+    _abi.check(lib.novic_set_use_graphs(st["handle"], 1))
+    work = algorithmic_work(embed.shape[0], dims)
+    total = sum(ms) or 1.0
+    out = {}
+    for i, name in enumerate(_abi.KERNEL_CLASSES):
+        if cnt[i] == 0:
+            continue
+        per_decode_ms = ms[i] / steps
+        entry = {"ms_per_step": per_decode_ms, "launches_per_step": cnt[i] // steps, "share": ms[i] / total}
+        if name in work:
+            bound, amount = work[name]
+            if bound == "hbm":
+                ach = amount / (per_decode_ms * 1e-3) / 1e9
+                entry.update(bound="hbm", achieved=ach, unit="GB/s", frac=ach / peaks["hbm_gbs"])
+            else:
+                ach = amount / (per_decode_ms * 1e-3) / 1e12
+                entry.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"])
+        out[name] = entry
+    return out
+
+
+def load_peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "bf16_tflops": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA (sm_100a) device: novic_b200 has no CPU fallback. Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from novic_b200 import _abi, default_decoder, synth
+    from novic_b200.dist import gather_generation
+    dims = synth.DecoderDims()
+    model = default_decoder(dims, synth.synth_state_dict(dims, seed=1)).to(dev)
+    B = args.batch
+    embed_host = synth.synth_embeddings(B, seed=1234 + rank).pin_memory()
+    embed = embed_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _abi.lib()
+
+    def step_device():
+        tok, pad, _, _, _, score = model.generate(embed, False, True, 1.0, 0.0, None, None, False)
+        if world > 1:
+            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world)
+        return tok, pad, score
+
+    def step_e2e():
+        e = embed_host.to(dev, non_blocking=True)
+        tok, pad, _, _, _, score = model.generate(e, False, True, 1.0, 0.0, None, None, False)
+        if world > 1:
+            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world)
+        return tok.cpu(), pad.cpu(), score.cpu()
+
+    def timed(fn, steps):
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n0 = lib.novic_launch_count()
+        for i in range(steps):
+            flush.zero_()                      # L2 flush, outside the timed span
+            starts[i].record()
+            out = fn()
+            ends[i].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        launches = lib.novic_launch_count() - n0
+        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches, out
+
+    with torch.inference_mode():
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+            step_e2e()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        total_ms, launches, out = timed(step_device, args.steps)
+        e2e_ms, _, out_host = timed(step_e2e, args.steps)
+        clocks = sampler.stop() if sampler else None
+    tok = out[0]
+    assert tok.shape[0] == B * world and tok.shape[-1] == dims.token_length - 1
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_per_step = total_ms / args.steps
+        value = B * world * args.steps / (total_ms / 1e3)
+        e2e_value = B * world * args.steps / (e2e_ms / 1e3)
+        kernels = kernel_breakdown(model, embed, min(args.steps, 5), peaks, dims)
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        d = kernels[dom]
+        roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
+                    "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],
+                    "how": "CUDA-event pair around every launch on the launching stream, direct-launch replay of the same decode; achieved = algorithmic work of all launches of the class / their summed duration",
+                    "kernels": kernels}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": B * dims.embed_dim * 4, "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host))},
+            "gpu_launches": int(launches), "roofline": roofline,
+        }
+        if not args.no_cpu_baseline:
+            times, cores = cpu_greedy_rate(args.cpu_sample, repeats=1, warmup=1)
+            line["cpu_baseline"] = {"value": args.cpu_sample / times[0], "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"oracle port of the reference greedy path (no KV cache), {args.cpu_sample} of the {B} embeddings, fp32, {cores} torch threads, 1 run after warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

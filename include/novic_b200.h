@@ -122,6 +122,13 @@ int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B
 int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,
                      int32_t block_n, void* stream);
 
+/* Per-kernel-class device timing for roofline reports.  novic_kernel_timing(1) makes every subsequent direct
+ * (non-graph) launch record a CUDA-event pair on its stream; novic_kernel_times() synchronises and returns the
+ * accumulated milliseconds and launch counts per class, then clears.  Classes, in order: embed-prep, prefix GEMM,
+ * QKV GEMM, attention, out-proj GEMM, FFN1 GEMM, FFN2 GEMM, logits GEMM, selection, other (n_classes >= 10). */
+int novic_kernel_timing(int32_t enable);
+int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes);
+
 /* Byte offset of a named workspace buffer (ein, ebf, x, xn, xfin, q, ao, hb, kv, part) for the same arguments as
  * novic_workspace_bytes; lets tests inspect intermediates. */
 int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq,

@@ -136,6 +136,34 @@ __global__ void tf_mask_kernel(const long long* __restrict__ target, const unsig
   }
 }
 
+// Optional per-kernel-class CUDA-event timing (bench.py's roofline numbers): only in direct-launch mode.
+enum KClass : int { kKPrep = 0, kKPrefix, kKQkv, kKAttn, kKOutProj, kKFfn1, kKFfn2, kKLogits, kKSelect, kKMisc, kKNumClasses };
+struct KTiming {
+  bool enabled = false;
+  std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> spans;
+};
+KTiming g_timing;
+int g_cur_class = kKMisc;
+
+struct KSpan {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  KSpan(int cls, cudaStream_t stream) : s(stream) {
+    g_cur_class = cls;
+    if (!g_timing.enabled) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &st);
+    if (st != cudaStreamCaptureStatusNone) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    g_timing.spans.emplace_back(cls, a, b);
+  }
+  ~KSpan() {
+    if (b != nullptr) cudaEventRecord(b, s);
+  }
+};
+
 struct Bump {
   size_t off = 0;
   size_t take(size_t bytes) {
@@ -275,20 +303,23 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
     __nv_bfloat16* kc = ws.kv + (static_cast<size_t>(l) * 2 + 0) * kv_layer;
     __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
     EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S};
-    if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq)) return 1;
+    { KSpan t(kKQkv, s); if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq)) return 1; }
     AttnParams pa;
     pa.q = ws.q; pa.kcache = kc; pa.vcache = vc; pa.out = ws.ao; pa.keypad = pc.keypad; pa.anc = pc.anc;
     pa.nseq = pc.nseq; pa.nq = pc.nq; pa.q0 = pc.q0; pa.smax = S; pa.P = c.prefix_len; pa.beams = pc.beams;
     pa.prefix_bidir = c.strictly_causal ? 0 : 1; pa.keypad_ld = pc.keypad_ld; pa.anc_ld = pc.anc_ld;
     pa.slot_mul = pc.slot_mul;
     pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
-    attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
-    ++g_launches;
+    {
+      KSpan t(kKAttn, s);
+      attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
+      ++g_launches;
+    }
     EpiRow::Params po{};
     po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
-    if (launch_gemm<EpiRow, kStagesRow>(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1;
+    { KSpan t(kKOutProj, s); if (launch_gemm<EpiRow, kStagesRow>(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1; }
     EpiGelu::Params pg{ws.hb, c.ffn_dim};
-    if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1;
+    { KSpan t(kKFfn1, s); if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1; }
     EpiRow::Params pf{};
     pf.x = ws.x; pf.pos = nullptr; pf.eps = c.ln_eps;
     if (l + 1 < L) {
@@ -298,7 +329,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       pf.xn = pc.remap_in > 0 ? ws.xfin : ws.xn;
       pf.remap_rows_in = pc.remap_in; pf.remap_skip = pc.remap_skip; pf.remap_rows_out = pc.remap_out;
     }
-    if (launch_gemm<EpiRow, kStagesRow>(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1;
+    { KSpan t(kKFfn2, s); if (launch_gemm<EpiRow, kStagesRow>(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1; }
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -308,13 +339,17 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
 int run_prefix(NovicHandle* h, const Workspace& ws, int rep, int rows_per_seq, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   const int B = static_cast<int>(ws.B);
-  embed_prep_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(ws.ein, ws.ebf, B, c.embed_dim);
-  ++g_launches;
+  {
+    KSpan t(kKPrep, s);
+    embed_prep_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(ws.ein, ws.ebf, B, c.embed_dim);
+    ++g_launches;
+  }
   CUtensorMap tm_e;
   if (make_tmap(&tm_e, ws.ebf, B, c.embed_dim, kBlockM)) return 1;
   EpiRow::Params pp{};
   pp.x = ws.x; pp.xn = ws.xn; pp.gain = h->w.norm1[0]; pp.pos = h->w.pos; pp.prefix_rep = rep;
   pp.prefix_rows_per_seq = rows_per_seq; pp.eps = c.ln_eps;
+  KSpan t(kKPrefix, s);
   return launch_gemm<EpiRow, kStagesRow>(s, tm_e, h->w.tm_embed_mlp, B, c.prefix_len * kE, c.embed_dim, pp);
 }
 
@@ -326,6 +361,7 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
   typename EpiLogits<kLogitBN, HCAP>::Params pl;
   pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
   pl.n_valid = h->cfg.vocab_size; pl.ntiles = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
+  KSpan t(kKLogits, s);
   return launch_gemm<EpiLogits<kLogitBN, HCAP>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
 }
 
@@ -356,10 +392,13 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
     float* lg = logits != nullptr ? logits + static_cast<size_t>(step - 1) * V : nullptr;
     if (run_logits(h, ws, a, B, lg, static_cast<long long>(G) * V, nullptr, inv_tau, step == 1 ? 1 : 0, s)) return 1;
     const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
-    select_greedy_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
-        ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
-        ws.xn, c.ln_eps);
-    ++g_launches;
+    {
+      KSpan t(kKSelect, s);
+      select_greedy_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+          ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
+          ws.xn, c.ln_eps);
+      ++g_launches;
+    }
     if (step < G) {
       PassCfg dec{B, B, 1, P + step - 1, 1, 1, nullptr, 0, nullptr, 0, 0, 0, 0};
       if (run_layers(h, ws, dec, s)) return 1;
@@ -375,6 +414,7 @@ template <int HCAP>
 void launch_select_beam(const Workspace& ws, NovicHandle* h, int step, float inv_tau, float alpha, const BeamState& st,
                         const float* pos_next, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
+  KSpan t(kKSelect, s);
   select_beam_kernel<HCAP><<<static_cast<unsigned>(ceil_div(ws.B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
       ws.part, ws.topv, ws.topi, ws.ntiles, static_cast<int>(ws.B), ws.H, h->G(), step, c.vocab_size, inv_tau, alpha, st,
       h->w.tok_f32, pos_next, h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
@@ -721,6 +761,28 @@ int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B
                                const float* normals_b, const float* row_a, const float* row_b, void* stream) {
   if (normals_a == nullptr) return fail("normals_a is required");
   return noise_launch(cfg, embed, B, normals_a, normals_b, row_a, row_b, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int novic_kernel_timing(int32_t enable) {
+  for (auto& sp : g_timing.spans) { cudaEventDestroy(std::get<1>(sp)); cudaEventDestroy(std::get<2>(sp)); }
+  g_timing.spans.clear();
+  g_timing.enabled = enable != 0;
+  return 0;
+}
+
+int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes) {
+  if (ms_out == nullptr || count_out == nullptr || n_classes < kKNumClasses) return fail("need room for %d classes", (int)kKNumClasses);
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (auto& sp : g_timing.spans) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, std::get<1>(sp), std::get<2>(sp)));
+    ms_out[std::get<0>(sp)] += ms;
+    count_out[std::get<0>(sp)] += 1;
+  }
+  for (auto& sp : g_timing.spans) { cudaEventDestroy(std::get<1>(sp)); cudaEventDestroy(std::get<2>(sp)); }
+  g_timing.spans.clear();
+  return 0;
 }
 
 int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq,

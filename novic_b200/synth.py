@@ -105,6 +105,17 @@ def make_eos_friendly(sd: dict, dims: DecoderDims = DecoderDims(), beta: float =
     return sd
 
 
+def make_eos_ragged(sd: dict, coeffs=(0.08, 0.12, 0.5)) -> dict:
+    """End-token row built from three position bands: every sample finishes, at different steps, so that a greedy /
+    beam decode takes the all-finished early exit (embedding_decoder.py:817-820, :964-967) with ragged lengths."""
+    sd = dict(sd)
+    pos = sd["pos_embedding.embedding.weight"]
+    w = sd["logits_linear.weight"].clone()
+    w[0] = coeffs[0] * pos[6:9].sum(dim=0) + coeffs[1] * pos[9:12].sum(dim=0) + coeffs[2] * pos[12:16].sum(dim=0)
+    sd["logits_linear.weight"] = w
+    return sd
+
+
 def synth_embeddings(batch: int, embed_dim: int = 1024, seed: int = 1234, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     rng = np.random.default_rng(seed)
     x = rng.standard_normal((batch, embed_dim)).astype(np.float32)

@@ -30,8 +30,8 @@ def weight_cases(dims):
     lively = synth.synth_state_dict(dims, seed=2, token_scale=0.25, jitter_norms=True)
     return {
         "lively": lively,
-        "eos": synth.make_eos_friendly(lively, dims, beta=0.8),
-        "eosall": synth.make_eos_friendly(lively, dims, beta=3.0),
+        "eos": synth.make_eos_friendly(lively, dims, beta=0.1),
+        "eosall": synth.make_eos_ragged(lively),
     }
 
 

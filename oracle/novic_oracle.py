@@ -67,8 +67,16 @@ def cfg_from_state_dict(sd: dict, token_length: Optional[int] = None, num_heads:
 # Building blocks
 # ----------------------------------------------------------------------------------------------------
 
+# The reference reaches torch's fused CPU kernels (native_layer_norm, gelu, scaled_dot_product_attention) through
+# nn.TransformerEncoder.  FUSED_OPS=True makes the oracle call the same torch functionals, so that timing it is a
+# fair port of the reference's CPU path; FUSED_OPS=False spells the maths out (tests check the two agree).
+FUSED_OPS = True
+
+
 def _layer_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
     # nn.LayerNorm(bias=False): biased variance, eps inside the sqrt (built at embedding_decoder.py:309-327)
+    if FUSED_OPS:
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, None, eps)
     mu = x.mean(dim=-1, keepdim=True)
     var = (x - mu).square().mean(dim=-1, keepdim=True)
     return (x - mu) * torch.rsqrt(var + eps) * w
@@ -76,6 +84,8 @@ def _layer_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
 
 def _gelu_erf(x: torch.Tensor) -> torch.Tensor:
     # exact GELU (utils.py:107 -> torch.nn.functional.gelu default)
+    if FUSED_OPS:
+        return torch.nn.functional.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
@@ -126,9 +136,12 @@ def transformer_stack(cfg: OracleCfg, sd: dict, x: torch.Tensor, bias: torch.Ten
         q = q.view(A, S, H, d).transpose(1, 2)
         k = k.view(A, S, H, d).transpose(1, 2)
         v = v.view(A, S, H, d).transpose(1, 2)
-        att = (q @ k.transpose(-1, -2)) * scale + bias
-        att = torch.softmax(att, dim=-1)
-        o = (att @ v).transpose(1, 2).reshape(A, S, E)
+        if FUSED_OPS:
+            o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=bias.expand(A, 1, S, S) if bias.shape[0] != A else bias)
+        else:
+            att = torch.softmax((q @ k.transpose(-1, -2)) * scale + bias, dim=-1)
+            o = att @ v
+        o = o.transpose(1, 2).reshape(A, S, E)
         x = x + o @ sd[p + "self_attn.out_proj.weight"].t()
         h = _layer_norm(x, sd[p + "norm2.weight"], cfg.ln_eps)
         h = _gelu_erf(h @ sd[p + "linear1.weight"].t())

@@ -1,0 +1,74 @@
+"""world_size-2 gloo test of the multi-GPU inference plumbing (contiguous shards + final gather), on CPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from novic_b200.dist import gather_generation, generate_sharded, shard_bounds
+
+
+def test_shard_bounds_partition():
+    for n in (0, 1, 7, 8, 4096, 65537):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeDecoder:
+    """Stands in for the CUDA decoder on CPU: deterministic outputs derived from the embedding rows, and a T that
+    depends on the shard (early exit is per shard)."""
+
+    def generate(self, embed, collect_logits, calc_loss, temperature, length_alpha, sample_weight, guide_targets, guide_renorm):
+        key = (embed[:, 0] * 1000).round().long()
+        T = 3 if int(key.min()) < 5 else 5
+        tok = (key.unsqueeze(1) + torch.arange(T)).clamp(min=1)
+        pad = torch.zeros_like(tok, dtype=torch.bool)
+        return tok, pad, None, None, None, key.float()
+
+    def generate_beam(self, embed, topk, temperature, length_alpha, vocab_targets, vocab_per_token, vocab_scaler, guide_targets, guide_renorm):
+        tok, pad, _, _, _, score = self.generate(embed, False, True, temperature, length_alpha, None, None, False)
+        return (tok.unsqueeze(1).repeat(1, topk, 1), pad.unsqueeze(1).repeat(1, topk, 1), score.unsqueeze(1) - torch.arange(topk))
+
+
+def _worker(rank, world, port, n, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        embed = torch.arange(n, dtype=torch.float32).unsqueeze(1).repeat(1, 4) / 1000
+        tok, pad, score = generate_sharded(_FakeDecoder(), embed, "greedy")
+        btok, bpad, bscore = generate_sharded(_FakeDecoder(), embed, "beam", topk=3)
+        if rank == 0:
+            results.put((tok, pad, score, btok, bpad, bscore))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", (9, 16))
+def test_two_rank_gather_matches_single_process(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    tok, pad, score, btok, bpad, bscore = results.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert tok.shape == (n, 1, 5) and btok.shape == (n, 3, 5) and score.shape == (n, 1) and bscore.shape == (n, 3)
+    key = torch.arange(n)
+    assert torch.equal(score[:, 0], key.float())                      # rank order preserved
+    lo, hi = shard_bounds(n, 2, 0)
+    # rank 0's shard stopped at T = 3: its extra columns are (id 0, padding True), like samples that finished early
+    assert (tok[lo:hi, 0, 3:] == 0).all() and pad[lo:hi, 0, 3:].all() and not pad[lo:hi, 0, :3].any()
+    assert not pad[hi:].any() and torch.equal(tok[hi:, 0, 0], key[hi:].clamp(min=1))
+    assert torch.equal(btok[:, 1], btok[:, 0]) and torch.equal(bscore[:, 2], key.float() - 2)
