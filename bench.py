@@ -104,7 +104,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -116,6 +116,15 @@ class ClockSampler:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
                 self.rows.append(parts)
+
+    def wait_started(self, timeout: float = 10.0) -> None:
+        """nvidia-smi takes a while to attach; wait for its first sample so start-up does not perturb the timed region."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self) -> None:
+        self.rows.clear()   # keep only samples taken during the timed region
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -271,10 +280,13 @@ def main():
         return t.item(), launches, out
 
     with torch.inference_mode():
+        sampler = ClockSampler(local_rank) if rank == 0 else None
         for _ in range(max(args.warmup, 3)):
             step_device()
             step_e2e()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.wait_started()
+            sampler.mark()
         total_ms, launches, out = timed(step_device, args.steps)
         e2e_ms, _, out_host = timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None

@@ -129,6 +129,10 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
 int novic_kernel_timing(int32_t enable);
 int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes);
 
+/* Tuning aid: enable = 1 + n arms CTA (0,1) of the n-th GEMM launch from now to record clock64() at numbered phase
+ * points; a later call returns the 16 recorded values (out16 may be NULL) and re-arms / disarms (enable = 0). */
+int novic_debug_trace(int64_t* out16, int32_t enable);
+
 /* Byte offset of a named workspace buffer (ein, ebf, x, xn, xfin, q, ao, hb, kv, part) for the same arguments as
  * novic_workspace_bytes; lets tests inspect intermediates. */
 int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq,

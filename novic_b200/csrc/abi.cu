@@ -77,7 +77,7 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
 // ---------------------------------------------------------------------------------------------------------
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kStagesQKV = 3, kStagesGelu = 3, kStagesRow = 2, kStagesLogits = 3;
+constexpr int kStagesQKV = 3, kStagesGelu = 3, kStagesRow = 4, kStagesLogits = 3;
 constexpr int kLogitBN = 128;
 
 template <class Epi, int STAGES>
@@ -92,6 +92,20 @@ int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, in
                 const typename Epi::Params& ep) {
   dim3 grid(static_cast<unsigned>(ceil_div(N, Epi::BN)), static_cast<unsigned>(ceil_div(M, kBlockM)));
   gemm_kernel<Epi, STAGES><<<grid, kGemmThreads, GemmSmem<Epi::BN>::bytes(STAGES), s>>>(ta, tb, M, K / kBlockK, ep);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int set_rowln_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowLnSmem::bytes(kStagesRow)));
+  return 0;
+}
+
+// N must be a multiple of 512: every 4 consecutive 128-column tiles form one cluster = one full residual row.
+int launch_rowln(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiRow::Params& ep) {
+  dim3 grid(static_cast<unsigned>(N / kRowBN), static_cast<unsigned>(ceil_div(M, kBlockM)));
+  gemm_rowln_kernel<kStagesRow><<<grid, kGemmThreads, RowLnSmem::bytes(kStagesRow), s>>>(ta, tb, M, K / kBlockK, ep);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -211,6 +225,9 @@ struct NovicHandle {
   int device = 0;
   bool weights_set = false;
   bool use_graphs = true;
+  bool attn_v1 = false;
+  int num_sms = 148;
+  int attn_smem_budget = 200 * 1024;
   WeightPtrs w;
   cudaStream_t capture_stream = nullptr;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -312,12 +329,23 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
     pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
     {
       KSpan t(kKAttn, s);
-      attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
+      if (h->attn_v1) {
+        attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
+      } else {
+        const int nk_max = std::max(c.strictly_causal ? 1 : c.prefix_len, pc.q0 + pc.nq);
+        const int stage_bytes = nk_max * 2048;
+        int nstages = std::max(2, std::min(kAttnMaxStages, (h->attn_smem_budget - 512) / stage_bytes));
+        const int ncons = std::min(kAttnConsumers, nstages);
+        nstages = nstages / ncons * ncons;
+        const int smem = nstages * stage_bytes + 2 * kAttnMaxStages * 8;
+        const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ceil_div(pc.nseq, 2)));
+        attention_bulk_kernel<<<grid, kAttnThreads, smem, s>>>(pa, nstages, stage_bytes, ncons);
+      }
       ++g_launches;
     }
     EpiRow::Params po{};
     po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
-    { KSpan t(kKOutProj, s); if (launch_gemm<EpiRow, kStagesRow>(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1; }
+    { KSpan t(kKOutProj, s); if (launch_rowln(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1; }
     EpiGelu::Params pg{ws.hb, c.ffn_dim};
     { KSpan t(kKFfn1, s); if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1; }
     EpiRow::Params pf{};
@@ -329,7 +357,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       pf.xn = pc.remap_in > 0 ? ws.xfin : ws.xn;
       pf.remap_rows_in = pc.remap_in; pf.remap_skip = pc.remap_skip; pf.remap_rows_out = pc.remap_out;
     }
-    { KSpan t(kKFfn2, s); if (launch_gemm<EpiRow, kStagesRow>(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1; }
+    { KSpan t(kKFfn2, s); if (launch_rowln(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1; }
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -350,7 +378,7 @@ int run_prefix(NovicHandle* h, const Workspace& ws, int rep, int rows_per_seq, c
   pp.x = ws.x; pp.xn = ws.xn; pp.gain = h->w.norm1[0]; pp.pos = h->w.pos; pp.prefix_rep = rep;
   pp.prefix_rows_per_seq = rows_per_seq; pp.eps = c.ln_eps;
   KSpan t(kKPrefix, s);
-  return launch_gemm<EpiRow, kStagesRow>(s, tm_e, h->w.tm_embed_mlp, B, c.prefix_len * kE, c.embed_dim, pp);
+  return launch_rowln(s, tm_e, h->w.tm_embed_mlp, B, c.prefix_len * kE, c.embed_dim, pp);
 }
 
 template <int HCAP>
@@ -503,10 +531,11 @@ const char* novic_last_error(void) { return g_err.c_str(); }
 int novic_version(void) { return 1; }
 int64_t novic_launch_count(void) { return g_launches; }
 
+static unsigned int* g_wd_host = nullptr;
+
 int novic_watchdog(uint32_t* code_out) {
-  unsigned int code = 0;
-  CUDA_TRY(cudaMemcpyFromSymbol(&code, g_watchdog_code, sizeof(code)));
-  *code_out = code;
+  // readable even after a trap killed the context: the kernel writes the code to mapped pinned host memory
+  *code_out = g_wd_host != nullptr ? *reinterpret_cast<volatile unsigned int*>(g_wd_host) : 0u;
   return 0;
 }
 
@@ -526,15 +555,26 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail("device %d is sm_%d%d; novic_b200 kernels are sm_100a only", dev, prop.major, prop.minor);
   if (load_driver_entry()) return 1;
-  if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_gemm_attr<EpiRow, kStagesRow>() ||
+  if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_rowln_attr() ||
       set_gemm_attr<EpiLogits<kLogitBN, 0>, kStagesLogits>() || set_gemm_attr<EpiLogits<kLogitBN, 4>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<kLogitBN, 16>, kStagesLogits>())
     return 1;
+  if (g_wd_host == nullptr) {
+    CUDA_TRY(cudaHostAlloc(&g_wd_host, sizeof(unsigned int), cudaHostAllocMapped));
+    *g_wd_host = 0;
+    unsigned int* dptr = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(&dptr, g_wd_host, 0));
+    CUDA_TRY(cudaMemcpyToSymbol(g_watchdog_host, &dptr, sizeof(dptr)));
+  }
   NovicHandle* h = new NovicHandle();
   h->cfg = *cfg;
   h->device = dev;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaMallocHost(&h->h_flags, sizeof(int) * (cfg->token_length + 2)));
+  h->num_sms = prop.multiProcessorCount;
+  h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
+  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
+  if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   const char* env = getenv("NOVIC_NO_GRAPHS");
   if (env != nullptr && env[0] == '1') h->use_graphs = false;
   *out = h;
@@ -607,13 +647,13 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
   o.final_norm = cpy(w->final_norm, E);
   for (size_t l = 0; l < L; ++l) { o.norm1[l] = cpy(w->norm1[l], E); o.norm2[l] = cpy(w->norm2[l], E); }
   CUDA_TRY(cudaGetLastError());
-  if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, 256)) return 1;
+  if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, kRowBN)) return 1;
   if (make_tmap(&o.tm_tok, o.tok, V, E, kLogitBN)) return 1;
   for (size_t l = 0; l < L; ++l) {
     if (make_tmap(&o.tm_in_proj[l], o.in_proj[l], 3 * E, E, 128)) return 1;
-    if (make_tmap(&o.tm_out_proj[l], o.out_proj[l], E, E, 256)) return 1;
+    if (make_tmap(&o.tm_out_proj[l], o.out_proj[l], E, E, kRowBN)) return 1;
     if (make_tmap(&o.tm_linear1[l], o.linear1[l], K, E, 128)) return 1;
-    if (make_tmap(&o.tm_linear2[l], o.linear2[l], E, K, 256)) return 1;
+    if (make_tmap(&o.tm_linear2[l], o.linear2[l], E, K, kRowBN)) return 1;
   }
   // the weight pointers are baked into captured graphs
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
@@ -782,6 +822,24 @@ int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes) {
   }
   for (auto& sp : g_timing.spans) { cudaEventDestroy(std::get<1>(sp)); cudaEventDestroy(std::get<2>(sp)); }
   g_timing.spans.clear();
+  return 0;
+}
+
+int novic_debug_trace(int64_t* out16, int32_t enable) {
+  {
+    const int zero = 0, target = enable - 1;   // enable = 1 + ordinal of the GEMM launch to record
+    CUDA_TRY(cudaMemcpyToSymbol(g_trace_counter, &zero, sizeof(int)));
+    CUDA_TRY(cudaMemcpyToSymbol(g_trace_target, &target, sizeof(int)));
+  }
+  static long long* dbuf = nullptr;
+  if (dbuf == nullptr) { CUDA_TRY(cudaMalloc(&dbuf, 16 * sizeof(long long))); }
+  if (out16 != nullptr) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out16, dbuf, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  CUDA_TRY(cudaMemset(dbuf, 0, 16 * sizeof(long long)));
+  long long* p = enable ? dbuf : nullptr;
+  CUDA_TRY(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
   return 0;
 }
 

@@ -337,6 +337,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.y * kBlockM;
   const int n0 = blockIdx.x * BN;
+  __shared__ int s_trace;
+  if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
@@ -355,6 +357,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const bool tr = s_trace != 0;
+  if (threadIdx.x == 0) trace_point(tr, 1);
 
   if (warp == 0) {
     if (elect_one()) {
@@ -368,14 +372,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < NMMA; ++j)
           tma_load_2d(sb + j * (UN * kBlockK * 2), &tmap_b, &full_bar[stage], kb * kBlockK, n0 + j * UN, kEvictLast);
+        if (kb == 0) trace_point(tr, 2);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      trace_point(tr, 3);
     }
   } else if (warp == 1) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < num_k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase, 2);
+        if (kb == 0) trace_point(tr, 4);
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(smem + stage * kStage);
         const uint32_t sb = sa + kABytes;
@@ -392,18 +399,214 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full_bar);        // accumulator complete
+      trace_point(tr, 5);
     }
   } else {
     const int quad = warp & 3;
     const int row_in_tile = quad * 32 + lane_id();
     mbar_wait(tmem_full_bar, 0, 3);
+    if (threadIdx.x == 64) trace_point(tr, 6);
     tc_fence_after_sync();
     Epi::run(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + row_in_tile, n0, M, blockIdx.x,
              epi_scratch);
+    if (threadIdx.x == 64) trace_point(tr, 8);
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) trace_point(tr, 10);
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Full-row GEMM + residual + LayerNorm, split over a 4-CTA cluster.
+//
+// The 512-wide output row of a 128-row tile is split across the 4 CTAs of a cluster (128 columns each), so a
+// decode step over 4096 sequences fills 128 SMs instead of 32.  Each epilogue thread keeps its 128 row values in
+// registers (single pass): the residual slice is prefetched while the MMAs run, the accumulator is added from
+// TMEM, the per-row (sum, sum of squares) partials are exchanged through distributed shared memory, and every
+// CTA then normalises and writes its own 128 columns of x (fp32) and LayerNorm(x) (bf16).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kRowBN = 128;
+constexpr int kRowCluster = kE / kRowBN;  // 4
+
+struct RowLnSmem {
+  static constexpr int kStageBytes = kABytes + kRowBN * kBlockK * 2;
+  static constexpr int bytes(int stages) { return stages * kStageBytes + 1024 + 256 + 128 * 8 /*stats*/ + kRowBN * 4 /*gain*/; }
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
+                  int num_k_blocks, EpiRow::Params ep) {
+  constexpr int BN = kRowBN;
+  constexpr int kStage = RowLnSmem::kStageBytes;
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float2* s_stats = reinterpret_cast<float2*>(smem + STAGES * kStage + 256);   // [128] (sum, sumsq) of this CTA's columns
+  float* s_gain = reinterpret_cast<float*>(smem + STAGES * kStage + 256 + 128 * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.y * kBlockM;
+  const int n0 = blockIdx.x * BN;               // column in the [*, P*512] / [*, 512] output
+  const uint32_t crank = cluster_ctarank();     // == blockIdx.x % 4
+  const int coff = static_cast<int>(crank) * BN;  // column offset inside the 512-wide row
+  const int ptok = blockIdx.x / kRowCluster;    // prefix mode: which prefix position
+  __shared__ int s_trace;
+  if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane_id() == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<BN>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool tr = s_trace != 0;
+  if (threadIdx.x == 0) trace_point(tr, 1);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        uint8_t* sa = smem + stage * kStage;
+        mbar_arrive_expect_tx(&full_bar[stage], kStage);
+        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
+        tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+        if (kb == 0) trace_point(tr, 2);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      trace_point(tr, 3);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 2);
+        if (kb == 0) trace_point(tr, 4);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(smem + stage * kStage);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)), umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)),
+                       kIdesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+      trace_point(tr, 5);
+    }
+  }
+
+  // ---- epilogue part 1 (warps 2..5): residual prefetch + accumulator + partial row statistics -------------
+  const bool is_epi = warp >= 2;
+  const int quad = warp & 3;
+  const int row_in_tile = quad * 32 + static_cast<int>(lane_id());
+  const int row = m0 + row_in_tile;
+  const bool prefix = ep.pos != nullptr;
+  const int reps = prefix ? ep.prefix_rep : 1;
+  float r[BN];
+  if (is_epi) {
+    s_gain[threadIdx.x - 64] = __ldg(ep.gain + coff + (threadIdx.x - 64));
+    if (row < M) {
+      if (prefix) {
+        const float4* p4 = reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(ptok) * kE + coff);
+#pragma unroll
+        for (int q = 0; q < BN / 4; ++q) { const float4 t = __ldg(p4 + q); r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w; }
+      } else {
+#pragma unroll
+        for (int q = 0; q < BN / 4; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (coff >> 2) + q));
+          r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) r[i] = 0.f;
+    }
+    if (threadIdx.x == 64) trace_point(tr, 11);
+    mbar_wait(tmem_full_bar, 0, 3);
+    if (threadIdx.x == 64) trace_point(tr, 6);
+    tc_fence_after_sync();
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int c = 0; c < BN / 16; ++c) {
+      float v[16];
+      tmem_ld_32x16(tmem_row + c * 16, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float t = r[c * 16 + j] + v[j];
+        r[c * 16 + j] = t;
+        sum += t;
+        sumsq = fmaf(t, t, sumsq);
+      }
+    }
+    s_stats[row_in_tile] = make_float2(sum, sumsq);
+    if (threadIdx.x == 64) trace_point(tr, 7);
+  }
+  __syncwarp();
+  cluster_sync_all();
+  if (threadIdx.x == 64) trace_point(tr, 8);   // every thread of the 4 CTAs: partial statistics are now visible cluster-wide
+
+  // ---- epilogue part 2: combine the 4 partials (fixed order -> identical mean/rstd in all CTAs), normalise, store
+  if (is_epi && row < M) {
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
+      const float2 t = dsmem_ld_f32x2(&s_stats[row_in_tile], pr);
+      sum += t.x;
+      sumsq += t.y;
+    }
+    const float mean = sum * (1.0f / kE);
+    const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
+    for (int j = 0; j < reps; ++j) {
+      const int orow = prefix ? ((row * reps + j) * ep.prefix_rows_per_seq + ptok) : row;
+#pragma unroll
+      for (int q = 0; q < BN / 4; ++q)
+        *reinterpret_cast<float4*>(ep.x + xblk_off(orow, (coff >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      int nrow = orow;
+      if (ep.remap_rows_in > 0) {
+        const int seq = orow / ep.remap_rows_in;
+        const int rr = orow - seq * ep.remap_rows_in;
+        if (rr < ep.remap_skip) continue;
+        nrow = seq * ep.remap_rows_out + (rr - ep.remap_skip);
+      }
+      uint4* dn = reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + coff);
+#pragma unroll
+      for (int q = 0; q < BN / 8; ++q) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain[q * 8 + i];
+        dn[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+    }
+  }
+
+  if (threadIdx.x == 64) trace_point(tr, 9);
+  tc_fence_before_sync();
+  __syncwarp();
+  cluster_sync_all();   // peers may still be reading this CTA's s_stats
+  if (threadIdx.x == 0) trace_point(tr, 10);
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
 }
 

@@ -198,6 +198,138 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) attention_kernel(const At
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Attention, bulk-async version (the one the decoder uses).  The kernel above keeps too few bytes in flight
+// (register-staged loads, 12 warps/SM): ncu showed 40 % of HBM peak.  Here a persistent CTA runs one producer warp
+// that streams each sequence's K and V pages into a shared-memory ring with cp.async.bulk (TMA engine, no
+// registers, completion on an mbarrier) while 8 consumer warps compute from shared memory: up to ~190 KB per SM
+// are in flight at all times.  One ring stage = all the K rows then all the V rows one sequence needs
+// (contiguous in its page unless beam search's ancestry table redirects token rows to sibling pages).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAttnConsumers = 8;
+constexpr int kAttnThreads = (kAttnConsumers + 1) * 32;
+constexpr int kAttnMaxStages = 16;
+
+// `ncons` consumer warps are active and nstages is a multiple of ncons: consumer c then owns ring stages c, c+ncons, ...
+// and visits them in order, so it observes every phase of their mbarriers (a parity wait can only tell the current
+// phase from the previous one - a waiter must never be a whole phase ahead).
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel(const AttnParams p, int nstages, int stage_bytes, int ncons) {
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(attn_smem);
+  uint64_t* empty_bar = full_bar + kAttnMaxStages;
+  uint8_t* ring = attn_smem + 2 * kAttnMaxStages * sizeof(uint64_t);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  const int per_cta = (p.nseq + gridDim.x - 1) / gridDim.x;
+  const int item0 = blockIdx.x * per_cta;
+  const int item1 = min(p.nseq, item0 + per_cta);
+  const int nk_max = max((p.prefix_bidir ? p.P : 1), p.q0 + p.nq);   // rows staged per sequence
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kAttnConsumers) {
+    // ------------------------------ producer ------------------------------
+    for (int it = item0, k = 0; it < item1; ++it, ++k) {
+      const int stage = k % nstages;
+      const uint32_t phase = static_cast<uint32_t>(k / nstages) & 1u;
+      const int a = it;
+      const int own_slot = a * p.slot_mul;
+      const int group0 = (own_slot / p.beams) * p.beams;
+      uint8_t* dst = ring + static_cast<size_t>(stage) * stage_bytes;
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u, 4);
+        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(nk_max) * 2048u);
+      }
+      __syncwarp();
+      const bool contiguous = (p.beams == 1);
+      if (contiguous) {
+        if (lane == 0) {
+          const size_t off = static_cast<size_t>(own_slot) * p.smax * kE;
+          bulk_load_1d(dst, p.kcache + off, static_cast<uint32_t>(nk_max) * 1024u, &full_bar[stage]);
+          bulk_load_1d(dst + nk_max * 1024, p.vcache + off, static_cast<uint32_t>(nk_max) * 1024u, &full_bar[stage]);
+        }
+      } else {
+        const int qlast = p.q0 + p.nq - 1;
+        for (int j = lane; j < nk_max; j += 32) {
+          int slot;
+          if (j < p.P) slot = group0;
+          else if (p.anc != nullptr && j < qlast) slot = group0 + p.anc[static_cast<size_t>(a) * p.anc_ld + (j - p.P)];
+          else slot = own_slot;
+          const size_t off = (static_cast<size_t>(slot) * p.smax + j) * kE;
+          bulk_load_1d(dst + j * 1024, p.kcache + off, 1024u, &full_bar[stage]);
+          bulk_load_1d(dst + (nk_max + j) * 1024, p.vcache + off, 1024u, &full_bar[stage]);
+        }
+      }
+    }
+  } else if (warp < ncons) {
+    // ------------------------------ consumers ------------------------------
+    for (int it = item0 + warp, k = warp; it < item1; it += ncons, k += ncons) {
+      const int stage = k % nstages;
+      const uint32_t phase = static_cast<uint32_t>(k / nstages) & 1u;
+      const int a = it;
+      const uint8_t* kbase = ring + static_cast<size_t>(stage) * stage_bytes;
+      const uint8_t* vbase = kbase + nk_max * 1024;
+      bool waited = false;
+      for (int qi = 0; qi < p.nq; ++qi) {
+        const int w = a * p.nq + qi;
+        const int qpos = p.q0 + qi;
+        const int nkeys = (p.prefix_bidir && qpos < p.P) ? p.P : qpos + 1;
+        float qf[16];
+        {
+          const uint4* q4 = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(w) * kE) + lane * 2;
+          const uint4 u0 = __ldg(q4), u1 = __ldg(q4 + 1);
+          bf16x8_to_f32(u0, qf);
+          bf16x8_to_f32(u1, qf + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) qf[i] *= p.scale_log2e;
+        }
+        if (!waited) { mbar_wait(&full_bar[stage], phase, 5); waited = true; }
+        float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < nkeys; ++j) {
+          if (p.keypad != nullptr && j > 0 && p.keypad[static_cast<size_t>(a) * p.keypad_ld + j]) continue;  // warp-uniform
+          const uint4* k4 = reinterpret_cast<const uint4*>(kbase + j * 1024) + lane * 2;
+          float kf[16];
+          bf16x8_to_f32(k4[0], kf);
+          bf16x8_to_f32(k4[1], kf + 8);
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s = fmaf(qf[i], kf[i], s);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          const float m_new = fmaxf(m, s);
+          const float corr = exp2f(m - m_new);
+          const float pj = exp2f(s - m_new);
+          l = l * corr + pj;
+          const uint4* v4 = reinterpret_cast<const uint4*>(vbase + j * 1024) + lane * 2;
+          float vf[16];
+          bf16x8_to_f32(v4[0], vf);
+          bf16x8_to_f32(v4[1], vf + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], corr, pj * vf[i]);
+          m = m_new;
+        }
+        const float inv = 1.0f / l;
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+        uint4* d = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(w) * kE) + lane * 2;
+        d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Merging the per-tile logits statistics of one row (executed by a full warp)
 // ---------------------------------------------------------------------------------------------------------
 struct RowStats {

@@ -61,17 +61,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Device-side watchdog word: a kernel that waits "forever" on an mbarrier (a descriptor or byte-count bug)
 // records where and traps, instead of hanging the GPU.
 __device__ unsigned int g_watchdog_code = 0;
+__device__ unsigned int* g_watchdog_host = nullptr;  // mapped pinned host word: survives the context-killing trap
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
-      atomicExch(&g_watchdog_code, 0x80000000u | (site << 16) | (blockIdx.x & 0xffffu));
+      const unsigned int code = 0x80000000u | (site << 24) | ((blockIdx.y & 0xfffu) << 12) | (blockIdx.x & 0xfffu);
+      atomicExch(&g_watchdog_code, code);
+      if (g_watchdog_host != nullptr) *reinterpret_cast<volatile unsigned int*>(g_watchdog_host) = code;
       __threadfence_system();
       asm volatile("trap;\n");
     }
   }
+}
+
+// Optional phase trace (bring-up / tuning): when g_trace != nullptr, CTA (0, by) records clock64() at numbered points.
+__device__ long long* g_trace = nullptr;
+__device__ int g_trace_counter = 0;   // GEMM launches seen since arming
+__device__ int g_trace_target = -1;   // ordinal of the launch to record
+// Called by thread 0 of every CTA at kernel entry; returns whether this CTA records.
+__device__ __forceinline__ bool trace_begin() {
+  if (g_trace == nullptr || blockIdx.x != 0 || blockIdx.y != 1) return false;
+  return atomicAdd(&g_trace_counter, 1) == g_trace_target;
+}
+__device__ __forceinline__ void trace_point(bool on, int idx) {
+  if (on) g_trace[idx] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -101,6 +117,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(cache_hint)
+      : "memory");
+}
+
+// 1-D bulk copy global -> shared (size and both addresses multiples of 16 B), completion on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
 
@@ -184,6 +208,42 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Same, 16 columns (fewer live registers in register-heavy epilogues).
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thread-block clusters / distributed shared memory
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+// All threads of all CTAs of the cluster (release/acquire: smem writes before are visible to peers after).
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ float2 dsmem_ld_f32x2(const void* local_smem_ptr, uint32_t peer_rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(smem_u32(local_smem_ptr)), "r"(peer_rank));
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(raddr) : "memory");
+  return v;
 }
 
 // ------------------------------------------------------------------------------------------------

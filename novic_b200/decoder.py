@@ -293,7 +293,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                 st = dict(handle=handle, wbuf=None, wkey=None, ws=None)
                 self._handles[idx] = st
             tensors = self._weight_tensors()
-            wkey = tuple((t.data_ptr(), t._version) for t in tensors)
+            wkey = tuple((t.data_ptr(), 0 if t.is_inference() else t._version) for t in tensors)
             if st['wkey'] != wkey:
                 for t in tensors:
                     if t.device.type != 'cuda' or t.device.index != idx or t.dtype != torch.float32 or not t.is_contiguous():

@@ -265,7 +265,12 @@ def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: 
 
 def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temperature: float = 1.0,
                   length_alpha: float = 0.0, early_exit: bool = True):
-    """Returns dict(target B x H x T, padding B x H x T, score B x H sorted descending)."""
+    """Returns dict(target B x H x T, padding B x H x T, score B x H sorted descending, margin B).
+
+    `margin` is test metadata, not part of the reference's outputs: per sample, the smallest gap seen at any step
+    between adjacent entries of the top-(H+1) ranking values, i.e. how far the search was from pruning or ordering
+    its candidates differently.  A lower-precision implementation can only be required to reproduce the beams of
+    samples whose margin exceeds its accumulated score tolerance."""
     B, H, G, V = embed.shape[0], topk, cfg.gen_len, cfg.vocab_size
     dtype = embed.dtype
     tok = torch.zeros(B, H, G, dtype=torch.int64)
@@ -277,6 +282,7 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
     seq_len = torch.zeros(B, H, dtype=dtype)
     seq_len[:, 0] = 1.0                                   # :899
     T = G
+    margin = torch.full((B,), float("inf"), dtype=dtype)
     for c in range(1, G + 1):
         cur_tok = tok[:, :, :c].reshape(B * H, c)
         cur_pad = pad[:, :, :c].reshape(B * H, c)
@@ -289,13 +295,18 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
             cand[:, 0, 0] = NEG_INF                                         # :940
         flat = cand.view(B, H * V)
         if length_alpha == 0:
+            ranked = flat
             best, idx = torch.topk(flat, k=H, dim=1, largest=True, sorted=True)  # :946
             score = best
         else:
             scale = seq_len.clamp(min=1).pow(-length_alpha).unsqueeze(2)         # :948
-            best, idx = torch.topk((cand * scale).view(B, H * V), k=H, dim=1, largest=True, sorted=True)  # :950
+            ranked = (cand * scale).view(B, H * V)
+            best, idx = torch.topk(ranked, k=H, dim=1, largest=True, sorted=True)  # :950
             score_normed = best
             score = flat.gather(1, idx)                                          # :951
+        top_h1 = torch.topk(ranked, k=H + 1, dim=1, largest=True, sorted=True).values
+        gaps = (top_h1[:, :-1] - top_h1[:, 1:]).nan_to_num(nan=float("inf"), posinf=float("inf"))
+        margin = torch.minimum(margin, gaps.min(dim=1).values)
         parent = idx // V                                                        # :953
         new_tok = idx % V                                                        # :954
         gather_idx = parent.unsqueeze(2)
@@ -314,7 +325,7 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
     tok = tok[:, :, :T].clone()
     pad = pad[:, :, :T].clone()
     tok.masked_fill_(pad, 0)                                                      # :980
-    return dict(target=tok, padding=pad, score=score_normed if length_alpha != 0 else score)
+    return dict(target=tok, padding=pad, score=score_normed if length_alpha != 0 else score, margin=margin)
 
 
 # ----------------------------------------------------------------------------------------------------
