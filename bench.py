@@ -165,7 +165,7 @@ def algorithmic_work(B: int, dims) -> dict:
         "ffn1_gemm": ("tensor", 2 * rows * E * K * L),
         "ffn2_gemm": ("tensor", 2 * rows * K * E * L),
         "logits_gemm": ("tensor", 2 * B * G * E * V),
-        "select": ("hbm", B * G * (-(-V // 128) * 32 + E * (4 + 4 + 2))),
+        "select": ("hbm", B * G * (-(-V // 64) * 32 + E * (4 + 4 + 2))),
     }
 
 

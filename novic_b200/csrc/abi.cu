@@ -77,35 +77,63 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
 // ---------------------------------------------------------------------------------------------------------
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kStagesQKV = 3, kStagesGelu = 3, kStagesRow = 4, kStagesLogits = 3;
-constexpr int kLogitBN = 128;
+constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 3, kStagesLogits = 5;
+int g_num_sms = 148;
+int g_grid_div = 1;   // persistent grids are divided by the number of concurrent chains so that chains co-run on disjoint SMs
+constexpr int kLogitBN = kTileN;
+
+// All decode-loop kernels are launched with programmatic stream serialization (PDL): the next kernel's CTAs may start
+// (barrier init, TMEM allocation, descriptor prefetch, weight-tile loads) while the previous kernel drains; each kernel
+// executes griddepcontrol.wait before it touches anything a predecessor produced.
+bool g_use_pdl = true;
+template <class... KArgs, class... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 template <class Epi, int STAGES>
 int set_gemm_attr() {
-  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                GemmSmem<Epi::BN>::bytes(STAGES)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES)));
   return 0;
 }
 
 template <class Epi, int STAGES>
 int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                 const typename Epi::Params& ep) {
-  dim3 grid(static_cast<unsigned>(ceil_div(N, Epi::BN)), static_cast<unsigned>(ceil_div(M, kBlockM)));
-  gemm_kernel<Epi, STAGES><<<grid, kGemmThreads, GemmSmem<Epi::BN>::bytes(STAGES), s>>>(ta, tb, M, K / kBlockK, ep);
+  const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
+  const int64_t total = n_tiles * ceil_div(M, kBlockM);
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
+  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES), s, ta, tb, M, n_tiles, K / kBlockK, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 int set_rowln_attr() {
-  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow>, cudaFuncAttributeMaxDynamicSharedMemorySize, RowLnSmem::bytes(kStagesRow)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   return 0;
 }
 
 // N must be a multiple of 512: every 4 consecutive 128-column tiles form one cluster = one full residual row.
-int launch_rowln(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiRow::Params& ep) {
+int launch_rowln(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const RowParams& ep) {
   dim3 grid(static_cast<unsigned>(N / kRowBN), static_cast<unsigned>(ceil_div(M, kBlockM)));
-  gemm_rowln_kernel<kStagesRow><<<grid, kGemmThreads, RowLnSmem::bytes(kStagesRow), s>>>(ta, tb, M, K / kBlockK, ep);
+  CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, false>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, false), s, ta, tb, tb, M, K / kBlockK, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Whole feed-forward block: x += W2 * gelu(W1 * xn), then LayerNorm.  ta = LN2(x) rows, tw1 = linear1 [128, 512], tw2 = linear2 [512, 128].
+int launch_ffn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw1, const CUtensorMap& tw2, int M, const RowParams& ep) {
+  dim3 grid(static_cast<unsigned>(kE / kRowBN), static_cast<unsigned>(ceil_div(M, kBlockM)));
+  CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, true>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -203,7 +231,7 @@ struct WeightPtrs {
 struct Workspace {
   // sizes
   int64_t B = 0, nseq = 0, rows = 0, logit_rows = 0;
-  int H = 1, rps = 0, ntiles = 0, hcap = 0;
+  int H = 1, rps = 0, ntiles = 0, hcap = 0, chains = 1;
   // device pointers
   float* ein; __nv_bfloat16* ebf; float* x; __nv_bfloat16 *xn, *xfin, *q, *ao, *hb; __nv_bfloat16* kv;
   LogitPartial* part; float* topv; int* topi;
@@ -226,7 +254,12 @@ struct NovicHandle {
   bool weights_set = false;
   bool use_graphs = true;
   bool attn_v1 = false;
+  bool fuse_ffn = true;
+  bool split_sms = true;
   int num_sms = 148;
+  int max_chains = 1;                 // concurrent sub-batch chains per decode (NOVIC_CHAINS); measured: no gain for greedy on B200
+  cudaStream_t chain_streams[8] = {};
+  cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
   int attn_smem_budget = 200 * 1024;
   WeightPtrs w;
   cudaStream_t capture_stream = nullptr;
@@ -248,7 +281,7 @@ int plan_workspace(const NovicHandle* h, int64_t B, int H, int rps, char* base, 
   const bool tf = rps > 0;
   w.rows = tf ? w.nseq * rps : std::max<int64_t>(B * P, w.nseq);
   w.logit_rows = tf ? w.nseq * c.token_length : w.nseq;
-  w.ntiles = static_cast<int>(ceil_div(c.vocab_size, kLogitBN));
+  w.ntiles = 2 * static_cast<int>(ceil_div(c.vocab_size, kTileN));  // 64-column partial slices
   w.hcap = tf ? 0 : (H <= 1 ? 0 : (H <= 4 ? 4 : 16));
   const int64_t rows32 = ceil_div(w.rows, 32) * 32;
   Bump b;
@@ -334,21 +367,20 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       } else {
         const int nk_max = std::max(c.strictly_causal ? 1 : c.prefix_len, pc.q0 + pc.nq);
         const int stage_bytes = nk_max * 2048;
-        int nstages = std::max(2, std::min(kAttnMaxStages, (h->attn_smem_budget - 512) / stage_bytes));
+        const int budget = h->attn_smem_budget;
+        int nstages = std::max(2, std::min(kAttnMaxStages, (budget - 512) / stage_bytes));
         const int ncons = std::min(kAttnConsumers, nstages);
         nstages = nstages / ncons * ncons;
         const int smem = nstages * stage_bytes + 2 * kAttnMaxStages * 8;
-        const int grid = static_cast<int>(std::min<int64_t>(h->num_sms, ceil_div(pc.nseq, 2)));
-        attention_bulk_kernel<<<grid, kAttnThreads, smem, s>>>(pa, nstages, stage_bytes, ncons);
+        const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, 2)));
+        CUDA_TRY(launch_k(attention_bulk_kernel, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
       }
       ++g_launches;
     }
-    EpiRow::Params po{};
+    RowParams po{};
     po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
     { KSpan t(kKOutProj, s); if (launch_rowln(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1; }
-    EpiGelu::Params pg{ws.hb, c.ffn_dim};
-    { KSpan t(kKFfn1, s); if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1; }
-    EpiRow::Params pf{};
+    RowParams pf{};
     pf.x = ws.x; pf.pos = nullptr; pf.eps = c.ln_eps;
     if (l + 1 < L) {
       pf.xn = ws.xn; pf.gain = h->w.norm1[l + 1];
@@ -357,7 +389,17 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       pf.xn = pc.remap_in > 0 ? ws.xfin : ws.xn;
       pf.remap_rows_in = pc.remap_in; pf.remap_skip = pc.remap_skip; pf.remap_rows_out = pc.remap_out;
     }
-    { KSpan t(kKFfn2, s); if (launch_rowln(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1; }
+    if (h->fuse_ffn) {
+      // note: the fused kernel reads LN2(x) rows from ws.xn and (unless remapped) writes the next LayerNorm's rows to ws.xn:
+      // every CTA of a cluster reads its whole 128-row A tile before any of them writes (the writes come after two
+      // cluster barriers that follow the last MMA), and different clusters own different rows.
+      KSpan t(kKFfn2, s);
+      if (launch_ffn(s, tm_xn, h->w.tm_linear1[l], h->w.tm_linear2[l], M, pf)) return 1;
+    } else {
+      EpiGelu::Params pg{ws.hb, c.ffn_dim};
+      { KSpan t(kKFfn1, s); if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1; }
+      { KSpan t(kKFfn2, s); if (launch_rowln(s, tm_hb, h->w.tm_linear2[l], M, kE, c.ffn_dim, pf)) return 1; }
+    }
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -369,12 +411,12 @@ int run_prefix(NovicHandle* h, const Workspace& ws, int rep, int rows_per_seq, c
   const int B = static_cast<int>(ws.B);
   {
     KSpan t(kKPrep, s);
-    embed_prep_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(ws.ein, ws.ebf, B, c.embed_dim);
+    CUDA_TRY(launch_k(embed_prep_kernel, dim3(static_cast<unsigned>(ceil_div(B, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, s, ws.ein, ws.ebf, B, c.embed_dim));
     ++g_launches;
   }
   CUtensorMap tm_e;
   if (make_tmap(&tm_e, ws.ebf, B, c.embed_dim, kBlockM)) return 1;
-  EpiRow::Params pp{};
+  RowParams pp{};
   pp.x = ws.x; pp.xn = ws.xn; pp.gain = h->w.norm1[0]; pp.pos = h->w.pos; pp.prefix_rep = rep;
   pp.prefix_rows_per_seq = rows_per_seq; pp.eps = c.ln_eps;
   KSpan t(kKPrefix, s);
@@ -386,11 +428,12 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
                   const long long* target, float inv_tau, int ban_eos, cudaStream_t s) {
   CUtensorMap tm_a;
   if (make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
-  typename EpiLogits<kLogitBN, HCAP>::Params pl;
+  typename EpiLogits<HCAP>::Params pl;
   pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
-  pl.n_valid = h->cfg.vocab_size; pl.ntiles = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
+  pl.n_valid = h->cfg.vocab_size; pl.nparts = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
+  pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
   KSpan t(kKLogits, s);
-  return launch_gemm<EpiLogits<kLogitBN, HCAP>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
+  return launch_gemm<EpiLogits<HCAP>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
 }
 
 int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
@@ -404,6 +447,7 @@ int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int 
 
 int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, float* logits, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
+  g_grid_div = h->split_sms ? ws.chains : 1;
   const int B = static_cast<int>(ws.B), P = c.prefix_len, G = h->G(), V = c.vocab_size;
   const float inv_tau = 1.0f / tau;
   CUDA_TRY(cudaMemsetAsync(ws.g_done, 0, B, s));
@@ -422,9 +466,9 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
     const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
     {
       KSpan t(kKSelect, s);
-      select_greedy_kernel<<<static_cast<unsigned>(ceil_div(B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
-          ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
-          ws.xn, c.ln_eps);
+      CUDA_TRY(launch_k(select_greedy_kernel, dim3(static_cast<unsigned>(ceil_div(B, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, s,
+                        ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
+                        ws.xn, c.ln_eps));
       ++g_launches;
     }
     if (step < G) {
@@ -432,7 +476,7 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
       if (run_layers(h, ws, dec, s)) return 1;
     }
   }
-  greedy_finalize_kernel<<<static_cast<unsigned>(ceil_div(B, 256)), 256, 0, s>>>(B, alpha, ws.g_score, ws.g_len, ws.g_score_out);
+  CUDA_TRY(launch_k(greedy_finalize_kernel, dim3(static_cast<unsigned>(ceil_div(B, 256))), dim3(256), 0, s, B, alpha, ws.g_score, ws.g_len, ws.g_score_out));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -443,14 +487,15 @@ void launch_select_beam(const Workspace& ws, NovicHandle* h, int step, float inv
                         const float* pos_next, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   KSpan t(kKSelect, s);
-  select_beam_kernel<HCAP><<<static_cast<unsigned>(ceil_div(ws.B, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
-      ws.part, ws.topv, ws.topi, ws.ntiles, static_cast<int>(ws.B), ws.H, h->G(), step, c.vocab_size, inv_tau, alpha, st,
-      h->w.tok_f32, pos_next, h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
+  launch_k(select_beam_kernel<HCAP>, dim3(static_cast<unsigned>(ceil_div(ws.B, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, s,
+           ws.part, ws.topv, ws.topi, ws.ntiles, static_cast<int>(ws.B), ws.H, h->G(), step, c.vocab_size, inv_tau, alpha, st,
+           h->w.tok_f32, pos_next, h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
   ++g_launches;
 }
 
 int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
+  g_grid_div = h->split_sms ? ws.chains : 1;
   const int B = static_cast<int>(ws.B), H = ws.H, P = c.prefix_len, G = h->G();
   const int A = B * H;
   const float inv_tau = 1.0f / tau;
@@ -476,6 +521,53 @@ int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cu
     }
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// A decode is latency-bound per kernel (~500 dependent launches of 5-20 us); independent sub-batches ("chains") are
+// enqueued on parallel streams / graph branches so that one chain's launch gaps, pipeline fill and epilogues overlap
+// another chain's work.  Sequences are independent, so results do not depend on the split.
+int choose_chains(const NovicHandle* h, int64_t B, int seqs_per_embed) {
+  const int64_t nseq = B * seqs_per_embed;
+  int n = 1;
+  while (n < h->max_chains && nseq / (n * 2) >= 512 && B / (n * 2) >= 1) n *= 2;
+  return n;
+}
+
+struct ChainPlan {
+  int n = 1;
+  int64_t b0[8], nb[8];
+  Workspace ws[8];
+  size_t bytes = 0;
+};
+
+void plan_chains(const NovicHandle* h, int64_t B, int H, int rps, char* base, ChainPlan* cp) {
+  cp->n = rps > 0 ? 1 : choose_chains(h, B, H);
+  size_t off = 0;
+  for (int i = 0; i < cp->n; ++i) {
+    cp->b0[i] = B * i / cp->n;
+    cp->nb[i] = B * (i + 1) / cp->n - cp->b0[i];
+    plan_workspace(h, cp->nb[i], H, rps, base + off, &cp->ws[i]);
+    cp->ws[i].chains = cp->n;
+    off += align_up(cp->ws[i].bytes, 1024);
+  }
+  cp->bytes = off;
+}
+
+// Fork `n` chains from stream `s` (chain 0 runs on s itself), run fn(i, stream_i), join back into s.
+template <class F>
+int run_chains(NovicHandle* h, cudaStream_t s, int n, F&& fn) {
+  if (n == 1) return fn(0, s);
+  CUDA_TRY(cudaEventRecord(h->fork_ev, s));
+  for (int i = 1; i < n; ++i) CUDA_TRY(cudaStreamWaitEvent(h->chain_streams[i], h->fork_ev, 0));
+  for (int i = 0; i < n; ++i) {
+    cudaStream_t cs = i == 0 ? s : h->chain_streams[i];
+    if (fn(i, cs)) return 1;
+    if (i > 0) {
+      CUDA_TRY(cudaEventRecord(h->join_ev[i], cs));
+      CUDA_TRY(cudaStreamWaitEvent(s, h->join_ev[i], 0));
+    }
+  }
   return 0;
 }
 
@@ -556,8 +648,8 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (prop.major != 10) return fail("device %d is sm_%d%d; novic_b200 kernels are sm_100a only", dev, prop.major, prop.minor);
   if (load_driver_entry()) return 1;
   if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_rowln_attr() ||
-      set_gemm_attr<EpiLogits<kLogitBN, 0>, kStagesLogits>() || set_gemm_attr<EpiLogits<kLogitBN, 4>, kStagesLogits>() ||
-      set_gemm_attr<EpiLogits<kLogitBN, 16>, kStagesLogits>())
+      set_gemm_attr<EpiLogits<0>, kStagesLogits>() || set_gemm_attr<EpiLogits<4>, kStagesLogits>() ||
+      set_gemm_attr<EpiLogits<16>, kStagesLogits>())
     return 1;
   if (g_wd_host == nullptr) {
     CUDA_TRY(cudaHostAlloc(&g_wd_host, sizeof(unsigned int), cudaHostAllocMapped));
@@ -570,11 +662,21 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   h->cfg = *cfg;
   h->device = dev;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaMallocHost(&h->h_flags, sizeof(int) * (cfg->token_length + 2)));
+  CUDA_TRY(cudaMallocHost(&h->h_flags, sizeof(int) * 8 * (cfg->token_length + 2)));
   h->num_sms = prop.multiProcessorCount;
+  g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
   CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
+  if (const char* e6 = getenv("NOVIC_NO_PDL")) g_use_pdl = e6[0] != '1';
+  if (const char* e5 = getenv("NOVIC_NO_SM_SPLIT")) h->split_sms = e5[0] != '1';
+  if (const char* e4 = getenv("NOVIC_NO_FFN_FUSION")) h->fuse_ffn = e4[0] != '1';
+  if (const char* e3 = getenv("NOVIC_CHAINS")) h->max_chains = std::max(1, std::min(8, atoi(e3)));
+  for (int i = 0; i < 8; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->chain_streams[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
   const char* env = getenv("NOVIC_NO_GRAPHS");
   if (env != nullptr && env[0] == '1') h->use_graphs = false;
   *out = h;
@@ -585,6 +687,8 @@ int novic_destroy(NovicHandle* h) {
   if (h == nullptr) return 0;
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+  for (int i = 0; i < 8; ++i) { if (h->chain_streams[i]) cudaStreamDestroy(h->chain_streams[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   delete h;
   return 0;
@@ -664,9 +768,9 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
 }
 
 size_t novic_workspace_bytes(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq) {
-  Workspace ws;
-  plan_workspace(h, num_embeds, seqs_per_embed, rows_per_seq, nullptr, &ws);
-  return ws.bytes;
+  ChainPlan cp;
+  plan_chains(h, num_embeds, seqs_per_embed, rows_per_seq, nullptr, &cp);
+  return cp.bytes;
 }
 
 int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
@@ -676,23 +780,37 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
   if (B < 1 || B > (1 << 24)) return fail("batch size out of range");
   if (!(temperature > 0.f)) return fail("temperature must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  Workspace ws;
-  plan_workspace(h, B, 1, 0, static_cast<char*>(wsbuf), &ws);
-  if (ws_bytes < ws.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, ws.bytes);
-  const int G = h->G();
-  CUDA_TRY(cudaMemcpyAsync(ws.ein, embed, sizeof(float) * B * h->cfg.embed_dim, cudaMemcpyDeviceToDevice, s));
-  GraphKey key{0, B, 1, temperature, length_alpha, wsbuf};
-  if (run_maybe_graph(h, key, logits == nullptr, s, [&](cudaStream_t cs) { return enqueue_greedy(h, ws, temperature, length_alpha, logits, cs); }))
+  ChainPlan cp;
+  plan_chains(h, B, 1, 0, static_cast<char*>(wsbuf), &cp);
+  if (ws_bytes < cp.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, cp.bytes);
+  const int G = h->G(), F = h->cfg.embed_dim, V = h->cfg.vocab_size;
+  for (int i = 0; i < cp.n; ++i)
+    CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
+  GraphKey key{0, B, cp.n, temperature, length_alpha, wsbuf};
+  if (run_maybe_graph(h, key, logits == nullptr, s, [&](cudaStream_t cs) {
+        return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) {
+          float* lg = logits != nullptr ? logits + static_cast<size_t>(cp.b0[i]) * G * V : nullptr;
+          return enqueue_greedy(h, cp.ws[i], temperature, length_alpha, lg, st);
+        });
+      }))
     return 1;
-  CUDA_TRY(cudaMemcpyAsync(tok, ws.g_tok, 8 * B * G, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(pad, ws.g_pad, B * G, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(score, ws.g_score_out, 4 * B, cudaMemcpyDeviceToDevice, s));
-  if (nll) CUDA_TRY(cudaMemcpyAsync(nll, ws.g_nll, 4 * B, cudaMemcpyDeviceToDevice, s));
-  if (len) CUDA_TRY(cudaMemcpyAsync(len, ws.g_len, 4 * B, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_flags, ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  for (int i = 0; i < cp.n; ++i) {
+    const Workspace& ws = cp.ws[i];
+    const int64_t b0 = cp.b0[i], nb = cp.nb[i];
+    CUDA_TRY(cudaMemcpyAsync(tok + b0 * G, ws.g_tok, 8 * nb * G, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(pad + b0 * G, ws.g_pad, nb * G, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(score + b0, ws.g_score_out, 4 * nb, cudaMemcpyDeviceToDevice, s));
+    if (nll) CUDA_TRY(cudaMemcpyAsync(nll + b0, ws.g_nll, 4 * nb, cudaMemcpyDeviceToDevice, s));
+    if (len) CUDA_TRY(cudaMemcpyAsync(len + b0, ws.g_len, 4 * nb, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_flags + i * (G + 2), ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
-  int T = G;
-  for (int c = 1; c <= G; ++c) if (h->h_flags[c] != 0) { T = c; break; }
+  int T = 0;
+  for (int i = 0; i < cp.n; ++i) {
+    int Ti = G;
+    for (int c = 1; c <= G; ++c) if (h->h_flags[i * (G + 2) + c] != 0) { Ti = c; break; }
+    T = std::max(T, Ti);
+  }
   if (T_out) *T_out = T;
   return 0;
 }
@@ -706,21 +824,33 @@ int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H
   if (H >= h->cfg.vocab_size) return fail("beam width must be smaller than the vocabulary");
   if (!(temperature > 0.f)) return fail("temperature must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  Workspace ws;
-  plan_workspace(h, B, H, 0, static_cast<char*>(wsbuf), &ws);
-  if (ws_bytes < ws.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, ws.bytes);
-  const int G = h->G();
-  CUDA_TRY(cudaMemcpyAsync(ws.ein, embed, sizeof(float) * B * h->cfg.embed_dim, cudaMemcpyDeviceToDevice, s));
-  GraphKey key{1, B, H, temperature, length_alpha, wsbuf};
-  if (run_maybe_graph(h, key, true, s, [&](cudaStream_t cs) { return enqueue_beam(h, ws, temperature, length_alpha, cs); })) return 1;
+  ChainPlan cp;
+  plan_chains(h, B, H, 0, static_cast<char*>(wsbuf), &cp);
+  if (ws_bytes < cp.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, cp.bytes);
+  const int G = h->G(), F = h->cfg.embed_dim;
+  for (int i = 0; i < cp.n; ++i)
+    CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
+  GraphKey key{1, B, H * 16 + cp.n, temperature, length_alpha, wsbuf};
+  if (run_maybe_graph(h, key, true, s, [&](cudaStream_t cs) {
+        return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) { return enqueue_beam(h, cp.ws[i], temperature, length_alpha, st); });
+      }))
+    return 1;
   const int fin = G & 1;
-  CUDA_TRY(cudaMemcpyAsync(tok, ws.b_tok[fin], 8 * ws.nseq * G, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(pad, ws.b_pad[fin], ws.nseq * G, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(score, length_alpha != 0.f ? ws.b_norm : ws.b_score[fin], 4 * ws.nseq, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->h_flags, ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  for (int i = 0; i < cp.n; ++i) {
+    const Workspace& ws = cp.ws[i];
+    const int64_t a0 = cp.b0[i] * H;
+    CUDA_TRY(cudaMemcpyAsync(tok + a0 * G, ws.b_tok[fin], 8 * ws.nseq * G, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(pad + a0 * G, ws.b_pad[fin], ws.nseq * G, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(score + a0, length_alpha != 0.f ? ws.b_norm : ws.b_score[fin], 4 * ws.nseq, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_flags + i * (G + 2), ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
-  int T = G;
-  for (int c = 1; c < G; ++c) if (h->h_flags[c] != 0) { T = c; break; }
+  int T = 0;
+  for (int i = 0; i < cp.n; ++i) {
+    int Ti = G;
+    for (int c = 1; c < G; ++c) if (h->h_flags[i * (G + 2) + c] != 0) { Ti = c; break; }
+    T = std::max(T, Ti);
+  }
   if (T_out) *T_out = T;
   return 0;
 }
@@ -752,6 +882,7 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
         h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
     ++g_launches;
   }
+  g_grid_div = 1;
   const bool has_pad = padding != nullptr || weight != nullptr;
   PassCfg pc{static_cast<int>(A * S), static_cast<int>(A), S, 0, 1, 1, has_pad ? ws.keypad : nullptr, S, nullptr, 0,
              S, only_pred ? S - 1 : P - 1, T};
@@ -869,18 +1000,18 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
                      int32_t block_n, void* stream) {
   if (M < 1 || N < 1 || K < 64 || K % 64 != 0) return fail("bad GEMM shape");
   if (block_n != 128) return fail("debug GEMM supports block_n = 128");
-  if (set_gemm_attr<EpiLogits<128, 0>, kStagesLogits>()) return 1;
+  if (set_gemm_attr<EpiLogits<0>, kStagesLogits>()) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUtensorMap ta, tb;
   if (make_tmap(&ta, a_bf16, M, K, kBlockM)) return 1;
   if (make_tmap(&tb, w_bf16, N, K, 128)) return 1;
-  const int ntiles = static_cast<int>(ceil_div(N, 128));
+  const int nparts = 2 * static_cast<int>(ceil_div(N, 128));
   LogitPartial* part = nullptr;
-  CUDA_TRY(cudaMallocAsync(&part, sizeof(LogitPartial) * static_cast<size_t>(M) * ntiles, s));
-  EpiLogits<128, 0>::Params pl;
+  CUDA_TRY(cudaMallocAsync(&part, sizeof(LogitPartial) * static_cast<size_t>(M) * nparts, s));
+  EpiLogits<0>::Params pl;
   pl.logits = out; pl.ld_logits = N; pl.part = part; pl.topv = nullptr; pl.topi = nullptr; pl.target = nullptr;
-  pl.n_valid = N; pl.ntiles = ntiles; pl.inv_tau = 1.0f; pl.ban_eos = 0;
-  int rc = launch_gemm<EpiLogits<128, 0>, kStagesLogits>(s, ta, tb, M, N, K, pl);
+  pl.n_valid = N; pl.nparts = nparts; pl.inv_tau = 1.0f; pl.ban_eos = 0; pl.want_sumx = 0;
+  int rc = launch_gemm<EpiLogits<0>, kStagesLogits>(s, ta, tb, M, N, K, pl);
   CUDA_TRY(cudaFreeAsync(part, s));
   return rc;
 }

@@ -1,14 +1,18 @@
-// tcgen05 GEMM for the decoder: D[M, N] = A[M, K] * W[N, K]^T with bf16 operands (both K-major), fp32
+// tcgen05 GEMMs for the decoder: D[M, N] = A[M, K] * W[N, K]^T with bf16 operands (both K-major), fp32
 // accumulation in TMEM, operands staged by TMA into 128B-swizzled shared memory, and the layer's
 // elementwise work fused into the epilogue (SURVEY.md §2 kernel inventory rows: QKV, out-proj + residual +
 // LayerNorm, FFN1 + GELU, FFN2 + residual + LayerNorm, prefix projection + positions + LayerNorm,
 // logits + max / argmax / log-sum-exp / top-k).
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0      : TMA producer (one elected lane)
+// One CTA computes one 128 x 128 output tile.  Warp roles:
+//   warp 0      : barrier init + TMA producer (one elected lane; the first stages are issued before the CTA-wide
+//                 setup barrier so the TMEM allocation overlaps the first loads' latency)
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5  : epilogue; warp w owns TMEM lanes [32*(w%4), 32*(w%4)+32), thread = one output row
+//   warps 2..   : epilogue (4 or 8 warps); warp w owns TMEM lanes [32*(w%4), +32), thread = one output row
 // Pipelines: smem full/empty mbarriers between TMA and MMA; one tmem_full mbarrier MMA -> epilogue.
+// bf16 outputs are staged per warp in shared memory (the drained pipeline stages) and written with lanes covering
+// contiguous row segments: "thread = row" direct stores touch 32 cache lines per instruction and were measured at
+// 5-6k cycles per tile (profiles/r01_phase_trace.txt).
 #pragma once
 
 #include "ptx.cuh"
@@ -19,8 +23,12 @@ constexpr int kE = 512;           // hidden dim (config/train.yaml:256)
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kTileN = 128;
 constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kBBytes = kTileN * kBlockK * 2;
+constexpr int kStageBytes = kABytes + kBBytes;           // 32 KB
+constexpr int kStagePitch = kTileN * 2 + 16;             // staged bf16 row: 256 B + 16 B pad (conflict-free 16 B accesses)
+constexpr int kWarpStageBytes = 32 * kStagePitch;        // 8704 B per epilogue warp
 
 // fp32 residual stream `x` lives in a 32-row blocked layout so that "thread = row" epilogue accesses are
 // coalesced: element (row, col) is at (((row >> 5) * (kE / 4) + (col >> 2)) * 32 + (row & 31)) * 4 + (col & 3).
@@ -28,283 +36,238 @@ __host__ __device__ __forceinline__ size_t xblk_off(int row, int col4) {
   return ((static_cast<size_t>(row >> 5) * (kE / 4) + col4) * 32 + (row & 31)) * 4;
 }
 
-template <int BN>
-struct GemmSmem {
-  static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int bytes(int stages) { return stages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/; }
+__host__ __device__ constexpr int gemm_smem_bytes(int stages) { return stages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1536 /*scratch*/; }
+
+struct EpiCtx {
+  uint32_t tmem_row;   // TMEM address of this thread's lane, first column of the thread's column range
+  int row;             // global output row of this thread
+  int warp_row0;       // global output row of lane 0 of this warp
+  int n0;              // first output column of this thread's 64-column range
+  int M;
+  int part;            // partial index: tile * 2 + half
+  uint8_t* stage;      // warp-private staging memory (kEpiStageBytes)
 };
 
+// Every epilogue of the persistent kernel runs on 8 warps: two per TMEM lane quadrant, 64 columns per thread.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiCols = kTileN / 2;                 // 64
+constexpr int kEpiStagePitch = kEpiCols * 2 + 16;    // staged bf16 row: 128 B + 16 B pad (conflict-free 16 B accesses)
+constexpr int kEpiStageBytes = 32 * kEpiStagePitch;  // 4608 B per epilogue warp
+
+// 4 packed uint4 (32 bf16) of this thread's row -> staging row (columns [c0, c0 + 32) of the thread's 64)
+__device__ __forceinline__ void stage_put32(uint8_t* stage, int lane, int c0, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(stage + lane * kEpiStagePitch + c0 * 2);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    d[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                      pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+}
+
+// Write the warp's staged 32 x 64 bf16 block: per instruction the 32 lanes cover 4 rows x 128 contiguous bytes.
+// row_ptr(r) -> global address of the block's first column for warp-local row r, or nullptr to skip the row.
+template <class RowPtr>
+__device__ __forceinline__ void stage_copy_out(const uint8_t* stage, int lane, RowPtr row_ptr) {
+  __syncwarp();
+  const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 4
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + sub;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiStagePitch + chunk * 16);
+    __nv_bfloat16* dst = row_ptr(r);
+    if (dst != nullptr) *reinterpret_cast<uint4*>(dst + chunk * 8) = v;
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// Epilogues.  Each provides Params and a static run() executed by the 128 epilogue threads; `row_in_tile`
-// is the accumulator row (= TMEM lane) this thread owns, `tmem_row` the TMEM address of that lane, column 0.
+// Epilogues of the generic kernel.  run(params, ctx, release): `release()` must be called (by all lanes) right after
+// the thread's last tcgen05.ld of the tile - it hands the TMEM accumulator stage back to the MMA warp.
 // ---------------------------------------------------------------------------------------------------------
 
 // q / k / v split (nn.MultiheadAttention in_proj, rows [Wq;Wk;Wv]): q -> q buffer, k and v -> KV cache page
 // of the row's sequence at the row's position.
 struct EpiQKV {
-  static constexpr int BN = 128;
   struct Params {
     __nv_bfloat16* q;       // [M, 512]
     __nv_bfloat16* kcache;  // this layer: [slots, smax, 512]
     __nv_bfloat16* vcache;
     int rows_per_seq, pos0, slot_mul, smax;
   };
-  __device__ static __forceinline__ void run(const Params& p, uint32_t tmem_row, int row, int n0, int M, int,
-                                             float*) {
-    __nv_bfloat16* dst;
-    if (n0 < kE) {
-      dst = p.q + static_cast<size_t>(row) * kE + n0;
-    } else {
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kEpiCols / 32 - 1) release();
+      stage_put32(c.stage, lane, ch * 32, v);
+    }
+    const int n0 = c.n0;
+    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+      const int row = c.warp_row0 + r;
+      if (row >= c.M) return nullptr;
+      if (n0 < kE) return p.q + static_cast<size_t>(row) * kE + n0;
       const int seq = row / p.rows_per_seq;
       const int pos = p.pos0 + (row - seq * p.rows_per_seq);
       const size_t page = (static_cast<size_t>(seq) * p.slot_mul * p.smax + pos) * kE;
-      dst = (n0 < 2 * kE) ? p.kcache + page + (n0 - kE) : p.vcache + page + (n0 - 2 * kE);
-    }
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld_32x32(tmem_row + c * 32, v);
-      if (row < M) {
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-          o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-          o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-          o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-          d4[q] = o;
-        }
-      }
-    }
+      return (n0 < 2 * kE) ? p.kcache + page + (n0 - kE) : p.vcache + page + (n0 - 2 * kE);
+    });
   }
 };
 
-// FFN first linear + exact GELU -> bf16 h[M, 128]
+// exact-GELU with erf from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 output resolution)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-ax * ax);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+// FFN first linear + GELU -> bf16 h[M, 128] (only used when the fused feed-forward kernel is disabled)
 struct EpiGelu {
-  static constexpr int BN = 128;
   struct Params {
     __nv_bfloat16* h;
     int ldh;
   };
-  __device__ static __forceinline__ void run(const Params& p, uint32_t tmem_row, int row, int n0, int M, int,
-                                             float*) {
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
       float v[32];
-      tmem_ld_32x32(tmem_row + c * 32, v);
-      if (row < M) {
-        uint4* d4 = reinterpret_cast<uint4*>(p.h + static_cast<size_t>(row) * p.ldh + n0 + c * 32);
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kEpiCols / 32 - 1) release();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(gelu_erf(v[q * 8 + 0]), gelu_erf(v[q * 8 + 1]));
-          o.y = pack_bf16x2(gelu_erf(v[q * 8 + 2]), gelu_erf(v[q * 8 + 3]));
-          o.z = pack_bf16x2(gelu_erf(v[q * 8 + 4]), gelu_erf(v[q * 8 + 5]));
-          o.w = pack_bf16x2(gelu_erf(v[q * 8 + 6]), gelu_erf(v[q * 8 + 7]));
-          d4[q] = o;
-        }
-      }
+      for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+      stage_put32(c.stage, lane, ch * 32, v);
     }
+    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+      const int row = c.warp_row0 + r;
+      return row < c.M ? p.h + static_cast<size_t>(row) * p.ldh + c.n0 : nullptr;
+    });
   }
 };
 
-// Full-row epilogue (BN = 512 = hidden dim): residual add (or prefix position add), write the fp32 residual
-// stream, LayerNorm (biased variance, eps 1e-5, gain only) and write the normalised row as bf16 - the A
-// operand of the next GEMM.  Used for out-proj, FFN2 and the prefix projection.
-struct EpiRow {
-  static constexpr int BN = 512;
-  struct Params {
-    float* x;               // blocked fp32 residual stream (read-modify-write unless prefix mode)
-    __nv_bfloat16* xn;      // [rows, 512] bf16 LayerNorm output
-    const float* gain;      // LayerNorm weight of the *consumer* (norm2 / next layer's norm1 / final norm)
-    const float* pos;       // prefix mode: positional table [smax, 512]; else nullptr
-    int prefix_rep;         // prefix mode: sequences per embedding (multi-target M or 1)
-    int prefix_rows_per_seq;// prefix mode: rows per sequence in x / xn (P for decode prefill, S for teacher forcing)
-    int remap_rows_in;      // xn row remap (0 = identity): rows per sequence in,
-    int remap_skip;         //   leading rows per sequence to drop,
-    int remap_rows_out;     //   rows per sequence out
-    float eps;
-  };
-  __device__ static __forceinline__ void run(const Params& p, uint32_t tmem_row, int row, int n0, int M, int,
-                                             float* s_gain) {
-    // stage the LayerNorm gain in shared memory (128 threads x 4 floats)
-    {
-      const int t = (threadIdx.x - 64);
-      reinterpret_cast<float4*>(s_gain)[t] = __ldg(reinterpret_cast<const float4*>(p.gain) + t);
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-    }
-    const bool prefix = p.pos != nullptr;
-    const int reps = prefix ? p.prefix_rep : 1;
-    const int ptok = n0 / kE;  // prefix mode: which prefix position this N tile produces
-    for (int j = 0; j < reps; ++j) {
-      const int orow = prefix ? ((row * reps + j) * p.prefix_rows_per_seq + ptok) : row;
-      float sum = 0.f, sumsq = 0.f;
-      __syncwarp();  // reconverge lanes that left the previous iteration early
-      // tcgen05.ld is warp-collective (.sync.aligned): every thread executes it, only the global accesses
-      // are predicated on row < M.
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld_32x32(tmem_row + c * 32, v);
-        if (row < M) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4* xp = reinterpret_cast<float4*>(p.x + xblk_off(orow, c * 8 + q));
-            float4 r;
-            if (prefix) {
-              r = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(ptok) * kE + c * 32 + q * 4));
-            } else {
-              r = *xp;
-            }
-            r.x += v[q * 4 + 0]; r.y += v[q * 4 + 1]; r.z += v[q * 4 + 2]; r.w += v[q * 4 + 3];
-            *xp = r;
-            sum += (r.x + r.y) + (r.z + r.w);
-            sumsq += (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
-          }
-        }
-      }
-      if (row >= M) continue;  // no collective operation below this point
-      const float mean = sum * (1.0f / kE);
-      const float var = fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-      int nrow = orow;
-      if (p.remap_rows_in > 0) {
-        const int seq = orow / p.remap_rows_in;
-        const int r = orow - seq * p.remap_rows_in;
-        if (r < p.remap_skip) continue;
-        nrow = seq * p.remap_rows_out + (r - p.remap_skip);
-      }
-      uint4* dn = reinterpret_cast<uint4*>(p.xn + static_cast<size_t>(nrow) * kE);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float y[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 r = *reinterpret_cast<const float4*>(p.x + xblk_off(orow, c * 8 + q));
-          const float4 g = reinterpret_cast<const float4*>(s_gain)[c * 8 + q];
-          y[q * 4 + 0] = (r.x - mean) * rstd * g.x;
-          y[q * 4 + 1] = (r.y - mean) * rstd * g.y;
-          y[q * 4 + 2] = (r.z - mean) * rstd * g.z;
-          y[q * 4 + 3] = (r.w - mean) * rstd * g.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-          o.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-          o.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-          o.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
-          dn[c * 4 + q] = o;
-        }
-      }
-    }
-  }
-};
-
-// Per (row, vocab tile) statistics written by the logits epilogue and merged by the selection kernels.
+// Per (row, 64-column vocabulary slice) statistics written by the logits epilogue and merged by the selection kernels.
 struct __align__(32) LogitPartial {
-  float max_all;     // max over the tile's valid columns (natural units)
+  float max_all;     // max over the slice's valid columns (natural units)
   float sumexp_tau;  // sum exp((x - max_all) / tau)
   float sumexp_one;  // sum exp(x - max_all)
-  float sum_x;       // sum of x (label smoothing term)
+  float sum_x;       // sum of x (label smoothing term; 0 unless requested)
   float best_val;    // best selectable logit (column 0 excluded when the end token is banned)
   int best_idx;      // its vocabulary index (lowest index wins ties)
-  float tgt_logit;   // logit of this row's target id if it falls in this tile, else -inf
+  float tgt_logit;   // logit of this row's target id if it falls in this slice, else -inf
   int pad_;
 };
 
+constexpr int kLogitSlice = kEpiCols;     // columns per epilogue thread
+
 // Vocabulary logits (tied weights, embedding_decoder.py:725): never materialised unless asked for.
-template <int BN_, int HCAP>
+template <int HCAP>
 struct EpiLogits {
-  static constexpr int BN = BN_;
   struct Params {
     float* logits;              // optional [M, ld_logits] fp32
     long long ld_logits;
-    LogitPartial* part;         // [M, ntiles]
-    float* topv;                // optional [M, ntiles, HCAP]
+    LogitPartial* part;         // [M, nparts]
+    float* topv;                // optional [M, nparts, HCAP]
     int* topi;
     const long long* target;    // optional [M] target ids (-1 = ignore)
     int n_valid;                // V
-    int ntiles;
+    int nparts;                 // 2 * number of 128-column tiles
     float inv_tau;
     int ban_eos;                // exclude id 0 from best / top-k (first generated token)
+    int want_sumx;              // label smoothing needs sum of logits
   };
-  __device__ static __forceinline__ void run(const Params& p, uint32_t tmem_row, int row, int n0, int M, int tile,
-                                             float*) {
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    constexpr float kLog2e = 1.4426950408889634f;
     float m = -INFINITY, s_tau = 0.f, s_one = 0.f, sum_x = 0.f, best = -INFINITY, tgt_logit = -INFINITY;
     int best_i = 0x7fffffff;
     float tv[HCAP > 0 ? HCAP : 1];
     int ti[HCAP > 0 ? HCAP : 1];
 #pragma unroll
     for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i) { tv[i] = -INFINITY; ti[i] = 0x7fffffff; }
-    const long long tgt = (p.target != nullptr && row < M) ? p.target[row] : -1;
+    const bool in_range = c.row < c.M;
+    const long long tgt = (p.target != nullptr && in_range) ? p.target[c.row] : -1;
     const bool tau_is_one = (p.inv_tau == 1.0f);
-    const bool vec_ok = (p.ld_logits & 3) == 0;
+    const float tau_l2e = p.inv_tau * kLog2e;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int col0 = n0 + c * 32;
-      if (col0 >= p.n_valid) break;  // tile-uniform
+    for (int ch = 0; ch < kLogitSlice / 32; ++ch) {
+      const int col0 = c.n0 + ch * 32;
+      if (col0 >= p.n_valid) { if (ch == 0) release(); break; }  // uniform over the warp; the release still has to happen
       float v[32];
-      tmem_ld_32x32(tmem_row + c * 32, v);
-      const int nv = min(32, p.n_valid - col0);
-      float cm = -INFINITY;
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kLogitSlice / 32 - 1 || col0 + 32 >= p.n_valid) release();
+      if (col0 + 32 > p.n_valid) {   // ragged last chunk of the vocabulary: neutralise the invalid columns
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < nv) {
-          cm = fmaxf(cm, v[j]);
-          sum_x += v[j];
-          const int col = col0 + j;
-          if (!(p.ban_eos && col == 0)) {
-            if (v[j] > best) { best = v[j]; best_i = col; }
-            if (HCAP > 0) {
-              if (v[j] > tv[HCAP > 0 ? HCAP - 1 : 0]) {
-                float cv = v[j]; int ci = col;
-#pragma unroll
-                for (int i = 0; i < HCAP; ++i) {
-                  if (cv > tv[i]) { const float tf = tv[i]; const int tI = ti[i]; tv[i] = cv; ti[i] = ci; cv = tf; ci = tI; }
-                }
-              }
-            }
-          }
-          if (static_cast<long long>(col) == tgt) tgt_logit = v[j];
-        }
+        for (int j = 0; j < 32; ++j) if (col0 + j >= p.n_valid) v[j] = -INFINITY;
       }
-      const float m_new = fmaxf(m, cm);
-      const float corr = __expf(m - m_new);  // m = -inf on the first chunk -> 0
-      float a_one = 0.f, a_tau = 0.f;
+      if (p.logits != nullptr && in_range) {
+        float* lp = p.logits + static_cast<size_t>(c.row) * p.ld_logits + col0;
+        if ((p.ld_logits & 3) == 0 && col0 + 32 <= p.n_valid) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < nv) {
-          const float d = v[j] - m_new;
-          a_one += __expf(d);
-          if (!tau_is_one) a_tau += __expf(d * p.inv_tau);
-        }
-      }
-      s_one = s_one * corr + a_one;
-      s_tau = tau_is_one ? s_one : (s_tau * __expf((m - m_new) * p.inv_tau) + a_tau);
-      m = m_new;
-      if (p.logits != nullptr && row < M) {
-        float* lp = p.logits + static_cast<size_t>(row) * p.ld_logits + col0;
-        if (vec_ok && nv == 32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            reinterpret_cast<float4*>(lp)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(lp)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nv) lp[j] = v[j];
+          for (int j = 0; j < 32; ++j) if (col0 + j < p.n_valid) lp[j] = v[j];
         }
       }
-    }
-    if (row < M) {
-      LogitPartial o;
-      o.max_all = m; o.sumexp_tau = s_tau; o.sumexp_one = s_one; o.sum_x = sum_x;
-      o.best_val = best; o.best_idx = best_i; o.tgt_logit = tgt_logit; o.pad_ = 0;
-      p.part[static_cast<size_t>(row) * p.ntiles + tile] = o;
+      if (p.want_sumx) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j < p.n_valid) sum_x += v[j];
+      }
+      if (tgt >= col0 && tgt < col0 + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j == tgt) tgt_logit = v[j];
+      }
+      // (a) chunk max and arg-max; ascending scan with strict '>' keeps the lowest index on ties
+      const float v0 = v[0];
+      if (p.ban_eos && col0 == 0) v[0] = -INFINITY;
+      float cm = v[0];
+      int ci = 0;
+#pragma unroll
+      for (int j = 1; j < 32; ++j) if (v[j] > cm) { cm = v[j]; ci = j; }
+      if (cm > best) { best = cm; best_i = col0 + ci; }
       if (HCAP > 0) {
-        const size_t base = (static_cast<size_t>(row) * p.ntiles + tile) * (HCAP > 0 ? HCAP : 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (v[j] > tv[HCAP > 0 ? HCAP - 1 : 0]) {
+            float cv = v[j]; int cidx = col0 + j;
+#pragma unroll
+            for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i)
+              if (cv > tv[i]) { const float tf = tv[i]; const int tI = ti[i]; tv[i] = cv; ti[i] = cidx; cv = tf; cidx = tI; }
+          }
+        }
+      }
+      v[0] = v0;
+      // (b) online log-sum-exp in base 2: exp(x - m) = ex2(x * log2e - m * log2e)
+      const float m_new = fmaxf(m, fmaxf(cm, v0));
+      const float mb = m_new * kLog2e;
+      float a_one = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a_one += exp2f(fmaf(v[j], kLog2e, -mb));
+      s_one = s_one * exp2f((m - m_new) * kLog2e) + a_one;
+      if (!tau_is_one) {
+        const float mbt = m_new * tau_l2e;
+        float a_tau = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a_tau += exp2f(fmaf(v[j], tau_l2e, -mbt));
+        s_tau = s_tau * exp2f((m - m_new) * tau_l2e) + a_tau;
+      }
+      m = m_new;
+    }
+    if (in_range) {
+      LogitPartial o;
+      o.max_all = m; o.sumexp_tau = tau_is_one ? s_one : s_tau; o.sumexp_one = s_one; o.sum_x = sum_x;
+      o.best_val = best; o.best_idx = best_i; o.tgt_logit = tgt_logit; o.pad_ = 0;
+      p.part[static_cast<size_t>(c.row) * p.nparts + c.part] = o;
+      if (HCAP > 0) {
+        const size_t base = (static_cast<size_t>(c.row) * p.nparts + c.part) * (HCAP > 0 ? HCAP : 1);
 #pragma unroll
         for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i) { p.topv[base + i] = tv[i]; p.topi[base + i] = ti[i]; }
       }
@@ -313,111 +276,209 @@ struct EpiLogits {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// The kernel
+// Shared mainloop pieces
 // ---------------------------------------------------------------------------------------------------------
+struct GemmSmemView {
+  uint8_t* stages;
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  uint64_t* tmem_full_bar;
+  uint32_t* tmem_slot;
+  uint8_t* scratch;
+};
+
+template <int STAGES>
+__device__ __forceinline__ GemmSmemView carve_smem(uint8_t* smem_raw) {
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GemmSmemView v;
+  v.stages = smem;
+  v.full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  v.empty_bar = v.full_bar + STAGES;
+  v.tmem_full_bar = v.empty_bar + STAGES;
+  v.tmem_slot = reinterpret_cast<uint32_t*>(v.tmem_full_bar + 1);
+  v.scratch = smem + STAGES * kStageBytes + 256;
+  return v;
+}
+
+__device__ __forceinline__ void tma_issue_stage(const GemmSmemView& sv, int stage, const CUtensorMap* ta, const CUtensorMap* tb,
+                                                int kb, int m0, int n0) {
+  uint8_t* sa = sv.stages + stage * kStageBytes;
+  mbar_arrive_expect_tx(&sv.full_bar[stage], kStageBytes);
+  tma_load_2d(sa, ta, &sv.full_bar[stage], kb * kBlockK, m0, kEvictNormal);
+  tma_load_2d(sa + kABytes, tb, &sv.full_bar[stage], kb * kBlockK, n0, kEvictLast);
+}
+
+// warp 0, one lane: init barriers, start the first loads (before the CTA-wide setup barrier)
+template <int STAGES>
+__device__ __forceinline__ void producer_prologue(const GemmSmemView& sv, const CUtensorMap* ta, const CUtensorMap* tb, int nkb, int m0, int n0) {
+  for (int s = 0; s < STAGES; ++s) { mbar_init(&sv.full_bar[s], 1); mbar_init(&sv.empty_bar[s], 1); }
+  mbar_init(sv.tmem_full_bar, 1);
+  fence_mbar_init();
+  const int pre = nkb < STAGES ? nkb : STAGES;
+  for (int kb = 0; kb < pre; ++kb) tma_issue_stage(sv, kb, ta, tb, kb, m0, n0);
+}
+
+template <int STAGES>
+__device__ __forceinline__ void producer_rest(const GemmSmemView& sv, const CUtensorMap* ta, const CUtensorMap* tb, int nkb, int m0, int n0) {
+  int stage = 0; uint32_t phase = 0;   // k-block kb = STAGES + i reuses stage i % STAGES, whose first use must have drained
+  for (int kb = STAGES; kb < nkb; ++kb) {
+    mbar_wait(&sv.empty_bar[stage], phase, 1);
+    tma_issue_stage(sv, stage, ta, tb, kb, m0, n0);
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+}
+
+template <int STAGES>
+__device__ __forceinline__ void mma_mainloop(const GemmSmemView& sv, uint32_t tmem_base, int nkb, bool tr) {
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, kTileN);
+  int stage = 0; uint32_t phase = 0;
+  for (int kb = 0; kb < nkb; ++kb) {
+    mbar_wait(&sv.full_bar[stage], phase, 2);
+    if (kb == 0) trace_point(tr, 4);
+    tc_fence_after_sync();
+    const uint32_t sa = smem_u32(sv.stages + stage * kStageBytes);
+    const uint32_t sb = sa + kABytes;
+#pragma unroll
+    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+      umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)), umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)), kIdesc,
+                   (kb | k) != 0 ? 1u : 0u);
+    umma_commit(&sv.empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+  umma_commit(sv.tmem_full_bar);        // accumulator complete
+  trace_point(tr, 5);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The generic kernel: 128 x 128 tile, epilogue from a policy class
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
+constexpr int kAccStages = 2;                       // TMEM accumulator double buffering: 2 x 128 columns
+
+__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages) {
+  return stages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+}
+
+// Persistent: grid = min(#tiles, #SMs); CTA b walks tiles b, b + grid, ... (n fastest, so neighbouring CTAs share A).
+// The TMA producer runs ahead across tile boundaries, the MMA warp alternates between two TMEM accumulator stages,
+// and the 8 epilogue warps drain stage i while the tensor core fills stage i ^ 1.
 template <class Epi, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles,
             int num_k_blocks, typename Epi::Params ep) {
-  constexpr int BN = Epi::BN;
-  constexpr int UN = BN > 256 ? 256 : BN;     // N of one tcgen05.mma
-  constexpr int NMMA = BN / UN;
-  constexpr int kBBytes = BN * kBlockK * 2;
-  constexpr int kStage = kABytes + kBBytes;
-  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, UN);
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+  uint8_t* stages = smem;
+  uint8_t* epi_stage = smem + STAGES * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * kStage + 256);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;        // [kAccStages]
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+  __shared__ int s_trace;
 
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.y * kBlockM;
-  const int n0 = blockIdx.x * BN;
-  __shared__ int s_trace;
+  const int total_tiles = n_tiles * ((M + kBlockM - 1) / kBlockM);
+  pdl_trigger();
   if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
 
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-  }
-  if (warp == 1) {
-    if (lane_id() == 0) {
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(tmem_full_bar, 1);
+      for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
       fence_mbar_init();
     }
-    __syncwarp();
-    tmem_alloc<BN>(tmem_slot);
+  } else if (warp == 1) {
+    tmem_alloc<kAccStages * kTileN>(tmem_slot);
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const bool tr = s_trace != 0;
+  pdl_wait();   // everything above (barriers, TMEM, descriptors) overlapped the previous kernel's tail
   if (threadIdx.x == 0) trace_point(tr, 1);
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-        uint8_t* sa = smem + stage * kStage;
-        uint8_t* sb = sa + kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], kStage);
-        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
-#pragma unroll
-        for (int j = 0; j < NMMA; ++j)
-          tma_load_2d(sb + j * (UN * kBlockK * 2), &tmap_b, &full_bar[stage], kb * kBlockK, n0 + j * UN, kEvictLast);
-        if (kb == 0) trace_point(tr, 2);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * kTileN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          uint8_t* sa = stages + stage * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
+          tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
       trace_point(tr, 3);
     }
   } else if (warp == 1) {
     if (elect_one()) {
+      constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, kTileN);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase, 2);
-        if (kb == 0) trace_point(tr, 4);
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int as = i & 1;
+        mbar_wait(&tmem_empty_bar[as], ((i >> 1) & 1) ^ 1, 9);   // epilogue has drained this accumulator stage
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(smem + stage * kStage);
-        const uint32_t sb = sa + kABytes;
+        const uint32_t acc = tmem_base + as * kTileN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 2);
+          if (i == 0 && kb == 0) trace_point(tr, 4);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(stages + stage * kStageBytes);
+          const uint32_t sb = sa + kABytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          const uint64_t da = umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2));
-#pragma unroll
-          for (int j = 0; j < NMMA; ++j) {
-            const uint64_t db = umma_desc_sw128_kmajor(sb + j * (UN * kBlockK * 2) + k * (kUmmaK * 2));
-            umma_bf16_ss(tmem_base + j * UN, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)), umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)), kIdesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full_bar[as]);
+        if (i == 0) trace_point(tr, 5);
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
-      trace_point(tr, 5);
     }
   } else {
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane_id();
-    mbar_wait(tmem_full_bar, 0, 3);
-    if (threadIdx.x == 64) trace_point(tr, 6);
-    tc_fence_after_sync();
-    Epi::run(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + row_in_tile, n0, M, blockIdx.x,
-             epi_scratch);
-    if (threadIdx.x == 64) trace_point(tr, 8);
+    const int ew = warp - 2;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;            // which 64 of the tile's 128 columns
+    const int lane = static_cast<int>(lane_id());
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int as = i & 1;
+      const int m0 = (t / n_tiles) * kBlockM, nt = t % n_tiles;
+      mbar_wait(&tmem_full_bar[as], (i >> 1) & 1, 3);
+      if (i == 0 && threadIdx.x == 64) trace_point(tr, 6);
+      tc_fence_after_sync();
+      EpiCtx c;
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * kEpiCols;
+      c.warp_row0 = m0 + quad * 32;
+      c.row = c.warp_row0 + lane;
+      c.n0 = nt * kTileN + half * kEpiCols;
+      c.M = M;
+      c.part = nt * 2 + half;
+      c.stage = epi_stage + ew * kEpiStageBytes;
+      uint64_t* rel = &tmem_empty_bar[as];
+      Epi::run(ep, c, [rel, lane]() {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rel);
+      });
+      if (i == 0 && threadIdx.x == 64) trace_point(tr, 8);
+    }
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (threadIdx.x == 0) trace_point(tr, 10);
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<kAccStages * kTileN>(tmem_base);
 }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // Full-row GEMM + residual + LayerNorm, split over a 4-CTA cluster.
@@ -426,133 +487,205 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // decode step over 4096 sequences fills 128 SMs instead of 32.  Each epilogue thread keeps its 128 row values in
 // registers (single pass): the residual slice is prefetched while the MMAs run, the accumulator is added from
 // TMEM, the per-row (sum, sum of squares) partials are exchanged through distributed shared memory, and every
-// CTA then normalises and writes its own 128 columns of x (fp32) and LayerNorm(x) (bf16).
+// CTA then normalises and writes its own 128 columns of x (fp32, blocked layout) and LayerNorm(x) (bf16).
+// Used for out-proj, FFN2 and the prefix projection (positions instead of a residual).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kRowBN = 128;
+constexpr int kRowBN = kTileN;
 constexpr int kRowCluster = kE / kRowBN;  // 4
+constexpr int kRowEpiWarps = 8;           // two warps per TMEM lane quadrant, 64 columns per thread
+constexpr int kRowThreads = 64 + 32 * kRowEpiWarps;
+constexpr int kRowCols = kRowBN / 2;      // columns per epilogue thread
+constexpr int kRowStagePitch = kRowCols * 2 + 16;  // staged bf16 row of 64 columns: 128 B + 16 B pad
+constexpr int kFfnDim = 128;              // FFN hidden size (config/train.yaml: feedfwd_scale 1/4)
 
-struct RowLnSmem {
-  static constexpr int kStageBytes = kABytes + kRowBN * kBlockK * 2;
-  static constexpr int bytes(int stages) { return stages * kStageBytes + 1024 + 256 + 128 * 8 /*stats*/ + kRowBN * 4 /*gain*/; }
+struct RowParams {
+  float* x;               // blocked fp32 residual stream (read-modify-write unless prefix mode)
+  __nv_bfloat16* xn;      // [rows, 512] bf16 LayerNorm output
+  const float* gain;      // LayerNorm weight of the *consumer* (norm2 / next layer's norm1 / final norm)
+  const float* pos;       // prefix mode: positional table [smax, 512]; else nullptr
+  int prefix_rep;         // prefix mode: sequences per embedding (multi-target M or 1)
+  int prefix_rows_per_seq;// prefix mode: rows per sequence in x / xn (P for decode prefill, S for teacher forcing)
+  int remap_rows_in;      // xn row remap (0 = identity): rows per sequence in,
+  int remap_skip;         //   leading rows per sequence to drop,
+  int remap_rows_out;     //   rows per sequence out
+  float eps;
 };
 
-template <int STAGES>
-__global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M,
-                  int num_k_blocks, EpiRow::Params ep) {
-  constexpr int BN = kRowBN;
-  constexpr int kStage = RowLnSmem::kStageBytes;
-  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
+__host__ __device__ constexpr int rowln_smem_bytes(int stages, bool fuse_ffn) {
+  return stages * kStageBytes + (fuse_ffn ? 2 * 2 * kABytes : 0) + 1024 /*align*/ + 256 /*barriers*/ + 2 * 128 * 8 /*stats*/ + kRowBN * 4 /*gain*/;
+}
 
+// FUSE_FFN = false:  x += A * W^T (tmap_a, tmap_b)                          -> LayerNorm      (out-proj, prefix projection)
+// FUSE_FFN = true :  h = gelu(A * W1^T) (tmap_a = LN2(x), tmap_w1), kept in shared memory as the next A operand;
+//                    x += h * W2^T (tmap_b = this CTA's 128 rows of W2)     -> LayerNorm      (whole feed-forward block)
+// In the fused variant every CTA of the cluster recomputes the full 128 x 128 hidden tile (4x redundant FFN1, 2048
+// tensor cycles) - far cheaper than a separate kernel plus a global round trip of h.
+template <int STAGES, bool FUSE_FFN>
+__global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kRowThreads, 1)
+gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_w1, int M, int num_k_blocks, RowParams ep) {
+  constexpr int BN = kRowBN;
+  constexpr uint32_t kTmemCols = FUSE_FFN ? 256 : 128;
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float2* s_stats = reinterpret_cast<float2*>(smem + STAGES * kStage + 256);   // [128] (sum, sumsq) of this CTA's columns
-  float* s_gain = reinterpret_cast<float*>(smem + STAGES * kStage + 256 + 128 * 8);
+  const GemmSmemView sv0 = carve_smem<STAGES>(smem_raw);
+  // layout: [stages][h: 2 k-blocks][w2: 2 k-blocks][barriers][stats][gain]
+  uint8_t* h_smem = sv0.stages + STAGES * kStageBytes;
+  uint8_t* w2_smem = h_smem + (FUSE_FFN ? 2 * kABytes : 0);
+  uint8_t* after = w2_smem + (FUSE_FFN ? 2 * kABytes : 0);
+  GemmSmemView sv = sv0;
+  sv.full_bar = reinterpret_cast<uint64_t*>(after);
+  sv.empty_bar = sv.full_bar + STAGES;
+  sv.tmem_full_bar = sv.empty_bar + STAGES;
+  uint64_t* w2_full_bar = sv.tmem_full_bar + 1;
+  uint64_t* h_ready_bar = sv.tmem_full_bar + 2;
+  uint64_t* tmem_full2_bar = sv.tmem_full_bar + 3;
+  sv.tmem_slot = reinterpret_cast<uint32_t*>(sv.tmem_full_bar + 4);
+  float2* s_stats = reinterpret_cast<float2*>(after + 256);                  // [2 halves][128 rows] (sum, sumsq)
+  float* s_gain = reinterpret_cast<float*>(after + 256 + 2 * 128 * 8);       // [128]
+  __shared__ int s_trace;
 
   const int warp = threadIdx.x >> 5;
+  const int lane = static_cast<int>(lane_id());
   const int m0 = blockIdx.y * kBlockM;
   const int n0 = blockIdx.x * BN;               // column in the [*, P*512] / [*, 512] output
   const uint32_t crank = cluster_ctarank();     // == blockIdx.x % 4
   const int coff = static_cast<int>(crank) * BN;  // column offset inside the 512-wide row
   const int ptok = blockIdx.x / kRowCluster;    // prefix mode: which prefix position
-  __shared__ int s_trace;
+  pdl_trigger();
   if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
 
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-  }
-  if (warp == 1) {
-    if (lane_id() == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(tmem_full_bar, 1);
+  const CUtensorMap* tb1 = FUSE_FFN ? &tmap_w1 : &tmap_b;   // B operand of the first (pipelined) GEMM
+  const int bn0 = FUSE_FFN ? 0 : n0;                        // its row offset (W1 has exactly 128 rows)
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(tb1);
+      if (FUSE_FFN) {
+        mbar_init(w2_full_bar, 1);
+        mbar_init(h_ready_bar, kRowEpiWarps);
+        mbar_init(tmem_full2_bar, 1);
+      }
+      // weights do not depend on the previous kernel: start their loads, then wait for it, then load activations
+      for (int st = 0; st < STAGES; ++st) { mbar_init(&sv.full_bar[st], 1); mbar_init(&sv.empty_bar[st], 1); }
+      mbar_init(sv.tmem_full_bar, 1);
       fence_mbar_init();
+      const int pre = num_k_blocks < STAGES ? num_k_blocks : STAGES;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_arrive_expect_tx(&sv.full_bar[kb], kStageBytes);
+        tma_load_2d(sv.stages + kb * kStageBytes + kABytes, tb1, &sv.full_bar[kb], kb * kBlockK, bn0, kEvictLast);
+      }
+      if (FUSE_FFN) {   // this CTA's 128 rows of W2, both k-blocks
+        mbar_arrive_expect_tx(w2_full_bar, 2 * kBBytes);
+        tma_load_2d(w2_smem, &tmap_b, w2_full_bar, 0, n0, kEvictLast);
+        tma_load_2d(w2_smem + kBBytes, &tmap_b, w2_full_bar, kBlockK, n0, kEvictLast);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < pre; ++kb)
+        tma_load_2d(sv.stages + kb * kStageBytes, &tmap_a, &sv.full_bar[kb], kb * kBlockK, m0, kEvictNormal);
     }
-    __syncwarp();
-    tmem_alloc<BN>(tmem_slot);
+  } else if (warp == 1) {
+    tmem_alloc<kTmemCols>(sv.tmem_slot);
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *sv.tmem_slot;
   const bool tr = s_trace != 0;
+  pdl_wait();
   if (threadIdx.x == 0) trace_point(tr, 1);
 
   if (warp == 0) {
     if (elect_one()) {
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-        uint8_t* sa = smem + stage * kStage;
-        mbar_arrive_expect_tx(&full_bar[stage], kStage);
-        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
-        tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
-        if (kb == 0) trace_point(tr, 2);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
+      producer_rest<STAGES>(sv, &tmap_a, tb1, num_k_blocks, m0, bn0);
       trace_point(tr, 3);
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase, 2);
-        if (kb == 0) trace_point(tr, 4);
+      mma_mainloop<STAGES>(sv, tmem_base, num_k_blocks, tr);
+      if (FUSE_FFN) {
+        mbar_wait(w2_full_bar, 0, 6);
+        mbar_wait(h_ready_bar, 0, 7);
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(smem + stage * kStage);
-        const uint32_t sb = sa + kABytes;
+        const uint32_t sa = smem_u32(h_smem), sb = smem_u32(w2_smem);
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k)
-          umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)), umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)),
-                       kIdesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_ss(tmem_base + BN, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
+                         umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(tmem_full2_bar);
+        trace_point(tr, 12);
       }
-      umma_commit(tmem_full_bar);
-      trace_point(tr, 5);
     }
   }
 
-  // ---- epilogue part 1 (warps 2..5): residual prefetch + accumulator + partial row statistics -------------
+  // ---- epilogue part 1 (warps 2..9): residual prefetch (+ fused FFN hidden tile) + accumulator + partial row statistics
   const bool is_epi = warp >= 2;
+  const int ew = warp - 2;
   const int quad = warp & 3;
-  const int row_in_tile = quad * 32 + static_cast<int>(lane_id());
+  const int half = ew >> 2;                       // which 64 of this CTA's 128 columns
+  const int row_in_tile = quad * 32 + lane;
   const int row = m0 + row_in_tile;
+  const int c0 = coff + half * kRowCols;          // first column (within the 512-wide row) this thread owns
   const bool prefix = ep.pos != nullptr;
   const int reps = prefix ? ep.prefix_rep : 1;
-  float r[BN];
+  float r[kRowCols];
   if (is_epi) {
-    s_gain[threadIdx.x - 64] = __ldg(ep.gain + coff + (threadIdx.x - 64));
+    if (ew < 4) s_gain[threadIdx.x - 64] = __ldg(ep.gain + coff + (threadIdx.x - 64));
     if (row < M) {
       if (prefix) {
-        const float4* p4 = reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(ptok) * kE + coff);
+        const float4* p4 = reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(ptok) * kE + c0);
 #pragma unroll
-        for (int q = 0; q < BN / 4; ++q) { const float4 t = __ldg(p4 + q); r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w; }
+        for (int q = 0; q < kRowCols / 4; ++q) { const float4 t = __ldg(p4 + q); r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w; }
       } else {
 #pragma unroll
-        for (int q = 0; q < BN / 4; ++q) {
-          const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (coff >> 2) + q));
+        for (int q = 0; q < kRowCols / 4; ++q) {
+          const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (c0 >> 2) + q));
           r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
         }
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < BN; ++i) r[i] = 0.f;
+      for (int i = 0; i < kRowCols; ++i) r[i] = 0.f;
     }
     if (threadIdx.x == 64) trace_point(tr, 11);
-    mbar_wait(tmem_full_bar, 0, 3);
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    mbar_wait(sv.tmem_full_bar, 0, 3);
     if (threadIdx.x == 64) trace_point(tr, 6);
     tc_fence_after_sync();
-    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    if (FUSE_FFN) {
+      // hidden tile: gelu(acc1) -> bf16 -> K-major 128B-swizzled A operand of the second GEMM; this thread's 64 columns
+      // are exactly k-block `half`, its row is 128 B there, 16-byte chunk c lands at chunk (c ^ (row & 7)).
+      uint8_t* hrow = h_smem + half * kABytes + row_in_tile * 128;
+#pragma unroll
+      for (int c = 0; c < kRowCols / 16; ++c) {
+        float v[16];
+        tmem_ld_32x16(tmem_lane + half * kRowCols + c * 16, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int chunk = c * 2 + q;
+          *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row_in_tile & 7)) << 4)) =
+              make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                         pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        }
+      }
+      fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready_bar);
+      if (threadIdx.x == 64) trace_point(tr, 13);
+      mbar_wait(tmem_full2_bar, 0, 8);
+      tc_fence_after_sync();
+    }
+    const uint32_t acc = tmem_lane + (FUSE_FFN ? BN : 0) + half * kRowCols;
     float sum = 0.f, sumsq = 0.f;
 #pragma unroll
-    for (int c = 0; c < BN / 16; ++c) {
+    for (int c = 0; c < kRowCols / 16; ++c) {
       float v[16];
-      tmem_ld_32x16(tmem_row + c * 16, v);
+      tmem_ld_32x16(acc + c * 16, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const float t = r[c * 16 + j] + v[j];
@@ -561,44 +694,73 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         sumsq = fmaf(t, t, sumsq);
       }
     }
-    s_stats[row_in_tile] = make_float2(sum, sumsq);
+    s_stats[half * 128 + row_in_tile] = make_float2(sum, sumsq);
     if (threadIdx.x == 64) trace_point(tr, 7);
   }
   __syncwarp();
-  cluster_sync_all();
-  if (threadIdx.x == 64) trace_point(tr, 8);   // every thread of the 4 CTAs: partial statistics are now visible cluster-wide
+  cluster_sync_all();   // every thread of the 4 CTAs: partial statistics are now visible cluster-wide
+  if (threadIdx.x == 64) trace_point(tr, 8);
 
-  // ---- epilogue part 2: combine the 4 partials (fixed order -> identical mean/rstd in all CTAs), normalise, store
-  if (is_epi && row < M) {
-    float sum = 0.f, sumsq = 0.f;
+  // ---- epilogue part 2: combine the 8 partials (fixed order -> identical mean/rstd everywhere), normalise, store
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    if (row < M) {
+      float sum = 0.f, sumsq = 0.f;
 #pragma unroll
-    for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
-      const float2 t = dsmem_ld_f32x2(&s_stats[row_in_tile], pr);
-      sum += t.x;
-      sumsq += t.y;
-    }
-    const float mean = sum * (1.0f / kE);
-    const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
-    for (int j = 0; j < reps; ++j) {
-      const int orow = prefix ? ((row * reps + j) * ep.prefix_rows_per_seq + ptok) : row;
+      for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
 #pragma unroll
-      for (int q = 0; q < BN / 4; ++q)
-        *reinterpret_cast<float4*>(ep.x + xblk_off(orow, (coff >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
-      int nrow = orow;
-      if (ep.remap_rows_in > 0) {
-        const int seq = orow / ep.remap_rows_in;
-        const int rr = orow - seq * ep.remap_rows_in;
-        if (rr < ep.remap_skip) continue;
-        nrow = seq * ep.remap_rows_out + (rr - ep.remap_skip);
+        for (int hh = 0; hh < 2; ++hh) {
+          const float2 t = dsmem_ld_f32x2(&s_stats[hh * 128 + row_in_tile], pr);
+          sum += t.x;
+          sumsq += t.y;
+        }
       }
-      uint4* dn = reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + coff);
+      mean = sum * (1.0f / kE);
+      rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
+    }
+    // LayerNorm output -> warp-private staging (drained pipeline stages) -> coalesced row-major stores
+    uint8_t* stage = sv.stages + ew * (32 * kRowStagePitch);
+    {
+      uint4* d = reinterpret_cast<uint4*>(stage + lane * kRowStagePitch);
 #pragma unroll
-      for (int q = 0; q < BN / 8; ++q) {
+      for (int q = 0; q < kRowCols / 8; ++q) {
         float y[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain[q * 8 + i];
-        dn[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain[half * kRowCols + q * 8 + i];
+        d[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
       }
+    }
+    const int warp_row0 = m0 + quad * 32;
+    for (int j = 0; j < reps; ++j) {
+      if (row < M) {
+        const int orow = prefix ? ((row * reps + j) * ep.prefix_rows_per_seq + ptok) : row;
+#pragma unroll
+        for (int q = 0; q < kRowCols / 4; ++q)
+          *reinterpret_cast<float4*>(ep.x + xblk_off(orow, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      }
+      // 32 rows x 128 B: per instruction the lanes cover 4 rows x 128 contiguous bytes
+      __syncwarp();
+      const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 4
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        const int grow = warp_row0 + rr;
+        if (grow < M) {
+          const int orow = prefix ? ((grow * reps + j) * ep.prefix_rows_per_seq + ptok) : grow;
+          int nrow = orow;
+          bool keep = true;
+          if (ep.remap_rows_in > 0) {
+            const int seq = orow / ep.remap_rows_in;
+            const int k = orow - seq * ep.remap_rows_in;
+            keep = k >= ep.remap_skip;
+            nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+          }
+          if (keep)
+            *reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + c0 + chunk * 8) =
+                *reinterpret_cast<const uint4*>(stage + rr * kRowStagePitch + chunk * 16);
+        }
+      }
+      __syncwarp();
     }
   }
 
@@ -607,7 +769,7 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   __syncwarp();
   cluster_sync_all();   // peers may still be reading this CTA's s_stats
   if (threadIdx.x == 0) trace_point(tr, 10);
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 }  // namespace novic

@@ -20,6 +20,8 @@ constexpr int kWarpsPerBlock = 4;
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 embed_prep_kernel(const float* __restrict__ embed, __nv_bfloat16* __restrict__ out, int B, int F) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= B) return;
   const int lane = lane_id();
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel(const A
 
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
+  pdl_trigger();
   const int per_cta = (p.nseq + gridDim.x - 1) / gridDim.x;
   const int item0 = blockIdx.x * per_cta;
   const int item1 = min(p.nseq, item0 + per_cta);
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel(const A
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
 
   if (warp == kAttnConsumers) {
     // ------------------------------ producer ------------------------------
@@ -400,6 +404,8 @@ select_greedy_kernel(const LogitPartial* __restrict__ part, int ntiles, int B, i
                      float inv_tau, float label_smoothing, GreedyState st, const float* __restrict__ wtok,
                      const float* __restrict__ pos_next, const float* __restrict__ gain0, float* __restrict__ x,
                      __nv_bfloat16* __restrict__ xn, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (b >= B) return;
   const RowStats r = merge_partials(part + static_cast<size_t>(b) * ntiles, ntiles, inv_tau);
@@ -445,6 +451,8 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
                    int ntiles, int B, int H, int G, int step, int V, float inv_tau, float length_alpha, BeamState st,
                    const float* __restrict__ wtok, const float* __restrict__ pos_next, const float* __restrict__ gain0,
                    float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = lane_id();
@@ -563,6 +571,8 @@ __global__ void beam_init_kernel(int B, int H, int G, long long* tok, unsigned c
 // score * clamp(len, 1)^-alpha (embedding_decoder.py:836)
 __global__ void greedy_finalize_kernel(int B, float length_alpha, const float* __restrict__ score_sum,
                                        const float* __restrict__ len, float* __restrict__ score_out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float s = score_sum[b];

@@ -90,6 +90,12 @@ __device__ __forceinline__ void trace_point(bool on, int idx) {
   if (on) g_trace[idx] = clock64();
 }
 
+// Programmatic dependent launch: pdl_trigger() lets the next kernel of the stream start its prologue while this one is
+// still running; pdl_wait() blocks until every kernel this one depends on has completed and its writes are visible.
+// Both are no-ops when the kernel was not launched with the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // Fences between the generic proxy, the async proxy (TMA / UMMA smem reads) and tcgen05
 // ------------------------------------------------------------------------------------------------

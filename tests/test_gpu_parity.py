@@ -171,18 +171,14 @@ def test_beam_vs_reference_outputs(gold, models, tag, name, H, tau, alpha):
         #     literal equality cannot be demanded row by row; what must hold is:
         #     - beams that are literally the reference's carry the reference's score and padding,
         #     - the large majority of beams (and of best beams) are literally identical,
-        #     - search quality is the same: the best beam is at least as good as the greedy path of the same model
-        #        and, on average over the batch, as good as the reference's best beam.
+        #     - search quality is the same: on (almost) every sample the best beam scores like the reference's best beam.
         if tok.shape == g_tok.shape:
             same = (tok == g_tok).all(dim=2)
             assert same[:, 0].float().mean() >= 0.8
             assert same.float().mean() >= 0.6
             assert torch.equal(pad[same], g_pad[same])
             assert (sc - g_sc)[same].abs().max() <= tol
-        if alpha == 0:
-            greedy = models(tag).generate(gold_embed().to(DEV), False, True, tau, alpha, None, None, False)[5].cpu()
-            assert (sc[:, 0] >= greedy - MARGIN_TOL).all()
-        assert abs(sc[:, 0].mean().item() - g_sc[:, 0].mean().item()) <= LOGIT_TOL
+        assert ((sc[:, 0] - g_sc[:, 0]).abs() <= tol).float().mean() >= 0.9
 
 
 @pytest.mark.parametrize("B,C,use_pad,only_pred", [(1, 1, False, False), (3, 2, True, False), (129, 16, True, False), (40, 7, False, True), (64, 16, True, True)])
@@ -296,7 +292,7 @@ def test_noise_statistics_and_in_place_contract():
     for scheme, check in (
         ("GaussElem", lambda c, a: abs(c.mean().item() - 1 / math.sqrt(1 + 3.25 ** 2)) < 0.01),
         ("UniformAngle", lambda c, a: a.min() >= 45.0 - 1e-2 and a.max() <= 75.0 + 1e-2 and abs(a.mean().item() - 60.0) < 0.5),
-        ("GaussAngle", lambda c, a: a.max() <= 40.0 + 1e-2 and abs(a.std().item() - 30.0 * 0.6) < 6.0),
+        ("GaussAngle", lambda c, a: a.max() <= 75.0 + 1e-2 and abs(a.std().item() - 30.0 * 0.6028) < 1.5),  # |N(0, 30)| clamped at 75
         ("GaussVec", lambda c, a: c.min() > 0.0),
         ("GaussElemUniformAngle", lambda c, a: 0.28 < c.mean().item() < 0.36 and a.min() >= 45.0 - 1e-2),
     ):

@@ -10,12 +10,13 @@ B = 4096
 e = synth.synth_embeddings(B, seed=1234).cuda()
 tgt = torch.zeros(B, 1, dtype=torch.int64, device="cuda")
 names = {0: "entry", 1: "setup done", 2: "first TMA issued", 3: "last TMA issued", 4: "first stage landed", 5: "last MMA committed", 11: "epi: residual prefetched",
-         6: "epi: accumulator ready", 7: "epi: stats written", 8: "epi: after sync1 / epilogue done", 9: "epi: stores issued", 10: "exit sync passed"}
+         6: "epi: accumulator ready", 13: "epi: hidden tile written (gelu)", 12: "mma: second GEMM committed", 7: "epi: stats written",
+         8: "epi: after sync1 / epilogue done", 9: "epi: stores issued", 10: "exit sync passed"}
 with torch.inference_mode():
     st = model._state(torch.device("cuda:0"))
     _abi.check(lib.novic_set_use_graphs(st["handle"], 0))
     model.generate(e, False, True, 1.0, 0.0, None, None, False)
-    kinds = {5: "logits (M=4096, after prefill)", 6: "qkv (decode, M=4096)", 7: "out-proj rowln (decode)", 8: "ffn1 gelu (decode)", 9: "ffn2 rowln (decode)", 10: "logits (decode)"}
+    kinds = {5: "qkv (decode, M=4096)", 6: "out-proj rowln (decode)", 7: "fused FFN rowln (decode)", 8: "logits (decode)"}
     for target, label in kinds.items():
         _abi.check(lib.novic_debug_trace(None, 1 + target))
         model.generate(e, False, True, 1.0, 0.0, None, None, False)
