@@ -302,9 +302,12 @@ def main():
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tpath):
-            traffic = json.load(open(tpath)).get(dom)
         d = kernels[dom]
+        if os.path.isfile(tpath) and d.get("bound") == "hbm":
+            entry = json.load(open(tpath)).get(dom)
+            if entry:  # ncu-measured DRAM bytes of one launch / that launch's algorithmic bytes, applied to the average launch
+                work = algorithmic_work(B, dims)[dom][1]
+                traffic = entry["ratio_to_algorithmic"] * work / max(1, d["launches_per_step"])
         roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
                     "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],
                     "how": "CUDA-event pair around every launch on the launching stream, direct-launch replay of the same decode; achieved = algorithmic work of all launches of the class / their summed duration",

@@ -110,6 +110,17 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
                   const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
                   uint8_t* pad_out, float* loss, uint8_t* correct, void* ws, size_t ws_bytes, void* stream);
 
+/* Replaces the forward + backward of one training batch (train.py:1270-1273: model(..., calc_loss=True, calc_correct=True,
+ * only_pred=False) followed by loss.backward()) with dropout disabled.  Same inputs as novic_forward (C >= 2).
+ * Outputs (device): loss [2] = {loss_sum, loss_basis}; correct [A, C] u8 and pad_out [A, C] u8 (may be NULL); `grads`
+ * holds fp32 device buffers shaped like the parameters of NovicWeights and receives d(loss_sum) / d(parameter)
+ * (overwritten).  The caller applies the 1 / (loss_basis * accumulation) factor, gradient clipping and the optimizer,
+ * exactly as train.py:1272-1286 does. */
+size_t novic_train_workspace_bytes(const NovicHandle* h, int64_t B, int32_t M, int32_t C);
+int novic_train_fwd_bwd(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                        const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* Replaces EmbeddingNoise.forward (embedding_noise.py:72-75, :90-95, :105-112, :169-172): in place on
  * embed [B, F] fp32 device; random draws come from Philox (seed, offset). */
 int novic_noise_apply(const NovicNoiseCfg* cfg, float* embed, int64_t B, uint64_t seed, uint64_t offset, void* stream);

@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/novic_b200.h"
-#include "kernels.cuh"
+#include "train.cuh"
 
 using namespace novic;
 
@@ -58,12 +58,17 @@ int load_driver_entry() {
 }
 
 // Row-major bf16 matrix [rows, cols]; boxes of [box_rows, 64] elements, 128-byte swizzle (K-major UMMA operand).
-int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows) {
+// `ld` (elements, default = cols) lets the K extent be ragged: columns >= cols are out of bounds and read as zero.
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int64_t ld = 0) {
   if (load_driver_entry()) return 1;
-  if (cols % kBlockK != 0) return fail("TMA operand inner dimension %lld is not a multiple of %d", (long long)cols, kBlockK);
+  if (ld == 0) {
+    ld = cols;
+    if (cols % kBlockK != 0) return fail("TMA operand inner dimension %lld is not a multiple of %d", (long long)cols, kBlockK);
+  }
+  if (ld % 8 != 0) return fail("TMA operand row pitch %lld is not a multiple of 16 bytes", (long long)ld);
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA operand base is not 16-byte aligned");
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -105,11 +110,11 @@ int set_gemm_attr() {
 
 template <class Epi, int STAGES>
 int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                const typename Epi::Params& ep) {
+                const typename Epi::Params& ep, int k_splits = 1) {
   const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
-  const int64_t total = n_tiles * ceil_div(M, kBlockM);
+  const int64_t total = n_tiles * ceil_div(M, kBlockM) * k_splits;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
-  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES), s, ta, tb, M, n_tiles, K / kBlockK, ep));
+  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -226,6 +231,9 @@ struct WeightPtrs {
   const float *tok_f32, *pos, *final_norm, *norm1[NOVIC_MAX_LAYERS], *norm2[NOVIC_MAX_LAYERS];
   CUtensorMap tm_embed_mlp, tm_tok, tm_in_proj[NOVIC_MAX_LAYERS], tm_out_proj[NOVIC_MAX_LAYERS], tm_linear1[NOVIC_MAX_LAYERS],
       tm_linear2[NOVIC_MAX_LAYERS];
+  // transposed bf16 copies (B operands of the backward dgrad GEMMs: dX = dY * W needs W^T in K-major form)
+  const __nv_bfloat16 *tok_t, *in_proj_t[NOVIC_MAX_LAYERS], *out_proj_t[NOVIC_MAX_LAYERS], *linear1_t[NOVIC_MAX_LAYERS], *linear2_t[NOVIC_MAX_LAYERS];
+  CUtensorMap tm_tok_t, tm_in_proj_t[NOVIC_MAX_LAYERS], tm_out_proj_t[NOVIC_MAX_LAYERS], tm_linear1_t[NOVIC_MAX_LAYERS], tm_linear2_t[NOVIC_MAX_LAYERS];
 };
 
 struct Workspace {
@@ -524,6 +532,8 @@ int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cu
   return 0;
 }
 
+#include "train_host.inc"
+
 // A decode is latency-bound per kernel (~500 dependent launches of 5-20 us); independent sub-batches ("chains") are
 // enqueued on parallel streams / graph branches so that one chain's launch gaps, pipeline fill and epilogues overlap
 // another chain's work.  Sequences are independent, so results do not depend on the split.
@@ -649,8 +659,10 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (load_driver_entry()) return 1;
   if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_rowln_attr() ||
       set_gemm_attr<EpiLogits<0>, kStagesLogits>() || set_gemm_attr<EpiLogits<4>, kStagesLogits>() ||
-      set_gemm_attr<EpiLogits<16>, kStagesLogits>())
+      set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
+      set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
     return 1;
+  CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 6 * kAttnBwdMaxS * kAttnBwdStride * 4));
   if (g_wd_host == nullptr) {
     CUDA_TRY(cudaHostAlloc(&g_wd_host, sizeof(unsigned int), cudaHostAllocMapped));
     *g_wd_host = 0;
@@ -712,6 +724,9 @@ size_t novic_weight_bytes(const NovicHandle* h) {
   b.take(4 * S * E);
   b.take(4 * E);
   for (size_t l = 0; l < L; ++l) { b.take(4 * E); b.take(4 * E); }
+  const size_t Vp = align_up(V, 64);
+  b.take(2 * E * Vp);
+  for (size_t l = 0; l < L; ++l) { b.take(2 * 3 * E * E); b.take(2 * E * E); b.take(2 * K * E); b.take(2 * E * K); }
   return b.off;
 }
 
@@ -750,7 +765,31 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
   o.pos = cpy(w->pos_embed, S * E);
   o.final_norm = cpy(w->final_norm, E);
   for (size_t l = 0; l < L; ++l) { o.norm1[l] = cpy(w->norm1[l], E); o.norm2[l] = cpy(w->norm2[l], E); }
+  // transposed copies for the backward pass
+  const size_t Vp = align_up(V, 64);
+  auto tr = [&](const __nv_bfloat16* src, size_t rows, size_t cols, size_t ld_dst) -> const __nv_bfloat16* {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base + b.take(2 * cols * ld_dst));
+    cudaMemsetAsync(dst, 0, 2 * cols * ld_dst, s);
+    dim3 grid(static_cast<unsigned>(ceil_div(cols, 64)), static_cast<unsigned>(ceil_div(rows, 64)));
+    transpose_bf16_kernel<<<grid, 256, 0, s>>>(src, static_cast<int>(rows), static_cast<int>(cols), static_cast<int>(cols), dst, static_cast<int>(ld_dst));
+    ++g_launches;
+    return dst;
+  };
+  o.tok_t = tr(o.tok, V, E, Vp);
+  for (size_t l = 0; l < L; ++l) {
+    o.in_proj_t[l] = tr(o.in_proj[l], 3 * E, E, 3 * E);
+    o.out_proj_t[l] = tr(o.out_proj[l], E, E, E);
+    o.linear1_t[l] = tr(o.linear1[l], K, E, K);
+    o.linear2_t[l] = tr(o.linear2[l], E, K, E);
+  }
   CUDA_TRY(cudaGetLastError());
+  if (make_tmap(&o.tm_tok_t, o.tok_t, E, Vp, kTileN)) return 1;
+  for (size_t l = 0; l < L; ++l) {
+    if (make_tmap(&o.tm_in_proj_t[l], o.in_proj_t[l], E, 3 * E, kTileN)) return 1;
+    if (make_tmap(&o.tm_out_proj_t[l], o.out_proj_t[l], E, E, kTileN)) return 1;
+    if (make_tmap(&o.tm_linear1_t[l], o.linear1_t[l], E, K, kTileN)) return 1;
+    if (make_tmap(&o.tm_linear2_t[l], o.linear2_t[l], K, E, kTileN)) return 1;
+  }
   if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, kRowBN)) return 1;
   if (make_tmap(&o.tm_tok, o.tok, V, E, kLogitBN)) return 1;
   for (size_t l = 0; l < L; ++l) {
@@ -901,6 +940,53 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
     if (correct != nullptr) CUDA_TRY(cudaMemcpyAsync(correct, ws.correct, A * T, cudaMemcpyDeviceToDevice, s));
   }
   if (pad_out != nullptr) CUDA_TRY(cudaMemcpyAsync(pad_out, ws.effpad, A * T, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+size_t novic_train_workspace_bytes(const NovicHandle* h, int64_t B, int32_t M, int32_t C) {
+  TrainPlan t;
+  plan_train(h, B, M, C, nullptr, &t);
+  return t.bytes;
+}
+
+int novic_train_fwd_bwd(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                        const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
+                        void* wsbuf, size_t ws_bytes, void* stream) {
+  if (check_ready(h)) return 1;
+  const NovicCfg& c = h->cfg;
+  if (B < 1 || M < 1 || C < 2 || C > c.token_length) return fail("bad B / M / C (C must be in [2, token_length])");
+  if (target == nullptr || grads == nullptr || loss == nullptr) return fail("target, grads and loss are required");
+  if (B * M * static_cast<int64_t>(c.prefix_len + C - 1) > (1LL << 24)) return fail("too many rows for one training call; split the batch");
+  if (c.prefix_len + C - 1 > kAttnBwdMaxS) return fail("sequence too long for the attention backward kernel");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  TrainPlan t;
+  plan_train(h, B, M, C, static_cast<char*>(wsbuf), &t);
+  if (ws_bytes < t.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, t.bytes);
+  t.has_pad = padding != nullptr || weight != nullptr;
+  const size_t E = kE, K = c.ffn_dim, F = c.embed_dim, P = c.prefix_len, V = c.vocab_size, L = c.num_layers, S = c.prefix_len + c.token_length - 1;
+  TrainGrads g;
+  auto zero = [&](const float* p, size_t n) -> float* { cudaMemsetAsync(const_cast<float*>(p), 0, 4 * n, s); return const_cast<float*>(p); };
+  g.embed_mlp = zero(grads->embed_mlp, P * E * F);
+  g.tok = zero(grads->tok_embed, V * E);
+  g.pos = zero(grads->pos_embed, S * E);
+  g.final_norm = zero(grads->final_norm, E);
+  for (size_t l = 0; l < L; ++l) {
+    g.in_proj[l] = zero(grads->in_proj[l], 3 * E * E); g.out_proj[l] = zero(grads->out_proj[l], E * E);
+    g.linear1[l] = zero(grads->linear1[l], K * E); g.linear2[l] = zero(grads->linear2[l], E * K);
+    g.norm1[l] = zero(grads->norm1[l], E); g.norm2[l] = zero(grads->norm2[l], E);
+  }
+  CUDA_TRY(cudaMemcpyAsync(t.ein, embed, sizeof(float) * B * F, cudaMemcpyDeviceToDevice, s));
+  g_grid_div = 1;
+  const bool pdl = g_use_pdl;
+  g_use_pdl = false;   // the training path mixes in plainly launched kernels; keep ordinary stream ordering
+  int rc = train_forward(h, t, reinterpret_cast<const long long*>(target), padding, weight, s);
+  if (!rc) rc = train_backward(h, t, reinterpret_cast<const long long*>(target), weight, g, s);
+  g_use_pdl = pdl;
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(loss, t.loss, 8, cudaMemcpyDeviceToDevice, s));
+  if (correct != nullptr) CUDA_TRY(cudaMemcpyAsync(correct, t.correct, t.Rt, cudaMemcpyDeviceToDevice, s));
+  if (pad_out != nullptr) CUDA_TRY(cudaMemcpyAsync(pad_out, t.effpad, t.Rt, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

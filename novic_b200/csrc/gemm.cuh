@@ -365,7 +365,7 @@ __host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages) {
 template <class Epi, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles,
-            int num_k_blocks, typename Epi::Params ep) {
+            int num_k_blocks, int k_splits, typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -378,7 +378,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   __shared__ int s_trace;
 
   const int warp = threadIdx.x >> 5;
-  const int total_tiles = n_tiles * ((M + kBlockM - 1) / kBlockM);
+  const int mn_tiles = n_tiles * ((M + kBlockM - 1) / kBlockM);
+  const int total_tiles = mn_tiles * k_splits;                       // split-K: tile t covers k-blocks [kb0, kb1) of (t % mn_tiles)
+  const int kb_per_split = (num_k_blocks + k_splits - 1) / k_splits;
   pdl_trigger();
   if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
 
@@ -405,8 +407,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * kTileN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int tt = t % mn_tiles, sp = t / mn_tiles;
+        const int m0 = (tt / n_tiles) * kBlockM, n0 = (tt % n_tiles) * kTileN;
+        const int kb0 = sp * kb_per_split, kb1 = min(num_k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* sa = stages + stage * kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
@@ -427,16 +431,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         mbar_wait(&tmem_empty_bar[as], ((i >> 1) & 1) ^ 1, 9);   // epilogue has drained this accumulator stage
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + as * kTileN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int sp = t / mn_tiles;
+        const int kb0 = sp * kb_per_split, kb1 = min(num_k_blocks, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 2);
-          if (i == 0 && kb == 0) trace_point(tr, 4);
+          if (i == 0 && kb == kb0) trace_point(tr, 4);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(stages + stage * kStageBytes);
           const uint32_t sb = sa + kABytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
             umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)), umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)), kIdesc,
-                         (kb | k) != 0 ? 1u : 0u);
+                         (kb > kb0 || k != 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -452,7 +458,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
       const int as = i & 1;
-      const int m0 = (t / n_tiles) * kBlockM, nt = t % n_tiles;
+      const int tt = t % mn_tiles;
+      const int m0 = (tt / n_tiles) * kBlockM, nt = tt % n_tiles;
       mbar_wait(&tmem_full_bar[as], (i >> 1) & 1, 3);
       if (i == 0 && threadIdx.x == 64) trace_point(tr, 6);
       tc_fence_after_sync();
@@ -499,7 +506,8 @@ constexpr int kRowStagePitch = kRowCols * 2 + 16;  // staged bf16 row of 64 colu
 constexpr int kFfnDim = 128;              // FFN hidden size (config/train.yaml: feedfwd_scale 1/4)
 
 struct RowParams {
-  float* x;               // blocked fp32 residual stream (read-modify-write unless prefix mode)
+  float* x;               // blocked fp32 residual stream, output
+  const float* x_in;      // residual input (nullptr: same buffer as x, i.e. in place; ignored in prefix mode)
   __nv_bfloat16* xn;      // [rows, 512] bf16 LayerNorm output
   const float* gain;      // LayerNorm weight of the *consumer* (norm2 / next layer's norm1 / final norm)
   const float* pos;       // prefix mode: positional table [smax, 512]; else nullptr
@@ -641,7 +649,7 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       } else {
 #pragma unroll
         for (int q = 0; q < kRowCols / 4; ++q) {
-          const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (c0 >> 2) + q));
+          const float4 t = *reinterpret_cast<const float4*>((ep.x_in != nullptr ? ep.x_in : ep.x) + xblk_off(row, (c0 >> 2) + q));
           r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
         }
       }

@@ -1,0 +1,485 @@
+// Backward-pass kernels of the teacher-forced training step (train.py:1263-1286 -> embedding_decoder.py:659-761):
+// everything that is not a GEMM.  The GEMMs (dgrad: dX = dY * W, wgrad: dW = dY^T * X) run on the same persistent
+// tcgen05 kernel as the forward pass with the epilogues at the bottom of this file.
+//
+// Gradient tensors that flow along the residual stream are kept in three formats, each produced where it is cheap:
+//   fp32 "blocked" [R, 512]  (same layout as x: coalesced for thread-per-row kernels; the accumulation format)
+//   bf16 row-major [R, 512]  (A operand of the next dgrad GEMM)
+//   bf16 transposed [512, R] (A operand of the next wgrad GEMM, whose contraction runs over the R rows)
+#pragma once
+
+#include "kernels.cuh"
+
+namespace novic {
+
+// ---------------------------------------------------------------------------------------------------------
+// bf16 transpose: dst[c, r] = src[r, c]   (src row-major [R, C] with leading dimension ld_src; dst [C, ld_dst])
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int R, int C, int ld_src,
+                                                             __nv_bfloat16* __restrict__ dst, int ld_dst) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + tx * 2 + h;
+      tile[i][tx * 2 + h] = (r < R && c < C) ? src[static_cast<size_t>(r) * ld_src + c] : __float2bfloat16(0.f);
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = r0 + tx * 2 + h;
+      if (c < C && r < R) dst[static_cast<size_t>(c) * ld_dst + r] = tile[tx * 2 + h][i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm backward + residual merge.  Thread = row (blocked fp32 tensors are coalesced that way).
+//   y = (x - mean) * rstd * g          dxhat = dy * g
+//   dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))           dg[c] += sum_rows dy * xhat
+//   out = dx + (resid ? resid : 0)     written as fp32 blocked, bf16 row-major (via smem staging) and bf16 transposed
+// ---------------------------------------------------------------------------------------------------------
+struct LnBwdParams {
+  const float* x;        // blocked: the LayerNorm input saved by the forward pass
+  const float* dy;       // blocked: gradient w.r.t. the LayerNorm output
+  const float* resid;    // blocked or nullptr: gradient arriving through the residual connection
+  const float* gain;     // [512]
+  float* out;            // blocked
+  __nv_bfloat16* out_bf; // [R, 512] row-major or nullptr
+  __nv_bfloat16* out_t;  // [512, ld_t] transposed or nullptr
+  float* dgain;          // [512] accumulated with atomics
+  int R, ld_t;
+  float eps;
+};
+
+__global__ void __launch_bounds__(128) ln_bwd_kernel(const LnBwdParams p) {
+  __shared__ float s_gain[kE];
+  __shared__ __align__(16) uint8_t s_stage[4][32 * kEpiStagePitch];
+  for (int i = threadIdx.x; i < kE; i += 128) s_gain[i] = p.gain[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int row0 = (blockIdx.x * 4 + warp) * 32;
+  const int row = row0 + lane;
+  const bool ok = row < p.R;
+  // pass 1: statistics of x and the two row reductions
+  float sum = 0.f, sumsq = 0.f;
+  if (ok) {
+    for (int q = 0; q < kE / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q));
+      sum += (v.x + v.y) + (v.z + v.w);
+      sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  }
+  const float mean = sum * (1.0f / kE);
+  const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + p.eps);
+  float s1 = 0.f, s2 = 0.f;
+  if (ok) {
+    for (int q = 0; q < kE / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q));
+      const float4 d = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, q));
+      const float4 g = *reinterpret_cast<const float4*>(&s_gain[q * 4]);
+      const float a0 = d.x * g.x, a1 = d.y * g.y, a2 = d.z * g.z, a3 = d.w * g.w;
+      s1 += (a0 + a1) + (a2 + a3);
+      s2 += a0 * (v.x - mean) * rstd + a1 * (v.y - mean) * rstd + a2 * (v.z - mean) * rstd + a3 * (v.w - mean) * rstd;
+    }
+  }
+  const float m1 = s1 * (1.0f / kE), m2 = s2 * (1.0f / kE);
+  // pass 2: dx, outputs, dgain.  64 columns at a time so the bf16 row-major copy can go through the warp's staging tile.
+  for (int c0 = 0; c0 < kE; c0 += kEpiCols) {
+    float o[kEpiCols];
+#pragma unroll
+    for (int q = 0; q < kEpiCols / 4; ++q) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), d = v, r = v;
+      if (ok) {
+        v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, (c0 >> 2) + q));
+        d = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, (c0 >> 2) + q));
+        if (p.resid != nullptr) r = *reinterpret_cast<const float4*>(p.resid + xblk_off(row, (c0 >> 2) + q));
+      }
+      const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w}, rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + q * 4 + i;
+        const float xhat = (xv[i] - mean) * rstd;
+        const float dx = ok ? rstd * (dv[i] * s_gain[c] - m1 - xhat * m2) : 0.f;
+        o[q * 4 + i] = dx + rv[i];
+        float dg = ok ? dv[i] * xhat : 0.f;   // column reduction over the warp's 32 rows
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) dg += __shfl_xor_sync(0xffffffffu, dg, off);
+        if (lane == 0) atomicAdd(p.dgain + c, dg);
+      }
+      if (ok) *reinterpret_cast<float4*>(p.out + xblk_off(row, (c0 >> 2) + q)) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+    }
+    if (p.out_t != nullptr && ok) {
+#pragma unroll
+      for (int i = 0; i < kEpiCols; ++i) p.out_t[static_cast<size_t>(c0 + i) * p.ld_t + row] = __float2bfloat16_rn(o[i]);
+    }
+    if (p.out_bf != nullptr) {
+      uint8_t* stage = s_stage[warp];
+      uint4* d = reinterpret_cast<uint4*>(stage + lane * kEpiStagePitch);
+#pragma unroll
+      for (int q = 0; q < kEpiCols / 8; ++q)
+        d[q] = make_uint4(pack_bf16x2(o[q * 8], o[q * 8 + 1]), pack_bf16x2(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16x2(o[q * 8 + 4], o[q * 8 + 5]),
+                          pack_bf16x2(o[q * 8 + 6], o[q * 8 + 7]));
+      stage_copy_out(stage, lane, [&](int r) -> __nv_bfloat16* {
+        return row0 + r < p.R ? p.out_bf + static_cast<size_t>(row0 + r) * kE + c0 : nullptr;
+      });
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GELU backward, elementwise on row-major bf16: dpre = dh * (Phi(pre) + pre * phi(pre))
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ pre,
+                                                       __nv_bfloat16* __restrict__ dpre, size_t n) {
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i >= n) return;
+  const uint4 a = *reinterpret_cast<const uint4*>(dh + i), b = *reinterpret_cast<const uint4*>(pre + i);
+  float d[8], x[8];
+  bf16x8_to_f32(a, d);
+  bf16x8_to_f32(b, x);
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    float r[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float v = x[k + j];
+      const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+      r[j] = d[k + j] * (cdf + v * pdf);
+    }
+    o[k / 2] = pack_bf16x2(r[0], r[1]);
+  }
+  *reinterpret_cast<uint4*>(dpre + i) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Attention backward for the teacher-forced pass (S <= 32 positions per sequence, 8 heads x 64).
+// One warp per (sequence, head): q, k, v, dO rows of the head are staged in shared memory (fp32), probabilities are
+// recomputed, lanes own key positions for the score work and channels for the dQ / dK / dV accumulation.
+//   P = softmax(Q K^T / 8 + mask)   dV = P^T dO   dP = dO V^T   dS = P o (dP - rowsum(dP o P))   dQ = dS K / 8   dK = dS^T Q / 8
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAttnBwdMaxS = 32;
+constexpr int kAttnBwdStride = kHeadDim + 1;   // padded row stride: lanes that own different key rows hit different banks
+
+struct AttnBwdParams {
+  const __nv_bfloat16* q;       // [nseq * S, 512]
+  const __nv_bfloat16* kcache;  // [nseq, smax, 512]
+  const __nv_bfloat16* vcache;
+  const __nv_bfloat16* dout;    // [nseq * S, 512] gradient w.r.t. the attention output
+  __nv_bfloat16* dqkv;          // [nseq * S, 1536] row-major: dq | dk | dv
+  const unsigned char* keypad;  // optional [nseq, S]
+  int nseq, S, smax, P, prefix_bidir;
+  float scale;                  // 1 / sqrt(64)
+};
+
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
+  extern __shared__ float sm_attn[];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int item = blockIdx.x * 4 + warp;
+  if (item >= p.nseq * kHeads) return;
+  const int a = item / kHeads, head = item - a * kHeads;
+  const int S = p.S;
+  constexpr int HS = kAttnBwdStride;
+  float* base = sm_attn + static_cast<size_t>(warp) * (6 * S * HS);
+  float* sq = base;                       // [S][65]
+  float* sk = sq + S * HS;
+  float* sv = sk + S * HS;
+  float* sdo = sv + S * HS;
+  float* sdk = sdo + S * HS;
+  float* sdv = sdk + S * HS;
+  for (int i = lane; i < S * (kHeadDim / 2); i += 32) {
+    const int s = i / (kHeadDim / 2), c = (i - s * (kHeadDim / 2)) * 2;
+    const size_t rq = (static_cast<size_t>(a) * S + s) * kE + head * kHeadDim + c;
+    const size_t rk = (static_cast<size_t>(a) * p.smax + s) * kE + head * kHeadDim + c;
+    const float2 fq = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.q + rq));
+    const float2 fk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.kcache + rk));
+    const float2 fv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.vcache + rk));
+    const float2 fd = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.dout + rq));
+    sq[s * HS + c] = fq.x; sq[s * HS + c + 1] = fq.y;
+    sk[s * HS + c] = fk.x; sk[s * HS + c + 1] = fk.y;
+    sv[s * HS + c] = fv.x; sv[s * HS + c + 1] = fv.y;
+    sdo[s * HS + c] = fd.x; sdo[s * HS + c + 1] = fd.y;
+    sdk[s * HS + c] = 0.f; sdk[s * HS + c + 1] = 0.f;
+    sdv[s * HS + c] = 0.f; sdv[s * HS + c + 1] = 0.f;
+  }
+  __syncwarp();
+  const int j = lane;  // key position owned by this lane
+  const bool key_ok = j < S && !(p.keypad != nullptr && j > 0 && p.keypad[static_cast<size_t>(a) * S + j]);
+  for (int i = 0; i < S; ++i) {
+    const int nkeys = (p.prefix_bidir && i < p.P) ? p.P : i + 1;
+    const bool vis = key_ok && j < nkeys;
+    float s = -INFINITY, dp = 0.f;
+    if (vis) {
+      float acc = 0.f, accd = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < kHeadDim; ++c) {
+        acc = fmaf(sq[i * HS + c], sk[j * HS + c], acc);
+        accd = fmaf(sdo[i * HS + c], sv[j * HS + c], accd);
+      }
+      s = acc * p.scale;
+      dp = accd;
+    }
+    const float mx = warp_max(s);
+    const float e = vis ? __expf(s - mx) : 0.f;
+    const float pj = e / warp_sum(e);
+    const float dsum = warp_sum(pj * dp);
+    const float ds = pj * (dp - dsum) * p.scale;   // gradient w.r.t. q_i . k_j
+    // dq_i = sum_j ds_ij k_j ; dk_j += ds_ij q_i ; dv_j += p_ij do_i   (lanes now own channels c = lane, lane + 32)
+    float dq0 = 0.f, dq1 = 0.f;
+    for (int jj = 0; jj < nkeys; ++jj) {
+      const float dsj = __shfl_sync(0xffffffffu, ds, jj);
+      const float pjj = __shfl_sync(0xffffffffu, pj, jj);
+      dq0 = fmaf(dsj, sk[jj * HS + lane], dq0);
+      dq1 = fmaf(dsj, sk[jj * HS + lane + 32], dq1);
+      sdk[jj * HS + lane] = fmaf(dsj, sq[i * HS + lane], sdk[jj * HS + lane]);
+      sdk[jj * HS + lane + 32] = fmaf(dsj, sq[i * HS + lane + 32], sdk[jj * HS + lane + 32]);
+      sdv[jj * HS + lane] = fmaf(pjj, sdo[i * HS + lane], sdv[jj * HS + lane]);
+      sdv[jj * HS + lane + 32] = fmaf(pjj, sdo[i * HS + lane + 32], sdv[jj * HS + lane + 32]);
+    }
+    __nv_bfloat16* dq = p.dqkv + (static_cast<size_t>(a) * S + i) * (3 * kE) + head * kHeadDim;
+    dq[lane] = __float2bfloat16_rn(dq0);
+    dq[lane + 32] = __float2bfloat16_rn(dq1);
+  }
+  __syncwarp();
+  for (int i = lane; i < S * kHeadDim; i += 32) {
+    const int s = i / kHeadDim, c = i - s * kHeadDim;
+    __nv_bfloat16* row = p.dqkv + (static_cast<size_t>(a) * S + s) * (3 * kE) + head * kHeadDim + c;
+    row[kE] = __float2bfloat16_rn(sdk[s * HS + c]);
+    row[2 * kE] = __float2bfloat16_rn(sdv[s * HS + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Input-embedding backward: dx0 (blocked fp32, rows a * S + s) ->
+//   dpos[s] += sum_a dx0[a, s]                      (learned positions, embedding_decoder.py:1297)
+//   dtok[target[a, i]] += dx0[a, P + i]             (tied token embedding, :692)
+//   dprefix_t[(p, e), b] = sum_j dx0[(b * M + j), p][e]   bf16, the A operand of the prefix-projection wgrad
+// Warp per row; lane owns 16 channels.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ target, int ld_target,
+                                                        int nseq, int S, int P, int V, int Mrep, int B, float* __restrict__ dpos,
+                                                        float* __restrict__ dtok, __nv_bfloat16* __restrict__ dprefix_t, int ld_pt) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= nseq * S) return;
+  const int lane = lane_id();
+  const int a = w / S, s = w - a * S;
+  float v[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(dx0 + xblk_off(w, lane * 4 + q));
+    v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) atomicAdd(dpos + static_cast<size_t>(s) * kE + lane * 16 + i, v[i]);
+  if (s >= P) {
+    long long tok = target[static_cast<size_t>(a) * ld_target + (s - P)];
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) atomicAdd(dtok + static_cast<size_t>(tok) * kE + lane * 16 + i, v[i]);
+  } else if (Mrep == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dprefix_t[static_cast<size_t>(s * kE + lane * 16 + i) * ld_pt + a] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+// multi-target case: sum the M sequences that share an embedding before the transposed bf16 store
+__global__ void __launch_bounds__(128) prefix_grad_reduce_kernel(const float* __restrict__ dx0, int B, int Mrep, int S, int P,
+                                                                 __nv_bfloat16* __restrict__ dprefix_t, int ld_pt) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= B * P) return;
+  const int lane = lane_id();
+  const int b = w / P, pp = w - b * P;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int j = 0; j < Mrep; ++j) {
+    const int row = (b * Mrep + j) * S + pp;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(dx0 + xblk_off(row, lane * 4 + q));
+      acc[q * 4] += t.x; acc[q * 4 + 1] += t.y; acc[q * 4 + 2] += t.z; acc[q * 4 + 3] += t.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dprefix_t[static_cast<size_t>(pp * kE + lane * 16 + i) * ld_pt + b] = __float2bfloat16_rn(acc[i]);
+}
+
+// log-sum-exp per logits row from the forward partials (needed by the dlogits epilogue)
+__global__ void __launch_bounds__(128) row_lse_kernel(const LogitPartial* __restrict__ part, int nparts, int nrows, float* __restrict__ lse) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= nrows) return;
+  const RowStats s = merge_partials(part + static_cast<size_t>(r) * nparts, nparts, 1.0f);
+  if (lane_id() == 0) lse[r] = s.lse_one;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GEMM epilogues of the backward pass
+// ---------------------------------------------------------------------------------------------------------
+
+// plain bf16 row-major store: C[M, ldc]
+struct EpiStoreBF16 {
+  struct Params {
+    __nv_bfloat16* c;
+    int ldc;
+  };
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kEpiCols / 32 - 1) release();
+      stage_put32(c.stage, lane, ch * 32, v);
+    }
+    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+      const int row = c.warp_row0 + r;
+      return row < c.M ? p.c + static_cast<size_t>(row) * p.ldc + c.n0 : nullptr;
+    });
+  }
+};
+
+// FFN1 of the training forward: keeps the pre-activation (for GELU backward) and the activation
+struct EpiGeluTrain {
+  struct Params {
+    __nv_bfloat16* pre;
+    __nv_bfloat16* h;
+    int ldh;
+  };
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    const int lane = lane_id();
+    float v[kEpiCols];
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      float t[32];
+      tmem_ld_32x32(c.tmem_row + ch * 32, t);
+      if (ch == kEpiCols / 32 - 1) release();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[ch * 32 + j] = t[j];
+      stage_put32(c.stage, lane, ch * 32, t);
+    }
+    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+      const int row = c.warp_row0 + r;
+      return row < c.M ? p.pre + static_cast<size_t>(row) * p.ldh + c.n0 : nullptr;
+    });
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = gelu_fast(__bfloat162float(__float2bfloat16_rn(v[ch * 32 + j])));  // from the stored pre-activation
+      stage_put32(c.stage, lane, ch * 32, t);
+    }
+    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+      const int row = c.warp_row0 + r;
+      return row < c.M ? p.h + static_cast<size_t>(row) * p.ldh + c.n0 : nullptr;
+    });
+  }
+};
+
+// fp32 store into a blocked [rows, 512] gradient tensor (N = 512 GEMMs), optional output-row remap (logits rows -> sequence rows)
+struct EpiGradBlocked {
+  struct Params {
+    float* g;
+    int remap_rows_in, remap_rows_out, remap_offset;  // out_row = (row / in) * out + offset + row % in   (in = 0: identity)
+  };
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    int orow = c.row;
+    if (p.remap_rows_in > 0) {
+      const int seq = c.row / p.remap_rows_in;
+      orow = seq * p.remap_rows_out + p.remap_offset + (c.row - seq * p.remap_rows_in);
+    }
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kEpiCols / 32 - 1) release();
+      if (c.row < c.M) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(p.g + xblk_off(orow, ((c.n0 + ch * 32) >> 2) + q)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+      }
+    }
+  }
+};
+
+// weight gradient: fp32 atomic accumulation into dW[M = out features, N = in features] (split-K over the row dimension)
+struct EpiAtomicF32 {
+  struct Params {
+    float* dw;
+    int ldw;   // in features
+    int ncols; // valid columns (in features)
+  };
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kEpiCols / 32 - 1) release();
+      if (c.row < c.M) {
+        float* d = p.dw + static_cast<size_t>(c.row) * p.ldw + c.n0 + ch * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c.n0 + ch * 32 + j < p.ncols) atomicAdd(d + j, v[j]);
+      }
+    }
+  }
+};
+
+// dlogits = (softmax(logits) - smoothed one-hot(target)) * row_weight, bf16 row-major [rows, V]
+struct EpiDLogits {
+  struct Params {
+    __nv_bfloat16* dl;          // [M, ld]
+    long long ld;
+    const float* lse;           // [M]
+    const long long* target;    // [M], -1 = ignored row (zero gradient)
+    const float* row_weight;    // optional [M / rows_per_seq]
+    int rows_per_seq;
+    int n_valid;                // V
+    float label_smoothing;
+  };
+  template <class Release>
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+    const int lane = lane_id();
+    const bool in_range = c.row < c.M;
+    const long long tgt = in_range ? p.target[c.row] : -1;
+    const float lse = in_range ? p.lse[c.row] : 0.f;
+    float w = tgt >= 0 ? 1.0f : 0.0f;
+    if (p.row_weight != nullptr && in_range) w *= p.row_weight[c.row / p.rows_per_seq];
+    const float on = 1.0f - p.label_smoothing, off = p.label_smoothing / static_cast<float>(p.n_valid);
+#pragma unroll
+    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+      const int col0 = c.n0 + ch * 32;
+      float v[32];
+      tmem_ld_32x32(c.tmem_row + ch * 32, v);
+      if (ch == kEpiCols / 32 - 1) release();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        float g = __expf(v[j] - lse) - off - (static_cast<long long>(col) == tgt ? on : 0.f);
+        v[j] = col < p.n_valid ? g * w : 0.f;
+      }
+      stage_put32(c.stage, lane, ch * 32, v);
+    }
+    const long long ld = p.ld;
+    const int nv = p.n_valid;
+    const int n0 = c.n0;
+    // rows of dl are padded to a multiple of 64 columns by the caller (ld >= round_up(V, 64)), so the 64-column block is in range
+    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+      const int row = c.warp_row0 + r;
+      return (row < c.M && n0 < nv) ? p.dl + static_cast<size_t>(row) * ld + n0 : nullptr;
+    });
+  }
+};
+
+}  // namespace novic

@@ -274,7 +274,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                    layer.norm1.weight, layer.norm2.weight]
         return ts
 
-    def _state(self, device: torch.device) -> dict:
+    def _state(self, device: torch.device, refresh: bool = False) -> dict:
         if device.type != 'cuda':
             raise RuntimeError("novic_b200.PrefixedIterDecoder computes on CUDA (sm_100a) only; there is no CPU path. "
                                f"Got tensors on {device}.")
@@ -294,7 +294,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                 self._handles[idx] = st
             tensors = self._weight_tensors()
             wkey = tuple((t.data_ptr(), 0 if t.is_inference() else t._version) for t in tensors)
-            if st['wkey'] != wkey:
+            if st['wkey'] != wkey or refresh:
                 for t in tensors:
                     if t.device.type != 'cuda' or t.device.index != idx or t.dtype != torch.float32 or not t.is_contiguous():
                         raise RuntimeError("decoder parameters must be contiguous fp32 tensors on the same CUDA device as the input "
@@ -314,6 +314,19 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                 _abi.check(lib.novic_set_weights(st['handle'], C.byref(w), st['wbuf'].data_ptr(), st['wbuf'].numel(), stream))
                 st['wkey'] = wkey
         return st
+
+    def train(self, mode: bool = True):
+        # Fused optimizers update parameters without bumping tensor version counters, so the (data_ptr, version) key
+        # cannot see their updates: re-pack the bf16 operand copies on every training forward and whenever the mode flips.
+        for st in getattr(self, '_handles', {}).values():
+            st['wkey'] = None
+        return super().train(mode)
+
+    def refresh_weights(self) -> None:
+        """Force the next call to re-convert the fp32 parameters (needed only if they were modified in place by an
+        operation that does not bump tensor versions while the module stayed in eval mode)."""
+        for st in self._handles.values():
+            st['wkey'] = None
 
     def _workspace(self, st: dict, device: torch.device, num_embeds: int, seqs_per_embed: int, rows_per_seq: int) -> torch.Tensor:
         need = _abi.lib().novic_workspace_bytes(st['handle'], num_embeds, seqs_per_embed, rows_per_seq)
@@ -344,10 +357,9 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     def forward(self, embed, target, target_padding, target_weight, calc_loss, calc_correct, only_pred, guide_targets):
         if guide_targets is not None:
             raise NotImplementedError("guided correctness evaluation (embedding_decoder.py:754-760) is not implemented in novic_b200 yet")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("novic_b200 forward is inference-only in this release (no autograd graph is built); "
-                                      "call under torch.no_grad()/inference_mode() or .eval()")
         embed = self._check_embed(embed)
+        if self.training and torch.is_grad_enabled() and target is not None:
+            return self._forward_train(embed, target, target_padding, target_weight, calc_loss, calc_correct, only_pred)
         if target is None:
             raise NotImplementedError("forward without targets (prefix-only logits) is not part of the accelerated path")
         B = embed.shape[0]
@@ -406,6 +418,50 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                 out_pad = None if out_pad is None else out_pad.transpose(0, 1)
                 out_correct = None if out_correct is None else out_correct.transpose(0, 1)
         return logits, out_pad, loss_sum, loss_basis, out_correct
+
+    def _forward_train(self, embed, target, target_padding, target_weight, calc_loss, calc_correct, only_pred):
+        """Training-mode forward with autograd (train.py:1270-1273).  One fused forward+backward library call; the logits are
+        not materialised (the reference's training loop discards them, train.py:1271), so the first return value is None.
+        Dropout (input_dropout / layer_dropout) is NOT applied by the CUDA path."""
+        from . import training
+        if only_pred:
+            raise NotImplementedError("only_pred=True is not supported in training mode")
+        if (self.input_dropout > 0 or self.layer_dropout > 0) and not getattr(self, '_warned_dropout', False):
+            import warnings
+            warnings.warn("novic_b200 training forward does not apply dropout (input_dropout / layer_dropout are ignored)")
+            self._warned_dropout = True
+        B = embed.shape[0]
+        multi = target.ndim == 3
+        multi_first = bool(multi and getattr(self.data_config, 'multi_target', False) and getattr(self.data_config, 'multi_first', False))
+        if multi:
+            if multi_first:
+                target = target.transpose(0, 1)
+                target_padding = None if target_padding is None else target_padding.transpose(0, 1)
+                target_weight = None if target_weight is None else target_weight.transpose(0, 1)
+            M = target.shape[1]
+            target = target.reshape(B * M, target.shape[-1])
+            target_padding = None if target_padding is None else target_padding.reshape(B * M, -1)
+            target_weight = None if target_weight is None else target_weight.reshape(B * M)
+        else:
+            M = 1
+        tc = self.target_config
+        assert target.dtype == tc.token_dtype and target.ndim == 2 and target.shape[0] == B * M and target.shape[1] >= 2
+        assert target_padding is None or (target_padding.dtype == tc.mask_dtype and target_padding.shape == target.shape)
+        assert target_weight is None or (target_weight.dtype == self.embed_dtype and target_weight.ndim == 1 and target_weight.shape[0] == target.shape[0])
+        loss_sum, loss_basis, correct, pad_out = training.train_forward(self, embed, target, target_padding, target_weight, M)
+        has_pad = target_padding is not None or target_weight is not None
+        out_pad = pad_out.view(torch.bool) if has_pad else None
+        out_correct = correct.view(torch.bool) if calc_correct else None
+        if target_weight is None:
+            loss_basis = loss_basis.detach().round().to(torch.int64)
+        if multi:
+            T = target.shape[1]
+            out_pad = None if out_pad is None else out_pad.view(B, M, T)
+            out_correct = None if out_correct is None else out_correct.view(B, M, T)
+            if multi_first:
+                out_pad = None if out_pad is None else out_pad.transpose(0, 1)
+                out_correct = None if out_correct is None else out_correct.transpose(0, 1)
+        return None, out_pad, (loss_sum if calc_loss else None), (loss_basis if calc_loss else None), out_correct
 
     # ------------------------------------------------------------------------------------------------------
     # generate (embedding_decoder.py:779-850)

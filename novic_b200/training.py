@@ -1,0 +1,72 @@
+"""Training-mode forward/backward of the decoder (train.py:1263-1286).
+
+`PrefixedIterDecoder.forward` in training mode with autograd enabled routes here: one library call
+(`novic_train_fwd_bwd`) runs the teacher-forced forward *and* the full backward and leaves d(loss_sum)/d(parameter)
+for all parameters in fp32 buffers; the autograd Function hands them to torch scaled by the incoming gradient of
+loss_sum, so the reference's own `loss.backward()`, `clip_grad_norm_` and `torch.optim.AdamW.step()`
+(train.py:1273-1286) work unchanged on the module's parameters.  Dropout is not applied by the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+
+
+def _grad_struct(model, grads: list[torch.Tensor]) -> _abi.NovicWeights:
+    g = _abi.NovicWeights()
+    g.embed_mlp, g.tok_embed, g.pos_embed, g.final_norm = (t.data_ptr() for t in grads[:4])
+    for i in range(len(model.transformer.layers)):
+        base = 4 + 6 * i
+        g.in_proj[i], g.out_proj[i], g.linear1[i], g.linear2[i], g.norm1[i], g.norm2[i] = (t.data_ptr() for t in grads[base:base + 6])
+    return g
+
+
+class TrainStep(torch.autograd.Function):
+    """Inputs: (model, embed, target [A, C], padding u8 [A, C] | None, weight [A] | None, M, *parameters).
+    Outputs: loss_sum (0-dim fp32), loss_basis (0-dim fp32), correct (u8 [A, C]), effective padding (u8 [A, C])."""
+
+    @staticmethod
+    def forward(ctx, model, embed, target, padding, weight, M, *params):
+        dev = embed.device
+        st = model._state(dev, refresh=True)   # parameters may have been stepped by a fused optimizer since the last call
+        lib = _abi.lib()
+        B = embed.shape[0]
+        A, Ct = target.shape
+        need = lib.novic_train_workspace_bytes(st['handle'], B, M, Ct)
+        ws = st.get('train_ws')
+        if ws is None or ws.numel() < need:
+            st['train_ws'] = None
+            st['train_ws'] = ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
+        loss = torch.empty(2, dtype=torch.float32, device=dev)
+        correct = torch.empty((A, Ct), dtype=torch.uint8, device=dev)
+        pad_out = torch.empty((A, Ct), dtype=torch.uint8, device=dev)
+        gs = _grad_struct(model, grads)
+        with torch.cuda.device(dev):
+            _abi.check(lib.novic_train_fwd_bwd(
+                st['handle'], embed.data_ptr(), B, M, target.data_ptr(), None if padding is None else padding.data_ptr(),
+                None if weight is None else weight.data_ptr(), Ct, loss.data_ptr(), correct.data_ptr(), pad_out.data_ptr(), C.byref(gs),
+                ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.grads = grads
+        ctx.mark_non_differentiable(correct, pad_out)
+        return loss[0], loss[1], correct, pad_out
+
+    @staticmethod
+    def backward(ctx, g_loss_sum, g_loss_basis, g_correct, g_pad):
+        grads = ctx.grads
+        ctx.grads = None
+        if g_loss_sum is None:
+            return (None,) * 6 + tuple(None for _ in grads)
+        torch._foreach_mul_(grads, g_loss_sum)   # d(loss)/d(theta) = d(loss)/d(loss_sum) * d(loss_sum)/d(theta)
+        return (None,) * 6 + tuple(grads)
+
+
+def train_forward(model, embed: torch.Tensor, target: torch.Tensor, padding: Optional[torch.Tensor], weight: Optional[torch.Tensor], M: int):
+    params = model._weight_tensors()
+    pad_u8 = None if padding is None else padding.contiguous().view(torch.uint8)
+    w = None if weight is None else weight.contiguous()
+    return TrainStep.apply(model, embed, target.contiguous(), pad_u8, w, M, *params)
