@@ -247,14 +247,14 @@ def main():
     def step_device():
         tok, pad, _, _, _, score = model.generate(embed, False, True, 1.0, 0.0, None, None, False)
         if world > 1:
-            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world)
+            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world, gen_len=dims.token_length - 1)
         return tok, pad, score
 
     def step_e2e():
         e = embed_host.to(dev, non_blocking=True)
         tok, pad, _, _, _, score = model.generate(e, False, True, 1.0, 0.0, None, None, False)
         if world > 1:
-            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world)
+            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world, gen_len=dims.token_length - 1)
         return tok.cpu(), pad.cpu(), score.cpu()
 
     def timed(fn, steps):

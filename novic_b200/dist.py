@@ -27,34 +27,49 @@ def _pad_cols(t: torch.Tensor, T: int, dim: int, value) -> torch.Tensor:
 
 
 def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor, total: int,
-                      group: Optional[dist.ProcessGroup] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """All-gather the per-rank results of generate / generate_beam into the full batch, in rank order.
+                      group: Optional[dist.ProcessGroup] = None, gen_len: Optional[int] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All-gather the per-rank results of generate / generate_beam into the full batch, in rank order, with ONE collective.
 
-    tok / pad are [n_local, (H,) T_local], score is [n_local(, H)].  Ranks may have stopped at different T (early
-    exit is per shard): columns are padded to the global maximum with (id 0, padding True) - exactly what the
-    reference returns for samples that finished before the longest one.  Shards may differ in size by one row.
+    tok / pad are [n_local, K, T_local], score is [n_local, K].  Ranks may have stopped at different T (early exit is per
+    shard): every rank contributes fixed-size records of `gen_len` columns (ids 0 / padding True beyond its own T - exactly
+    what the reference returns for samples that finished before the longest one) plus its T, and the result is cut to the
+    global maximum T.  Shards may differ in size by one row.  The payload is one byte buffer:
+    per row and beam [gen_len int64 ids | gen_len u8 padding | fp32 score], then one int64 header holding T_local.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    tdim = tok.ndim - 1
-    t_max = torch.tensor([tok.shape[tdim]], dtype=torch.int64, device=tok.device)
-    dist.all_reduce(t_max, op=dist.ReduceOp.MAX, group=group)
-    T = int(t_max.item())
-    tok = _pad_cols(tok, T, tdim, 0)
-    pad = _pad_cols(pad, T, tdim, True)
+    n_local, K, T_local = tok.shape
+    G = int(gen_len) if gen_len is not None else T_local
+    if gen_len is None:  # callers that do not know the model's G: agree on the widest T first (one extra tiny collective)
+        t_max = torch.tensor([T_local], dtype=torch.int64, device=tok.device)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX, group=group)
+        G = int(t_max.item())
+    lo, hi = shard_bounds(total, world, rank)
+    assert n_local == hi - lo
     n_max = -(-total // world)
-    n_local = tok.shape[0]
-    assert (n_local,) == (shard_bounds(total, world, rank)[1] - shard_bounds(total, world, rank)[0],)
-
-    def gather(t: torch.Tensor, fill) -> torch.Tensor:
-        t = _pad_cols(t.contiguous(), n_max, 0, fill)      # equal-sized contributions
-        outs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outs, t, group=group)
-        sizes = [shard_bounds(total, world, r) for r in range(world)]
-        return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
-
-    pad_u8 = pad.to(torch.uint8)
-    return gather(tok, 0), gather(pad_u8, 1).to(torch.bool), gather(score, float("-inf"))
+    rec = G * 8 + G + 4
+    buf = torch.zeros(n_max * K * rec + 8, dtype=torch.uint8, device=tok.device)
+    body = buf[: n_max * K * rec].view(n_max, K, rec)
+    ids = torch.zeros((n_local, K, G), dtype=torch.int64, device=tok.device)
+    ids[:, :, :T_local] = tok
+    pd = torch.ones((n_local, K, G), dtype=torch.uint8, device=tok.device)
+    pd[:, :, :T_local] = pad.to(torch.uint8)
+    body[:n_local, :, : G * 8] = ids.view(torch.uint8).view(n_local, K, G * 8)
+    body[:n_local, :, G * 8: G * 9] = pd
+    body[:n_local, :, G * 9:] = score.to(torch.float32).contiguous().view(torch.uint8).view(n_local, K, 4)
+    buf[n_max * K * rec:] = torch.tensor([T_local], dtype=torch.int64, device=tok.device).view(torch.uint8)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    toks, pads, scores, T = [], [], [], 0
+    for r, o in enumerate(outs):
+        rlo, rhi = shard_bounds(total, world, r)
+        n = rhi - rlo
+        b = o[: n_max * K * rec].view(n_max, K, rec)[:n]
+        toks.append(b[:, :, : G * 8].contiguous().view(torch.int64).view(n, K, G))
+        pads.append(b[:, :, G * 8: G * 9].to(torch.bool))
+        scores.append(b[:, :, G * 9:].contiguous().view(torch.float32).view(n, K))
+        T = max(T, int(o[n_max * K * rec:].clone().view(torch.int64).item()))
+    return torch.cat(toks)[:, :, :T], torch.cat(pads)[:, :, :T], torch.cat(scores)
 
 
 def generate_sharded(model, embed_full: torch.Tensor, method: str = "greedy", topk: int = 1, temperature: float = 1.0,
@@ -73,4 +88,48 @@ def generate_sharded(model, embed_full: torch.Tensor, method: str = "greedy", to
         tok, pad, score = model.generate_beam(local, topk, temperature, length_alpha, None, False, 0.0, None, False)
     else:
         raise ValueError(f"Unsupported generation method: {method}")
-    return gather_generation(tok, pad, score, embed_full.shape[0], group)
+    return gather_generation(tok, pad, score, embed_full.shape[0], group, gen_len=model.target_config.token_length - 1 if hasattr(model, 'target_config') else None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Data-parallel training: gradients of the 40 parameter tensors are summed over ranks as one flat
+# bucket (12.73 M fp32 = 50.9 MB, a single NCCL all-reduce over NVLink), together with the two loss scalars.
+# ----------------------------------------------------------------------------------------------------------------
+def allreduce_gradients(params, extra: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None) -> Optional[torch.Tensor]:
+    """Sum `.grad` of `params` (and the optional small tensor `extra`, e.g. [loss_sum, loss_basis]) over all ranks, in
+    place.  One flat bucket -> one collective."""
+    grads = [p.grad for p in params if p.grad is not None]
+    pieces = grads + ([extra] if extra is not None else [])
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in pieces])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for t in grads:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n
+    if extra is not None:
+        return flat[off:off + extra.numel()].view_as(extra).to(extra.dtype)
+    return None
+
+
+def train_step(model, optimizer, embed: torch.Tensor, target: torch.Tensor, mask: Optional[torch.Tensor], weight: Optional[torch.Tensor],
+               noise=None, gradient_clip: float = 1.0, group: Optional[dist.ProcessGroup] = None):
+    """One optimizer step on this rank's shard of the batch, mirroring train.py:1263-1286 with accum_factor folded into
+    data parallelism: noise -> forward (loss_sum, loss_basis, correct) -> backward of loss_sum -> all-reduce of
+    (gradients, loss_sum, loss_basis) -> normalise by the GLOBAL loss basis -> clip -> AdamW.step().
+    Returns (global mean loss, global correct count, global token count, gradient norm)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if noise is not None:
+        embed = noise(embed)
+    optimizer.zero_grad(set_to_none=True)
+    _, padding, loss_sum, loss_basis, correct = model(embed, target, mask, weight, True, True, False, None)
+    loss_sum.backward()                                   # gradients of the local loss SUM (additive across shards)
+    stats = torch.stack((loss_sum.detach().float(), loss_basis.detach().float(), correct.sum().float()))
+    params = [p for p in model.parameters() if p.requires_grad]
+    if world > 1:
+        stats = allreduce_gradients(params, stats, group)
+    inv_basis = 1.0 / stats[1].clamp(min=1.0)
+    torch._foreach_mul_([p.grad for p in params if p.grad is not None], inv_basis)
+    norm = torch.nn.utils.clip_grad_norm_(params, max_norm=gradient_clip, error_if_nonfinite=True) if gradient_clip > 0 else None
+    optimizer.step()
+    return stats[0] * inv_basis, stats[2], stats[1], norm

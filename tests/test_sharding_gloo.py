@@ -72,3 +72,39 @@ def test_two_rank_gather_matches_single_process(n):
     assert (tok[lo:hi, 0, 3:] == 0).all() and pad[lo:hi, 0, 3:].all() and not pad[lo:hi, 0, :3].any()
     assert not pad[hi:].any() and torch.equal(tok[hi:, 0, 0], key[hi:].clamp(min=1))
     assert torch.equal(btok[:, 1], btok[:, 0]) and torch.equal(bscore[:, 2], key.float() - 2)
+
+
+def _grad_worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from novic_b200.dist import allreduce_gradients
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+        params[0].grad = torch.full((5, 3), float(rank + 1))
+        params[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+        params[2].grad = None                                   # parameters without a gradient are skipped consistently
+        extra = allreduce_gradients(params, torch.tensor([10.0 * (rank + 1), 1.0]))
+        if rank == 0:
+            results.put((params[0].grad.clone(), params[1].grad.clone(), extra))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    results = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, results)) for r in range(2)]
+    for p in procs:
+        p.start()
+    g0, g1, extra = results.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(g0, torch.full((5, 3), 3.0))
+    assert torch.equal(g1, torch.arange(7, dtype=torch.float32) * 3)
+    assert torch.equal(extra, torch.tensor([30.0, 2.0]))
