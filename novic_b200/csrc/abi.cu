@@ -82,7 +82,7 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
 // ---------------------------------------------------------------------------------------------------------
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 3, kStagesLogits = 5;
+constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 int g_num_sms = 148;
 int g_grid_div = 1;   // persistent grids are divided by the number of concurrent chains so that chains co-run on disjoint SMs
 constexpr int kLogitBN = kTileN;

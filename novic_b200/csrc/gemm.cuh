@@ -713,16 +713,15 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (is_epi) {
     float mean = 0.f, rstd = 0.f;
     if (row < M) {
-      float sum = 0.f, sumsq = 0.f;
+      float2 part[kRowCluster * 2];   // issue all remote loads first, then reduce in a fixed order
 #pragma unroll
       for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const float2 t = dsmem_ld_f32x2(&s_stats[hh * 128 + row_in_tile], pr);
-          sum += t.x;
-          sumsq += t.y;
-        }
+        for (int hh = 0; hh < 2; ++hh) part[pr * 2 + hh] = dsmem_ld_f32x2_addr(dsmem_addr(&s_stats[hh * 128 + row_in_tile], pr));
       }
+      float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+      for (int i = 0; i < kRowCluster * 2; ++i) { sum += part[i].x; sumsq += part[i].y; }
       mean = sum * (1.0f / kE);
       rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
     }
@@ -775,7 +774,7 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (threadIdx.x == 64) trace_point(tr, 9);
   tc_fence_before_sync();
   __syncwarp();
-  cluster_sync_all();   // peers may still be reading this CTA's s_stats
+  cluster_sync_relaxed();   // peers may still be reading this CTA's s_stats; no data hand-over, so no fence
   if (threadIdx.x == 0) trace_point(tr, 10);
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }

@@ -244,6 +244,23 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+// Exit barrier: only shared-memory lifetime matters (no data is handed over), so no release/acquire fence is needed.
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");
+}
+// Remote shared-memory address of `local_smem_ptr` in CTA `peer_rank` of the cluster.
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint32_t peer_rank) {
+  uint32_t raddr;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(smem_u32(local_smem_ptr)), "r"(peer_rank));
+  return raddr;
+}
+// Non-volatile so that several independent remote loads can be in flight at once (each costs ~200+ cycles).
+__device__ __forceinline__ float2 dsmem_ld_f32x2_addr(uint32_t raddr) {
+  float2 v;
+  asm("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(raddr));
+  return v;
+}
 __device__ __forceinline__ float2 dsmem_ld_f32x2(const void* local_smem_ptr, uint32_t peer_rank) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(smem_u32(local_smem_ptr)), "r"(peer_rank));
