@@ -262,6 +262,7 @@ struct NovicHandle {
   bool weights_set = false;
   bool use_graphs = true;
   bool attn_v1 = false;
+  bool attn_stream = true;            // decode steps use attention_stream_kernel (NOVIC_ATTN_STREAM=0: the bulk-ring kernel)
   bool fuse_ffn = true;
   bool split_sms = true;
   int num_sms = 148;
@@ -370,7 +371,10 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
     pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
     {
       KSpan t(kKAttn, s);
-      if (h->attn_v1) {
+      if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
+        const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, kAsWarps)));
+        CUDA_TRY(launch_k(attention_stream_kernel, dim3(grid), dim3(kAsThreads), kAsSmemBytes, s, pa));
+      } else if (h->attn_v1) {
         attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
       } else {
         const int nk_max = std::max(c.strictly_causal ? 1 : c.prefix_len, pc.q0 + pc.nq);
@@ -679,7 +683,9 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
   CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAsSmemBytes));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
+  if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';
   if (const char* e6 = getenv("NOVIC_NO_PDL")) g_use_pdl = e6[0] != '1';
   if (const char* e5 = getenv("NOVIC_NO_SM_SPLIT")) h->split_sms = e5[0] != '1';
   if (const char* e4 = getenv("NOVIC_NO_FFN_FUSION")) h->fuse_ffn = e4[0] != '1';

@@ -334,6 +334,174 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel(const A
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Attention, decode-step version (one query per sequence, no key padding): self-service streaming.
+//
+// ncu on the kernel above (profiles/r01_ncu_full_v3_summary.txt): 2.1 warps per scheduler, 6.7 cycles per issued
+// instruction, issue slots 32 % busy - the 8 (or fewer: one per ring stage) consumer warps walk a serial
+// online-softmax chain per key and are the bottleneck, not HBM.  Here 16 warps per CTA each stream their own
+// sequences: a warp owns three 4 KB slots, lane 0 issues cp.async.bulk copies of up to four K rows (then the same
+// four V rows) three copies ahead of consumption, and the four keys of a chunk are scored as independent chains
+// before one softmax update (4x fewer dependent exp2 / max steps, 4x the ILP).  No producer warp, no empty
+// barriers: a slot is refilled by the warp that just finished reading it.  Chunks that only hold rows written in
+// earlier decode steps are requested before griddepcontrol.wait, so the stream starts under the previous kernel's tail.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAsWarps = 16;
+constexpr int kAsSlots = 3;
+constexpr int kAsChunk = 4;                          // keys per chunk
+constexpr int kAsSlotBytes = kAsChunk * 1024;        // one chunk of K rows or of V rows
+constexpr int kAsThreads = kAsWarps * 32;
+constexpr int kAsSmemBytes = kAsWarps * kAsSlots * kAsSlotBytes + kAsWarps * kAsSlots * 8 + 128;
+
+__global__ void __launch_bounds__(kAsThreads, 1) attention_stream_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t as_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  uint8_t* slots = as_smem + static_cast<size_t>(warp) * (kAsSlots * kAsSlotBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(as_smem + kAsWarps * kAsSlots * kAsSlotBytes) + warp * kAsSlots;
+  pdl_trigger();
+
+  const int per_cta = (p.nseq + gridDim.x - 1) / gridDim.x;
+  const int item0 = blockIdx.x * per_cta;
+  const int item1 = min(p.nseq, item0 + per_cta);
+  const int qpos = p.q0;
+  const int nkeys = (p.prefix_bidir && qpos < p.P) ? p.P : qpos + 1;
+  const int nchunks = (nkeys + kAsChunk - 1) / kAsChunk;
+  const int per_item = 2 * nchunks;                                  // K chunk, V chunk, K chunk, ...
+  const int nitems = (item0 + warp < item1) ? (item1 - item0 - warp + kAsWarps - 1) / kAsWarps : 0;
+  const int nloads = nitems * per_item;
+  const bool contiguous = p.beams == 1;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kAsSlots; ++s) mbar_init(&full_bar[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+
+  // request load n of this warp's stream into slot n % kAsSlots
+  auto issue = [&](int n) {
+    const int i = n / per_item, r = n - i * per_item;
+    const int c = r >> 1, kv = r & 1;
+    const int a = item0 + warp + i * kAsWarps;
+    const int j0 = c * nkeys / nchunks, rows = (c + 1) * nkeys / nchunks - j0;
+    const __nv_bfloat16* base = kv ? p.vcache : p.kcache;
+    const int sl = n % kAsSlots;
+    uint8_t* dst = slots + sl * kAsSlotBytes;
+    const int own_slot = a * p.slot_mul;
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[sl], static_cast<uint32_t>(rows) * 1024u);
+    if (contiguous) {
+      if (lane == 0) bulk_load_1d(dst, base + (static_cast<size_t>(own_slot) * p.smax + j0) * kE, static_cast<uint32_t>(rows) * 1024u, &full_bar[sl]);
+    } else {
+      __syncwarp();
+      if (lane < rows) {
+        const int j = j0 + lane;
+        const int group0 = (own_slot / p.beams) * p.beams;
+        int slot;
+        if (j < p.P) slot = group0;
+        else if (p.anc != nullptr && j < qpos) slot = group0 + p.anc[static_cast<size_t>(a) * p.anc_ld + (j - p.P)];
+        else slot = own_slot;
+        bulk_load_1d(dst + lane * 1024, base + (static_cast<size_t>(slot) * p.smax + j) * kE, 1024u, &full_bar[sl]);
+      }
+    }
+  };
+
+  // chunks other than an item's last hold only rows written by earlier decode steps: safe to request before the wait
+  int issued = 0;
+  if (contiguous && nchunks >= 2) {
+    const int early = min(nloads, nchunks >= 3 ? 3 : 2);
+    for (; issued < early; ++issued) issue(issued);
+  }
+  pdl_wait();
+  for (; issued < min(nloads, kAsSlots); ++issued) issue(issued);
+
+  float qf[16], acc[16], pj[kAsChunk];
+  float m = -INFINITY, l = 0.f, corr = 0.f;
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+  if (nitems > 0) {
+    const uint4* q4 = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(item0 + warp) * kE) + lane * 2;
+    qa = __ldg(q4); qb = __ldg(q4 + 1);
+  }
+  int i = 0, r = 0;
+  for (int n = 0; n < nloads; ++n) {
+    const int a = item0 + warp + i * kAsWarps;
+    const int c = r >> 1;
+    const int j0 = c * nkeys / nchunks, rows = (c + 1) * nkeys / nchunks - j0;
+    if (r == 0) {
+      bf16x8_to_f32(qa, qf);
+      bf16x8_to_f32(qb, qf + 8);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { qf[k] *= p.scale_log2e; acc[k] = 0.f; }
+      m = -INFINITY; l = 0.f;
+      if (i + 1 < nitems) {   // next item's query: in flight while this item streams
+        const uint4* q4 = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(a + kAsWarps) * kE) + lane * 2;
+        qa = __ldg(q4); qb = __ldg(q4 + 1);
+      }
+    }
+    const int sl = n % kAsSlots;
+    const uint8_t* src = slots + sl * kAsSlotBytes + lane * 32;
+    mbar_wait(&full_bar[sl], static_cast<uint32_t>(n / kAsSlots) & 1u, 5);
+    if ((r & 1) == 0) {
+      float s[kAsChunk];
+#pragma unroll
+      for (int u = 0; u < kAsChunk; ++u) {
+        s[u] = -INFINITY;
+        if (u < rows) {
+          const uint4* k4 = reinterpret_cast<const uint4*>(src + u * 1024);
+          float kf[16];
+          bf16x8_to_f32(k4[0], kf);
+          bf16x8_to_f32(k4[1], kf + 8);
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { d0 = fmaf(qf[k], kf[k], d0); d1 = fmaf(qf[8 + k], kf[8 + k], d1); }
+          s[u] = d0 + d1;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kAsChunk; ++u) {
+        if (u < rows) {
+          s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
+          s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
+        }
+      }
+      const float m_new = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+      corr = exp2f(m - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int u = 0; u < kAsChunk; ++u) { pj[u] = exp2f(s[u] - m_new); psum += pj[u]; }
+      l = l * corr + psum;
+      m = m_new;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] *= corr;
+#pragma unroll
+      for (int u = 0; u < kAsChunk; ++u) {
+        if (u < rows) {
+          const uint4* v4 = reinterpret_cast<const uint4*>(src + u * 1024);
+          float vf[16];
+          bf16x8_to_f32(v4[0], vf);
+          bf16x8_to_f32(v4[1], vf + 8);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc[k] = fmaf(pj[u], vf[k], acc[k]);
+        }
+      }
+    }
+    __syncwarp();                       // every lane has consumed the slot: refill it
+    if (issued < nloads) { issue(issued); ++issued; }
+    if (++r == per_item) {
+      const float inv = 1.0f / l;
+      uint32_t o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = pack_bf16x2(acc[2 * k] * inv, acc[2 * k + 1] * inv);
+      uint4* d = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(a) * kE) + lane * 2;
+      d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      r = 0;
+      ++i;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Merging the per-tile logits statistics of one row (executed by a full warp)
 // ---------------------------------------------------------------------------------------------------------
 struct RowStats {
