@@ -149,7 +149,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # algorithmic work per kernel class for one greedy decode of B embeddings
 # ----------------------------------------------------------------------------------------------------------------
-def algorithmic_work(B: int, dims) -> dict:
+def algorithmic_work(B: int, dims, fused: bool = True) -> dict:
     F, E, K, L, P, V, G = dims.embed_dim, dims.hidden_dim, dims.ffn_dim, dims.num_layers, dims.prefix_len, dims.vocab_size, dims.token_length - 1
     rows = B * (P + G - 1)                       # residual rows that pass through the layers (prefill P + G-1 decode steps)
     attn_bytes = 0
@@ -159,13 +159,15 @@ def algorithmic_work(B: int, dims) -> dict:
     return {
         "embed_prep": ("hbm", B * F * (4 + 2)),
         "prefix_gemm": ("tensor", 2 * B * F * P * E),
-        "qkv_gemm": ("tensor", 2 * rows * E * 3 * E * L),
+        "qkv_gemm": ("tensor", 2 * rows * E * 3 * E * (1 if fused else L)),
         "attention": ("hbm", attn_bytes),
         "outproj_gemm": ("tensor", 2 * rows * E * E * L),
         "ffn1_gemm": ("tensor", 2 * rows * E * K * L),
         "ffn2_gemm": ("tensor", 2 * rows * K * E * L),
         "logits_gemm": ("tensor", 2 * B * G * E * V),
         "select": ("hbm", B * G * (-(-V // 64) * 32 + E * (4 + 4 + 2))),
+        # fused cluster kernel: out-proj + FFN of layer l + QKV of layer l+1 (the first layer's QKV is timed as qkv_gemm)
+        "layer_stack": ("tensor", 2 * rows * E * (E + 2 * K) * L + 2 * rows * E * 3 * E * (L - 1)),
     }
 
 
@@ -188,7 +190,7 @@ def kernel_breakdown(model, embed, steps: int, peaks: dict, dims) -> dict:
         _abi.check(lib.novic_kernel_times(ms, cnt, n))
         _abi.check(lib.novic_kernel_timing(0))
     _abi.check(lib.novic_set_use_graphs(st["handle"], 1))
-    work = algorithmic_work(embed.shape[0], dims)
+    work = algorithmic_work(embed.shape[0], dims, fused=cnt[list(_abi.KERNEL_CLASSES).index('layer_stack')] > 0)
     total = sum(ms) or 1.0
     out = {}
     for i, name in enumerate(_abi.KERNEL_CLASSES):
@@ -306,7 +308,7 @@ def main():
         if os.path.isfile(tpath) and d.get("bound") == "hbm":
             entry = json.load(open(tpath)).get(dom)
             if entry:  # ncu-measured DRAM bytes of one launch / that launch's algorithmic bytes, applied to the average launch
-                work = algorithmic_work(B, dims)[dom][1]
+                work = algorithmic_work(B, dims, fused='layer_stack' in kernels)[dom][1]
                 traffic = entry["ratio_to_algorithmic"] * work / max(1, d["launches_per_step"])
         roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
                     "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],

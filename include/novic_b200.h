@@ -136,12 +136,13 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
 /* Per-kernel-class device timing for roofline reports.  novic_kernel_timing(1) makes every subsequent direct
  * (non-graph) launch record a CUDA-event pair on its stream; novic_kernel_times() synchronises and returns the
  * accumulated milliseconds and launch counts per class, then clears.  Classes, in order: embed-prep, prefix GEMM,
- * QKV GEMM, attention, out-proj GEMM, FFN1 GEMM, FFN2 GEMM, logits GEMM, selection, other (n_classes >= 10). */
+ * QKV GEMM, attention, out-proj GEMM, FFN1 GEMM, FFN2 GEMM, logits GEMM, selection, other, fused layer stack (out-proj +
+ * FFN + next layer's QKV in one cluster kernel) (n_classes >= 11). */
 int novic_kernel_timing(int32_t enable);
 int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes);
 
 /* Tuning aid: enable = 1 + n arms CTA (0,1) of the n-th GEMM launch from now to record clock64() at numbered phase
- * points; a later call returns the 16 recorded values (out16 may be NULL) and re-arms / disarms (enable = 0). */
+ * points; a later call returns the 32 recorded slots (out16: room for 32 int64, may be NULL) and re-arms / disarms (enable = 0). */
 int novic_debug_trace(int64_t* out16, int32_t enable);
 
 /* Byte offset of a named workspace buffer (ein, ebf, x, xn, xfin, q, ao, hb, kv, part) for the same arguments as

@@ -74,7 +74,7 @@ SIGNATURES = {
 }
 
 KERNEL_CLASSES = ("embed_prep", "prefix_gemm", "qkv_gemm", "attention", "outproj_gemm", "ffn1_gemm", "ffn2_gemm", "logits_gemm",
-                  "select", "other")
+                  "select", "other", "layer_stack")
 
 _lib = None
 

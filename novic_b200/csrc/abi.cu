@@ -12,6 +12,7 @@
 
 #include "../../include/novic_b200.h"
 #include "train.cuh"
+#include "stack.cuh"
 
 using namespace novic;
 
@@ -144,6 +145,15 @@ int launch_ffn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw1, co
   return 0;
 }
 
+// The fused layer-stack kernel (stack.cuh): one 4-CTA cluster per 128 residual rows.
+int launch_stack(cudaStream_t s, const StackMaps& maps, const StackArgs& a) {
+  dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(a.M, kBlockM)));
+  CUDA_TRY(launch_k(layer_stack_kernel, grid, dim3(kStkThreads), kStkSmemBytes, s, maps, a));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 __global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
@@ -184,7 +194,7 @@ __global__ void tf_mask_kernel(const long long* __restrict__ target, const unsig
 }
 
 // Optional per-kernel-class CUDA-event timing (bench.py's roofline numbers): only in direct-launch mode.
-enum KClass : int { kKPrep = 0, kKPrefix, kKQkv, kKAttn, kKOutProj, kKFfn1, kKFfn2, kKLogits, kKSelect, kKMisc, kKNumClasses };
+enum KClass : int { kKPrep = 0, kKPrefix, kKQkv, kKAttn, kKOutProj, kKFfn1, kKFfn2, kKLogits, kKSelect, kKMisc, kKStack, kKNumClasses };
 struct KTiming {
   bool enabled = false;
   std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> spans;
@@ -262,8 +272,11 @@ struct NovicHandle {
   bool weights_set = false;
   bool use_graphs = true;
   bool attn_v1 = false;
+  int attn_early = 1;
   bool attn_stream = true;            // decode steps use attention_stream_kernel (NOVIC_ATTN_STREAM=0: the bulk-ring kernel)
   bool fuse_ffn = true;
+  bool stack_attn = true;             // decode steps run attention inside the stack kernel (NOVIC_STACK_ATTN=0: separate launches)
+  bool fuse_stack = false;            // experimental (NOVIC_STACK=1): whole layer stack as one cluster kernel, stack.cuh - measured slower, see DESIGN.md
   bool split_sms = true;
   int num_sms = 148;
   int max_chains = 1;                 // concurrent sub-batch chains per decode (NOVIC_CHAINS); measured: no gain for greedy on B200
@@ -350,9 +363,87 @@ struct PassCfg {
   int remap_in, remap_skip, remap_out;
 };
 
+int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int l, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const int S = h->S();
+  const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
+  __nv_bfloat16* kc = ws.kv + (static_cast<size_t>(l) * 2 + 0) * kv_layer;
+  __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
+  AttnParams pa{};
+  pa.q = ws.q; pa.kcache = kc; pa.vcache = vc; pa.out = ws.ao; pa.keypad = pc.keypad; pa.anc = pc.anc;
+  pa.nseq = pc.nseq; pa.nq = pc.nq; pa.q0 = pc.q0; pa.smax = S; pa.P = c.prefix_len; pa.beams = pc.beams;
+  pa.prefix_bidir = c.strictly_causal ? 0 : 1; pa.keypad_ld = pc.keypad_ld; pa.anc_ld = pc.anc_ld;
+  pa.slot_mul = pc.slot_mul;
+  pa.early_loads = h->fuse_stack ? 0 : h->attn_early;   // early bulk loads next to the stack kernel fault under graphs + PDL (unexplained)
+  pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+  KSpan t(kKAttn, s);
+  if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
+    const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, kAsWarps)));
+    CUDA_TRY(launch_k(attention_stream_kernel, dim3(grid), dim3(kAsThreads), kAsSmemBytes, s, pa));
+  } else if (h->attn_v1) {
+    attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
+  } else {
+    const int nk_max = std::max(c.strictly_causal ? 1 : c.prefix_len, pc.q0 + pc.nq);
+    const int stage_bytes = nk_max * 2048;
+    const int budget = h->attn_smem_budget;
+    int nstages = std::max(2, std::min(kAttnMaxStages, (budget - 512) / stage_bytes));
+    const int ncons = std::min(kAttnConsumers, nstages);
+    nstages = nstages / ncons * ncons;
+    const int smem = nstages * stage_bytes + 2 * kAttnMaxStages * 8;
+    const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, 2)));
+    CUDA_TRY(launch_k(attention_bulk_kernel, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
+  }
+  ++g_launches;
+  return 0;
+}
+
+// Fused schedule: QKV_0 | attention_0 | OUT_0 FFN_0 QKV_1 | attention_1 | ... | OUT_{L-1} FFN_{L-1}
+int run_layers_stack(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const int L = c.num_layers, S = h->S(), M = pc.M;
+  StackMaps maps;
+  if (make_tmap(&maps.xn, ws.xn, M, kE, kBlockM)) return 1;
+  if (make_tmap(&maps.ao, ws.ao, M, kE, kBlockM)) return 1;
+  StackArgs a{};
+  a.M = M; a.num_layers = L; a.x = ws.x; a.xn = ws.xn; a.q = ws.q; a.kv = ws.kv;
+  a.xfin = pc.remap_in > 0 ? ws.xfin : nullptr;
+  a.kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
+  a.rows_per_seq = pc.nq; a.pos0 = pc.q0; a.slot_mul = pc.slot_mul; a.smax = S;
+  a.remap_in = pc.remap_in; a.remap_skip = pc.remap_skip; a.remap_out = pc.remap_out;
+  a.eps = c.ln_eps;
+  for (int l = 0; l < L; ++l) {
+    maps.w[l].in_proj = h->w.tm_in_proj[l]; maps.w[l].out_proj = h->w.tm_out_proj[l];
+    maps.w[l].linear1 = h->w.tm_linear1[l]; maps.w[l].linear2 = h->w.tm_linear2[l];
+    a.gain_out[l] = h->w.norm2[l];
+    a.gain_ffn[l] = l + 1 < L ? h->w.norm1[l + 1] : h->w.final_norm;
+  }
+  for (int l = L; l < kStkMaxLayers; ++l) maps.w[l] = maps.w[0];
+  a.ao = ws.ao; a.anc = pc.anc; a.anc_ld = pc.anc_ld; a.beams = pc.beams; a.prefix_len = c.prefix_len;
+  a.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+  if (h->stack_attn && pc.nq == 1 && pc.keypad == nullptr && pc.q0 >= c.prefix_len) {
+    // decode step: the whole stack, attention included, is one launch
+    a.ph_begin = 0; a.ph_end = 4 * L; a.load_x = 1; a.store_x = 0;
+    KSpan t(kKStack, s);
+    return launch_stack(s, maps, a);
+  }
+  a.ph_begin = 0; a.ph_end = 1; a.load_x = 0; a.store_x = 0;
+  { KSpan t(kKQkv, s); if (launch_stack(s, maps, a)) return 1; }
+  for (int l = 0; l < L; ++l) {
+    if (launch_attention(h, ws, pc, l, s)) return 1;
+    a.ph_begin = 4 * l + kPhOut;
+    a.ph_end = l + 1 < L ? 4 * (l + 1) + kPhQkv + 1 : 4 * l + kPhFfn + 1;
+    a.load_x = 1; a.store_x = l + 1 < L ? 1 : 0;
+    KSpan t(kKStack, s);
+    if (launch_stack(s, maps, a)) return 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   const int L = c.num_layers, S = h->S(), M = pc.M;
+  if (h->fuse_stack && h->fuse_ffn && L <= kStkMaxLayers) return run_layers_stack(h, ws, pc, s);
   CUtensorMap tm_xn, tm_ao, tm_hb;
   if (make_tmap(&tm_xn, ws.xn, M, kE, kBlockM)) return 1;
   if (make_tmap(&tm_ao, ws.ao, M, kE, kBlockM)) return 1;
@@ -363,32 +454,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
     __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
     EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S};
     { KSpan t(kKQkv, s); if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq)) return 1; }
-    AttnParams pa;
-    pa.q = ws.q; pa.kcache = kc; pa.vcache = vc; pa.out = ws.ao; pa.keypad = pc.keypad; pa.anc = pc.anc;
-    pa.nseq = pc.nseq; pa.nq = pc.nq; pa.q0 = pc.q0; pa.smax = S; pa.P = c.prefix_len; pa.beams = pc.beams;
-    pa.prefix_bidir = c.strictly_causal ? 0 : 1; pa.keypad_ld = pc.keypad_ld; pa.anc_ld = pc.anc_ld;
-    pa.slot_mul = pc.slot_mul;
-    pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
-    {
-      KSpan t(kKAttn, s);
-      if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
-        const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, kAsWarps)));
-        CUDA_TRY(launch_k(attention_stream_kernel, dim3(grid), dim3(kAsThreads), kAsSmemBytes, s, pa));
-      } else if (h->attn_v1) {
-        attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
-      } else {
-        const int nk_max = std::max(c.strictly_causal ? 1 : c.prefix_len, pc.q0 + pc.nq);
-        const int stage_bytes = nk_max * 2048;
-        const int budget = h->attn_smem_budget;
-        int nstages = std::max(2, std::min(kAttnMaxStages, (budget - 512) / stage_bytes));
-        const int ncons = std::min(kAttnConsumers, nstages);
-        nstages = nstages / ncons * ncons;
-        const int smem = nstages * stage_bytes + 2 * kAttnMaxStages * 8;
-        const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, 2)));
-        CUDA_TRY(launch_k(attention_bulk_kernel, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
-      }
-      ++g_launches;
-    }
+    if (launch_attention(h, ws, pc, l, s)) return 1;
     RowParams po{};
     po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
     { KSpan t(kKOutProj, s); if (launch_rowln(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1; }
@@ -686,9 +752,14 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAsSmemBytes));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';
+  if (const char* e9 = getenv("NOVIC_ATTN_EARLY")) h->attn_early = atoi(e9);
   if (const char* e6 = getenv("NOVIC_NO_PDL")) g_use_pdl = e6[0] != '1';
   if (const char* e5 = getenv("NOVIC_NO_SM_SPLIT")) h->split_sms = e5[0] != '1';
   if (const char* e4 = getenv("NOVIC_NO_FFN_FUSION")) h->fuse_ffn = e4[0] != '1';
+  if (const char* e8 = getenv("NOVIC_STACK")) h->fuse_stack = e8[0] == '1';
+  if (const char* e10 = getenv("NOVIC_STACK_ATTN")) h->stack_attn = e10[0] != '0';
+  if (const char* e11 = getenv("NOVIC_STACK_FENCE")) { const int mode = atoi(e11); CUDA_TRY(cudaMemcpyToSymbol(g_stk_fence_mode, &mode, sizeof(int))); }
+  CUDA_TRY(cudaFuncSetAttribute(layer_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkSmemBytes));
   if (const char* e3 = getenv("NOVIC_CHAINS")) h->max_chains = std::max(1, std::min(8, atoi(e3)));
   for (int i = 0; i < 8; ++i) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->chain_streams[i], cudaStreamNonBlocking));
@@ -1055,12 +1126,12 @@ int novic_debug_trace(int64_t* out16, int32_t enable) {
     CUDA_TRY(cudaMemcpyToSymbol(g_trace_target, &target, sizeof(int)));
   }
   static long long* dbuf = nullptr;
-  if (dbuf == nullptr) { CUDA_TRY(cudaMalloc(&dbuf, 16 * sizeof(long long))); }
+  if (dbuf == nullptr) { CUDA_TRY(cudaMalloc(&dbuf, 32 * sizeof(long long))); }
   if (out16 != nullptr) {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out16, dbuf, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out16, dbuf, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
   }
-  CUDA_TRY(cudaMemset(dbuf, 0, 16 * sizeof(long long)));
+  CUDA_TRY(cudaMemset(dbuf, 0, 32 * sizeof(long long)));
   long long* p = enable ? dbuf : nullptr;
   CUDA_TRY(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
   return 0;

@@ -112,6 +112,7 @@ struct AttnParams {
   const unsigned char* keypad;  // optional [nseq, keypad_ld]
   const unsigned char* anc;     // optional [nseq, anc_ld]
   int nseq, nq, q0, smax, P, beams, slot_mul, prefix_bidir, keypad_ld, anc_ld;
+  int early_loads;              // stream kernel: request chunks of older rows before griddepcontrol.wait
   float scale_log2e;            // (1/sqrt(head_dim)) * log2(e)
 };
 
@@ -407,9 +408,14 @@ __global__ void __launch_bounds__(kAsThreads, 1) attention_stream_kernel(const A
 
   // chunks other than an item's last hold only rows written by earlier decode steps: safe to request before the wait
   int issued = 0;
-  if (contiguous && nchunks >= 2) {
+  if (p.early_loads == 1 && contiguous && nchunks >= 2) {
     const int early = min(nloads, nchunks >= 3 ? 3 : 2);
     for (; issued < early; ++issued) issue(issued);
+  } else if (p.early_loads == 3 && contiguous && nchunks >= 2 && nloads > 0) {   // diagnostic: generic-proxy probe of the same addresses
+    const int a0 = item0 + warp;
+    const uint4* probe = reinterpret_cast<const uint4*>(p.kcache + (static_cast<size_t>(a0 * p.slot_mul) * p.smax) * kE) + lane;
+    const uint4 t = __ldcg(probe);
+    if (t.x == 0x7fc12345u && t.y == 0x12345678u) as_smem[0] = 1;
   }
   pdl_wait();
   for (; issued < min(nloads, kAsSlots); ++issued) issue(issued);

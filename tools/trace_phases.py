@@ -20,7 +20,7 @@ with torch.inference_mode():
     for target, label in kinds.items():
         _abi.check(lib.novic_debug_trace(None, 1 + target))
         model.generate(e, False, True, 1.0, 0.0, None, None, False)
-        buf = (C.c_int64 * 16)()
+        buf = (C.c_int64 * 32)()
         _abi.check(lib.novic_debug_trace(buf, 0))
         t0 = buf[0]
         print(label)
