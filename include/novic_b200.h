@@ -66,6 +66,19 @@ typedef struct NovicNoiseCfg {
   float vec_norm, angle_min, angle_max, angle_std, mix_ratio;
 } NovicNoiseCfg;
 
+/* Guided decoding (embedding_decoder.py:802-813 greedy, :873-878 / :915-920 / :942-943 / :969-971 beam): the W x Cmax
+ * guide_targets tensor the reference receives (built at infer.py:687-710) as a token trie in CSR form, built on the host
+ * by novic_b200/guide.py.  Node 0 is the root; the ids allowed after a prefix are the token ids of its node's child
+ * edges.  All three arrays are int32 device pointers borrowed for the call. */
+typedef struct NovicGuide {
+  const int32_t* child_off;  /* [num_nodes + 1] */
+  const int32_t* child_tok;  /* [num_edges], ascending within a node */
+  const int32_t* child_node; /* [num_edges] */
+  int32_t num_nodes;
+  int32_t num_edges;
+  int32_t renorm;            /* guide_renorm: renormalise the scores over the allowed ids */
+} NovicGuide;
+
 typedef struct NovicHandle NovicHandle;
 
 const char* novic_last_error(void);
@@ -86,20 +99,20 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
  * rows per sequence (0 = decode: max(P, 1) rows; else P + C - 1 for teacher forcing). */
 size_t novic_workspace_bytes(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq);
 
-/* Replaces PrefixedIterDecoder.generate (embedding_decoder.py:779-850), unguided.
+/* Replaces PrefixedIterDecoder.generate (embedding_decoder.py:779-850); guide = NULL: unguided.
  *   embed [B, F] fp32 device.  Outputs (device): tok [B, G] int64, pad [B, G] u8, score [B] fp32,
  *   nll [B] fp32 (per-sample sum of -log p over unpadded tokens, label smoothing applied), len [B] fp32
  *   (unpadded tokens per sample), logits [B, G, V] fp32 or NULL.  *T_out (host) = number of columns the
  *   reference would return (early exit when every sample has emitted the end token). G = Cmax - 1. */
 int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
                           int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
-                          int32_t* T_out, void* ws, size_t ws_bytes, void* stream);
+                          int32_t* T_out, const NovicGuide* guide, void* ws, size_t ws_bytes, void* stream);
 
-/* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984), unguided, no vocab prior.
+/* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984), no vocab prior; guide = NULL: unguided.
  *   Outputs (device): tok [B, H, G] int64, pad [B, H, G] u8, score [B, H] fp32 sorted descending. */
 int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H, float temperature,
-                        float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, void* ws,
-                        size_t ws_bytes, void* stream);
+                        float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, const NovicGuide* guide,
+                        void* ws, size_t ws_bytes, void* stream);
 
 /* Replaces PrefixedIterDecoder.forward (embedding_decoder.py:659-777) with guide_targets=None.
  *   embed [B, F]; target [A, C] int64 with A = B * M (sequences of one embedding adjacent, multi_first=False);

@@ -43,6 +43,11 @@ class NovicNoiseCfg(C.Structure):
     ]
 
 
+class NovicGuide(C.Structure):
+    _fields_ = [("child_off", _FP), ("child_tok", _FP), ("child_node", _FP), ("num_nodes", C.c_int32), ("num_edges", C.c_int32),
+                ("renorm", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/novic_b200.h declares
 SIGNATURES = {
     "novic_last_error": (C.c_char_p, []),
@@ -53,9 +58,9 @@ SIGNATURES = {
     "novic_set_weights": (C.c_int, [C.c_void_p, C.POINTER(NovicWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "novic_generate_greedy": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_float, C.c_float, _FP, _FP, _FP, _FP, _FP, _FP,
-                                        C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
+                                        C.POINTER(C.c_int32), C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_generate_beam": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, C.c_float, C.c_float, _FP, _FP, _FP,
-                                      C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
+                                      C.POINTER(C.c_int32), C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_forward": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, C.c_int32, _FP, _FP, _FP,
                                 _FP, C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),

@@ -256,13 +256,15 @@ struct Workspace {
   long long* g_tok; unsigned char *g_pad, *g_done; float *g_score, *g_nll, *g_len, *g_score_out; int* flags;
   long long* b_tok[2]; unsigned char *b_pad[2], *b_anc[2], *b_fin[2]; float *b_score[2], *b_len[2], *b_norm;
   unsigned char *keypad, *effpad, *correct; long long* tgt_masked; float *nll_rows, *loss;
+  uint32_t* allow = nullptr; int allow_words = 0; int* g_node = nullptr; int* b_node[2] = {nullptr, nullptr};   // guided decoding
   size_t bytes = 0;
 };
 
 struct GraphKey {
   int mode; int64_t B; int H; float tau, alpha; void* ws;
+  const void* guide = nullptr; int guide_flags = 0;   // trie identity (child_off pointer) and renorm flag baked into the graph
   bool operator<(const GraphKey& o) const {
-    return std::tie(mode, B, H, tau, alpha, ws) < std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws);
+    return std::tie(mode, B, H, tau, alpha, ws, guide, guide_flags) < std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws, o.guide, o.guide_flags);
   }
 };
 
@@ -273,6 +275,7 @@ struct NovicHandle {
   bool use_graphs = true;
   bool attn_v1 = false;
   int attn_early = 1;
+  int attn_cfg = 0;                   // stream-attention shape (tuning): 0 = 16 warps x 3 slots x 4 keys
   bool attn_stream = true;            // decode steps use attention_stream_kernel (NOVIC_ATTN_STREAM=0: the bulk-ring kernel)
   bool fuse_ffn = true;
   bool stack_attn = true;             // decode steps run attention inside the stack kernel (NOVIC_STACK_ATTN=0: separate launches)
@@ -321,6 +324,13 @@ int plan_workspace(const NovicHandle* h, int64_t B, int H, int rps, char* base, 
   w.topv = reinterpret_cast<float*>(P_(sizeof(float) * w.logit_rows * w.ntiles * std::max(w.hcap, 1)));
   w.topi = reinterpret_cast<int*>(P_(sizeof(int) * w.logit_rows * w.ntiles * std::max(w.hcap, 1)));
   w.flags = reinterpret_cast<int*>(P_(sizeof(int) * (G + 2)));
+  if (!tf) {
+    w.allow_words = static_cast<int>(ceil_div(c.vocab_size, 32));
+    w.allow = reinterpret_cast<uint32_t*>(P_(sizeof(uint32_t) * w.logit_rows * w.allow_words));
+    w.g_node = reinterpret_cast<int*>(P_(sizeof(int) * w.nseq));
+    w.b_node[0] = w.g_node;
+    w.b_node[1] = reinterpret_cast<int*>(P_(sizeof(int) * w.nseq));
+  }
   if (!tf && H <= 1) {
     w.g_tok = reinterpret_cast<long long*>(P_(8 * B * G));
     w.g_pad = reinterpret_cast<unsigned char*>(P_(B * G));
@@ -378,8 +388,17 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
   KSpan t(kKAttn, s);
   if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
-    const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, kAsWarps)));
-    CUDA_TRY(launch_k(attention_stream_kernel, dim3(grid), dim3(kAsThreads), kAsSmemBytes, s, pa));
+    auto go = [&](auto kernel, int warps, int slots, int chunk) {
+      const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, warps)));
+      return launch_k(kernel, dim3(grid), dim3(warps * 32), as_smem_bytes(warps, slots, chunk), s, pa);
+    };
+    switch (h->attn_cfg) {
+      case 1: CUDA_TRY(go(attention_stream_kernel_t<12, 2, 8>, 12, 2, 8)); break;
+      case 2: CUDA_TRY(go(attention_stream_kernel_t<16, 2, 6>, 16, 2, 6)); break;
+      case 3: CUDA_TRY(go(attention_stream_kernel_t<8, 3, 8>, 8, 3, 8)); break;
+      case 4: CUDA_TRY(go(attention_stream_kernel_t<24, 2, 4>, 24, 2, 4)); break;
+      default: CUDA_TRY(go(attention_stream_kernel_t<16, 3, 4>, 16, 3, 4)); break;
+    }
   } else if (h->attn_v1) {
     attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
   } else {
@@ -501,29 +520,54 @@ int run_prefix(NovicHandle* h, const Workspace& ws, int rep, int rows_per_seq, c
   return launch_rowln(s, tm_e, h->w.tm_embed_mlp, B, c.prefix_len * kE, c.embed_dim, pp);
 }
 
-template <int HCAP>
+// Guided decoding state of one call: the trie (device pointers borrowed from the caller) and whether the guide
+// renormalises the temperature softmax (guide_renorm, embedding_decoder.py:920 / :829-830).
+struct GuideCfg {
+  GuideTrie trie{nullptr, nullptr, nullptr, 0};
+  bool on = false;
+  bool renorm = false;
+};
+
+template <int HCAP, bool MASKED>
 int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
-                  const long long* target, float inv_tau, int ban_eos, cudaStream_t s) {
+                  const long long* target, float inv_tau, int ban_eos, bool mask_lse, cudaStream_t s) {
   CUtensorMap tm_a;
   if (make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
-  typename EpiLogits<HCAP>::Params pl;
+  typename EpiLogits<HCAP, MASKED>::Params pl;
   pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
   pl.n_valid = h->cfg.vocab_size; pl.nparts = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
   pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
+  pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.mask_lse = mask_lse ? 1 : 0;
   KSpan t(kKLogits, s);
-  return launch_gemm<EpiLogits<HCAP>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
+  return launch_gemm<EpiLogits<HCAP, MASKED>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
 }
 
 int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
-               const long long* target, float inv_tau, int ban_eos, cudaStream_t s) {
+               const long long* target, float inv_tau, int ban_eos, cudaStream_t s, const GuideCfg* g = nullptr) {
+  if (g != nullptr && g->on) {
+    switch (ws.hcap) {
+      case 0: return launch_logits<0, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, s);
+      case 4: return launch_logits<4, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, s);
+      default: return launch_logits<16, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, s);
+    }
+  }
   switch (ws.hcap) {
-    case 0: return launch_logits<0>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, s);
-    case 4: return launch_logits<4>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, s);
-    default: return launch_logits<16>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, s);
+    case 0: return launch_logits<0, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, s);
+    case 4: return launch_logits<4, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, s);
+    default: return launch_logits<16, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, s);
   }
 }
 
-int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, float* logits, cudaStream_t s) {
+// allow[row, :] <- children of the rows' trie nodes (rows = logits rows of this step)
+int launch_guide_mask(const Workspace& ws, const GuideCfg& g, const int* node, int node_stride, int rows, cudaStream_t s) {
+  const size_t smem = sizeof(uint32_t) * kWarpsPerBlock * ws.allow_words;
+  CUDA_TRY(launch_k(guide_mask_kernel, dim3(static_cast<unsigned>(ceil_div(rows, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), smem, s,
+                    g.trie, node, node_stride, rows, ws.allow_words, ws.allow));
+  ++g_launches;
+  return 0;
+}
+
+int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, float* logits, const GuideCfg& guide, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   g_grid_div = h->split_sms ? ws.chains : 1;
   const int B = static_cast<int>(ws.B), P = c.prefix_len, G = h->G(), V = c.vocab_size;
@@ -533,6 +577,7 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
   CUDA_TRY(cudaMemsetAsync(ws.g_nll, 0, 4 * B, s));
   CUDA_TRY(cudaMemsetAsync(ws.g_len, 0, 4 * B, s));
   CUDA_TRY(cudaMemsetAsync(ws.flags, 1, sizeof(int) * (G + 2), s));  // bytes 0x01 -> non-zero flags
+  if (guide.on) CUDA_TRY(cudaMemsetAsync(ws.g_node, 0, sizeof(int) * B, s));   // every sample starts at the trie root
   if (run_prefix(h, ws, 1, P, s)) return 1;
   PassCfg pre{B * P, B, P, 0, 1, 1, nullptr, 0, nullptr, 0, P, P - 1, 1};
   if (run_layers(h, ws, pre, s)) return 1;
@@ -540,13 +585,15 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
   for (int step = 1; step <= G; ++step) {
     const __nv_bfloat16* a = (step == 1) ? ws.xfin : ws.xn;
     float* lg = logits != nullptr ? logits + static_cast<size_t>(step - 1) * V : nullptr;
-    if (run_logits(h, ws, a, B, lg, static_cast<long long>(G) * V, nullptr, inv_tau, step == 1 ? 1 : 0, s)) return 1;
+    if (guide.on && launch_guide_mask(ws, guide, ws.g_node, 1, B, s)) return 1;
+    // the guided branch of the reference does not ban the end token at the first position (embedding_decoder.py:806-810)
+    if (run_logits(h, ws, a, B, lg, static_cast<long long>(G) * V, nullptr, inv_tau, (step == 1 && !guide.on) ? 1 : 0, s, &guide)) return 1;
     const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
     {
       KSpan t(kKSelect, s);
       CUDA_TRY(launch_k(select_greedy_kernel, dim3(static_cast<unsigned>(ceil_div(B, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, s,
                         ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
-                        ws.xn, c.ln_eps));
+                        ws.xn, c.ln_eps, guide.trie, guide.on ? ws.g_node : static_cast<int*>(nullptr)));
       ++g_launches;
     }
     if (step < G) {
@@ -562,16 +609,16 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
 
 template <int HCAP>
 void launch_select_beam(const Workspace& ws, NovicHandle* h, int step, float inv_tau, float alpha, const BeamState& st,
-                        const float* pos_next, cudaStream_t s) {
+                        const float* pos_next, const GuideCfg& guide, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   KSpan t(kKSelect, s);
   launch_k(select_beam_kernel<HCAP>, dim3(static_cast<unsigned>(ceil_div(ws.B, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, s,
            ws.part, ws.topv, ws.topi, ws.ntiles, static_cast<int>(ws.B), ws.H, h->G(), step, c.vocab_size, inv_tau, alpha, st,
-           h->w.tok_f32, pos_next, h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
+           h->w.tok_f32, pos_next, h->w.norm1[0], ws.x, ws.xn, c.ln_eps, guide.trie);
   ++g_launches;
 }
 
-int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cudaStream_t s) {
+int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, const GuideCfg& guide, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   g_grid_div = h->split_sms ? ws.chains : 1;
   const int B = static_cast<int>(ws.B), H = ws.H, P = c.prefix_len, G = h->G();
@@ -579,7 +626,7 @@ int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cu
   const float inv_tau = 1.0f / tau;
   CUDA_TRY(cudaMemsetAsync(ws.flags, 1, sizeof(int) * (G + 2), s));
   beam_init_kernel<<<static_cast<unsigned>(ceil_div(A, 256)), 256, 0, s>>>(B, H, G, ws.b_tok[0], ws.b_pad[0], ws.b_anc[0],
-                                                                         ws.b_score[0], ws.b_len[0], ws.b_fin[0]);
+                                                                         ws.b_score[0], ws.b_len[0], ws.b_fin[0], ws.b_node[0]);
   ++g_launches;
   if (run_prefix(h, ws, 1, P, s)) return 1;
   PassCfg pre{B * P, B, P, 0, H, H, nullptr, 0, nullptr, 0, P, P - 1, 1};
@@ -587,12 +634,15 @@ int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, cu
   for (int step = 1; step <= G; ++step) {
     const int in = (step - 1) & 1, out = step & 1;
     const __nv_bfloat16* a = (step == 1) ? ws.xfin : ws.xn;
-    if (run_logits(h, ws, a, step == 1 ? B : A, nullptr, 0, nullptr, inv_tau, step == 1 ? 1 : 0, s)) return 1;
+    // step 1 has one logits row per sample (candidate 0, at the trie root); later steps one per candidate
+    if (guide.on && launch_guide_mask(ws, guide, ws.b_node[in], step == 1 ? H : 1, step == 1 ? B : A, s)) return 1;
+    if (run_logits(h, ws, a, step == 1 ? B : A, nullptr, 0, nullptr, inv_tau, step == 1 ? 1 : 0, s, &guide)) return 1;
     BeamState st{ws.b_tok[in], ws.b_tok[out], ws.b_pad[in], ws.b_pad[out], ws.b_anc[in], ws.b_anc[out], ws.b_score[in],
-                 ws.b_score[out], ws.b_norm, ws.b_len[in], ws.b_len[out], ws.b_fin[in], ws.b_fin[out], ws.flags};
+                 ws.b_score[out], ws.b_norm, ws.b_len[in], ws.b_len[out], ws.b_fin[in], ws.b_fin[out], ws.flags,
+                 guide.on ? ws.b_node[in] : static_cast<const int*>(nullptr), guide.on ? ws.b_node[out] : static_cast<int*>(nullptr)};
     const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
-    if (ws.hcap == 4) launch_select_beam<4>(ws, h, step, inv_tau, alpha, st, pos_next, s);
-    else launch_select_beam<16>(ws, h, step, inv_tau, alpha, st, pos_next, s);
+    if (ws.hcap == 4) launch_select_beam<4>(ws, h, step, inv_tau, alpha, st, pos_next, guide, s);
+    else launch_select_beam<16>(ws, h, step, inv_tau, alpha, st, pos_next, guide, s);
     if (step < G) {
       PassCfg dec{A, A, 1, P + step - 1, 1, H, nullptr, 0, ws.b_anc[out], G, 0, 0, 0};
       if (run_layers(h, ws, dec, s)) return 1;
@@ -729,7 +779,8 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (load_driver_entry()) return 1;
   if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_rowln_attr() ||
       set_gemm_attr<EpiLogits<0>, kStagesLogits>() || set_gemm_attr<EpiLogits<4>, kStagesLogits>() ||
-      set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
+      set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
+      set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
       set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
     return 1;
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 6 * kAttnBwdMaxS * kAttnBwdStride * 4));
@@ -749,7 +800,12 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
   CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
-  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAsSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 3, 4)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<12, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(12, 2, 8)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<8, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(8, 3, 8)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(24, 2, 4)));
+  if (const char* e12 = getenv("NOVIC_ATTN_CFG")) h->attn_cfg = atoi(e12);
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';
   if (const char* e9 = getenv("NOVIC_ATTN_EARLY")) h->attn_early = atoi(e9);
@@ -889,10 +945,23 @@ size_t novic_workspace_bytes(const NovicHandle* h, int64_t num_embeds, int32_t s
   return cp.bytes;
 }
 
+static int make_guide(const NovicGuide* guide, const NovicHandle* h, GuideCfg* out) {
+  if (guide == nullptr) return 0;
+  if (guide->child_off == nullptr || guide->child_tok == nullptr || guide->child_node == nullptr || guide->num_nodes < 1)
+    return fail("guide trie is incomplete (need child_off / child_tok / child_node and at least the root node)");
+  if (h->cfg.vocab_size > 65536) return fail("guided decoding supports vocabularies up to 65536 ids");
+  out->trie = GuideTrie{guide->child_off, guide->child_tok, guide->child_node, guide->num_nodes};
+  out->on = true;
+  out->renorm = guide->renorm != 0;
+  return 0;
+}
+
 int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
                           int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
-                          int32_t* T_out, void* wsbuf, size_t ws_bytes, void* stream) {
+                          int32_t* T_out, const NovicGuide* guide, void* wsbuf, size_t ws_bytes, void* stream) {
   if (check_ready(h)) return 1;
+  GuideCfg gcfg;
+  if (make_guide(guide, h, &gcfg)) return 1;
   if (B < 1 || B > (1 << 24)) return fail("batch size out of range");
   if (!(temperature > 0.f)) return fail("temperature must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -902,11 +971,12 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
   const int G = h->G(), F = h->cfg.embed_dim, V = h->cfg.vocab_size;
   for (int i = 0; i < cp.n; ++i)
     CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
-  GraphKey key{0, B, cp.n, temperature, length_alpha, wsbuf};
+  GraphKey key{0, B, cp.n, temperature, length_alpha, wsbuf, gcfg.on ? static_cast<const void*>(gcfg.trie.child_off) : nullptr,
+               (gcfg.on ? 1 : 0) | (gcfg.renorm ? 2 : 0)};
   if (run_maybe_graph(h, key, logits == nullptr, s, [&](cudaStream_t cs) {
         return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) {
           float* lg = logits != nullptr ? logits + static_cast<size_t>(cp.b0[i]) * G * V : nullptr;
-          return enqueue_greedy(h, cp.ws[i], temperature, length_alpha, lg, st);
+          return enqueue_greedy(h, cp.ws[i], temperature, length_alpha, lg, gcfg, st);
         });
       }))
     return 1;
@@ -932,9 +1002,11 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
 }
 
 int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H, float temperature,
-                        float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, void* wsbuf,
-                        size_t ws_bytes, void* stream) {
+                        float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, const NovicGuide* guide,
+                        void* wsbuf, size_t ws_bytes, void* stream) {
   if (check_ready(h)) return 1;
+  GuideCfg gcfg;
+  if (make_guide(guide, h, &gcfg)) return 1;
   if (B < 1 || B * H > (1 << 24)) return fail("batch size out of range");
   if (H < 2 || H > NOVIC_MAX_BEAMS) return fail("beam width must be in [2, %d] (got %d); use greedy for 1", NOVIC_MAX_BEAMS, H);
   if (H >= h->cfg.vocab_size) return fail("beam width must be smaller than the vocabulary");
@@ -946,9 +1018,10 @@ int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H
   const int G = h->G(), F = h->cfg.embed_dim;
   for (int i = 0; i < cp.n; ++i)
     CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
-  GraphKey key{1, B, H * 16 + cp.n, temperature, length_alpha, wsbuf};
+  GraphKey key{1, B, H * 16 + cp.n, temperature, length_alpha, wsbuf, gcfg.on ? static_cast<const void*>(gcfg.trie.child_off) : nullptr,
+               (gcfg.on ? 1 : 0) | (gcfg.renorm ? 2 : 0)};
   if (run_maybe_graph(h, key, true, s, [&](cudaStream_t cs) {
-        return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) { return enqueue_beam(h, cp.ws[i], temperature, length_alpha, st); });
+        return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) { return enqueue_beam(h, cp.ws[i], temperature, length_alpha, gcfg, st); });
       }))
     return 1;
   const int fin = G & 1;
@@ -1174,6 +1247,7 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
   EpiLogits<0>::Params pl;
   pl.logits = out; pl.ld_logits = N; pl.part = part; pl.topv = nullptr; pl.topi = nullptr; pl.target = nullptr;
   pl.n_valid = N; pl.nparts = nparts; pl.inv_tau = 1.0f; pl.ban_eos = 0; pl.want_sumx = 0;
+  pl.allow = nullptr; pl.allow_ld = 0; pl.mask_lse = 0;
   int rc = launch_gemm<EpiLogits<0>, kStagesLogits>(s, ta, tb, M, N, K, pl);
   CUDA_TRY(cudaFreeAsync(part, s));
   return rc;

@@ -168,7 +168,10 @@ struct __align__(32) LogitPartial {
 constexpr int kLogitSlice = kEpiCols;     // columns per epilogue thread
 
 // Vocabulary logits (tied weights, embedding_decoder.py:725): never materialised unless asked for.
-template <int HCAP>
+// MASKED = guided decoding (embedding_decoder.py:806-810, :915-920, :942-943): `allow` holds one bit per (row, vocabulary id);
+// only allowed ids can be selected (best / top-H), and with mask_lse (guide_renorm) the temperature log-sum-exp runs over
+// the allowed ids only.  The tau = 1 log-sum-exp (cross-entropy of the raw logits) and the optional logits copy are never masked.
+template <int HCAP, bool MASKED = false>
 struct EpiLogits {
   struct Params {
     float* logits;              // optional [M, ld_logits] fp32
@@ -182,11 +185,15 @@ struct EpiLogits {
     float inv_tau;
     int ban_eos;                // exclude id 0 from best / top-k (first generated token)
     int want_sumx;              // label smoothing needs sum of logits
+    const uint32_t* allow;      // MASKED: [M, allow_ld] bit masks (bit c & 31 of word c >> 5 = id c allowed)
+    int allow_ld;
+    int mask_lse;               // MASKED: renormalise the temperature softmax over the allowed ids
   };
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
     constexpr float kLog2e = 1.4426950408889634f;
     float m = -INFINITY, s_tau = 0.f, s_one = 0.f, sum_x = 0.f, best = -INFINITY, tgt_logit = -INFINITY;
+    float m_t = -INFINITY;       // MASKED: running max of the temperature softmax's support
     int best_i = 0x7fffffff;
     float tv[HCAP > 0 ? HCAP : 1];
     int ti[HCAP > 0 ? HCAP : 1];
@@ -225,46 +232,94 @@ struct EpiLogits {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (col0 + j == tgt) tgt_logit = v[j];
       }
-      // (a) chunk max and arg-max; ascending scan with strict '>' keeps the lowest index on ties
-      const float v0 = v[0];
-      if (p.ban_eos && col0 == 0) v[0] = -INFINITY;
-      float cm = v[0];
-      int ci = 0;
+      if (!MASKED) {
+        // (a) chunk max and arg-max; ascending scan with strict '>' keeps the lowest index on ties
+        const float v0 = v[0];
+        if (p.ban_eos && col0 == 0) v[0] = -INFINITY;
+        float cm = v[0];
+        int ci = 0;
 #pragma unroll
-      for (int j = 1; j < 32; ++j) if (v[j] > cm) { cm = v[j]; ci = j; }
-      if (cm > best) { best = cm; best_i = col0 + ci; }
-      if (HCAP > 0) {
+        for (int j = 1; j < 32; ++j) if (v[j] > cm) { cm = v[j]; ci = j; }
+        if (cm > best) { best = cm; best_i = col0 + ci; }
+        if (HCAP > 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (v[j] > tv[HCAP > 0 ? HCAP - 1 : 0]) {
-            float cv = v[j]; int cidx = col0 + j;
+          for (int j = 0; j < 32; ++j) {
+            if (v[j] > tv[HCAP > 0 ? HCAP - 1 : 0]) {
+              float cv = v[j]; int cidx = col0 + j;
 #pragma unroll
-            for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i)
-              if (cv > tv[i]) { const float tf = tv[i]; const int tI = ti[i]; tv[i] = cv; ti[i] = cidx; cv = tf; cidx = tI; }
+              for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i)
+                if (cv > tv[i]) { const float tf = tv[i]; const int tI = ti[i]; tv[i] = cv; ti[i] = cidx; cv = tf; cidx = tI; }
+            }
           }
         }
-      }
-      v[0] = v0;
-      // (b) online log-sum-exp in base 2: exp(x - m) = ex2(x * log2e - m * log2e)
-      const float m_new = fmaxf(m, fmaxf(cm, v0));
-      const float mb = m_new * kLog2e;
-      float a_one = 0.f;
+        v[0] = v0;
+        // (b) online log-sum-exp in base 2: exp(x - m) = ex2(x * log2e - m * log2e)
+        const float m_new = fmaxf(m, fmaxf(cm, v0));
+        const float mb = m_new * kLog2e;
+        float a_one = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a_one += exp2f(fmaf(v[j], kLog2e, -mb));
-      s_one = s_one * exp2f((m - m_new) * kLog2e) + a_one;
-      if (!tau_is_one) {
-        const float mbt = m_new * tau_l2e;
-        float a_tau = 0.f;
+        for (int j = 0; j < 32; ++j) a_one += exp2f(fmaf(v[j], kLog2e, -mb));
+        s_one = s_one * exp2f((m - m_new) * kLog2e) + a_one;
+        if (!tau_is_one) {
+          const float mbt = m_new * tau_l2e;
+          float a_tau = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a_tau += exp2f(fmaf(v[j], tau_l2e, -mbt));
-        s_tau = s_tau * exp2f((m - m_new) * tau_l2e) + a_tau;
+          for (int j = 0; j < 32; ++j) a_tau += exp2f(fmaf(v[j], tau_l2e, -mbt));
+          s_tau = s_tau * exp2f((m - m_new) * tau_l2e) + a_tau;
+        }
+        m = m_new;
+      } else {
+        uint32_t bits = in_range ? p.allow[static_cast<size_t>(c.row) * p.allow_ld + (col0 >> 5)] : 0u;
+        uint32_t sel = bits;
+        if (p.ban_eos && col0 == 0) sel &= ~1u;
+        // (a) best / top-H over the selectable ids only
+        float cm = -INFINITY, call = -INFINITY;
+        int ci = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          call = fmaxf(call, v[j]);
+          if (((sel >> j) & 1u) && v[j] > cm) { cm = v[j]; ci = j; }
+        }
+        if (cm > best) { best = cm; best_i = col0 + ci; }
+        if (HCAP > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (((sel >> j) & 1u) && v[j] > tv[HCAP > 0 ? HCAP - 1 : 0]) {
+              float cv = v[j]; int cidx = col0 + j;
+#pragma unroll
+              for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i)
+                if (cv > tv[i]) { const float tf = tv[i]; const int tI = ti[i]; tv[i] = cv; ti[i] = cidx; cv = tf; cidx = tI; }
+            }
+          }
+        }
+        // (b) tau = 1 log-sum-exp over every id; temperature log-sum-exp over its support (allowed ids when renormalising)
+        const float m_new = fmaxf(m, call);
+        const float mb = m_new * kLog2e;
+        float a_one = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a_one += exp2f(fmaf(v[j], kLog2e, -mb));
+        s_one = s_one * exp2f((m - m_new) * kLog2e) + a_one;
+        m = m_new;
+        const uint32_t sup = p.mask_lse ? bits : 0xffffffffu;
+        float cmt = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if ((sup >> j) & 1u) cmt = fmaxf(cmt, v[j]);
+        if (cmt > -INFINITY) {
+          const float mt_new = fmaxf(m_t, cmt);
+          const float mbt = mt_new * tau_l2e;
+          float a_tau = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if ((sup >> j) & 1u) a_tau += exp2f(fmaf(v[j], tau_l2e, -mbt));
+          s_tau = s_tau * exp2f((m_t - mt_new) * tau_l2e) + a_tau;   // m_t = -inf on the first contribution: factor 0
+          m_t = mt_new;
+        }
       }
-      m = m_new;
     }
     if (in_range) {
       LogitPartial o;
       o.max_all = m; o.sumexp_tau = tau_is_one ? s_one : s_tau; o.sumexp_one = s_one; o.sum_x = sum_x;
       o.best_val = best; o.best_idx = best_i; o.tgt_logit = tgt_logit; o.pad_ = 0;
+      if (MASKED) { o.sumexp_tau = s_tau; o.pad_ = __float_as_int(m_t); }   // the temperature sum has its own reference maximum
       p.part[static_cast<size_t>(c.row) * p.nparts + c.part] = o;
       if (HCAP > 0) {
         const size_t base = (static_cast<size_t>(c.row) * p.nparts + c.part) * (HCAP > 0 ? HCAP : 1);

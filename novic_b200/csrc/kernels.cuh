@@ -352,8 +352,13 @@ constexpr int kAsChunk = 4;                          // keys per chunk
 constexpr int kAsSlotBytes = kAsChunk * 1024;        // one chunk of K rows or of V rows
 constexpr int kAsThreads = kAsWarps * 32;
 constexpr int kAsSmemBytes = kAsWarps * kAsSlots * kAsSlotBytes + kAsWarps * kAsSlots * 8 + 128;
+__host__ __device__ constexpr int as_smem_bytes(int warps, int slots, int chunk) { return warps * slots * chunk * 1024 + warps * slots * 8 + 128; }
 
-__global__ void __launch_bounds__(kAsThreads, 1) attention_stream_kernel(const AttnParams p) {
+// WARPS x SLOTS x CHUNK KB of shared memory; the defaults are the configuration the decoder uses, the other instantiations
+// exist for tuning (NOVIC_ATTN_CFG).
+template <int WARPS, int SLOTS, int CHUNK>
+__global__ void __launch_bounds__(WARPS * 32, 1) attention_stream_kernel_t(const AttnParams p) {
+  constexpr int kAsWarps = WARPS, kAsSlots = SLOTS, kAsChunk = CHUNK, kAsSlotBytes = CHUNK * 1024;
   extern __shared__ __align__(128) uint8_t as_smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(kAsThreads, 1) attention_stream_kernel(const A
   // chunks other than an item's last hold only rows written by earlier decode steps: safe to request before the wait
   int issued = 0;
   if (p.early_loads == 1 && contiguous && nchunks >= 2) {
-    const int early = min(nloads, nchunks >= 3 ? 3 : 2);
+    const int early = min(min(nloads, kAsSlots), nchunks >= 3 ? 3 : 2);
     for (; issued < early; ++issued) issue(issued);
   } else if (p.early_loads == 3 && contiguous && nchunks >= 2 && nloads > 0) {   // diagnostic: generic-proxy probe of the same addresses
     const int a0 = item0 + warp;
@@ -469,7 +474,9 @@ __global__ void __launch_bounds__(kAsThreads, 1) attention_stream_kernel(const A
           s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
         }
       }
-      const float m_new = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+      float m_new = m;
+#pragma unroll
+      for (int u = 0; u < kAsChunk; ++u) m_new = fmaxf(m_new, s[u]);
       corr = exp2f(m - m_new);
       float psum = 0.f;
 #pragma unroll
@@ -520,23 +527,27 @@ struct RowStats {
   float tgt_logit;
 };
 
-__device__ __forceinline__ RowStats merge_partials(const LogitPartial* __restrict__ part, int ntiles, float inv_tau) {
+// masked = the partials come from the guided-decoding epilogue: the temperature sum has its own reference maximum (pad_)
+__device__ __forceinline__ RowStats merge_partials(const LogitPartial* __restrict__ part, int ntiles, float inv_tau, bool masked = false) {
   const int lane = lane_id();
-  float mx = -INFINITY, best = -INFINITY, sum_x = 0.f, tgt = -INFINITY;
+  float mx = -INFINITY, mxt = -INFINITY, best = -INFINITY, sum_x = 0.f, tgt = -INFINITY;
   int best_i = 0x7fffffff;
   for (int t = lane; t < ntiles; t += 32) {
     const LogitPartial q = part[t];
     mx = fmaxf(mx, q.max_all);
+    mxt = fmaxf(mxt, masked ? __int_as_float(q.pad_) : q.max_all);
     sum_x += q.sum_x;
     tgt = fmaxf(tgt, q.tgt_logit);
     if (q.best_val > best || (q.best_val == best && q.best_idx < best_i)) { best = q.best_val; best_i = q.best_idx; }
   }
   mx = warp_max(mx);
+  mxt = warp_max(mxt);
   float s_tau = 0.f, s_one = 0.f;
   for (int t = lane; t < ntiles; t += 32) {
     const LogitPartial q = part[t];
     s_one += q.sumexp_one * __expf(q.max_all - mx);
-    s_tau += q.sumexp_tau * __expf((q.max_all - mx) * inv_tau);
+    const float mt = masked ? __int_as_float(q.pad_) : q.max_all;
+    if (mt > -INFINITY) s_tau += q.sumexp_tau * __expf((mt - mxt) * inv_tau);
   }
   s_one = warp_sum(s_one);
   s_tau = warp_sum(s_tau);
@@ -551,12 +562,63 @@ __device__ __forceinline__ RowStats merge_partials(const LogitPartial* __restric
   RowStats r;
   r.max_all = mx;
   r.lse_one = mx + __logf(s_one);
-  r.lse_tau = mx * inv_tau + __logf(s_tau);
+  r.lse_tau = mxt > -INFINITY ? mxt * inv_tau + __logf(s_tau) : -INFINITY;
   r.sum_x = sum_x;
   r.best_val = best;
   r.best_idx = best_i;
   r.tgt_logit = tgt;
   return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Guided decoding (embedding_decoder.py:802-813, :873-878, :915-920, :969-971).  The reference keeps a B x H x W
+// mismatch mask over the W guide targets and scatters it into a B x H x (V+1) score tensor every step; here the guide
+// targets are a token trie (novic_b200/guide.py) and every sequence carries one trie node id: the ids allowed next are
+// the node's children.  guide_mask_kernel turns the node ids into one bit per (row, vocabulary id) for the logits
+// epilogue; the selection kernels walk the trie with the chosen token.
+// ---------------------------------------------------------------------------------------------------------
+struct GuideTrie {
+  const int* child_off;    // [num_nodes + 1] CSR offsets; node 0 = root (empty prefix)
+  const int* child_tok;    // [num_edges] token id of each child edge, ascending within a node
+  const int* child_node;   // [num_edges] node the edge leads to
+  int num_nodes;
+};
+
+// node reached from `node` by `tok`, or -1 (no guide target continues that way)
+__device__ __forceinline__ int guide_child(const GuideTrie& g, int node, int tok) {
+  if (node < 0 || node >= g.num_nodes) return -1;
+  int lo = g.child_off[node], hi = g.child_off[node + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int t = g.child_tok[mid];
+    if (t == tok) return g.child_node[mid];
+    if (t < tok) lo = mid + 1; else hi = mid;
+  }
+  return -1;
+}
+
+// allow[row, :] = bit set of the children tokens of node[row * node_stride].  One warp per row, bits assembled in shared memory.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+guide_mask_kernel(GuideTrie g, const int* __restrict__ node, int node_stride, int rows, int words, uint32_t* __restrict__ allow) {
+  extern __shared__ uint32_t gm_smem[];
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = lane_id();
+  uint32_t* bits = gm_smem + (threadIdx.x >> 5) * words;
+  for (int i = lane; i < words; i += 32) bits[i] = 0u;
+  __syncwarp();
+  const int n = node[static_cast<size_t>(row) * node_stride];
+  if (n >= 0 && n < g.num_nodes) {
+    const int e0 = g.child_off[n], e1 = g.child_off[n + 1];
+    for (int e = e0 + lane; e < e1; e += 32) {
+      const int t = g.child_tok[e];
+      atomicOr(&bits[t >> 5], 1u << (t & 31));
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < words; i += 32) allow[static_cast<size_t>(row) * words + i] = bits[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -577,14 +639,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 select_greedy_kernel(const LogitPartial* __restrict__ part, int ntiles, int B, int G, int step /*1-based*/, int V,
                      float inv_tau, float label_smoothing, GreedyState st, const float* __restrict__ wtok,
                      const float* __restrict__ pos_next, const float* __restrict__ gain0, float* __restrict__ x,
-                     __nv_bfloat16* __restrict__ xn, float eps) {
+                     __nv_bfloat16* __restrict__ xn, float eps, GuideTrie guide, int* __restrict__ guide_node) {
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (b >= B) return;
-  const RowStats r = merge_partials(part + static_cast<size_t>(b) * ntiles, ntiles, inv_tau);
+  const bool guided = guide_node != nullptr;
+  const RowStats r = merge_partials(part + static_cast<size_t>(b) * ntiles, ntiles, inv_tau, guided);
   const bool was_done = st.done[b] != 0;
-  const long long tok = r.best_idx;
+  const long long tok = r.best_idx < V ? r.best_idx : 0;   // no allowed id left: arg-max over all -inf = id 0 (the end token)
+  if (guided && lane_id() == 0) guide_node[b] = guide_child(guide, guide_node[b], static_cast<int>(tok));
   if (lane_id() == 0) {
     st.pad[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 1 : 0;
     st.tok[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 0 : tok;
@@ -617,6 +681,7 @@ struct BeamState {
   const float* len_in; float* len_out;                   // [B, H]
   const unsigned char* fin_in; unsigned char* fin_out;   // [B, H] candidate finished (its next position is padding)
   int* allfin;                                           // [G + 1]
+  const int* node_in; int* node_out;                     // [B, H] guide trie node per candidate (nullptr = unguided)
 };
 
 template <int HCAP>
@@ -624,12 +689,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restrict__ topv, const int* __restrict__ topi,
                    int ntiles, int B, int H, int G, int step, int V, float inv_tau, float length_alpha, BeamState st,
                    const float* __restrict__ wtok, const float* __restrict__ pos_next, const float* __restrict__ gain0,
-                   float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps) {
+                   float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps, GuideTrie guide) {
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (b >= B) return;
   const int lane = lane_id();
+  const bool guided = st.node_in != nullptr;
   const int nrows = (step == 1) ? 1 : H;                 // logits rows available for this sample
   const size_t row0 = (step == 1) ? static_cast<size_t>(b) : static_cast<size_t>(b) * H;
   __shared__ float s_lse[kWarpsPerBlock][16], s_base[kWarpsPerBlock][16], s_scale[kWarpsPerBlock][16];
@@ -641,7 +707,7 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
   for (int h = 0; h < H; ++h) {
     float l = 0.f;
     if (h < nrows) {
-      const RowStats r = merge_partials(part + (row0 + h) * ntiles, ntiles, inv_tau);
+      const RowStats r = merge_partials(part + (row0 + h) * ntiles, ntiles, inv_tau, guided);
       l = r.lse_tau;
     }
     if (lane == 0) {
@@ -691,12 +757,15 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
     }
     prev_v = bv;
     prev_f = bf;
+    const bool dead = bf == 0x7fffffffffffffffLL;          // fewer than H continuations exist (tiny guide sets): a -inf, finished filler
+    if (dead) { bf = 0; bv = -INFINITY; braw = -INFINITY; }
     const int parent = static_cast<int>(bf / V);
     const long long tok = bf - static_cast<long long>(parent) * V;
     const size_t o = static_cast<size_t>(b) * H + k;
     const size_t pi = static_cast<size_t>(b) * H + parent;
-    const bool parent_fin = fin[parent] != 0;
+    const bool parent_fin = fin[parent] != 0 || dead;
     const bool nxt_fin = parent_fin || tok == 0;
+    if (guided && lane == 0) st.node_out[o] = parent_fin ? st.node_in[pi] : guide_child(guide, st.node_in[pi], static_cast<int>(tok));
     // history: columns [0, step-1) come from the parent, column step-1 is the new token
     for (int j = lane; j < G; j += 32) {
       long long t = 0;
@@ -728,7 +797,7 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
 }
 
 __global__ void beam_init_kernel(int B, int H, int G, long long* tok, unsigned char* pad, unsigned char* anc, float* score,
-                                 float* len, unsigned char* fin) {
+                                 float* len, unsigned char* fin, int* node) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * H) return;
   const int h = i % H;
@@ -740,6 +809,7 @@ __global__ void beam_init_kernel(int B, int H, int G, long long* tok, unsigned c
   score[i] = (h == 0) ? 0.f : -INFINITY;                                // :863-864
   len[i] = (h == 0) ? 1.f : 0.f;                                        // :898-899
   fin[i] = (h == 0) ? 0 : 1;
+  node[i] = 0;                                                          // every candidate starts at the guide trie's root
 }
 
 // score * clamp(len, 1)^-alpha (embedding_decoder.py:836)

@@ -19,7 +19,7 @@ from typing import Any, Optional
 import torch
 import torch.nn as nn
 
-from . import _abi
+from . import _abi, guide
 
 MAX_SEQS_PER_CALL = 1 << 15  # sequences (embeddings x beams) decoded per library call; larger batches are chunked
 
@@ -466,9 +466,16 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     # ------------------------------------------------------------------------------------------------------
     # generate (embedding_decoder.py:779-850)
     # ------------------------------------------------------------------------------------------------------
+    def _guide_trie(self, guide_targets, device):
+        """W x Cmax guide targets -> cached device trie (novic_b200/guide.py), or None when unguided."""
+        if guide_targets is None:
+            return None
+        assert guide_targets.ndim == 2 and guide_targets.dtype == self.target_config.token_dtype
+        if not hasattr(self, "_trie_cache"):
+            self._trie_cache = guide.TrieCache()
+        return self._trie_cache.get(guide_targets, self.target_config.token_length - 1, self.target_config.vocab_size, device)
+
     def generate(self, embed, collect_logits, calc_loss, temperature, length_alpha, sample_weight, guide_targets, guide_renorm):
-        if guide_targets is not None:
-            raise NotImplementedError("guided greedy decoding (embedding_decoder.py:807-813) is not implemented in novic_b200 yet")
         if not temperature > 0:
             raise ValueError("temperature must be positive")
         embed = self._check_embed(embed)
@@ -488,6 +495,8 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         T = 0
         chunk = min(B, MAX_SEQS_PER_CALL)
         ws = self._workspace(st, dev, chunk, 1, 0)
+        trie = self._guide_trie(guide_targets, dev)
+        garg = guide.guide_arg(trie, bool(guide_renorm))
         with torch.cuda.device(dev):
             for b0 in range(0, B, chunk):
                 n = min(chunk, B - b0)
@@ -495,7 +504,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                 _abi.check(lib.novic_generate_greedy(
                     st['handle'], embed[b0:b0 + n].data_ptr(), n, float(temperature), float(length_alpha), tok[b0:b0 + n].data_ptr(),
                     pad[b0:b0 + n].data_ptr(), score[b0:b0 + n].data_ptr(), nll[b0:b0 + n].data_ptr(), length[b0:b0 + n].data_ptr(),
-                    None if logits is None else logits[b0:b0 + n].data_ptr(), C.byref(t_out), ws.data_ptr(), ws.numel(), stream))
+                    None if logits is None else logits[b0:b0 + n].data_ptr(), C.byref(t_out), garg, ws.data_ptr(), ws.numel(), stream))
                 T = max(T, t_out.value)
         target = tok[:, :T]
         target_padding = pad.view(torch.bool)[:, :T]
@@ -514,8 +523,6 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     # generate_beam (embedding_decoder.py:852-984)
     # ------------------------------------------------------------------------------------------------------
     def generate_beam(self, embed, topk, temperature, length_alpha, vocab_targets, vocab_per_token, vocab_scaler, guide_targets, guide_renorm):
-        if guide_targets is not None:
-            raise NotImplementedError("guided beam search (embedding_decoder.py:915-920) is not implemented in novic_b200 yet")
         if vocab_targets is not None and vocab_scaler != 0:
             raise NotImplementedError("vocabulary-prior scoring (embedding_decoder.py:924-936) is not implemented in novic_b200 yet")
         if not temperature > 0:
@@ -527,7 +534,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         G = self.target_config.token_length - 1
         if H == 1:
             # a beam of one is the greedy path; scores coincide (sum of log-probs, length-normalised)
-            t, p, _, _, _, s = self.generate(embed, False, True, temperature, length_alpha, None, None, False)
+            t, p, _, _, _, s = self.generate(embed, False, True, temperature, length_alpha, None, guide_targets, guide_renorm)
             return t.unsqueeze(1), p.unsqueeze(1), s.unsqueeze(1)
         st = self._state(dev)
         tok = torch.empty((B, H, G), dtype=torch.int64, device=dev)
@@ -538,13 +545,15 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         T = 0
         chunk = max(1, min(B, MAX_SEQS_PER_CALL // H))
         ws = self._workspace(st, dev, chunk, H, 0)
+        trie = self._guide_trie(guide_targets, dev)
+        garg = guide.guide_arg(trie, bool(guide_renorm))
         with torch.cuda.device(dev):
             for b0 in range(0, B, chunk):
                 n = min(chunk, B - b0)
                 t_out = C.c_int32(0)
                 _abi.check(lib.novic_generate_beam(
                     st['handle'], embed[b0:b0 + n].data_ptr(), n, H, float(temperature), float(length_alpha), tok[b0:b0 + n].data_ptr(),
-                    pad[b0:b0 + n].data_ptr(), score[b0:b0 + n].data_ptr(), C.byref(t_out), ws.data_ptr(), ws.numel(), stream))
+                    pad[b0:b0 + n].data_ptr(), score[b0:b0 + n].data_ptr(), C.byref(t_out), garg, ws.data_ptr(), ws.numel(), stream))
                 T = max(T, t_out.value)
         return tok[:, :, :T], pad.view(torch.bool)[:, :, :T], score
 

@@ -138,3 +138,22 @@ def synth_targets(batch: int, dims: DecoderDims = DecoderDims(), seed: int = 7, 
     if multi > 0:
         t, p = t.view(batch, multi, C), p.view(batch, multi, C)
     return t, p
+
+
+def synth_guide_targets(num_targets: int, dims: DecoderDims = DecoderDims(), seed: int = 21, max_tokens: int = 6,
+                        first_pool: int = 0) -> torch.Tensor:
+    """Synthetic guide vocabulary (infer.py:687-710 builds the real one by tokenising noun strings): W unique rows of
+    1..max_tokens token ids in [1, V) followed by the end token 0 and zero padding, shaped W x Cmax int64.
+    first_pool > 0 draws the tokens from a pool of that many ids so that the nouns share prefixes (a deep trie)."""
+    rng = np.random.default_rng(seed)
+    C, V = dims.token_length, dims.vocab_size
+    pool = rng.choice(np.arange(1, V), size=first_pool, replace=False) if first_pool > 0 else None
+    rows = set()
+    while len(rows) < num_targets:
+        n = int(rng.integers(1, max_tokens + 1))
+        ids = rng.choice(pool, size=n) if pool is not None else rng.integers(1, V, size=n)
+        rows.add(tuple(int(t) for t in ids))
+    out = np.zeros((num_targets, C), dtype=np.int64)
+    for i, r in enumerate(sorted(rows)):
+        out[i, :len(r)] = r
+    return torch.from_numpy(out[rng.permutation(num_targets)])

@@ -96,6 +96,20 @@ def main():
                 out[f"{tag}/{name}/tok"] = t.numpy()
                 out[f"{tag}/{name}/pad"] = p.numpy()
                 out[f"{tag}/{name}/score"] = sc.numpy()
+            # guided decoding (embedding_decoder.py:802-813, :915-920, :942-943): synthetic guide vocabularies, flat and deep tries
+            for gname, W, pool in (("gflat", 300, 0), ("gdeep", 400, 24)):
+                gt = synth.synth_guide_targets(W, dims, seed=21, first_pool=pool)
+                for rname, renorm in (("p", False), ("r", True)):
+                    t, p, lg, gls, glb, sc = model.generate(embed, True, True, 0.8, 0.3, None, gt, renorm)
+                    out[f"{tag}/{gname}/greedy_{rname}/tok"] = t.numpy()
+                    out[f"{tag}/{gname}/greedy_{rname}/pad"] = p.numpy()
+                    out[f"{tag}/{gname}/greedy_{rname}/score"] = sc.numpy()
+                    out[f"{tag}/{gname}/greedy_{rname}/loss"] = np.array([gls.item(), float(glb)], dtype=np.float64)
+                    for H in (3, 10):   # beam_k10_vnone_gp_t1_a0 is the reference's default generation config (infer.py:55)
+                        t, p, sc = model.generate_beam(embed, H, 1.0, 0.0, None, False, 0.0, gt, renorm)
+                        out[f"{tag}/{gname}/beam{H}_{rname}/tok"] = t.numpy()
+                        out[f"{tag}/{gname}/beam{H}_{rname}/pad"] = p.numpy()
+                        out[f"{tag}/{gname}/beam{H}_{rname}/score"] = sc.numpy()
     # embedding noise (embedding_noise.py): outputs of the reference modules and the draws they consumed
     N = ref.embedding_noise
     e0 = synth.synth_embeddings(16, seed=9)

@@ -215,15 +215,27 @@ def forward_loss(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: torch.Te
 # Greedy decode (embedding_decoder.py:779-850, unguided)
 # ----------------------------------------------------------------------------------------------------
 
+def guide_score_dense(guide_tok: torch.Tensor, guide_mask: torch.Tensor, V: int, dtype: torch.dtype) -> torch.Tensor:
+    """0 where a still-matching guide target continues with that token id, -inf elsewhere
+    (embedding_decoder.py:807, :916-917).  guide_tok: W ids of the current position, guide_mask: ... x W mismatch flags."""
+    idx = guide_tok.expand(guide_mask.shape).masked_fill(guide_mask, V)
+    full = torch.full(guide_mask.shape[:-1] + (V + 1,), NEG_INF, dtype=dtype)
+    return full.scatter_(-1, idx, 0.0)[..., :-1]
+
+
 def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: float = 1.0, length_alpha: float = 0.0,
-                    sample_weight: Optional[torch.Tensor] = None, early_exit: bool = True):
-    """Returns dict(target B x T int64, padding B x T bool, logits B x T x V, loss_sum, loss_basis, score B)."""
+                    sample_weight: Optional[torch.Tensor] = None, early_exit: bool = True,
+                    guide_targets: Optional[torch.Tensor] = None, guide_renorm: bool = False):
+    """Returns dict(target B x T int64, padding B x T bool, logits B x T x V, loss_sum, loss_basis, score B).
+    guide_targets (W x Cmax, :802-813): the generated ids must spell one of the guide targets."""
     B = embed.shape[0]
     G = cfg.gen_len
     tok = torch.zeros(B, G, dtype=torch.int64)
     pad = torch.zeros(B, G, dtype=torch.bool)
     done = torch.zeros(B, dtype=torch.bool)
     step_logits = []
+    guide_scores = []
+    guide_mask = torch.zeros(B, guide_targets.shape[0], dtype=torch.bool) if guide_targets is not None else None  # :788
     T = G
     for c in range(1, G + 1):
         if c > 1:
@@ -231,7 +243,13 @@ def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: 
         logits, _ = forward_logits(cfg, sd, embed, tok[:, :c], done.unsqueeze(1).expand(-1, c), only_pred=True)
         logits = logits[:, 0, :]
         step_logits.append(logits)
-        if c == 1:
+        if guide_targets is not None:
+            gt = guide_targets[:, c - 1]
+            gs = guide_score_dense(gt, guide_mask, cfg.vocab_size, logits.dtype)  # :806-807
+            guide_scores.append(gs)
+            nxt = (gs + logits).argmax(dim=1)                                      # :810 (no end-token ban in the guided branch)
+            guide_mask = guide_mask | (nxt.unsqueeze(1) != gt.unsqueeze(0))         # :811
+        elif c == 1:
             nxt = logits[:, 1:].argmax(dim=1) + 1  # first token may not be EOS (:804)
         else:
             nxt = logits.argmax(dim=1)
@@ -244,7 +262,10 @@ def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: 
     pad = pad[:, :T].clone()
     seq_logits = torch.stack(step_logits, dim=1)
     tok.masked_fill_(pad, 0)  # :824
-    logp_t = torch.log_softmax(seq_logits / temperature, dim=2)
+    score_logits = seq_logits / temperature
+    if guide_targets is not None and guide_renorm:
+        score_logits = score_logits + torch.stack(guide_scores, dim=1)  # :829-830: renormalise over the allowed ids
+    logp_t = torch.log_softmax(score_logits, dim=2)
     score = logp_t.gather(2, tok.unsqueeze(2)).squeeze(2).masked_fill(pad, 0.0).sum(dim=1)  # :831-834
     length = (T - pad.sum(dim=1)).to(score.dtype)
     if length_alpha != 0:
@@ -264,7 +285,8 @@ def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: 
 # ----------------------------------------------------------------------------------------------------
 
 def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temperature: float = 1.0,
-                  length_alpha: float = 0.0, early_exit: bool = True):
+                  length_alpha: float = 0.0, early_exit: bool = True, guide_targets: Optional[torch.Tensor] = None,
+                  guide_renorm: bool = False):
     """Returns dict(target B x H x T, padding B x H x T, score B x H sorted descending, margin B).
 
     `margin` is test metadata, not part of the reference's outputs: per sample, the smallest gap seen at any step
@@ -283,6 +305,10 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
     seq_len[:, 0] = 1.0                                   # :899
     T = G
     margin = torch.full((B,), float("inf"), dtype=dtype)
+    guide_mask = None
+    if guide_targets is not None:                                             # :873-878
+        guide_mask = torch.ones(B, H, guide_targets.shape[0], dtype=torch.bool)
+        guide_mask[:, 0, :] = False
     for c in range(1, G + 1):
         cur_tok = tok[:, :, :c].reshape(B * H, c)
         cur_pad = pad[:, :, :c].reshape(B * H, c)
@@ -290,9 +316,17 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
         logits = logits.view(B, H, V) / temperature
         finished = lpad.view(B, H, 1)
         logits[:, :, 1:] = logits[:, :, 1:].masked_fill(finished, NEG_INF)  # finished candidates extend with EOS at zero cost (:913)
+        gs = None
+        if guide_targets is not None:
+            gs = guide_score_dense(guide_targets[:, c - 1], guide_mask, V, logits.dtype)  # :916-917
+            gs[:, :, :1] = gs[:, :, :1].masked_fill(finished, 0.0)                        # :918
+            if guide_renorm:
+                logits = logits + gs                                                        # :920
         cand = torch.log_softmax(logits, dim=2) + score.unsqueeze(2)        # :922, :938
         if c == 1:
             cand[:, 0, 0] = NEG_INF                                         # :940
+        if gs is not None and not guide_renorm:
+            cand = cand + gs                                                # :943
         flat = cand.view(B, H * V)
         if length_alpha == 0:
             ranked = flat
@@ -320,6 +354,9 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
             if early_exit and bool(nxt_pad.all()):                                # :964-967
                 T = c
                 break
+            if guide_targets is not None:                                         # :969-971
+                guide_mask = guide_mask.gather(1, gather_idx.expand(-1, -1, guide_mask.shape[2])) | \
+                    (new_tok.unsqueeze(2) != guide_targets[:, c - 1].view(1, 1, -1))
             if length_alpha != 0:
                 seq_len = seq_len.gather(1, parent) + (~nxt_pad).to(dtype)        # :978
     tok = tok[:, :, :T].clone()
