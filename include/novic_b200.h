@@ -123,6 +123,16 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
                   const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
                   uint8_t* pad_out, float* loss, uint8_t* correct, void* ws, size_t ws_bytes, void* stream);
 
+/* Replaces the scoring loop of PrefixedIterDecoder.generate_all (embedding_decoder.py:1063-1072): the teacher-forced
+ * log-probability of M given token sequences for each of B embeddings, without materialising logits.
+ *   target [A, C] int64 and padding [A, C] u8 (may be NULL) with A = B * M, the M sequences of an embedding adjacent.
+ *   score [A] fp32 (device) = sum over unpadded positions c of log softmax(logits[a, c] / temperature)[target[a, c]].
+ *   guide != NULL with renorm set (guide_renorm): the softmax at position c runs over the ids that continue a guide target
+ *   matching target[a, :c]; the masks are built from the first M target rows and shared by all embeddings, so `target`
+ *   must repeat with period M (what generate_all passes: the same guide targets for every embedding). */
+int novic_score_targets(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                        int32_t C, float temperature, const NovicGuide* guide, float* score, void* ws, size_t ws_bytes, void* stream);
+
 /* Replaces the forward + backward of one training batch (train.py:1270-1273: model(..., calc_loss=True, calc_correct=True,
  * only_pred=False) followed by loss.backward()) with dropout disabled.  Same inputs as novic_forward (C >= 2).
  * Outputs (device): loss [2] = {loss_sum, loss_basis}; correct [A, C] u8 and pad_out [A, C] u8 (may be NULL); `grads`

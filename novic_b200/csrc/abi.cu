@@ -324,6 +324,10 @@ int plan_workspace(const NovicHandle* h, int64_t B, int H, int rps, char* base, 
   w.topv = reinterpret_cast<float*>(P_(sizeof(float) * w.logit_rows * w.ntiles * std::max(w.hcap, 1)));
   w.topi = reinterpret_cast<int*>(P_(sizeof(int) * w.logit_rows * w.ntiles * std::max(w.hcap, 1)));
   w.flags = reinterpret_cast<int*>(P_(sizeof(int) * (G + 2)));
+  if (tf) {   // teacher-forced scoring with guide_renorm: one mask row per (sequence of an embedding, position)
+    w.allow_words = static_cast<int>(ceil_div(c.vocab_size, 32));
+    w.allow = reinterpret_cast<uint32_t*>(P_(sizeof(uint32_t) * static_cast<size_t>(H) * c.token_length * w.allow_words));
+  }
   if (!tf) {
     w.allow_words = static_cast<int>(ceil_div(c.vocab_size, 32));
     w.allow = reinterpret_cast<uint32_t*>(P_(sizeof(uint32_t) * w.logit_rows * w.allow_words));
@@ -530,31 +534,31 @@ struct GuideCfg {
 
 template <int HCAP, bool MASKED>
 int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
-                  const long long* target, float inv_tau, int ban_eos, bool mask_lse, cudaStream_t s) {
+                  const long long* target, float inv_tau, int ban_eos, bool mask_lse, int allow_mod, cudaStream_t s) {
   CUtensorMap tm_a;
   if (make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
   typename EpiLogits<HCAP, MASKED>::Params pl;
   pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
   pl.n_valid = h->cfg.vocab_size; pl.nparts = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
   pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
-  pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.mask_lse = mask_lse ? 1 : 0;
+  pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.allow_mod = allow_mod; pl.mask_lse = mask_lse ? 1 : 0;
   KSpan t(kKLogits, s);
   return launch_gemm<EpiLogits<HCAP, MASKED>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
 }
 
 int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
-               const long long* target, float inv_tau, int ban_eos, cudaStream_t s, const GuideCfg* g = nullptr) {
+               const long long* target, float inv_tau, int ban_eos, cudaStream_t s, const GuideCfg* g = nullptr, int allow_mod = 0) {
   if (g != nullptr && g->on) {
     switch (ws.hcap) {
-      case 0: return launch_logits<0, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, s);
-      case 4: return launch_logits<4, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, s);
-      default: return launch_logits<16, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, s);
+      case 0: return launch_logits<0, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
+      case 4: return launch_logits<4, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
+      default: return launch_logits<16, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
     }
   }
   switch (ws.hcap) {
-    case 0: return launch_logits<0, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, s);
-    case 4: return launch_logits<4, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, s);
-    default: return launch_logits<16, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, s);
+    case 0: return launch_logits<0, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
+    case 4: return launch_logits<4, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
+    default: return launch_logits<16, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
   }
 }
 
@@ -1094,6 +1098,53 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
   return 0;
 }
 
+int novic_score_targets(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                        int32_t C, float temperature, const NovicGuide* guide, float* score, void* wsbuf, size_t ws_bytes, void* stream) {
+  if (check_ready(h)) return 1;
+  const NovicCfg& c = h->cfg;
+  if (B < 1 || M < 1 || C < 1 || C > c.token_length) return fail("bad B / M / C (C must be in [1, token_length])");
+  if (target == nullptr || score == nullptr) return fail("target and score are required");
+  if (!(temperature > 0.f)) return fail("temperature must be positive");
+  GuideCfg gcfg;
+  if (make_guide(guide, h, &gcfg)) return 1;
+  const bool masked = gcfg.on && gcfg.renorm;   // without renormalisation the guide does not change a given target's score
+  gcfg.on = masked;
+  const int64_t A = B * M;
+  const int P = c.prefix_len, S = P + C - 1, T = C;
+  if (A * S > (1LL << 30)) return fail("too many rows for one call; split the batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Workspace ws;
+  plan_workspace(h, B, M, h->S(), static_cast<char*>(wsbuf), &ws);
+  if (ws_bytes < ws.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, ws.bytes);
+  CUDA_TRY(cudaMemcpyAsync(ws.ein, embed, sizeof(float) * B * c.embed_dim, cudaMemcpyDeviceToDevice, s));
+  tf_mask_kernel<<<static_cast<unsigned>(ceil_div(A, 128)), 128, 0, s>>>(
+      reinterpret_cast<const long long*>(target), padding, nullptr, static_cast<int>(A), C, S, P, c.num_end_loss, T, 0, ws.keypad,
+      ws.effpad, ws.tgt_masked);
+  ++g_launches;
+  if (run_prefix(h, ws, M, S, s)) return 1;
+  if (C > 1) {
+    token_embed_kernel<<<static_cast<unsigned>(ceil_div(A * (C - 1), kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+        reinterpret_cast<const long long*>(target), C, static_cast<int>(A), C - 1, S, P, c.vocab_size, h->w.tok_f32, h->w.pos,
+        h->w.norm1[0], ws.x, ws.xn, c.ln_eps);
+    ++g_launches;
+  }
+  g_grid_div = 1;
+  PassCfg pc{static_cast<int>(A * S), static_cast<int>(A), S, 0, 1, 1, padding != nullptr ? ws.keypad : nullptr, S, nullptr, 0, S, P - 1, T};
+  if (run_layers(h, ws, pc, s)) return 1;
+  if (masked) {   // the first M target rows are embedding 0's sequences; every embedding shares their masks
+    const size_t smem = sizeof(uint32_t) * kWarpsPerBlock * ws.allow_words;
+    guide_path_mask_kernel<<<static_cast<unsigned>(ceil_div(M, kWarpsPerBlock)), kWarpsPerBlock * 32, smem, s>>>(
+        gcfg.trie, reinterpret_cast<const long long*>(target), C, M, T, ws.allow_words, ws.allow);
+    ++g_launches;
+  }
+  if (run_logits(h, ws, ws.xfin, static_cast<int>(A * T), nullptr, 0, ws.tgt_masked, 1.0f / temperature, 0, s, &gcfg, M * T)) return 1;
+  score_rows_kernel<<<static_cast<unsigned>(ceil_div(A, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
+      ws.part, ws.ntiles, static_cast<int>(A), T, 1.0f / temperature, ws.tgt_masked, masked ? 1 : 0, score);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 size_t novic_train_workspace_bytes(const NovicHandle* h, int64_t B, int32_t M, int32_t C) {
   TrainPlan t;
   plan_train(h, B, M, C, nullptr, &t);
@@ -1247,7 +1298,7 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
   EpiLogits<0>::Params pl;
   pl.logits = out; pl.ld_logits = N; pl.part = part; pl.topv = nullptr; pl.topi = nullptr; pl.target = nullptr;
   pl.n_valid = N; pl.nparts = nparts; pl.inv_tau = 1.0f; pl.ban_eos = 0; pl.want_sumx = 0;
-  pl.allow = nullptr; pl.allow_ld = 0; pl.mask_lse = 0;
+  pl.allow = nullptr; pl.allow_ld = 0; pl.allow_mod = 0; pl.mask_lse = 0;
   int rc = launch_gemm<EpiLogits<0>, kStagesLogits>(s, ta, tb, M, N, K, pl);
   CUDA_TRY(cudaFreeAsync(part, s));
   return rc;

@@ -187,6 +187,7 @@ struct EpiLogits {
     int want_sumx;              // label smoothing needs sum of logits
     const uint32_t* allow;      // MASKED: [M, allow_ld] bit masks (bit c & 31 of word c >> 5 = id c allowed)
     int allow_ld;
+    int allow_mod;              // MASKED: mask row = row % allow_mod when > 0 (teacher forcing: masks shared by all embeddings)
     int mask_lse;               // MASKED: renormalise the temperature softmax over the allowed ids
   };
   template <class Release>
@@ -269,7 +270,8 @@ struct EpiLogits {
         }
         m = m_new;
       } else {
-        uint32_t bits = in_range ? p.allow[static_cast<size_t>(c.row) * p.allow_ld + (col0 >> 5)] : 0u;
+        const int mrow = p.allow_mod > 0 ? c.row % p.allow_mod : c.row;
+        uint32_t bits = in_range ? p.allow[static_cast<size_t>(mrow) * p.allow_ld + (col0 >> 5)] : 0u;
         uint32_t sel = bits;
         if (p.ban_eos && col0 == 0) sel &= ~1u;
         // (a) best / top-H over the selectable ids only

@@ -621,6 +621,50 @@ guide_mask_kernel(GuideTrie g, const int* __restrict__ node, int node_stride, in
   for (int i = lane; i < words; i += 32) allow[static_cast<size_t>(row) * words + i] = bits[i];
 }
 
+// Teacher-forced variant (generate_all with guide_renorm, embedding_decoder.py:1008-1018): sequence m is a given token
+// row; the mask of position t holds the children of the node reached by its first t tokens.  One warp per sequence.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+guide_path_mask_kernel(GuideTrie g, const long long* __restrict__ target, int ld_target, int M, int T, int words, uint32_t* __restrict__ allow) {
+  extern __shared__ uint32_t gm_smem[];
+  const int m = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = lane_id();
+  uint32_t* bits = gm_smem + (threadIdx.x >> 5) * words;
+  int n = 0;
+  for (int t = 0; t < T; ++t) {
+    for (int i = lane; i < words; i += 32) bits[i] = 0u;
+    __syncwarp();
+    if (n >= 0 && n < g.num_nodes) {
+      const int e0 = g.child_off[n], e1 = g.child_off[n + 1];
+      for (int e = e0 + lane; e < e1; e += 32) {
+        const int tk = g.child_tok[e];
+        atomicOr(&bits[tk >> 5], 1u << (tk & 31));
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < words; i += 32) allow[(static_cast<size_t>(m) * T + t) * words + i] = bits[i];
+    __syncwarp();
+    n = guide_child(g, n, static_cast<int>(target[static_cast<size_t>(m) * ld_target + t]));
+  }
+}
+
+// score[a] = sum over the unpadded positions t of  logit[a, t, target] / tau - logsumexp(logits[a, t, support] / tau)
+// (embedding_decoder.py:1067-1072).  One warp per sequence; target < 0 marks a padded position.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+score_rows_kernel(const LogitPartial* __restrict__ part, int ntiles, int A, int T, float inv_tau, const long long* __restrict__ target,
+                  int masked, float* __restrict__ score) {
+  const int a = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (a >= A) return;
+  float total = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const size_t r = static_cast<size_t>(a) * T + t;
+    if (target[r] < 0) continue;   // warp-uniform
+    const RowStats st = merge_partials(part + r * ntiles, ntiles, inv_tau, masked != 0);
+    total += st.tgt_logit * inv_tau - st.lse_tau;
+  }
+  if (lane_id() == 0) score[a] = total;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Greedy step (embedding_decoder.py:802-817): pick the arg-max token, update padding / done / score / loss
 // accumulators and emit the next step's input row (token embedding + position + layer-0 LayerNorm).

@@ -557,8 +557,73 @@ class PrefixedIterDecoder(EmbeddingDecoder):
                 T = max(T, t_out.value)
         return tok[:, :, :T], pad.view(torch.bool)[:, :, :T], score
 
+    # ------------------------------------------------------------------------------------------------------
+    # generate_all (embedding_decoder.py:986-1079): score every guide target by teacher forcing, return the top-k
+    # ------------------------------------------------------------------------------------------------------
     def precompute_generate_all(self, length_alpha, vocab_targets, vocab_per_token, vocab_scaler, guide_targets, guide_renorm):
-        raise NotImplementedError("generate_all (embedding_decoder.py:986-1079) is not implemented in novic_b200 yet")
+        """Embedding-independent part of generate_all (embedding_decoder.py:986-1050).  Returns the same 5-tuple shape as the
+        reference, except that the third item is the guide trie (or None) where the reference holds its dense
+        1 x W x C x V guide-score tensor - callers treat the tuple as opaque (infer.py:535-541)."""
+        W, Cmax = guide_targets.shape
+        paddings = guide.target_paddings(guide_targets)                                    # :991-994
+        C = Cmax - int(paddings.all(dim=0).sum().item())                                   # :996
+        paddings = paddings[:, :C].contiguous()
+        targets = guide_targets[:, :C].masked_fill(paddings, 0).contiguous()               # :997-998
+        trie = self._guide_trie(guide_targets, guide_targets.device) if guide_renorm else None
+        if vocab_targets is None or vocab_scaler == 0:
+            vocab_scores = None
+        else:                                                                              # :1020-1044
+            vs = guide.vocab_prior_scores(targets, paddings, vocab_targets[:, :C], bool(vocab_per_token), self.target_config.vocab_size)
+            vocab_scores = (vs.to(device=guide_targets.device, dtype=self.embed_dtype) * vocab_scaler).unsqueeze(0)
+        if length_alpha == 0:
+            alpha_scale = None
+        else:                                                                              # :1046-1050
+            n = (C - paddings.sum(dim=1)).clamp(min=1).to(self.embed_dtype)
+            alpha_scale = n.pow(-length_alpha).unsqueeze(0)
+        return targets, paddings, trie, vocab_scores, alpha_scale
 
     def generate_all(self, embed, topk, temperature, length_alpha, vocab_targets, vocab_per_token, vocab_scaler, guide_targets, guide_renorm, precompute=None):
-        raise NotImplementedError("generate_all (embedding_decoder.py:986-1079) is not implemented in novic_b200 yet")
+        if not temperature > 0:
+            raise ValueError("temperature must be positive")
+        if precompute is None:
+            precompute = self.precompute_generate_all(length_alpha=length_alpha, vocab_targets=vocab_targets, vocab_per_token=vocab_per_token,
+                                                      vocab_scaler=vocab_scaler, guide_targets=guide_targets, guide_renorm=guide_renorm)
+        targets, paddings, trie, vocab_scores, alpha_scale = precompute
+        embed = self._check_embed(embed)
+        B, K = embed.shape[0], int(topk)
+        W, C = targets.shape
+        dev = embed.device
+        if targets.device != dev:
+            targets, paddings = targets.to(dev), paddings.to(dev)
+        if trie is not None and trie.child_off.device != dev:
+            trie = trie.to(dev)
+        st = self._state(dev)
+        lib = _abi.lib()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        garg = guide.guide_arg(trie, True)
+        scores = torch.empty((B, W), dtype=torch.float32, device=dev)
+        bc = max(1, min(B, MAX_SEQS_PER_CALL // 16))               # embeddings per call
+        mc = max(1, min(W, MAX_SEQS_PER_CALL // bc))                # guide targets per embedding per call
+        ws = self._workspace(st, dev, bc, mc, self.max_seq_len)
+        pad_u8 = paddings.view(torch.uint8)
+        with torch.cuda.device(dev):
+            for w0 in range(0, W, mc):
+                m = min(mc, W - w0)
+                for b0 in range(0, B, bc):
+                    n = min(bc, B - b0)
+                    tgt = targets[w0:w0 + m].unsqueeze(0).expand(n, -1, -1).reshape(n * m, C).contiguous()      # :1064
+                    pad = pad_u8[w0:w0 + m].unsqueeze(0).expand(n, -1, -1).reshape(n * m, C).contiguous()
+                    out = torch.empty(n * m, dtype=torch.float32, device=dev)
+                    _abi.check(lib.novic_score_targets(st['handle'], embed[b0:b0 + n].data_ptr(), n, m, tgt.data_ptr(), pad.data_ptr(), C,
+                                                       float(temperature), garg, out.data_ptr(), ws.data_ptr(), ws.numel(), stream))
+                    scores[b0:b0 + n, w0:w0 + m] = out.view(n, m)
+        if vocab_scores is not None:
+            scores.sub_(vocab_scores.to(dev))                                              # :1074-1075
+        if alpha_scale is not None:
+            scores.mul_(alpha_scale.to(dev))                                               # :1076-1077
+        topk_scores, topk_indices = torch.topk(scores, k=K, dim=1, largest=True, sorted=True)   # :1079-1083
+        idx3 = topk_indices.unsqueeze(2).expand(-1, -1, C)
+        topk_targets = targets.expand(B, -1, -1).gather(dim=1, index=idx3)
+        topk_paddings = paddings.expand(B, -1, -1).gather(dim=1, index=idx3)
+        return topk_targets, topk_paddings, topk_scores
+

@@ -28,9 +28,12 @@ class GuideTrie:
     num_nodes: int
     num_edges: int
     depth: int
+    child_count: torch.Tensor = None   # int64 [num_edges] guide targets below each child (host only; vocabulary priors)
+    node_count: torch.Tensor = None    # int64 [num_nodes] guide targets below each node (host only)
 
     def to(self, device) -> "GuideTrie":
-        return GuideTrie(self.child_off.to(device), self.child_tok.to(device), self.child_node.to(device), self.num_nodes, self.num_edges, self.depth)
+        return GuideTrie(self.child_off.to(device), self.child_tok.to(device), self.child_node.to(device), self.num_nodes, self.num_edges,
+                         self.depth, self.child_count, self.node_count)
 
     def as_struct(self, renorm: bool) -> _abi.NovicGuide:
         return _abi.NovicGuide(self.child_off.data_ptr(), self.child_tok.data_ptr(), self.child_node.data_ptr(), self.num_nodes,
@@ -70,8 +73,51 @@ def build_trie(guide_targets: torch.Tensor, gen_len: int, vocab_size: int) -> Gu
     child_off = np.zeros(num_nodes + 1, dtype=np.int64)
     np.add.at(child_off, parent + 1, 1)
     child_off = np.cumsum(child_off)
+    # rows below each node: consecutive in the sorted order, so the count is the distance to the next node of the same depth
+    node_count = np.zeros(num_nodes, dtype=np.int64)
+    for d in range(G + 1):
+        starts = np.nonzero(new[:, d])[0]
+        node_count[base[d]:base[d + 1]] = np.diff(np.concatenate((starts, [W])))
     return GuideTrie(torch.from_numpy(child_off.astype(np.int32)), torch.from_numpy(tok.astype(np.int32)),
-                     torch.from_numpy(child.astype(np.int32)), num_nodes, int(tok.shape[0]), G)
+                     torch.from_numpy(child.astype(np.int32)), num_nodes, int(tok.shape[0]), G,
+                     torch.from_numpy(node_count[child]), torch.from_numpy(node_count))
+
+
+def target_paddings(guide_targets: torch.Tensor) -> torch.Tensor:
+    """W x Cmax bool: position c is padding iff an earlier position holds the end token 0 (embedding_decoder.py:991-994)."""
+    pads = torch.zeros_like(guide_targets, dtype=torch.bool)
+    pads[:, 1:] = (guide_targets[:, :-1] == 0).cummax(dim=1).values
+    return pads
+
+
+def vocab_prior_scores(targets: torch.Tensor, paddings: torch.Tensor, vocab_targets: torch.Tensor, per_token: bool,
+                       vocab_size: int) -> torch.Tensor:
+    """Sum over the unpadded positions of log p_vocab(target token | target prefix) for each of the W targets
+    (embedding_decoder.py:1020-1044, before the vocab_scaler factor): p_vocab is uniform over the distinct continuations of
+    the vocabulary nouns sharing the prefix (per_token) or proportional to how many of them take each continuation.
+    A target that leaves the vocabulary trie gets +inf, like the reference's nan_to_num(log 0)."""
+    W, C = targets.shape
+    trie = build_trie(vocab_targets, C, vocab_size)
+    off = trie.child_off.numpy().astype(np.int64)
+    keys = np.repeat(np.arange(trie.num_nodes, dtype=np.int64), np.diff(off)) * vocab_size + trie.child_tok.numpy().astype(np.int64)
+    child = trie.child_node.numpy().astype(np.int64)
+    ccount, ncount = trie.child_count.numpy().astype(np.float64), trie.node_count.numpy().astype(np.float64)
+    nchild = np.diff(off).astype(np.float64)
+    tg, pd = targets.cpu().numpy().astype(np.int64), paddings.cpu().numpy()
+    node = np.zeros(W, dtype=np.int64)
+    alive = np.ones(W, dtype=bool)
+    total = np.zeros(W, dtype=np.float64)
+    for c in range(min(C, trie.depth)):
+        q = node * vocab_size + tg[:, c]
+        idx = np.minimum(np.searchsorted(keys, q), len(keys) - 1) if len(keys) else np.zeros(W, dtype=np.int64)
+        found = alive & (len(keys) > 0) & (keys[idx] == q)
+        p = np.where(found, (1.0 / np.maximum(nchild[node], 1.0)) if per_token else ccount[idx] / np.maximum(ncount[node], 1.0), 0.0)
+        with np.errstate(divide="ignore"):
+            lp = np.where(p > 0, np.log(np.maximum(p, 1e-300)), np.inf)
+        total += np.where(pd[:, c], 0.0, lp)
+        alive = found
+        node = np.where(found, child[idx], 0)
+    return torch.from_numpy(total.astype(np.float32))
 
 
 class TrieCache:

@@ -110,6 +110,17 @@ def main():
                         out[f"{tag}/{gname}/beam{H}_{rname}/tok"] = t.numpy()
                         out[f"{tag}/{gname}/beam{H}_{rname}/pad"] = p.numpy()
                         out[f"{tag}/{gname}/beam{H}_{rname}/score"] = sc.numpy()
+            # generate_all (embedding_decoder.py:986-1079): all guide targets scored by teacher forcing; K = W keeps the whole ranking
+            if tag != "eosall":
+                gt = synth.synth_guide_targets(200, dims, seed=23, first_pool=24)
+                vt = torch.cat((gt[:150], synth.synth_guide_targets(120, dims, seed=24, first_pool=24)))
+                for aname, renorm, vocab, per_token, scaler, tau, alpha in (
+                        ("plain", False, None, False, 0.0, 1.0, 0.0), ("renorm", True, None, False, 0.0, 0.8, 0.4),
+                        ("vcount", True, vt, False, 0.7, 1.0, 0.0), ("vtoken", False, vt, True, 0.5, 1.0, 0.3)):
+                    t, p, sc = model.generate_all(embed[:16], gt.shape[0], tau, alpha, vocab, per_token, scaler, gt, renorm)
+                    out[f"{tag}/all_{aname}/score"] = sc.numpy()
+                    out[f"{tag}/all_{aname}/tok10"] = t[:, :10].numpy()
+                    out[f"{tag}/all_{aname}/pad10"] = p[:, :10].numpy()
     # embedding noise (embedding_noise.py): outputs of the reference modules and the draws they consumed
     N = ref.embedding_noise
     e0 = synth.synth_embeddings(16, seed=9)

@@ -366,6 +366,64 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
 
 
 # ----------------------------------------------------------------------------------------------------
+# generate_all (embedding_decoder.py:986-1079): score every guide target by teacher forcing, keep the top-k
+# ----------------------------------------------------------------------------------------------------
+
+def generate_all(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temperature: float, length_alpha: float,
+                 guide_targets: torch.Tensor, guide_renorm: bool, vocab_targets: Optional[torch.Tensor] = None,
+                 vocab_per_token: bool = False, vocab_scaler: float = 0.0):
+    """Returns dict(target B x K x C, padding B x K x C, score B x K sorted descending, all_scores B x W)."""
+    W, Cmax = guide_targets.shape
+    V = cfg.vocab_size
+    pads = torch.zeros(W, Cmax, dtype=torch.bool)
+    pads[:, 1:] = (guide_targets[:, :-1] == 0).cummax(dim=1).values                      # :991-994
+    C = Cmax - int(pads.all(dim=0).sum())                                                 # :996
+    pads = pads[:, :C]
+    gt = guide_targets[:, :C].masked_fill(pads, 0)                                        # :997-998
+    mism = torch.zeros(W, C, W, dtype=torch.bool)                                         # :1002-1005: target w' mismatches w before position c
+    mism[:, 1:, :] = (gt[:, :-1, None] != gt.t()[None, :-1, :]).cummax(dim=1).values
+    guide_scores = None
+    if guide_renorm:                                                                      # :1006-1007
+        idx = gt.t().expand(W, -1, -1).masked_fill(mism, V)
+        guide_scores = torch.full((W, C, V + 1), NEG_INF).scatter_(2, idx, 0.0)[:, :, :-1]
+    vocab_scores = None
+    if vocab_targets is not None and vocab_scaler != 0:                                   # :1011-1036
+        vt = vocab_targets[:, :C]
+        Z = vt.shape[0]
+        vm = torch.zeros(W, C, Z, dtype=torch.bool)
+        vm[:, 1:, :] = (gt[:, :-1, None] != vt.t()[None, :-1, :]).cummax(dim=1).values
+        vidx = vt.t().expand(W, -1, -1).masked_fill(vm, V)
+        if vocab_per_token:
+            vs = torch.zeros(W, C, V + 1).scatter_(2, vidx, 1.0)[:, :, :-1]
+            vs = vs / vs.sum(dim=2, keepdim=True)
+        else:
+            cnt = torch.zeros(W, C, V + 1).scatter_add_(2, vidx, torch.ones(W, C, Z))
+            vs = cnt[:, :, :-1] / (Z - cnt[:, :, -1:])
+        vs = vs.gather(2, gt.unsqueeze(2)).squeeze(2).log().nan_to_num(nan=float("inf"), neginf=float("inf"), posinf=float("inf"))
+        vocab_scores = vs.masked_fill(pads, 0.0).sum(dim=1) * vocab_scaler
+    B = embed.shape[0]
+    scores = torch.empty(B, W)
+    for w0 in range(0, W, 64):
+        tg = gt[w0:w0 + 64]
+        M = tg.shape[0]
+        full_t = tg.unsqueeze(0).expand(B, -1, -1).reshape(B * M, C)
+        full_p = pads[w0:w0 + 64].unsqueeze(0).expand(B, -1, -1).reshape(B * M, C)
+        logits, _ = forward_logits(cfg, sd, embed.repeat_interleave(M, dim=0), full_t, full_p, only_pred=False)   # :1065
+        logits = logits.view(B, M, C, V) / temperature                                                             # :1066
+        if guide_scores is not None:
+            logits = logits + guide_scores[None, w0:w0 + 64]                                                        # :1068
+        lp = torch.log_softmax(logits, dim=3).gather(3, tg[None, :, :, None].expand(B, -1, -1, 1)).squeeze(3)    # :1069-1070
+        scores[:, w0:w0 + 64] = lp.masked_fill(pads[None, w0:w0 + 64], 0.0).sum(dim=2)                             # :1071-1072
+    if vocab_scores is not None:
+        scores = scores - vocab_scores.unsqueeze(0)                                        # :1075
+    if length_alpha != 0:
+        scores = scores * (C - pads.sum(dim=1)).clamp(min=1).float().pow(-length_alpha).unsqueeze(0)   # :1046-1050, :1077
+    best, idx = torch.topk(scores, k=topk, dim=1, largest=True, sorted=True)             # :1079
+    idx3 = idx.unsqueeze(2).expand(-1, -1, C)
+    return dict(target=gt.expand(B, -1, -1).gather(1, idx3), padding=pads.expand(B, -1, -1).gather(1, idx3), score=best, all_scores=scores)
+
+
+# ----------------------------------------------------------------------------------------------------
 # Embedding noise (embedding_noise.py).  The random draws are explicit inputs so that the CUDA kernel's
 # "debug" entry point (pre-drawn normals / uniforms) can be compared bit-for-bit-ish against this.
 # ----------------------------------------------------------------------------------------------------

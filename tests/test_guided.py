@@ -215,3 +215,93 @@ def test_guided_full_size_properties(models):
     # greedy follows the locally best allowed id; a width-10 beam almost always ends at least as well (it can prune the greedy
     # path, so this is a statistical property, not an invariant)
     assert (score[:, 0] >= g[5].cpu() - 1e-3).float().mean() >= 0.95
+
+
+# ------------------------------------------------------------------------------------------------------------
+# generate_all (embedding_decoder.py:986-1079)
+# ------------------------------------------------------------------------------------------------------------
+ALL_CASES = {   # name: (guide_renorm, vocab prior?, vocab_per_token, vocab_scaler, tau, alpha)
+    "plain": (False, False, False, 0.0, 1.0, 0.0), "renorm": (True, False, False, 0.0, 0.8, 0.4),
+    "vcount": (True, True, False, 0.7, 1.0, 0.0), "vtoken": (False, True, True, 0.5, 1.0, 0.3),
+}
+
+
+def all_sets():
+    dims = synth.DecoderDims()
+    gt = synth.synth_guide_targets(200, dims, seed=23, first_pool=24)
+    vt = torch.cat((gt[:150], synth.synth_guide_targets(120, dims, seed=24, first_pool=24)))
+    return gt, vt
+
+
+@pytest.mark.parametrize("aname", ("renorm", "vcount"))
+def test_oracle_generate_all_vs_reference_outputs(gold, aname):
+    renorm, use_vocab, per_token, scaler, tau, alpha = ALL_CASES[aname]
+    sd = weight_case("lively")
+    cfg = orc.cfg_from_state_dict(sd)
+    gt, vt = all_sets()
+    with torch.inference_mode():
+        o = orc.generate_all(cfg, sd, gold_embed()[:4], gt.shape[0], tau, alpha, gt, renorm, vt if use_vocab else None, per_token, scaler)
+    rs = gold[f"lively/all_{aname}/score"][:4]
+    fin = torch.isfinite(rs)
+    assert (torch.isfinite(o["score"]) == fin).all()
+    assert (o["score"] - rs)[fin].abs().max() < 2e-3
+    assert torch.equal(o["target"][:, :10], gold[f"lively/all_{aname}/tok10"][:4])
+    assert torch.equal(o["padding"][:, :10], gold[f"lively/all_{aname}/pad10"][:4])
+
+
+def test_generate_all_precompute_matches_oracle_semantics():
+    """Host-side pieces of generate_all (no GPU needed): trimmed targets / paddings, vocabulary-prior sums (count-based and
+    per-token, +inf when a guide target leaves the vocabulary trie) and the length scale, against a dense restatement."""
+    dims = synth.DecoderDims()
+    gt, vt = all_sets()
+    model = default_decoder(dims, weight_case("lively"))
+    for per_token in (False, True):
+        targets, pads, trie, vscores, ascale = model.precompute_generate_all(0.4, vt, per_token, 0.7, gt, True)
+        W, C = targets.shape
+        assert C == 7 and trie is not None and vscores.shape == (1, W) and ascale.shape == (1, W)
+        assert torch.equal(pads[:, 1:], (gt[:, :C - 1] == 0).cummax(dim=1).values) and not pads[:, 0].any()
+        for w in (0, 17, 151, 199):   # dense check of a few rows
+            total = 0.0
+            for c in range(C):
+                if pads[w, c]:
+                    continue
+                match = (vt[:, :c] == gt[w, :c]).all(dim=1)
+                nxt = vt[match, c]
+                if per_token:
+                    p = (1.0 / len(set(nxt.tolist()))) if (nxt == gt[w, c]).any() else 0.0
+                else:
+                    p = float((nxt == gt[w, c]).sum()) / max(int(match.sum()), 1)
+                total += float("inf") if p == 0 else -np.log(p) * -1.0
+            want = total * 0.7
+            got = vscores[0, w].item()
+            assert (np.isinf(want) and np.isinf(got)) or abs(want - got) < 1e-4
+        n = (C - pads.sum(dim=1)).clamp(min=1).float()
+        assert torch.allclose(ascale[0], n.pow(-0.4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ("lively", "eos"))
+@pytest.mark.parametrize("aname", sorted(ALL_CASES))
+def test_generate_all_vs_reference_outputs(gold, models, tag, aname):
+    renorm, use_vocab, per_token, scaler, tau, alpha = ALL_CASES[aname]
+    gt, vt = all_sets()
+    W = gt.shape[0]
+    with torch.inference_mode():
+        tok, pad, score = models(tag).generate_all(gold_embed()[:16].to(DEV), W, tau, alpha, vt.to(DEV) if use_vocab else None, per_token, scaler,
+                                                   gt.to(DEV), renorm)
+        tok10, pad10, score10 = models(tag).generate_all(gold_embed()[:16].to(DEV), 10, tau, alpha, vt.to(DEV) if use_vocab else None, per_token,
+                                                         scaler, gt.to(DEV), renorm)
+    tok, pad, score = tok.cpu(), pad.cpu(), score.cpu()
+    rs = gold[f"{tag}/all_{aname}/score"]
+    assert tok.shape[:2] == (16, W) and (score[:, :-1] >= score[:, 1:]).all()
+    assert torch.equal(tok10.cpu(), tok[:, :10]) and torch.equal(score10.cpu(), score[:, :10]) and torch.equal(pad10.cpu(), pad[:, :10])
+    fin = torch.isfinite(rs)
+    assert (torch.isfinite(score) == fin).all()                      # guide targets outside the vocabulary score -inf on both sides
+    tol = 0.06 / tau * 7                                             # |d logit| <= 0.06 per position, at most 7 positions (C = 7)
+    assert (score - rs)[fin].abs().max() <= tol                      # the whole ranking, rank by rank
+    # the top-10 sets agree up to near-ties: every returned target is a guide target, and most are the reference's
+    assert spells_a_guide_target(tok[:, :10].flatten(0, 1), pad[:, :10].flatten(0, 1), gt).all()
+    r10 = gold[f"{tag}/all_{aname}/tok10"]
+    agree = sum(len({tuple(r) for r in tok[b, :10].tolist()} & {tuple(r) for r in r10[b].tolist()}) for b in range(16))
+    assert agree >= 0.9 * 160
+    assert (tok[:, 0] == r10[:, 0]).all(dim=1).float().mean() >= 0.8
