@@ -77,6 +77,9 @@ typedef struct NovicGuide {
   int32_t num_nodes;
   int32_t num_edges;
   int32_t renorm;            /* guide_renorm: renormalise the scores over the allowed ids */
+  const float* child_bias;   /* optional [num_edges] fp32, beam search only: additive score of taking each edge - the
+                              * vocabulary prior -vocab_scaler * log p_vocab(token | prefix) of embedding_decoder.py:924-936
+                              * (-inf: no vocabulary noun continues that way).  NULL = no prior. */
 } NovicGuide;
 
 typedef struct NovicHandle NovicHandle;
@@ -108,7 +111,8 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
                           int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
                           int32_t* T_out, const NovicGuide* guide, void* ws, size_t ws_bytes, void* stream);
 
-/* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984), no vocab prior; guide = NULL: unguided.
+/* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984); guide = NULL: unguided, no vocabulary prior.
+ * With a vocabulary prior and no guide_targets the caller passes the vocabulary trie as the guide (renorm = 0) with child_bias set.
  *   Outputs (device): tok [B, H, G] int64, pad [B, H, G] u8, score [B, H] fp32 sorted descending. */
 int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H, float temperature,
                         float length_alpha, int64_t* tok, uint8_t* pad, float* score, int32_t* T_out, const NovicGuide* guide,

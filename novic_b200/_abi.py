@@ -45,7 +45,7 @@ class NovicNoiseCfg(C.Structure):
 
 class NovicGuide(C.Structure):
     _fields_ = [("child_off", _FP), ("child_tok", _FP), ("child_node", _FP), ("num_nodes", C.c_int32), ("num_edges", C.c_int32),
-                ("renorm", C.c_int32)]
+                ("renorm", C.c_int32), ("child_bias", _FP)]
 
 
 # name -> (restype, argtypes); every symbol include/novic_b200.h declares

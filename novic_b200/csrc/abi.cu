@@ -256,15 +256,17 @@ struct Workspace {
   long long* g_tok; unsigned char *g_pad, *g_done; float *g_score, *g_nll, *g_len, *g_score_out; int* flags;
   long long* b_tok[2]; unsigned char *b_pad[2], *b_anc[2], *b_fin[2]; float *b_score[2], *b_len[2], *b_norm;
   unsigned char *keypad, *effpad, *correct; long long* tgt_masked; float *nll_rows, *loss;
-  uint32_t* allow = nullptr; int allow_words = 0; int* g_node = nullptr; int* b_node[2] = {nullptr, nullptr};   // guided decoding
+  uint32_t* allow = nullptr; int allow_words = 0; int* allow_edge0 = nullptr; int* g_node = nullptr; int* b_node[2] = {nullptr, nullptr};   // guided decoding
   size_t bytes = 0;
 };
 
 struct GraphKey {
   int mode; int64_t B; int H; float tau, alpha; void* ws;
   const void* guide = nullptr; int guide_flags = 0;   // trie identity (child_off pointer) and renorm flag baked into the graph
+  const void* bias = nullptr;                         // vocabulary-prior edge scores baked into the graph
   bool operator<(const GraphKey& o) const {
-    return std::tie(mode, B, H, tau, alpha, ws, guide, guide_flags) < std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws, o.guide, o.guide_flags);
+    return std::tie(mode, B, H, tau, alpha, ws, guide, guide_flags, bias) <
+           std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws, o.guide, o.guide_flags, o.bias);
   }
 };
 
@@ -331,6 +333,7 @@ int plan_workspace(const NovicHandle* h, int64_t B, int H, int rps, char* base, 
   if (!tf) {
     w.allow_words = static_cast<int>(ceil_div(c.vocab_size, 32));
     w.allow = reinterpret_cast<uint32_t*>(P_(sizeof(uint32_t) * w.logit_rows * w.allow_words));
+    if (H > 1) w.allow_edge0 = reinterpret_cast<int*>(P_(sizeof(int) * w.logit_rows * w.allow_words));   // vocabulary prior (beam only)
     w.g_node = reinterpret_cast<int*>(P_(sizeof(int) * w.nseq));
     w.b_node[0] = w.g_node;
     w.b_node[1] = reinterpret_cast<int*>(P_(sizeof(int) * w.nseq));
@@ -530,24 +533,31 @@ struct GuideCfg {
   GuideTrie trie{nullptr, nullptr, nullptr, 0};
   bool on = false;
   bool renorm = false;
+  const float* bias = nullptr;   // per-edge additive score (vocabulary prior of the beam search); nullptr = none
 };
 
-template <int HCAP, bool MASKED>
+template <int HCAP, bool MASKED, bool BIAS = false>
 int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
-                  const long long* target, float inv_tau, int ban_eos, bool mask_lse, int allow_mod, cudaStream_t s) {
+                  const long long* target, float inv_tau, int ban_eos, bool mask_lse, int allow_mod, cudaStream_t s,
+                  const float* bias = nullptr) {
   CUtensorMap tm_a;
   if (make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
-  typename EpiLogits<HCAP, MASKED>::Params pl;
+  typename EpiLogits<HCAP, MASKED, BIAS>::Params pl;
+  pl.edge0 = ws.allow_edge0; pl.bias = bias; pl.tau = 1.0f / inv_tau;
   pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
   pl.n_valid = h->cfg.vocab_size; pl.nparts = ws.ntiles; pl.inv_tau = inv_tau; pl.ban_eos = ban_eos;
   pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
   pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.allow_mod = allow_mod; pl.mask_lse = mask_lse ? 1 : 0;
   KSpan t(kKLogits, s);
-  return launch_gemm<EpiLogits<HCAP, MASKED>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
+  return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
 }
 
 int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
                const long long* target, float inv_tau, int ban_eos, cudaStream_t s, const GuideCfg* g = nullptr, int allow_mod = 0) {
+  if (g != nullptr && g->on && g->bias != nullptr) {
+    if (ws.hcap == 4) return launch_logits<4, true, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s, g->bias);
+    return launch_logits<16, true, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s, g->bias);
+  }
   if (g != nullptr && g->on) {
     switch (ws.hcap) {
       case 0: return launch_logits<0, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
@@ -566,7 +576,7 @@ int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int 
 int launch_guide_mask(const Workspace& ws, const GuideCfg& g, const int* node, int node_stride, int rows, cudaStream_t s) {
   const size_t smem = sizeof(uint32_t) * kWarpsPerBlock * ws.allow_words;
   CUDA_TRY(launch_k(guide_mask_kernel, dim3(static_cast<unsigned>(ceil_div(rows, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), smem, s,
-                    g.trie, node, node_stride, rows, ws.allow_words, ws.allow));
+                    g.trie, node, node_stride, rows, ws.allow_words, ws.allow, g.bias != nullptr ? ws.allow_edge0 : static_cast<int*>(nullptr)));
   ++g_launches;
   return 0;
 }
@@ -784,7 +794,8 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (set_gemm_attr<EpiQKV, kStagesQKV>() || set_gemm_attr<EpiGelu, kStagesGelu>() || set_rowln_attr() ||
       set_gemm_attr<EpiLogits<0>, kStagesLogits>() || set_gemm_attr<EpiLogits<4>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
+      set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
+      set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
       set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
     return 1;
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 6 * kAttnBwdMaxS * kAttnBwdStride * 4));
@@ -957,6 +968,7 @@ static int make_guide(const NovicGuide* guide, const NovicHandle* h, GuideCfg* o
   out->trie = GuideTrie{guide->child_off, guide->child_tok, guide->child_node, guide->num_nodes};
   out->on = true;
   out->renorm = guide->renorm != 0;
+  out->bias = guide->child_bias;
   return 0;
 }
 
@@ -966,6 +978,7 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
   if (check_ready(h)) return 1;
   GuideCfg gcfg;
   if (make_guide(guide, h, &gcfg)) return 1;
+  if (gcfg.bias != nullptr) return fail("child_bias (vocabulary prior) applies to novic_generate_beam only");
   if (B < 1 || B > (1 << 24)) return fail("batch size out of range");
   if (!(temperature > 0.f)) return fail("temperature must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1023,7 +1036,7 @@ int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H
   for (int i = 0; i < cp.n; ++i)
     CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
   GraphKey key{1, B, H * 16 + cp.n, temperature, length_alpha, wsbuf, gcfg.on ? static_cast<const void*>(gcfg.trie.child_off) : nullptr,
-               (gcfg.on ? 1 : 0) | (gcfg.renorm ? 2 : 0)};
+               (gcfg.on ? 1 : 0) | (gcfg.renorm ? 2 : 0), gcfg.bias};
   if (run_maybe_graph(h, key, true, s, [&](cudaStream_t cs) {
         return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) { return enqueue_beam(h, cp.ws[i], temperature, length_alpha, gcfg, st); });
       }))
@@ -1107,6 +1120,7 @@ int novic_score_targets(NovicHandle* h, const float* embed, int64_t B, int32_t M
   if (!(temperature > 0.f)) return fail("temperature must be positive");
   GuideCfg gcfg;
   if (make_guide(guide, h, &gcfg)) return 1;
+  if (gcfg.bias != nullptr) return fail("child_bias (vocabulary prior) applies to novic_generate_beam only");
   const bool masked = gcfg.on && gcfg.renorm;   // without renormalisation the guide does not change a given target's score
   gcfg.on = masked;
   const int64_t A = B * M;

@@ -171,7 +171,11 @@ constexpr int kLogitSlice = kEpiCols;     // columns per epilogue thread
 // MASKED = guided decoding (embedding_decoder.py:806-810, :915-920, :942-943): `allow` holds one bit per (row, vocabulary id);
 // only allowed ids can be selected (best / top-H), and with mask_lse (guide_renorm) the temperature log-sum-exp runs over
 // the allowed ids only.  The tau = 1 log-sum-exp (cross-entropy of the raw logits) and the optional logits copy are never masked.
-template <int HCAP, bool MASKED = false>
+// BIAS (beam search with a vocabulary prior, embedding_decoder.py:924-936; implies MASKED): every allowed id is a trie edge with
+// an additive score; the top-H lists rank and store  logit + tau * bias  so that the selection kernel's
+// (value / tau - logsumexp) is the reference's  log_softmax - vocab_scaler * log p_vocab.  `edge0` names the edge of the lowest
+// allowed id of each 32-id mask word; the others follow in id order.
+template <int HCAP, bool MASKED = false, bool BIAS = false>
 struct EpiLogits {
   struct Params {
     float* logits;              // optional [M, ld_logits] fp32
@@ -189,6 +193,9 @@ struct EpiLogits {
     int allow_ld;
     int allow_mod;              // MASKED: mask row = row % allow_mod when > 0 (teacher forcing: masks shared by all embeddings)
     int mask_lse;               // MASKED: renormalise the temperature softmax over the allowed ids
+    const int* edge0;           // BIAS: [M, allow_ld] trie edge of the lowest allowed id of each mask word
+    const float* bias;          // BIAS: [num_edges]
+    float tau;
   };
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
@@ -284,10 +291,15 @@ struct EpiLogits {
         }
         if (cm > best) { best = cm; best_i = col0 + ci; }
         if (HCAP > 0) {
+          const float* eb = nullptr;
+          if (BIAS && bits != 0u) eb = p.bias + p.edge0[static_cast<size_t>(mrow) * p.allow_ld + (col0 >> 5)];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (((sel >> j) & 1u) && v[j] > tv[HCAP > 0 ? HCAP - 1 : 0]) {
-              float cv = v[j]; int cidx = col0 + j;
+            if (!((sel >> j) & 1u)) continue;
+            float key = v[j];
+            if (BIAS) key = fmaf(eb[__popc(bits & ((1u << j) - 1u))], p.tau, key);
+            if (key > tv[HCAP > 0 ? HCAP - 1 : 0]) {
+              float cv = key; int cidx = col0 + j;
 #pragma unroll
               for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i)
                 if (cv > tv[i]) { const float tf = tv[i]; const int tI = ti[i]; tv[i] = cv; ti[i] = cidx; cv = tf; cidx = tI; }

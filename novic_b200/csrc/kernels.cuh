@@ -599,7 +599,8 @@ __device__ __forceinline__ int guide_child(const GuideTrie& g, int node, int tok
 
 // allow[row, :] = bit set of the children tokens of node[row * node_stride].  One warp per row, bits assembled in shared memory.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-guide_mask_kernel(GuideTrie g, const int* __restrict__ node, int node_stride, int rows, int words, uint32_t* __restrict__ allow) {
+guide_mask_kernel(GuideTrie g, const int* __restrict__ node, int node_stride, int rows, int words, uint32_t* __restrict__ allow,
+                  int* __restrict__ edge0) {
   extern __shared__ uint32_t gm_smem[];
   pdl_trigger();
   pdl_wait();
@@ -615,6 +616,8 @@ guide_mask_kernel(GuideTrie g, const int* __restrict__ node, int node_stride, in
     for (int e = e0 + lane; e < e1; e += 32) {
       const int t = g.child_tok[e];
       atomicOr(&bits[t >> 5], 1u << (t & 31));
+      // vocabulary prior: the logits epilogue finds an allowed id's edge as edge0[word] + (allowed ids below it in the word)
+      if (edge0 != nullptr && (e == e0 || (g.child_tok[e - 1] >> 5) != (t >> 5))) edge0[static_cast<size_t>(row) * words + (t >> 5)] = e;
     }
   }
   __syncwarp();
@@ -711,7 +714,7 @@ select_greedy_kernel(const LogitPartial* __restrict__ part, int ntiles, int B, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Beam step (embedding_decoder.py:911-978, unguided, no vocab prior).  One warp per sample.  Every live
+// Beam step (embedding_decoder.py:911-978; guide masks and the vocabulary prior are already folded into the top lists).  One warp per sample.  Every live
 // candidate row contributes its per-tile top-HCAP logits (the H best continuations of a row are among the
 // union of its tiles' H best); a finished candidate contributes exactly (its score, end token).  The H best
 // totals are drawn in (score descending, flat index ascending) order.

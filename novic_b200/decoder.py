@@ -475,6 +475,28 @@ class PrefixedIterDecoder(EmbeddingDecoder):
             self._trie_cache = guide.TrieCache()
         return self._trie_cache.get(guide_targets, self.target_config.token_length - 1, self.target_config.vocab_size, device)
 
+    def _vocab_prior(self, guide_targets, vocab_targets, per_token, scaler, device):
+        """(trie, per-edge prior scores) of a beam search with a vocabulary prior (embedding_decoder.py:881-891, :924-936), cached
+        per (guide tensor, vocabulary tensor, mode, scaler)."""
+        assert vocab_targets.ndim == 2 and vocab_targets.dtype == self.target_config.token_dtype
+        if not hasattr(self, "_prior_cache"):
+            self._prior_cache = []
+        ident = lambda t: None if t is None else (t.data_ptr(), tuple(t.shape), guide.tensor_version(t), str(t.device))  # noqa: E731
+        key = (ident(guide_targets), ident(vocab_targets), per_token, scaler, str(device))
+        for k, v in self._prior_cache:
+            if k == key:
+                return v
+        G, V = self.target_config.token_length - 1, self.target_config.vocab_size
+        is_guide = guide_targets is not None and (vocab_targets is guide_targets or (
+            vocab_targets.shape == guide_targets.shape and bool(torch.equal(vocab_targets, guide_targets))))     # :885
+        gtrie = None if guide_targets is None else guide.build_trie(guide_targets, G, V)
+        trie, bias = guide.prior_bias(gtrie, vocab_targets, is_guide, per_token, scaler, G, V)
+        value = (trie.to(device), bias.to(device))
+        self._prior_cache.append((key, value))
+        if len(self._prior_cache) > 4:
+            self._prior_cache.pop(0)
+        return value
+
     def generate(self, embed, collect_logits, calc_loss, temperature, length_alpha, sample_weight, guide_targets, guide_renorm):
         if not temperature > 0:
             raise ValueError("temperature must be positive")
@@ -523,8 +545,9 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     # generate_beam (embedding_decoder.py:852-984)
     # ------------------------------------------------------------------------------------------------------
     def generate_beam(self, embed, topk, temperature, length_alpha, vocab_targets, vocab_per_token, vocab_scaler, guide_targets, guide_renorm):
-        if vocab_targets is not None and vocab_scaler != 0:
-            raise NotImplementedError("vocabulary-prior scoring (embedding_decoder.py:924-936) is not implemented in novic_b200 yet")
+        vocab_on = vocab_targets is not None and vocab_scaler != 0                       # :881
+        if vocab_on and vocab_scaler < 0:
+            raise ValueError("vocab_scaler must be >= 0: a negative scaler gives +inf scores to ids outside the vocabulary (:934-936)")
         if not temperature > 0:
             raise ValueError("temperature must be positive")
         embed = self._check_embed(embed)
@@ -532,6 +555,8 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         H = int(topk)
         dev = embed.device
         G = self.target_config.token_length - 1
+        if H == 1 and vocab_on:
+            raise NotImplementedError("a beam of one with a vocabulary prior is not implemented in novic_b200 (use topk >= 2)")
         if H == 1:
             # a beam of one is the greedy path; scores coincide (sum of log-probs, length-normalised)
             t, p, _, _, _, s = self.generate(embed, False, True, temperature, length_alpha, None, guide_targets, guide_renorm)
@@ -545,8 +570,12 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         T = 0
         chunk = max(1, min(B, MAX_SEQS_PER_CALL // H))
         ws = self._workspace(st, dev, chunk, H, 0)
-        trie = self._guide_trie(guide_targets, dev)
-        garg = guide.guide_arg(trie, bool(guide_renorm))
+        if vocab_on:
+            trie, bias = self._vocab_prior(guide_targets, vocab_targets, bool(vocab_per_token), float(vocab_scaler), dev)
+            garg = guide.guide_arg(trie, bool(guide_renorm) and guide_targets is not None, bias)
+        else:
+            trie = self._guide_trie(guide_targets, dev)
+            garg = guide.guide_arg(trie, bool(guide_renorm))
         with torch.cuda.device(dev):
             for b0 in range(0, B, chunk):
                 n = min(chunk, B - b0)

@@ -35,9 +35,11 @@ class GuideTrie:
         return GuideTrie(self.child_off.to(device), self.child_tok.to(device), self.child_node.to(device), self.num_nodes, self.num_edges,
                          self.depth, self.child_count, self.node_count)
 
-    def as_struct(self, renorm: bool) -> _abi.NovicGuide:
+    def as_struct(self, renorm: bool, bias: torch.Tensor = None) -> _abi.NovicGuide:
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() == self.num_edges and bias.device == self.child_off.device
         return _abi.NovicGuide(self.child_off.data_ptr(), self.child_tok.data_ptr(), self.child_node.data_ptr(), self.num_nodes,
-                               self.num_edges, 1 if renorm else 0)
+                               self.num_edges, 1 if renorm else 0, None if bias is None else bias.data_ptr())
 
 
 def build_trie(guide_targets: torch.Tensor, gen_len: int, vocab_size: int) -> GuideTrie:
@@ -120,6 +122,65 @@ def vocab_prior_scores(targets: torch.Tensor, paddings: torch.Tensor, vocab_targ
     return torch.from_numpy(total.astype(np.float32))
 
 
+def _edge_logp(trie: GuideTrie, per_token: bool) -> np.ndarray:
+    """log p(child | node) for every edge of a trie: uniform over the node's distinct continuations (per_token), else the
+    fraction of the node's targets that take the edge (embedding_decoder.py:926-933)."""
+    off = trie.child_off.numpy().astype(np.int64)
+    parent = np.repeat(np.arange(trie.num_nodes, dtype=np.int64), np.diff(off))
+    if per_token:
+        p = 1.0 / np.diff(off)[parent].astype(np.float64)
+    else:
+        p = trie.child_count.numpy().astype(np.float64) / trie.node_count.numpy().astype(np.float64)[parent]
+    return np.log(p)
+
+
+def prior_bias(guide_trie, vocab_targets: torch.Tensor, vocab_is_guide: bool, per_token: bool, scaler: float, gen_len: int,
+               vocab_size: int):
+    """Vocabulary prior of the beam search (embedding_decoder.py:924-936) as one additive term per trie edge:
+    -scaler * log p_vocab(token | prefix), or -inf for a continuation no vocabulary noun takes.  Returns (trie, bias[num_edges]):
+    the guide trie when decoding is guided (its edges looked up in the vocabulary trie along the same prefixes), else the
+    vocabulary trie itself - without a guide the prior alone restricts decoding to the vocabulary nouns."""
+    if guide_trie is None or vocab_is_guide:
+        trie = guide_trie if guide_trie is not None else build_trie(vocab_targets, gen_len, vocab_size)
+        return trie, torch.from_numpy((-scaler * _edge_logp(trie, per_token)).astype(np.float32))
+    vt = build_trie(vocab_targets, gen_len, vocab_size)
+    v_off = vt.child_off.numpy().astype(np.int64)
+    v_keys = np.repeat(np.arange(vt.num_nodes, dtype=np.int64), np.diff(v_off)) * vocab_size + vt.child_tok.numpy().astype(np.int64)
+    v_child = vt.child_node.numpy().astype(np.int64)
+    v_logp = _edge_logp(vt, per_token)
+    g_off = guide_trie.child_off.numpy().astype(np.int64)
+    g_parent = np.repeat(np.arange(guide_trie.num_nodes, dtype=np.int64), np.diff(g_off))
+    g_tok = guide_trie.child_tok.numpy().astype(np.int64)
+    g_child = guide_trie.child_node.numpy().astype(np.int64)
+    vmap = np.full(guide_trie.num_nodes, -1, dtype=np.int64)    # guide node -> vocabulary node with the same prefix
+    vmap[0] = 0
+    logp = np.full(guide_trie.num_edges, -np.inf)
+    # walk both tries level by level: the vocabulary node of a guide node's prefix, and the prior of every guide edge
+    depth = np.zeros(guide_trie.num_nodes, dtype=np.int64)      # node depth: parents precede children, one relaxation per level
+    for _ in range(guide_trie.depth):
+        depth[g_child] = depth[g_parent] + 1
+    for d in range(guide_trie.depth):
+        es = np.nonzero(depth[g_parent] == d)[0]
+        if es.size == 0:
+            continue
+        vp = vmap[g_parent[es]]
+        q = np.where(vp >= 0, vp, 0) * vocab_size + g_tok[es]
+        idx = np.minimum(np.searchsorted(v_keys, q), len(v_keys) - 1) if len(v_keys) else np.zeros(es.size, dtype=np.int64)
+        found = (vp >= 0) & (len(v_keys) > 0) & (v_keys[idx] == q)
+        vmap[g_child[es]] = np.where(found, v_child[idx], -1)
+        logp[es] = np.where(found, v_logp[idx], -np.inf)
+    with np.errstate(invalid="ignore"):
+        bias = np.where(np.isfinite(logp), -scaler * logp, -np.inf)
+    return guide_trie, torch.from_numpy(bias.astype(np.float32))
+
+
+def tensor_version(t: torch.Tensor) -> int:
+    try:
+        return t._version
+    except RuntimeError:                # inference tensors do not track versions; they cannot be modified in place either
+        return -1
+
+
 class TrieCache:
     """Tries keyed by the identity and version of the guide tensor (infer.py hands the same tensor to every batch)."""
 
@@ -128,10 +189,7 @@ class TrieCache:
         self.max_entries = max_entries
 
     def get(self, guide_targets: torch.Tensor, gen_len: int, vocab_size: int, device) -> GuideTrie:
-        try:
-            version = guide_targets._version
-        except RuntimeError:            # inference tensors do not track versions; they cannot be modified in place either
-            version = -1
+        version = tensor_version(guide_targets)
         key = (guide_targets.data_ptr(), tuple(guide_targets.shape), version, str(guide_targets.device), str(device), gen_len, vocab_size)
         for k, trie in self.entries:
             if k == key:
@@ -143,6 +201,6 @@ class TrieCache:
         return trie
 
 
-def guide_arg(trie, renorm: bool):
+def guide_arg(trie, renorm: bool, bias: torch.Tensor = None):
     """ctypes argument for the `const NovicGuide*` parameter (None = unguided)."""
-    return None if trie is None else C.byref(trie.as_struct(renorm))
+    return None if trie is None else C.byref(trie.as_struct(renorm, bias))

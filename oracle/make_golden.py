@@ -110,6 +110,18 @@ def main():
                         out[f"{tag}/{gname}/beam{H}_{rname}/tok"] = t.numpy()
                         out[f"{tag}/{gname}/beam{H}_{rname}/pad"] = p.numpy()
                         out[f"{tag}/{gname}/beam{H}_{rname}/score"] = sc.numpy()
+            # beam search with a vocabulary prior (embedding_decoder.py:881-891, :924-936): vocabulary alone, vocabulary = guide,
+            # vocabulary != guide (shares 250 nouns with it); counts and per-token modes
+            gt = synth.synth_guide_targets(400, dims, seed=21, first_pool=24)
+            vt = torch.cat((gt[:250], synth.synth_guide_targets(200, dims, seed=25, first_pool=24)))
+            for vname, H, g, v, per_token, scaler, renorm, tau, alpha in (
+                    ("vonly_c", 3, None, vt, False, 0.6, False, 1.0, 0.0), ("vonly_t", 10, None, vt, True, 0.4, False, 0.9, 0.3),
+                    ("vguide_c", 10, gt, gt, False, 0.5, False, 1.0, 0.0), ("vguide_t", 3, gt, gt.clone(), True, 0.8, True, 1.0, 0.0),
+                    ("vdiff_c", 10, gt, vt, False, 0.5, True, 1.0, 0.0), ("vdiff_t", 3, gt, vt, True, 0.3, False, 1.2, 0.5)):
+                t, p, sc = model.generate_beam(embed, H, tau, alpha, v, per_token, scaler, g, renorm)
+                out[f"{tag}/{vname}/tok"] = t.numpy()
+                out[f"{tag}/{vname}/pad"] = p.numpy()
+                out[f"{tag}/{vname}/score"] = sc.numpy()
             # generate_all (embedding_decoder.py:986-1079): all guide targets scored by teacher forcing; K = W keeps the whole ranking
             if tag != "eosall":
                 gt = synth.synth_guide_targets(200, dims, seed=23, first_pool=24)

@@ -286,7 +286,8 @@ def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: 
 
 def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temperature: float = 1.0,
                   length_alpha: float = 0.0, early_exit: bool = True, guide_targets: Optional[torch.Tensor] = None,
-                  guide_renorm: bool = False):
+                  guide_renorm: bool = False, vocab_targets: Optional[torch.Tensor] = None, vocab_per_token: bool = False,
+                  vocab_scaler: float = 0.0):
     """Returns dict(target B x H x T, padding B x H x T, score B x H sorted descending, margin B).
 
     `margin` is test metadata, not part of the reference's outputs: per sample, the smallest gap seen at any step
@@ -309,6 +310,12 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
     if guide_targets is not None:                                             # :873-878
         guide_mask = torch.ones(B, H, guide_targets.shape[0], dtype=torch.bool)
         guide_mask[:, 0, :] = False
+    vocab_on = vocab_targets is not None and vocab_scaler != 0                # :880-891
+    vocab_is_guide = vocab_on and guide_targets is not None and (vocab_targets is guide_targets or torch.equal(vocab_targets, guide_targets))
+    vocab_mask = None
+    if vocab_on and not vocab_is_guide:
+        vocab_mask = torch.ones(B, H, vocab_targets.shape[0], dtype=torch.bool)
+        vocab_mask[:, 0, :] = False
     for c in range(1, G + 1):
         cur_tok = tok[:, :, :c].reshape(B * H, c)
         cur_pad = pad[:, :, :c].reshape(B * H, c)
@@ -322,7 +329,23 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
             gs[:, :, :1] = gs[:, :, :1].masked_fill(finished, 0.0)                        # :918
             if guide_renorm:
                 logits = logits + gs                                                        # :920
-        cand = torch.log_softmax(logits, dim=2) + score.unsqueeze(2)        # :922, :938
+        cand = torch.log_softmax(logits, dim=2)                             # :922
+        if vocab_on:                                                        # :924-936: divide out the vocabulary prior
+            if vocab_is_guide:
+                vidx = guide_targets[:, c - 1].expand(B, H, -1).masked_fill(guide_mask, V)
+            else:
+                vidx = vocab_targets[:, c - 1].expand(B, H, -1).masked_fill(vocab_mask, V)
+            Z = vidx.shape[2]
+            if vocab_per_token:
+                vp = torch.zeros(B, H, V + 1, dtype=dtype).scatter_(2, vidx, 1.0)[:, :, :-1]
+                vp = vp / vp.sum(dim=2, keepdim=True)
+            else:
+                cnt = torch.zeros(B, H, V + 1, dtype=dtype).scatter_add_(2, vidx, torch.ones(B, H, Z, dtype=dtype))
+                vp = cnt[:, :, :-1] / (Z - cnt[:, :, -1:])
+            vlp = vp.log().nan_to_num(nan=float("inf"), neginf=float("inf"), posinf=float("inf"))
+            vlp[:, :, :1] = vlp[:, :, :1].masked_fill(finished, 0.0)
+            cand = cand - vocab_scaler * vlp
+        cand = cand + score.unsqueeze(2)                                    # :938
         if c == 1:
             cand[:, 0, 0] = NEG_INF                                         # :940
         if gs is not None and not guide_renorm:
@@ -357,6 +380,9 @@ def generate_beam(cfg: OracleCfg, sd: dict, embed: torch.Tensor, topk: int, temp
             if guide_targets is not None:                                         # :969-971
                 guide_mask = guide_mask.gather(1, gather_idx.expand(-1, -1, guide_mask.shape[2])) | \
                     (new_tok.unsqueeze(2) != guide_targets[:, c - 1].view(1, 1, -1))
+            if vocab_mask is not None:                                            # :972-975
+                vocab_mask = vocab_mask.gather(1, gather_idx.expand(-1, -1, vocab_mask.shape[2])) | \
+                    (new_tok.unsqueeze(2) != vocab_targets[:, c - 1].view(1, 1, -1))
             if length_alpha != 0:
                 seq_len = seq_len.gather(1, parent) + (~nxt_pad).to(dtype)        # :978
     tok = tok[:, :, :T].clone()

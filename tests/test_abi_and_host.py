@@ -111,12 +111,14 @@ def test_unsupported_features_raise_not_fallback():
     model = novic_b200.default_decoder()
     e = synth.synth_embeddings(2)
     guide = torch.zeros(3, 16, dtype=torch.int64)
-    with pytest.raises(NotImplementedError):   # vocabulary-prior scoring (embedding_decoder.py:924-936)
-        model.generate_beam(e, 3, 1.0, 0.0, guide, False, 0.5, None, False)
-    with pytest.raises(NotImplementedError):   # generate_all (embedding_decoder.py:986-1079)
-        model.generate_all(e, 3, 1.0, 0.0, None, False, 0.0, guide, False)
+    with pytest.raises(NotImplementedError):   # a beam of one with a vocabulary prior is the one unsupported corner of generate_beam
+        model.generate_beam(e, 1, 1.0, 0.0, guide, False, 0.5, None, False)
+    with pytest.raises(ValueError):            # negative prior scaler: +inf scores outside the vocabulary in the reference
+        model.generate_beam(e, 3, 1.0, 0.0, guide, False, -0.5, None, False)
     with pytest.raises(ValueError):
         model.generate(e, False, True, 0.0, 0.0, None, None, False)
+    with pytest.raises(RuntimeError, match="no CPU path"):   # everything else computes on the GPU or raises
+        model.generate_beam(e, 3, 1.0, 0.0, guide, False, 0.5, None, False)
 
 
 @pytest.mark.reference
