@@ -80,10 +80,33 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, in
   return 0;
 }
 
+// The same matrix as a 3-D map (64 columns, rows, k-blocks): a box of [64, box_rows, kbs] is kbs consecutive k-block tiles in the
+// K-major 128B-swizzled operand layout, fetched by ONE request (gemm_kernel<..., KBS>).  cols must be a multiple of 64 * kbs.
+int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int kbs) {
+  if (load_driver_entry()) return 1;
+  if (cols % (kBlockK * kbs) != 0) return fail("3-D TMA operand: K = %lld is not a multiple of %d", (long long)cols, kBlockK * kbs);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA operand base is not 16-byte aligned");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(kBlockK), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / kBlockK)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(kBlockK) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(kbs)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows=%lld cols=%lld box_rows=%d kbs=%d)", (int)r,
+                                     (long long)rows, (long long)cols, box_rows, kbs);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
+int g_row_stages = 4;                          // NOVIC_ROW_STAGES=2|3: shallower row-kernel pipelines (tuning: co-residency with the next kernel)
+bool g_split_ffn = true;                       // NOVIC_SPLIT_FFN=0: every CTA of a cluster recomputes the whole hidden tile
+bool g_early_b = true;                         // NOVIC_EARLY_B=0: no weight-tile requests before griddepcontrol.wait
+bool g_wide_gemm = true;                       // NOVIC_WIDE_GEMM=0: the 16 KB-request pipeline (5 stages of one k-block)
+constexpr int kWideKbs = 2, kWideStages = 3;   // decode-path QKV / logits GEMMs: 3 stages of 2 k-blocks, 32 KB TMA requests
 int g_num_sms = 148;
 int g_grid_div = 1;   // persistent grids are divided by the number of concurrent chains so that chains co-run on disjoint SMs
 constexpr int kLogitBN = kTileN;
@@ -92,8 +115,11 @@ constexpr int kLogitBN = kTileN;
 // (barrier init, TMEM allocation, descriptor prefetch, weight-tile loads) while the previous kernel drains; each kernel
 // executes griddepcontrol.wait before it touches anything a predecessor produced.
 bool g_use_pdl = true;
+int g_cur_class = 9;           // KClass of the launches that follow (set by KSpan); 9 = kKMisc
+unsigned g_skip_classes = 0;   // diagnostic (NOVIC_SKIP_CLASSES, tools/ablate.py): bit k set = launches of kernel class k are dropped
 template <class... KArgs, class... Args>
 cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  if ((g_skip_classes >> g_cur_class) & 1u) return cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -103,19 +129,22 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-template <class Epi, int STAGES>
+template <class Epi, int STAGES, int KBS = 1>
 int set_gemm_attr() {
-  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES)));
+  static_assert(gemm_persistent_smem_bytes(STAGES, KBS) <= 227 * 1024, "GEMM pipeline does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES, KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES, KBS)));
   return 0;
 }
 
-template <class Epi, int STAGES>
+// KBS > 1: ta / tb are 3-D maps (make_tmap3 with kbs = KBS), K a multiple of 64 * KBS, no split-K.
+template <class Epi, int STAGES, int KBS = 1>
 int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
-                const typename Epi::Params& ep, int k_splits = 1) {
+                const typename Epi::Params& ep, int k_splits = 1, bool b_is_static = false) {
   const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
   const int64_t total = n_tiles * ceil_div(M, kBlockM) * k_splits;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
-  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, ep));
+  if (KBS > 1 && (k_splits != 1 || K % (kBlockK * KBS) != 0)) return fail("wide-stage GEMM needs K %% %d == 0 and no split-K", kBlockK * KBS);
+  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, KBS>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES, KBS), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, b_is_static ? 1 : 0, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -124,22 +153,33 @@ int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, in
 int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(3, false)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(3, true)));
   return 0;
 }
 
 // N must be a multiple of 512: every 4 consecutive 128-column tiles form one cluster = one full residual row.
 int launch_rowln(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const RowParams& ep) {
   dim3 grid(static_cast<unsigned>(N / kRowBN), static_cast<unsigned>(ceil_div(M, kBlockM)));
-  CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, false>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, false), s, ta, tb, tb, M, K / kBlockK, ep));
+  if (g_row_stages == 2) CUDA_TRY(launch_k(gemm_rowln_kernel<2, false>, grid, dim3(kRowThreads), rowln_smem_bytes(2, false), s, ta, tb, tb, M, K / kBlockK, ep));
+  else if (g_row_stages == 3) CUDA_TRY(launch_k(gemm_rowln_kernel<3, false>, grid, dim3(kRowThreads), rowln_smem_bytes(3, false), s, ta, tb, tb, M, K / kBlockK, ep));
+  else CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, false>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, false), s, ta, tb, tb, M, K / kBlockK, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 // Whole feed-forward block: x += W2 * gelu(W1 * xn), then LayerNorm.  ta = LN2(x) rows, tw1 = linear1 [128, 512], tw2 = linear2 [512, 128].
-int launch_ffn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw1, const CUtensorMap& tw2, int M, const RowParams& ep) {
+// split_h: tw1 has a 32-row box and every CTA of a cluster computes a quarter of the hidden tile (gemm_rowln_kernel<., 2>).
+int launch_ffn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw1, const CUtensorMap& tw2, int M, const RowParams& ep, bool split_h = false) {
   dim3 grid(static_cast<unsigned>(kE / kRowBN), static_cast<unsigned>(ceil_div(M, kBlockM)));
-  CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, true>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
+  if (split_h && g_row_stages == 2) CUDA_TRY(launch_k(gemm_rowln_kernel<2, 2>, grid, dim3(kRowThreads), rowln_smem_bytes(2, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
+  else if (split_h && g_row_stages == 3) CUDA_TRY(launch_k(gemm_rowln_kernel<3, 2>, grid, dim3(kRowThreads), rowln_smem_bytes(3, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
+  else if (split_h) CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, 2>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
+  else CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, true>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -200,7 +240,7 @@ struct KTiming {
   std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> spans;
 };
 KTiming g_timing;
-int g_cur_class = kKMisc;
+static_assert(kKMisc == 9, "g_cur_class initialiser");
 
 struct KSpan {
   cudaEvent_t a = nullptr, b = nullptr;
@@ -239,6 +279,8 @@ struct WeightPtrs {
   const __nv_bfloat16 *embed_mlp, *tok;
   const __nv_bfloat16 *in_proj[NOVIC_MAX_LAYERS], *out_proj[NOVIC_MAX_LAYERS], *linear1[NOVIC_MAX_LAYERS], *linear2[NOVIC_MAX_LAYERS];
   const float *tok_f32, *pos, *final_norm, *norm1[NOVIC_MAX_LAYERS], *norm2[NOVIC_MAX_LAYERS];
+  CUtensorMap tm_linear1_q[NOVIC_MAX_LAYERS];            // linear1 with a 32-row box (split-hidden feed-forward kernel)
+  CUtensorMap tm_tok3, tm_in_proj3[NOVIC_MAX_LAYERS];   // 3-D maps (kWideKbs k-blocks per request) for the wide-stage decode GEMMs
   CUtensorMap tm_embed_mlp, tm_tok, tm_in_proj[NOVIC_MAX_LAYERS], tm_out_proj[NOVIC_MAX_LAYERS], tm_linear1[NOVIC_MAX_LAYERS],
       tm_linear2[NOVIC_MAX_LAYERS];
   // transposed bf16 copies (B operands of the backward dgrad GEMMs: dX = dY * W needs W^T in K-major form)
@@ -404,6 +446,10 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
       case 2: CUDA_TRY(go(attention_stream_kernel_t<16, 2, 6>, 16, 2, 6)); break;
       case 3: CUDA_TRY(go(attention_stream_kernel_t<8, 3, 8>, 8, 3, 8)); break;
       case 4: CUDA_TRY(go(attention_stream_kernel_t<24, 2, 4>, 24, 2, 4)); break;
+      case 5: CUDA_TRY(go(attention_stream_kernel_t<14, 3, 4>, 14, 3, 4)); break;   // 28 sequences per CTA = 2 per warp exactly
+      case 6: CUDA_TRY(go(attention_stream_kernel_t<14, 4, 4>, 14, 4, 4)); break;
+      case 7: CUDA_TRY(go(attention_stream_kernel_t<28, 2, 4>, 28, 2, 4)); break;   // one sequence per warp
+      case 8: CUDA_TRY(go(attention_stream_kernel_t<16, 2, 4>, 16, 2, 4)); break;   // 128 KB: can share an SM with a 2-stage row kernel
       default: CUDA_TRY(go(attention_stream_kernel_t<16, 3, 4>, 16, 3, 4)); break;
     }
   } else if (h->attn_v1) {
@@ -474,12 +520,20 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   if (make_tmap(&tm_xn, ws.xn, M, kE, kBlockM)) return 1;
   if (make_tmap(&tm_ao, ws.ao, M, kE, kBlockM)) return 1;
   if (make_tmap(&tm_hb, ws.hb, M, c.ffn_dim, kBlockM)) return 1;
+  CUtensorMap tm_xn3;
+  if (make_tmap3(&tm_xn3, ws.xn, M, kE, kBlockM, kWideKbs)) return 1;
   const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
   for (int l = 0; l < L; ++l) {
     __nv_bfloat16* kc = ws.kv + (static_cast<size_t>(l) * 2 + 0) * kv_layer;
     __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
     EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S};
-    { KSpan t(kKQkv, s); if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq)) return 1; }
+    if (g_wide_gemm) {
+      KSpan t(kKQkv, s);
+      if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+    } else {
+      KSpan t(kKQkv, s);
+      if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+    }
     if (launch_attention(h, ws, pc, l, s)) return 1;
     RowParams po{};
     po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
@@ -498,7 +552,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       // every CTA of a cluster reads its whole 128-row A tile before any of them writes (the writes come after two
       // cluster barriers that follow the last MMA), and different clusters own different rows.
       KSpan t(kKFfn2, s);
-      if (launch_ffn(s, tm_xn, h->w.tm_linear1[l], h->w.tm_linear2[l], M, pf)) return 1;
+      if (launch_ffn(s, tm_xn, g_split_ffn ? h->w.tm_linear1_q[l] : h->w.tm_linear1[l], h->w.tm_linear2[l], M, pf, g_split_ffn)) return 1;
     } else {
       EpiGelu::Params pg{ws.hb, c.ffn_dim};
       { KSpan t(kKFfn1, s); if (launch_gemm<EpiGelu, kStagesGelu>(s, tm_xn, h->w.tm_linear1[l], M, c.ffn_dim, kE, pg)) return 1; }
@@ -541,7 +595,7 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
                   const long long* target, float inv_tau, int ban_eos, bool mask_lse, int allow_mod, cudaStream_t s,
                   const float* bias = nullptr) {
   CUtensorMap tm_a;
-  if (make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
+  if (g_wide_gemm ? make_tmap3(&tm_a, a, M, kE, kBlockM, kWideKbs) : make_tmap(&tm_a, a, M, kE, kBlockM)) return 1;
   typename EpiLogits<HCAP, MASKED, BIAS>::Params pl;
   pl.edge0 = ws.allow_edge0; pl.bias = bias; pl.tau = 1.0f / inv_tau;
   pl.logits = logits; pl.ld_logits = ld_logits; pl.part = ws.part; pl.topv = ws.topv; pl.topi = ws.topi; pl.target = target;
@@ -549,7 +603,8 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
   pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
   pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.allow_mod = allow_mod; pl.mask_lse = mask_lse ? 1 : 0;
   KSpan t(kKLogits, s);
-  return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl);
+  if (g_wide_gemm) return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kWideStages, kWideKbs>(s, tm_a, h->w.tm_tok3, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
+  return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
 }
 
 int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int M, float* logits, long long ld_logits,
@@ -795,7 +850,12 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<0>, kStagesLogits>() || set_gemm_attr<EpiLogits<4>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
+      set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiLogits<0>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<4>, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiLogits<16>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<0, true>, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiLogits<4, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<16, true>, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiLogits<4, true, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<16, true, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
       set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
     return 1;
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 6 * kAttnBwdMaxS * kAttnBwdStride * 4));
@@ -820,7 +880,16 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<8, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(8, 3, 8)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<24, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(24, 2, 4)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<14, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(14, 3, 4)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<14, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(14, 4, 4)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<28, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(28, 2, 4)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 4)));
   if (const char* e12 = getenv("NOVIC_ATTN_CFG")) h->attn_cfg = atoi(e12);
+  if (const char* e14 = getenv("NOVIC_WIDE_GEMM")) g_wide_gemm = e14[0] != '0';
+  if (const char* e15 = getenv("NOVIC_EARLY_B")) g_early_b = e15[0] != '0';
+  if (const char* e16 = getenv("NOVIC_SPLIT_FFN")) g_split_ffn = e16[0] != '0';
+  if (const char* e17 = getenv("NOVIC_ROW_STAGES")) g_row_stages = atoi(e17);
+  if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';
   if (const char* e9 = getenv("NOVIC_ATTN_EARLY")) h->attn_early = atoi(e9);
@@ -940,10 +1009,13 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
   }
   if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, kRowBN)) return 1;
   if (make_tmap(&o.tm_tok, o.tok, V, E, kLogitBN)) return 1;
+  if (make_tmap3(&o.tm_tok3, o.tok, V, E, kLogitBN, kWideKbs)) return 1;
   for (size_t l = 0; l < L; ++l) {
     if (make_tmap(&o.tm_in_proj[l], o.in_proj[l], 3 * E, E, 128)) return 1;
+    if (make_tmap3(&o.tm_in_proj3[l], o.in_proj[l], 3 * E, E, 128, kWideKbs)) return 1;
     if (make_tmap(&o.tm_out_proj[l], o.out_proj[l], E, E, kRowBN)) return 1;
     if (make_tmap(&o.tm_linear1[l], o.linear1[l], K, E, 128)) return 1;
+    if (make_tmap(&o.tm_linear1_q[l], o.linear1[l], K, E, kFfnDim / kRowCluster)) return 1;
     if (make_tmap(&o.tm_linear2[l], o.linear2[l], E, K, kRowBN)) return 1;
   }
   // the weight pointers are baked into captured graphs

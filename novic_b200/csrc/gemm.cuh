@@ -51,15 +51,22 @@ struct EpiCtx {
 // Every epilogue of the persistent kernel runs on 8 warps: two per TMEM lane quadrant, 64 columns per thread.
 constexpr int kEpiWarps = 8;
 constexpr int kEpiCols = kTileN / 2;                 // 64
-constexpr int kEpiStagePitch = kEpiCols * 2 + 16;    // staged bf16 row: 128 B + 16 B pad (conflict-free 16 B accesses)
-constexpr int kEpiStageBytes = 32 * kEpiStagePitch;  // 4608 B per epilogue warp
+constexpr int kEpiStagePitch = kEpiCols * 2;         // staged bf16 row: 128 B, 16-byte chunks XOR-swizzled by the row (conflict-free)
+constexpr int kEpiStageBytes = 32 * kEpiStagePitch;  // 4096 B per epilogue warp
+
+// 16-byte chunk `chunk` (0..7) of staged row `row` (0..31)
+__device__ __forceinline__ uint4* stage_chunk(uint8_t* stage, int row, int chunk) {
+  return reinterpret_cast<uint4*>(stage + row * kEpiStagePitch + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ const uint4* stage_chunk(const uint8_t* stage, int row, int chunk) {
+  return reinterpret_cast<const uint4*>(stage + row * kEpiStagePitch + ((chunk ^ (row & 7)) << 4));
+}
 
 // 4 packed uint4 (32 bf16) of this thread's row -> staging row (columns [c0, c0 + 32) of the thread's 64)
 __device__ __forceinline__ void stage_put32(uint8_t* stage, int lane, int c0, const float (&v)[32]) {
-  uint4* d = reinterpret_cast<uint4*>(stage + lane * kEpiStagePitch + c0 * 2);
 #pragma unroll
   for (int q = 0; q < 4; ++q)
-    d[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+    *stage_chunk(stage, lane, (c0 >> 3) + q) = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
                       pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
 }
 
@@ -72,7 +79,7 @@ __device__ __forceinline__ void stage_copy_out(const uint8_t* stage, int lane, R
 #pragma unroll 4
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + sub;
-    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * kEpiStagePitch + chunk * 16);
+    const uint4 v = *stage_chunk(stage, r, chunk);
     __nv_bfloat16* dst = row_ptr(r);
     if (dst != nullptr) *reinterpret_cast<uint4*>(dst + chunk * 8) = v;
   }
@@ -370,9 +377,9 @@ __device__ __forceinline__ GemmSmemView carve_smem(uint8_t* smem_raw) {
 }
 
 __device__ __forceinline__ void tma_issue_stage(const GemmSmemView& sv, int stage, const CUtensorMap* ta, const CUtensorMap* tb,
-                                                int kb, int m0, int n0) {
+                                                int kb, int m0, int n0, uint32_t stage_tx = kStageBytes) {
   uint8_t* sa = sv.stages + stage * kStageBytes;
-  mbar_arrive_expect_tx(&sv.full_bar[stage], kStageBytes);
+  mbar_arrive_expect_tx(&sv.full_bar[stage], stage_tx);
   tma_load_2d(sa, ta, &sv.full_bar[stage], kb * kBlockK, m0, kEvictNormal);
   tma_load_2d(sa + kABytes, tb, &sv.full_bar[stage], kb * kBlockK, n0, kEvictLast);
 }
@@ -388,18 +395,19 @@ __device__ __forceinline__ void producer_prologue(const GemmSmemView& sv, const 
 }
 
 template <int STAGES>
-__device__ __forceinline__ void producer_rest(const GemmSmemView& sv, const CUtensorMap* ta, const CUtensorMap* tb, int nkb, int m0, int n0) {
+__device__ __forceinline__ void producer_rest(const GemmSmemView& sv, const CUtensorMap* ta, const CUtensorMap* tb, int nkb, int m0, int n0,
+                                              uint32_t stage_tx = kStageBytes) {
   int stage = 0; uint32_t phase = 0;   // k-block kb = STAGES + i reuses stage i % STAGES, whose first use must have drained
   for (int kb = STAGES; kb < nkb; ++kb) {
     mbar_wait(&sv.empty_bar[stage], phase, 1);
-    tma_issue_stage(sv, stage, ta, tb, kb, m0, n0);
+    tma_issue_stage(sv, stage, ta, tb, kb, m0, n0, stage_tx);
     if (++stage == STAGES) { stage = 0; phase ^= 1; }
   }
 }
 
-template <int STAGES>
+template <int STAGES, int BN = kTileN>
 __device__ __forceinline__ void mma_mainloop(const GemmSmemView& sv, uint32_t tmem_base, int nkb, bool tr) {
-  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, kTileN);
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
   int stage = 0; uint32_t phase = 0;
   for (int kb = 0; kb < nkb; ++kb) {
     mbar_wait(&sv.full_bar[stage], phase, 2);
@@ -424,17 +432,21 @@ __device__ __forceinline__ void mma_mainloop(const GemmSmemView& sv, uint32_t tm
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kAccStages = 2;                       // TMEM accumulator double buffering: 2 x 128 columns
 
-__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages) {
-  return stages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs = 1) {
+  return stages * kbs * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 // Persistent: grid = min(#tiles, #SMs); CTA b walks tiles b, b + grid, ... (n fastest, so neighbouring CTAs share A).
 // The TMA producer runs ahead across tile boundaries, the MMA warp alternates between two TMEM accumulator stages,
 // and the 8 epilogue warps drain stage i while the tensor core fills stage i ^ 1.
-template <class Epi, int STAGES>
+// KBS = k-blocks per pipeline stage.  KBS > 1 takes 3-D tensor maps (make_tmap3): one TMA request then brings KBS k-block tiles of
+// an operand.  The TMA unit serves ~2 requests at a time at ~0.4-0.5 k cycles each regardless of their size (tools/tmabench.cu),
+// so with 16 KB requests a 128 x 128 x 512 tile takes ~6 k cycles to load against 2 k cycles of MMA; 32 KB requests halve that.
+template <class Epi, int STAGES, int KBS = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles,
-            int num_k_blocks, int k_splits, typename Epi::Params ep) {
+            int num_k_blocks, int k_splits, int b_is_static, typename Epi::Params ep) {
+  constexpr int kStageBytes = KBS * novic::kStageBytes;   // this kernel's stage: [A: KBS k-blocks][B: KBS k-blocks]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -452,6 +464,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int kb_per_split = (num_k_blocks + k_splits - 1) / k_splits;
   pdl_trigger();
   if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
+  // The B operand (weights) does not depend on the previous kernel: the first pipeline fill's weight halves are requested
+  // before griddepcontrol.wait (the whole fill belongs to this CTA's first tile), the activation halves after it.
+  const int first_loads = (min(num_k_blocks, kb_per_split) + KBS - 1) / KBS;
+  const int early_b = (b_is_static && static_cast<int>(blockIdx.x) < total_tiles) ? min(STAGES, first_loads) : 0;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -460,6 +476,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
       for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
       fence_mbar_init();
+      if (early_b > 0) {
+        const int tt = blockIdx.x % mn_tiles, sp = blockIdx.x / mn_tiles;
+        const int n0 = (tt % n_tiles) * kTileN, kb0 = sp * kb_per_split;
+        for (int i = 0; i < early_b; ++i) {
+          uint8_t* sa = stages + i * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[i], kStageBytes);
+          if (KBS == 1) tma_load_2d(sa + kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kBlockK, n0, kEvictLast);
+          else tma_load_3d(sa + KBS * kABytes, &tmap_b, &full_bar[i], n0, kb0 + i * KBS, kEvictLast);
+        }
+      }
     }
   } else if (warp == 1) {
     tmem_alloc<kAccStages * kTileN>(tmem_slot);
@@ -469,22 +495,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const bool tr = s_trace != 0;
-  pdl_wait();   // everything above (barriers, TMEM, descriptors) overlapped the previous kernel's tail
+  pdl_wait();   // everything above (barriers, TMEM, descriptors, first weight tiles) overlapped the previous kernel's tail
   if (threadIdx.x == 0) trace_point(tr, 1);
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      int nload = 0;                      // loads issued so far; the B halves of the first `early_b` were issued before the wait
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int tt = t % mn_tiles, sp = t / mn_tiles;
         const int m0 = (tt / n_tiles) * kBlockM, n0 = (tt % n_tiles) * kTileN;
         const int kb0 = sp * kb_per_split, kb1 = min(num_k_blocks, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        for (int kb = kb0; kb < kb1; kb += KBS, ++nload) {
           uint8_t* sa = stages + stage * kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
-          tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+          if (nload >= early_b) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          }
+          if (KBS == 1) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
+            if (nload >= early_b) tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+          } else {
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], m0, kb, kEvictNormal);
+            if (nload >= early_b) tma_load_3d(sa + KBS * kABytes, &tmap_b, &full_bar[stage], n0, kb, kEvictLast);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -502,16 +536,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const uint32_t acc = tmem_base + as * kTileN;
         const int sp = t / mn_tiles;
         const int kb0 = sp * kb_per_split, kb1 = min(num_k_blocks, kb0 + kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; kb += KBS) {
           mbar_wait(&full_bar[stage], phase, 2);
           if (i == 0 && kb == kb0) trace_point(tr, 4);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(stages + stage * kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sb = sa + KBS * kABytes;
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)), umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)), kIdesc,
-                         (kb > kb0 || k != 0) ? 1u : 0u);
+          for (int j = 0; j < KBS; ++j)
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + j * kABytes + k * (kUmmaK * 2)),
+                           umma_desc_sw128_kmajor(sb + j * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb > kb0 || (j | k) != 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -531,6 +567,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m0 = (tt / n_tiles) * kBlockM, nt = tt % n_tiles;
       mbar_wait(&tmem_full_bar[as], (i >> 1) & 1, 3);
       if (i == 0 && threadIdx.x == 64) trace_point(tr, 6);
+      if (i < 8 && threadIdx.x == 64) trace_point(tr, 16 + 2 * i);   // per-tile: accumulator ready / epilogue done
       tc_fence_after_sync();
       EpiCtx c;
       c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * kEpiCols;
@@ -547,6 +584,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (lane == 0) mbar_arrive(rel);
       });
       if (i == 0 && threadIdx.x == 64) trace_point(tr, 8);
+      if (i < 8 && threadIdx.x == 64) trace_point(tr, 17 + 2 * i);
     }
   }
 
@@ -597,10 +635,18 @@ __host__ __device__ constexpr int rowln_smem_bytes(int stages, bool fuse_ffn) {
 //                    x += h * W2^T (tmap_b = this CTA's 128 rows of W2)     -> LayerNorm      (whole feed-forward block)
 // In the fused variant every CTA of the cluster recomputes the full 128 x 128 hidden tile (4x redundant FFN1, 2048
 // tensor cycles) - far cheaper than a separate kernel plus a global round trip of h.
-template <int STAGES, bool FUSE_FFN>
+// FFN = 2 (split hidden tile): CTA r of the cluster computes only hidden columns [32 r, 32 r + 32) (tmap_w1 has a 32-row box),
+// applies GELU and stores the bf16 values into the h operand of all four CTAs through distributed shared memory; one cluster
+// barrier later every CTA holds the complete 128 x 128 hidden tile.  4x less GELU work, W1 traffic and FFN1 MMA per CTA
+// (the phase trace of the redundant variant shows 5.1 k cycles of GELU per CTA, profiles/r01_phase_trace_v6.txt).
+template <int STAGES, int FFN>
 __global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kRowThreads, 1)
 gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_w1, int M, int num_k_blocks, RowParams ep) {
+  constexpr bool FUSE_FFN = FFN != 0;
+  constexpr bool SPLIT_H = FFN == 2;
+  constexpr int kHSplit = kFfnDim / kRowCluster;                                  // 32 hidden columns per CTA
+  constexpr uint32_t kStageTx = SPLIT_H ? kABytes + kHSplit * kBlockK * 2 : kStageBytes;
   constexpr int BN = kRowBN;
   constexpr uint32_t kTmemCols = FUSE_FFN ? 256 : 128;
   constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
@@ -633,7 +679,7 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
 
   const CUtensorMap* tb1 = FUSE_FFN ? &tmap_w1 : &tmap_b;   // B operand of the first (pipelined) GEMM
-  const int bn0 = FUSE_FFN ? 0 : n0;                        // its row offset (W1 has exactly 128 rows)
+  const int bn0 = SPLIT_H ? static_cast<int>(crank) * kHSplit : (FUSE_FFN ? 0 : n0);   // its row offset (W1 has exactly 128 rows)
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(&tmap_a);
@@ -649,7 +695,7 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       fence_mbar_init();
       const int pre = num_k_blocks < STAGES ? num_k_blocks : STAGES;
       for (int kb = 0; kb < pre; ++kb) {
-        mbar_arrive_expect_tx(&sv.full_bar[kb], kStageBytes);
+        mbar_arrive_expect_tx(&sv.full_bar[kb], kStageTx);
         tma_load_2d(sv.stages + kb * kStageBytes + kABytes, tb1, &sv.full_bar[kb], kb * kBlockK, bn0, kEvictLast);
       }
       if (FUSE_FFN) {   // this CTA's 128 rows of W2, both k-blocks
@@ -672,28 +718,30 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   pdl_wait();
   if (threadIdx.x == 0) trace_point(tr, 1);
 
+  // second GEMM of the fused feed-forward block: x_delta = h * W2^T from shared memory (issued by one thread of warp 1)
+  auto issue_ffn2 = [&]() {
+    mbar_wait(w2_full_bar, 0, 6);
+    if (!SPLIT_H) mbar_wait(h_ready_bar, 0, 7);
+    tc_fence_after_sync();
+    const uint32_t sa = smem_u32(h_smem), sb = smem_u32(w2_smem);
+#pragma unroll
+    for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
+#pragma unroll
+      for (int k = 0; k < kBlockK / kUmmaK; ++k)
+        umma_bf16_ss(tmem_base + BN, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
+                     umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
+    umma_commit(tmem_full2_bar);
+    trace_point(tr, 12);
+  };
   if (warp == 0) {
     if (elect_one()) {
-      producer_rest<STAGES>(sv, &tmap_a, tb1, num_k_blocks, m0, bn0);
+      producer_rest<STAGES>(sv, &tmap_a, tb1, num_k_blocks, m0, bn0, kStageTx);
       trace_point(tr, 3);
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      mma_mainloop<STAGES>(sv, tmem_base, num_k_blocks, tr);
-      if (FUSE_FFN) {
-        mbar_wait(w2_full_bar, 0, 6);
-        mbar_wait(h_ready_bar, 0, 7);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_u32(h_smem), sb = smem_u32(w2_smem);
-#pragma unroll
-        for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16_ss(tmem_base + BN, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
-                         umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(tmem_full2_bar);
-        trace_point(tr, 12);
-      }
+      mma_mainloop<STAGES, SPLIT_H ? kHSplit : kTileN>(sv, tmem_base, num_k_blocks, tr);
+      if (FUSE_FFN && !SPLIT_H) issue_ffn2();
     }
   }
 
@@ -731,7 +779,27 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     mbar_wait(sv.tmem_full_bar, 0, 3);
     if (threadIdx.x == 64) trace_point(tr, 6);
     tc_fence_after_sync();
-    if (FUSE_FFN) {
+    if (SPLIT_H) {
+      // this CTA's 32 hidden columns: the thread's 16 (two 16-byte chunks of the row) go to the h operand of all four CTAs
+      float v[16];
+      tmem_ld_32x16(tmem_lane + half * 16, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+      const int hcol = static_cast<int>(crank) * kHSplit + half * 16;              // first hidden column of this thread
+      uint8_t* hrow = h_smem + (hcol >> 6) * kABytes + row_in_tile * 128;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int chunk = ((hcol & 63) >> 3) + q;
+        const uint4 pk = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                    pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        uint8_t* dst = hrow + ((chunk ^ (row_in_tile & 7)) << 4);
+#pragma unroll
+        for (uint32_t pr = 0; pr < kRowCluster; ++pr) dsmem_st_v4(dsmem_addr(dst, pr), pk);
+      }
+      fence_proxy_async_any();       // generic-proxy writes into the peers' shared memory -> visible to their tensor cores
+      tc_fence_before_sync();
+      if (threadIdx.x == 64) trace_point(tr, 13);
+    } else if (FUSE_FFN) {
       // hidden tile: gelu(acc1) -> bf16 -> K-major 128B-swizzled A operand of the second GEMM; this thread's 64 columns
       // are exactly k-block `half`, its row is 128 B there, 16-byte chunk c lands at chunk (c ^ (row & 7)).
       uint8_t* hrow = h_smem + half * kABytes + row_in_tile * 128;
@@ -757,6 +825,21 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       mbar_wait(tmem_full2_bar, 0, 8);
       tc_fence_after_sync();
     }
+  }
+  if (SPLIT_H) {
+    __syncwarp();
+    cluster_sync_all();              // the whole hidden tile now sits in every CTA's h operand
+    if (warp == 1) {
+      if (elect_one()) { fence_proxy_async_any(); issue_ffn2(); }
+    }
+    __syncwarp();
+    if (is_epi) {
+      mbar_wait(tmem_full2_bar, 0, 8);
+      tc_fence_after_sync();
+    }
+  }
+  if (is_epi) {
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t acc = tmem_lane + (FUSE_FFN ? BN : 0) + half * kRowCols;
     float sum = 0.f, sumsq = 0.f;
 #pragma unroll

@@ -83,7 +83,7 @@ __device__ int g_trace_counter = 0;   // GEMM launches seen since arming
 __device__ int g_trace_target = -1;   // ordinal of the launch to record
 // Called by thread 0 of every CTA at kernel entry; returns whether this CTA records.
 __device__ __forceinline__ bool trace_begin() {
-  if (g_trace == nullptr || blockIdx.x != 0 || blockIdx.y != 1) return false;
+  if (g_trace == nullptr || blockIdx.x != 0 || blockIdx.y != (gridDim.y > 1 ? 1u : 0u)) return false;
   return atomicAdd(&g_trace_counter, 1) == g_trace_target;
 }
 __device__ __forceinline__ void trace_point(bool on, int idx) {
@@ -123,6 +123,18 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(cache_hint)
+      : "memory");
+}
+
+// 3-D tiled load over the (64 columns, rows, k-blocks) view of a row-major bf16 matrix: c1 = row index, c2 = first k-block.
+// One request brings several consecutive [rows x 128 B] swizzled k-block tiles - the TMA unit serves about two requests at a
+// time at ~0.5 k cycles each whatever their size (tools/tmabench.cu), so operand delivery scales with the request size.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c1, int32_t c2,
+                                            uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(0), "r"(c1), "r"(c2), "l"(cache_hint)
       : "memory");
 }
 
@@ -268,6 +280,12 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint3
   return raddr;
 }
 // Non-volatile so that several independent remote loads can be in flight at once (each costs ~200+ cycles).
+// 16-byte store into a peer CTA's shared memory (address from dsmem_addr)
+__device__ __forceinline__ void dsmem_st_v4(uint32_t raddr, const uint4& v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// generic-proxy writes (any state space, peers' shared memory included) -> visible to async-proxy reads ordered after it
+__device__ __forceinline__ void fence_proxy_async_any() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ float2 dsmem_ld_f32x2_addr(uint32_t raddr) {
   float2 v;
   asm("ld.shared::cluster.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(raddr));

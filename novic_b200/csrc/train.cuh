@@ -121,10 +121,9 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const LnBwdParams p) {
     }
     if (p.out_bf != nullptr) {
       uint8_t* stage = s_stage[warp];
-      uint4* d = reinterpret_cast<uint4*>(stage + lane * kEpiStagePitch);
 #pragma unroll
       for (int q = 0; q < kEpiCols / 8; ++q)
-        d[q] = make_uint4(pack_bf16x2(o[q * 8], o[q * 8 + 1]), pack_bf16x2(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16x2(o[q * 8 + 4], o[q * 8 + 5]),
+        *stage_chunk(stage, lane, q) = make_uint4(pack_bf16x2(o[q * 8], o[q * 8 + 1]), pack_bf16x2(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16x2(o[q * 8 + 4], o[q * 8 + 5]),
                           pack_bf16x2(o[q * 8 + 6], o[q * 8 + 7]));
       stage_copy_out(stage, lane, [&](int r) -> __nv_bfloat16* {
         return row0 + r < p.R ? p.out_bf + static_cast<size_t>(row0 + r) * kE + c0 : nullptr;

@@ -27,3 +27,6 @@ with torch.inference_mode():
         for i in sorted(names, key=lambda k: buf[k]):
             if buf[i]:
                 print(f"   {names[i]:36s} +{buf[i] - t0:7d} cycles")
+        for i in range(8):   # persistent kernels: per-tile epilogue spans of CTA 0
+            if buf[16 + 2 * i]:
+                print(f"   tile {i}: accumulator ready +{buf[16 + 2 * i] - t0:7d}, epilogue done +{buf[17 + 2 * i] - t0:7d}")
