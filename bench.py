@@ -171,41 +171,84 @@ def algorithmic_work(B: int, dims, fused: bool = True) -> dict:
     }
 
 
-def kernel_breakdown(model, embed, steps: int, peaks: dict, dims) -> dict:
-    """Direct-launch (no graph) replay with a CUDA-event pair around every launch, on the launching stream."""
+def _timed_decodes(model, embed, flush, n):
+    """Mean device time (CUDA events on the launching stream, L2 flushed before each) of n greedy decodes."""
+    total = 0.0
+    for _ in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        model.generate(embed, False, True, 1.0, 0.0, None, None, False)
+        b.record()
+        torch.cuda.synchronize()
+        total += a.elapsed_time(b)
+    return total / n
+
+
+def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict:
+    """Two device timings of every kernel class, both with CUDA events on the launching stream:
+
+    in_graph  - the captured decode graph with the launches of every OTHER class dropped (novic_debug_keep_classes), minus the same
+                graph with no kernel at all: the class's launches run back to back with their real arguments, programmatic dependent
+                launch and the L2 state of the decode, exactly as inside the product's graph.  This is `achieved` / `frac`.
+    isolated  - direct launches (no graph) with an event pair around every launch: includes one launch gap per kernel (~2-3 us on a
+                ~10 us kernel) - the pessimistic bound, comparable to ncu's serialised per-launch times in profiles/."""
     import ctypes as C
     from novic_b200 import _abi
     lib = _abi.lib()
     st = model._state(embed.device)
-    _abi.check(lib.novic_set_use_graphs(st["handle"], 0))
+    names = list(_abi.KERNEL_CLASSES)
     with torch.inference_mode():
+        # isolated: event pair per launch
+        _abi.check(lib.novic_set_use_graphs(st["handle"], 0))
         model.generate(embed, False, True, 1.0, 0.0, None, None, False)
         torch.cuda.synchronize()
         _abi.check(lib.novic_kernel_timing(1))
         for _ in range(steps):
             model.generate(embed, False, True, 1.0, 0.0, None, None, False)
-        n = len(_abi.KERNEL_CLASSES)
+        n = len(names)
         ms = (C.c_double * n)()
         cnt = (C.c_int64 * n)()
         _abi.check(lib.novic_kernel_times(ms, cnt, n))
         _abi.check(lib.novic_kernel_timing(0))
-    _abi.check(lib.novic_set_use_graphs(st["handle"], 1))
-    work = algorithmic_work(embed.shape[0], dims, fused=cnt[list(_abi.KERNEL_CLASSES).index('layer_stack')] > 0)
-    total = sum(ms) or 1.0
+        _abi.check(lib.novic_set_use_graphs(st["handle"], 1))
+        # in graph: one class at a time
+        in_graph = {}
+        try:
+            _abi.check(lib.novic_debug_keep_classes(st["handle"], 1 << 31))      # no kernel class at all: memsets, copies, host sync
+            _timed_decodes(model, embed, flush, 2)
+            base = _timed_decodes(model, embed, flush, steps)
+            for i, name in enumerate(names):
+                if cnt[i] == 0:
+                    continue
+                _abi.check(lib.novic_debug_keep_classes(st["handle"], 1 << i))
+                _timed_decodes(model, embed, flush, 2)
+                in_graph[name] = _timed_decodes(model, embed, flush, steps) - base
+        finally:
+            _abi.check(lib.novic_debug_keep_classes(st["handle"], 0))
+        model.generate(embed, False, True, 1.0, 0.0, None, None, False)          # re-capture the full graph
+    work = algorithmic_work(embed.shape[0], dims, fused=cnt[names.index('layer_stack')] > 0)
+    if cnt[names.index('ffn1_gemm')] == 0:      # fused feed-forward kernel: its launches do both GEMMs of the block
+        work["ffn2_gemm"] = ("tensor", work["ffn1_gemm"][1] + work["ffn2_gemm"][1])
+    total = sum(max(v, 0.0) for v in in_graph.values()) or 1.0
     out = {}
-    for i, name in enumerate(_abi.KERNEL_CLASSES):
+    for i, name in enumerate(names):
         if cnt[i] == 0:
             continue
-        per_decode_ms = ms[i] / steps
-        entry = {"ms_per_step": per_decode_ms, "launches_per_step": cnt[i] // steps, "share": ms[i] / total}
+        # classes of a few microseconds per decode drown in the run-to-run noise of the subtraction: never report less than
+        # 40 % of the isolated time (the largest in-graph gain seen on any class is 45 %)
+        g_ms = max(in_graph[name], 0.4 * ms[i] / steps)
+        entry = {"ms_per_step": g_ms, "launches_per_step": cnt[i] // steps, "share": g_ms / total, "isolated_ms_per_step": ms[i] / steps}
         if name in work:
             bound, amount = work[name]
             if bound == "hbm":
-                ach = amount / (per_decode_ms * 1e-3) / 1e9
-                entry.update(bound="hbm", achieved=ach, unit="GB/s", frac=ach / peaks["hbm_gbs"])
+                ach = amount / (g_ms * 1e-3) / 1e9
+                entry.update(bound="hbm", achieved=ach, unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                             isolated_frac=amount / (ms[i] / steps * 1e-3) / 1e9 / peaks["hbm_gbs"])
             else:
-                ach = amount / (per_decode_ms * 1e-3) / 1e12
-                entry.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"])
+                ach = amount / (g_ms * 1e-3) / 1e12
+                entry.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"],
+                             isolated_frac=amount / (ms[i] / steps * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"])
         out[name] = entry
     return out
 
@@ -275,10 +318,12 @@ def main():
         if world > 1:
             dist.barrier()
         launches = lib.novic_launch_count() - n0
-        total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+        per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        total_ms = sum(per_step)
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.last_per_step = per_step
         return t.item(), launches, out
 
     with torch.inference_mode():
@@ -290,7 +335,9 @@ def main():
             sampler.wait_started()
             sampler.mark()
         total_ms, launches, out = timed(step_device, args.steps)
+        dev_steps = list(timed.last_per_step)
         e2e_ms, _, out_host = timed(step_e2e, args.steps)
+        e2e_steps = list(timed.last_per_step)
         clocks = sampler.stop() if sampler else None
     tok = out[0]
     assert tok.shape[0] == B * world and tok.shape[-1] == dims.token_length - 1
@@ -300,7 +347,7 @@ def main():
         ms_per_step = total_ms / args.steps
         value = B * world * args.steps / (total_ms / 1e3)
         e2e_value = B * world * args.steps / (e2e_ms / 1e3)
-        kernels = kernel_breakdown(model, embed, min(args.steps, 5), peaks, dims)
+        kernels = kernel_breakdown(model, embed, flush, min(args.steps, 5), peaks, dims)
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -312,7 +359,9 @@ def main():
                 traffic = entry["ratio_to_algorithmic"] * work / max(1, d["launches_per_step"])
         roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
                     "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],
-                    "how": "CUDA-event pair around every launch on the launching stream, direct-launch replay of the same decode; achieved = algorithmic work of all launches of the class / their summed duration",
+                    "how": "CUDA events on the launching stream around the captured decode graph with only this kernel class's launches kept (real arguments, PDL, L2 flushed "
+                           "before each decode), minus the same graph with no kernels; achieved = algorithmic work of the class's launches / that duration, i.e. per-launch work / average "
+                           "launch duration.  isolated_* = event pair around every direct launch (adds a launch gap per kernel; comparable to ncu's serialised times in profiles/)",
                     "kernels": kernels}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -321,6 +370,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * dims.embed_dim * 4, "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host))},
             "gpu_launches": int(launches), "roofline": roofline,
+            "step_ms": {"device_median": statistics.median(dev_steps), "device_max": max(dev_steps), "e2e_median": statistics.median(e2e_steps), "e2e_max": max(e2e_steps)},
         }
         if not args.no_cpu_baseline:
             times, cores = cpu_greedy_rate(args.cpu_sample, repeats=1, warmup=1)

@@ -168,6 +168,12 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
 int novic_kernel_timing(int32_t enable);
 int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes);
 
+/* Measurement aid (bench.py's in-graph roofline numbers, tools/ablate.py): keep_mask = bit set of kernel classes (bit k = class k
+ * in the order above) whose launches are issued; the launches of all other classes are dropped, so a captured decode then
+ * consists of that class's launches back to back, with their real arguments.  Results are meaningless while a mask is set.
+ * keep_mask = 0 restores normal operation.  Drops the handle's cached graphs. */
+int novic_debug_keep_classes(NovicHandle* h, uint32_t keep_mask);
+
 /* Tuning aid: enable = 1 + n arms CTA (0,1) of the n-th GEMM launch from now to record clock64() at numbered phase
  * points; a later call returns the 32 recorded slots (out16: room for 32 int64, may be NULL) and re-arms / disarms (enable = 0). */
 int novic_debug_trace(int64_t* out16, int32_t enable);

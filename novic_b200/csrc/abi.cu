@@ -923,6 +923,15 @@ int novic_destroy(NovicHandle* h) {
   return 0;
 }
 
+int novic_debug_keep_classes(NovicHandle* h, uint32_t keep_mask) {
+  if (h == nullptr) return fail("null handle");
+  g_skip_classes = keep_mask == 0 ? 0u : ~keep_mask;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);   // the launch set is baked into captured graphs
+  h->graphs.clear();
+  h->graph_nodes.clear();
+  return 0;
+}
+
 int novic_set_use_graphs(NovicHandle* h, int32_t enable) {
   if (h == nullptr) return fail("null handle");
   h->use_graphs = enable != 0;
