@@ -102,6 +102,7 @@ int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, i
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
+int g_attn_hint = 1;                           // NOVIC_ATTN_HINT bit 0: evict-first L2 policy on the streamed K/V rows; bit 1: evict-last on new K/V rows
 int g_row_stages = 4;                          // NOVIC_ROW_STAGES=2|3: shallower row-kernel pipelines (tuning: co-residency with the next kernel)
 bool g_split_ffn = true;                       // NOVIC_SPLIT_FFN=0: every CTA of a cluster recomputes the whole hidden tile
 bool g_early_b = true;                         // NOVIC_EARLY_B=0: no weight-tile requests before griddepcontrol.wait
@@ -435,6 +436,7 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   pa.slot_mul = pc.slot_mul;
   pa.early_loads = h->fuse_stack ? 0 : h->attn_early;   // early bulk loads next to the stack kernel fault under graphs + PDL (unexplained)
   pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
+  pa.stream_hint = g_attn_hint;
   KSpan t(kKAttn, s);
   if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
     auto go = [&](auto kernel, int warps, int slots, int chunk) {
@@ -526,7 +528,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   for (int l = 0; l < L; ++l) {
     __nv_bfloat16* kc = ws.kv + (static_cast<size_t>(l) * 2 + 0) * kv_layer;
     __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
-    EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S};
+    EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S, (g_attn_hint & 2) ? 1 : 0};
     if (g_wide_gemm) {
       KSpan t(kKQkv, s);
       if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
@@ -889,6 +891,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e15 = getenv("NOVIC_EARLY_B")) g_early_b = e15[0] != '0';
   if (const char* e16 = getenv("NOVIC_SPLIT_FFN")) g_split_ffn = e16[0] != '0';
   if (const char* e17 = getenv("NOVIC_ROW_STAGES")) g_row_stages = atoi(e17);
+  if (const char* e18 = getenv("NOVIC_ATTN_HINT")) g_attn_hint = atoi(e18);
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';

@@ -113,6 +113,7 @@ struct AttnParams {
   const unsigned char* anc;     // optional [nseq, anc_ld]
   int nseq, nq, q0, smax, P, beams, slot_mul, prefix_bidir, keypad_ld, anc_ld;
   int early_loads;              // stream kernel: request chunks of older rows before griddepcontrol.wait
+  int stream_hint;              // stream kernel: K/V rows are requested with an evict-first L2 policy (NOVIC_ATTN_HINT)
   float scale_log2e;            // (1/sqrt(head_dim)) * log2(e)
 };
 
@@ -396,7 +397,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attention_stream_kernel_t(const
     const int own_slot = a * p.slot_mul;
     if (lane == 0) mbar_arrive_expect_tx(&full_bar[sl], static_cast<uint32_t>(rows) * 1024u);
     if (contiguous) {
-      if (lane == 0) bulk_load_1d(dst, base + (static_cast<size_t>(own_slot) * p.smax + j0) * kE, static_cast<uint32_t>(rows) * 1024u, &full_bar[sl]);
+      if (lane == 0) {
+        const void* src = base + (static_cast<size_t>(own_slot) * p.smax + j0) * kE;
+        if (p.stream_hint) bulk_load_1d_hint(dst, src, static_cast<uint32_t>(rows) * 1024u, &full_bar[sl], 0x12F0000000000000ull /* evict first */);
+        else bulk_load_1d(dst, src, static_cast<uint32_t>(rows) * 1024u, &full_bar[sl]);
+      }
     } else {
       __syncwarp();
       if (lane < rows) {

@@ -146,6 +146,19 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 
+__device__ __forceinline__ void bulk_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(cache_hint)
+      : "memory");
+}
+
+// 16-byte global store with an L2 eviction-priority hint
+__device__ __forceinline__ void st_global_v4_hint(void* gdst, const uint4& v, uint64_t cache_hint) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(gdst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(cache_hint)
+               : "memory");
+}
+
 // createpolicy-encoded L2 hints (same encodings CUTLASS uses for sm_90+)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
