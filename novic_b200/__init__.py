@@ -4,14 +4,15 @@ Public surface (mirrors the reference's classes for this path):
   PrefixedIterDecoder, EmbeddingDecoder  - embedding_decoder.py
   EmbeddingNoise and its five schemes     - embedding_noise.py
   register(module)                        - make `getattr(embedding_decoder, 'PrefixedIterDecoder')` resolve here
+  cache.EmbeddingCacheReader              - embedding_cache.py's file format -> batches on the device (training feeder)
 """
 from .decoder import EmbeddingDecoder, ParamCount, PrefixedIterDecoder
 from .noise import (AngleNoise, EmbeddingNoise, GaussAngleNoise, GaussElemNoise, GaussElemUniformAngleNoise, GaussVecNoise,
                     UniformAngleNoise)
 from .factory import DEFAULT_DECODER_KWARGS, default_decoder, register
-from . import synth
+from . import cache, synth
 
 __all__ = [
     "EmbeddingDecoder", "ParamCount", "PrefixedIterDecoder", "EmbeddingNoise", "AngleNoise", "GaussAngleNoise", "GaussElemNoise",
-    "GaussElemUniformAngleNoise", "GaussVecNoise", "UniformAngleNoise", "DEFAULT_DECODER_KWARGS", "default_decoder", "register", "synth",
+    "GaussElemUniformAngleNoise", "GaussVecNoise", "UniformAngleNoise", "DEFAULT_DECODER_KWARGS", "default_decoder", "register", "synth", "cache",
 ]

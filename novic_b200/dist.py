@@ -33,8 +33,8 @@ def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor,
     tok / pad are [n_local, K, T_local], score is [n_local, K].  Ranks may have stopped at different T (early exit is per
     shard): every rank contributes fixed-size records of `gen_len` columns (ids 0 / padding True beyond its own T - exactly
     what the reference returns for samples that finished before the longest one) plus its T, and the result is cut to the
-    global maximum T.  Shards may differ in size by one row.  The payload is one byte buffer:
-    per row and beam [gen_len int64 ids | gen_len u8 padding | fp32 score], then one int64 header holding T_local.
+    global maximum T.  Shards may differ in size by one row.  The payload is one byte buffer of four 8-byte aligned sections:
+    [int64 ids | fp32 scores | u8 padding | int64 T_local], each a typed view - a handful of copies to pack, none to unpack.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -47,29 +47,35 @@ def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor,
     lo, hi = shard_bounds(total, world, rank)
     assert n_local == hi - lo
     n_max = -(-total // world)
-    rec = G * 8 + G + 4
-    buf = torch.zeros(n_max * K * rec + 8, dtype=torch.uint8, device=tok.device)
-    body = buf[: n_max * K * rec].view(n_max, K, rec)
-    ids = torch.zeros((n_local, K, G), dtype=torch.int64, device=tok.device)
-    ids[:, :, :T_local] = tok
-    pd = torch.ones((n_local, K, G), dtype=torch.uint8, device=tok.device)
-    pd[:, :, :T_local] = pad.to(torch.uint8)
-    body[:n_local, :, : G * 8] = ids.view(torch.uint8).view(n_local, K, G * 8)
-    body[:n_local, :, G * 8: G * 9] = pd
-    body[:n_local, :, G * 9:] = score.to(torch.float32).contiguous().view(torch.uint8).view(n_local, K, 4)
-    buf[n_max * K * rec:] = torch.tensor([T_local], dtype=torch.int64, device=tok.device).view(torch.uint8)
-    outs = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf, group=group)
-    toks, pads, scores, T = [], [], [], 0
-    for r, o in enumerate(outs):
-        rlo, rhi = shard_bounds(total, world, r)
-        n = rhi - rlo
-        b = o[: n_max * K * rec].view(n_max, K, rec)[:n]
-        toks.append(b[:, :, : G * 8].contiguous().view(torch.int64).view(n, K, G))
-        pads.append(b[:, :, G * 8: G * 9].to(torch.bool))
-        scores.append(b[:, :, G * 9:].contiguous().view(torch.float32).view(n, K))
-        T = max(T, int(o[n_max * K * rec:].clone().view(torch.int64).item()))
-    return torch.cat(toks)[:, :, :T], torch.cat(pads)[:, :, :T], torch.cat(scores)
+    # sections at 8-byte aligned offsets so that each is a typed view of the one byte buffer
+    rows = n_max * K
+    o_ids, o_score = 0, rows * G * 8
+    o_pad = o_score + rows * 4
+    o_hdr = (o_pad + rows * G + 7) // 8 * 8
+    nbytes = o_hdr + 8
+    dev = tok.device
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    buf[o_ids:o_score].view(torch.int64).view(n_max, K, G)[:n_local, :, :T_local] = tok
+    buf[o_score:o_pad].view(torch.float32).view(n_max, K)[:n_local] = score
+    pd = buf[o_pad:o_pad + rows * G].view(n_max, K, G)
+    pd[:n_local, :, T_local:] = 1
+    pd[:n_local, :, :T_local] = pad.view(torch.uint8) if pad.dtype == torch.bool else pad
+    buf[o_hdr:].view(torch.int64).fill_(T_local)
+    out = torch.empty((world, nbytes), dtype=torch.uint8, device=dev)
+    dist.all_gather(list(out.unbind(0)), buf, group=group)
+    T = int(out[:, o_hdr:].contiguous().view(torch.int64).max().item())          # the one host sync of the gather
+    sizes = [shard_bounds(total, world, r) for r in range(world)]
+    even = all(hi_ - lo_ == n_max for lo_, hi_ in sizes)
+    ids_all = out[:, o_ids:o_score].contiguous().view(torch.int64).view(world, n_max, K, G)
+    sc_all = out[:, o_score:o_pad].contiguous().view(torch.float32).view(world, n_max, K)
+    pd_all = out[:, o_pad:o_pad + rows * G].view(world, n_max, K, G)
+    if even:
+        toks, scores, pads = ids_all.flatten(0, 1), sc_all.flatten(0, 1), pd_all.flatten(0, 1)
+    else:
+        toks = torch.cat([ids_all[r, : hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)])
+        scores = torch.cat([sc_all[r, : hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)])
+        pads = torch.cat([pd_all[r, : hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)])
+    return toks[:, :, :T], pads[:, :, :T].to(torch.bool), scores
 
 
 def generate_sharded(model, embed_full: torch.Tensor, method: str = "greedy", topk: int = 1, temperature: float = 1.0,
