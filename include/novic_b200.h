@@ -111,6 +111,14 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
                           int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
                           int32_t* T_out, const NovicGuide* guide, void* ws, size_t ws_bytes, void* stream);
 
+/* The same decode without the host synchronisation: everything is enqueued on `stream` and the early-exit length is written to
+ * T_dev (device int32) instead of being returned, so a serving loop can enqueue the next batch while this one runs
+ * (novic_b200/serve.py).  tok / pad hold all G columns; the caller cuts them to T_dev[0] once it has read the results back.
+ * The workspace may be reused by the next call on the same stream. */
+int novic_generate_greedy_async(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
+                                int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, int32_t* T_dev,
+                                const NovicGuide* guide, void* ws, size_t ws_bytes, void* stream);
+
 /* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984); guide = NULL: unguided, no vocabulary prior.
  * With a vocabulary prior and no guide_targets the caller passes the vocabulary trie as the guide (renorm = 0) with child_bias set.
  *   Outputs (device): tok [B, H, G] int64, pad [B, H, G] u8, score [B, H] fp32 sorted descending. */

@@ -59,6 +59,8 @@ SIGNATURES = {
     "novic_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "novic_generate_greedy": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_float, C.c_float, _FP, _FP, _FP, _FP, _FP, _FP,
                                         C.POINTER(C.c_int32), C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "novic_generate_greedy_async": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_float, C.c_float, _FP, _FP, _FP, _FP, _FP, _FP,
+                                              C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_generate_beam": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, C.c_float, C.c_float, _FP, _FP, _FP,
                                       C.POINTER(C.c_int32), C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_forward": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, C.c_int32, _FP, _FP, _FP,

@@ -1056,9 +1056,23 @@ static int make_guide(const NovicGuide* guide, const NovicHandle* h, GuideCfg* o
   return 0;
 }
 
-int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
-                          int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
-                          int32_t* T_out, const NovicGuide* guide, void* wsbuf, size_t ws_bytes, void* stream) {
+// T[0] = max over the chains of the first step whose "every row finished" flag is still set (else G): the number of columns
+// the reference returns (embedding_decoder.py:817-820).  Device-side twin of the host loop in novic_generate_greedy.
+struct FlagPtrs { const int* f[8]; int n; };
+__global__ void early_exit_len_kernel(FlagPtrs fp, int G, int* T) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int t = 0;
+  for (int i = 0; i < fp.n; ++i) {
+    int ti = G;
+    for (int c = 1; c <= G; ++c) if (fp.f[i][c] != 0) { ti = c; break; }
+    t = max(t, ti);
+  }
+  T[0] = t;
+}
+
+static int greedy_impl(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
+                       int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
+                       int32_t* T_out, int32_t* T_dev, const NovicGuide* guide, void* wsbuf, size_t ws_bytes, void* stream) {
   if (check_ready(h)) return 1;
   GuideCfg gcfg;
   if (make_guide(guide, h, &gcfg)) return 1;
@@ -1089,7 +1103,16 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
     CUDA_TRY(cudaMemcpyAsync(score + b0, ws.g_score_out, 4 * nb, cudaMemcpyDeviceToDevice, s));
     if (nll) CUDA_TRY(cudaMemcpyAsync(nll + b0, ws.g_nll, 4 * nb, cudaMemcpyDeviceToDevice, s));
     if (len) CUDA_TRY(cudaMemcpyAsync(len + b0, ws.g_len, 4 * nb, cudaMemcpyDeviceToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(h->h_flags + i * (G + 2), ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+    if (T_dev == nullptr) CUDA_TRY(cudaMemcpyAsync(h->h_flags + i * (G + 2), ws.flags, sizeof(int) * (G + 2), cudaMemcpyDeviceToHost, s));
+  }
+  if (T_dev != nullptr) {   // asynchronous variant: the early-exit length stays on the device, no host synchronisation
+    FlagPtrs fp{};
+    fp.n = cp.n;
+    for (int i = 0; i < cp.n; ++i) fp.f[i] = cp.ws[i].flags;
+    early_exit_len_kernel<<<1, 32, 0, s>>>(fp, G, T_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
   }
   CUDA_TRY(cudaStreamSynchronize(s));
   int T = 0;
@@ -1100,6 +1123,19 @@ int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float t
   }
   if (T_out) *T_out = T;
   return 0;
+}
+
+int novic_generate_greedy(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
+                          int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, float* logits,
+                          int32_t* T_out, const NovicGuide* guide, void* wsbuf, size_t ws_bytes, void* stream) {
+  return greedy_impl(h, embed, B, temperature, length_alpha, tok, pad, score, nll, len, logits, T_out, nullptr, guide, wsbuf, ws_bytes, stream);
+}
+
+int novic_generate_greedy_async(NovicHandle* h, const float* embed, int64_t B, float temperature, float length_alpha,
+                                int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, int32_t* T_dev,
+                                const NovicGuide* guide, void* wsbuf, size_t ws_bytes, void* stream) {
+  if (T_dev == nullptr) return fail("novic_generate_greedy_async needs a device pointer for the early-exit length");
+  return greedy_impl(h, embed, B, temperature, length_alpha, tok, pad, score, nll, len, nullptr, nullptr, T_dev, guide, wsbuf, ws_bytes, stream);
 }
 
 int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H, float temperature,

@@ -541,6 +541,33 @@ class PrefixedIterDecoder(EmbeddingDecoder):
             loss_basis = sample_weight.dot(length)
         return target, target_padding, seq_logits, loss_sum, loss_basis, score
 
+    def generate_async(self, embed, temperature=1.0, length_alpha=0.0, guide_targets=None, guide_renorm=False):
+        """generate() without its host synchronisation (serving loops, novic_b200/serve.py): everything is enqueued on the current
+        stream.  Returns (target B x G int64, target_padding B x G bool, target_score B, T int32 device tensor of one element);
+        the reference's outputs are target[:, :T], target_padding[:, :T] once T has been read back.  One library call, so B is
+        limited to MAX_SEQS_PER_CALL."""
+        if not temperature > 0:
+            raise ValueError("temperature must be positive")
+        embed = self._check_embed(embed)
+        B = embed.shape[0]
+        if B > MAX_SEQS_PER_CALL:
+            raise ValueError(f"generate_async decodes at most {MAX_SEQS_PER_CALL} embeddings per call (got {B}); split the batch")
+        dev = embed.device
+        G = self.target_config.token_length - 1
+        st = self._state(dev)
+        tok = torch.empty((B, G), dtype=torch.int64, device=dev)
+        pad = torch.empty((B, G), dtype=torch.uint8, device=dev)
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        T = torch.empty(1, dtype=torch.int32, device=dev)
+        ws = self._workspace(st, dev, B, 1, 0)
+        trie = self._guide_trie(guide_targets, dev)
+        garg = guide.guide_arg(trie, bool(guide_renorm))
+        with torch.cuda.device(dev):
+            _abi.check(_abi.lib().novic_generate_greedy_async(
+                st['handle'], embed.data_ptr(), B, float(temperature), float(length_alpha), tok.data_ptr(), pad.data_ptr(), score.data_ptr(),
+                None, None, T.data_ptr(), garg, ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        return tok, pad.view(torch.bool), score, T
+
     # ------------------------------------------------------------------------------------------------------
     # generate_beam (embedding_decoder.py:852-984)
     # ------------------------------------------------------------------------------------------------------

@@ -26,28 +26,23 @@ def _pad_cols(t: torch.Tensor, T: int, dim: int, value) -> torch.Tensor:
     return torch.cat((t, torch.full(shape, value, dtype=t.dtype, device=t.device)), dim=dim)
 
 
-def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor, total: int,
-                      group: Optional[dist.ProcessGroup] = None, gen_len: Optional[int] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """All-gather the per-rank results of generate / generate_beam into the full batch, in rank order, with ONE collective.
+def gather_generation_async(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor, total: int, gen_len: int,
+                            T_local=None, group: Optional[dist.ProcessGroup] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All-gather the per-rank results of generate / generate_beam with ONE collective and no host synchronisation.
 
-    tok / pad are [n_local, K, T_local], score is [n_local, K].  Ranks may have stopped at different T (early exit is per
-    shard): every rank contributes fixed-size records of `gen_len` columns (ids 0 / padding True beyond its own T - exactly
-    what the reference returns for samples that finished before the longest one) plus its T, and the result is cut to the
-    global maximum T.  Shards may differ in size by one row.  The payload is one byte buffer of four 8-byte aligned sections:
-    [int64 ids | fp32 scores | u8 padding | int64 T_local], each a typed view - a handful of copies to pack, none to unpack.
-    """
+    tok / pad are [n_local, K, T_have] with T_have <= gen_len columns present, score is [n_local, K]; T_local is this shard's early-exit
+    length as a python int or a device int32/int64 tensor (default: T_have).  Returns (tok [total, K, gen_len], pad [total, K, gen_len]
+    bool, score [total, K], T int64 device scalar = global maximum early-exit length): the caller cuts the columns to T once it is on
+    the host.  Columns at or beyond a rank's own T hold id 0 / padding True - exactly what the reference returns for samples that finished
+    before the longest one.  Shards may differ in size by one row.  The payload is one byte buffer of four 8-byte aligned sections:
+    [int64 ids | fp32 scores | u8 padding | int64 T_local], each a typed view - a handful of copies to pack, none to unpack."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    n_local, K, T_local = tok.shape
-    G = int(gen_len) if gen_len is not None else T_local
-    if gen_len is None:  # callers that do not know the model's G: agree on the widest T first (one extra tiny collective)
-        t_max = torch.tensor([T_local], dtype=torch.int64, device=tok.device)
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX, group=group)
-        G = int(t_max.item())
+    n_local, K, T_have = tok.shape
+    G = int(gen_len)
     lo, hi = shard_bounds(total, world, rank)
-    assert n_local == hi - lo
+    assert n_local == hi - lo and T_have <= G
     n_max = -(-total // world)
-    # sections at 8-byte aligned offsets so that each is a typed view of the one byte buffer
     rows = n_max * K
     o_ids, o_score = 0, rows * G * 8
     o_pad = o_score + rows * 4
@@ -55,15 +50,21 @@ def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor,
     nbytes = o_hdr + 8
     dev = tok.device
     buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-    buf[o_ids:o_score].view(torch.int64).view(n_max, K, G)[:n_local, :, :T_local] = tok
+    buf[o_ids:o_score].view(torch.int64).view(n_max, K, G)[:n_local, :, :T_have] = tok
     buf[o_score:o_pad].view(torch.float32).view(n_max, K)[:n_local] = score
     pd = buf[o_pad:o_pad + rows * G].view(n_max, K, G)
-    pd[:n_local, :, T_local:] = 1
-    pd[:n_local, :, :T_local] = pad.view(torch.uint8) if pad.dtype == torch.bool else pad
-    buf[o_hdr:].view(torch.int64).fill_(T_local)
+    pd[:n_local, :, T_have:] = 1
+    pd[:n_local, :, :T_have] = pad.view(torch.uint8) if pad.dtype == torch.bool else pad
+    hdr = buf[o_hdr:].view(torch.int64)
+    if T_local is None:
+        hdr.fill_(T_have)
+    elif isinstance(T_local, torch.Tensor):
+        hdr.copy_(T_local.reshape(1))
+    else:
+        hdr.fill_(int(T_local))
     out = torch.empty((world, nbytes), dtype=torch.uint8, device=dev)
     dist.all_gather(list(out.unbind(0)), buf, group=group)
-    T = int(out[:, o_hdr:].contiguous().view(torch.int64).max().item())          # the one host sync of the gather
+    T = out[:, o_hdr:].contiguous().view(torch.int64).max()
     sizes = [shard_bounds(total, world, r) for r in range(world)]
     even = all(hi_ - lo_ == n_max for lo_, hi_ in sizes)
     ids_all = out[:, o_ids:o_score].contiguous().view(torch.int64).view(world, n_max, K, G)
@@ -75,7 +76,22 @@ def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor,
         toks = torch.cat([ids_all[r, : hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)])
         scores = torch.cat([sc_all[r, : hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)])
         pads = torch.cat([pd_all[r, : hi_ - lo_] for r, (lo_, hi_) in enumerate(sizes)])
-    return toks[:, :, :T], pads[:, :, :T].to(torch.bool), scores
+    return toks, pads.to(torch.bool), scores, T
+
+
+def gather_generation(tok: torch.Tensor, pad: torch.Tensor, score: torch.Tensor, total: int,
+                      group: Optional[dist.ProcessGroup] = None, gen_len: Optional[int] = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """All-gather the per-rank results of generate / generate_beam into the full batch, in rank order, cut to the global early-exit
+    length (one collective, one host synchronisation to learn that length).  tok / pad are [n_local, K, T_local], score [n_local, K];
+    ranks may have stopped at different T (early exit is per shard)."""
+    G = int(gen_len) if gen_len is not None else None
+    if G is None:  # callers that do not know the model's G: agree on the widest T first (one extra tiny collective)
+        t_max = torch.tensor([tok.shape[2]], dtype=torch.int64, device=tok.device)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX, group=group)
+        G = int(t_max.item())
+    toks, pads, scores, T = gather_generation_async(tok, pad, score, total, G, None, group)
+    T = int(T.item())                                                          # the one host sync of the gather
+    return toks[:, :, :T], pads[:, :, :T], scores
 
 
 def generate_sharded(model, embed_full: torch.Tensor, method: str = "greedy", topk: int = 1, temperature: float = 1.0,
