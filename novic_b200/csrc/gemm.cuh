@@ -349,8 +349,14 @@ struct EpiLogits {
       p.part[static_cast<size_t>(c.row) * p.nparts + c.part] = o;
       if (HCAP > 0) {
         const size_t base = (static_cast<size_t>(c.row) * p.nparts + c.part) * (HCAP > 0 ? HCAP : 1);
+        // the list is sorted, unused slots (index 0x7fffffff) come last: store up to and including the first unused slot - the
+        // selection kernel stops there.  Guided rows have a handful of allowed ids, so most slices store one terminator only.
+        bool live = true;
 #pragma unroll
-        for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i) { p.topv[base + i] = tv[i]; p.topi[base + i] = ti[i]; }
+        for (int i = 0; i < (HCAP > 0 ? HCAP : 1); ++i) {
+          if (live) { p.topv[base + i] = tv[i]; p.topi[base + i] = ti[i]; }
+          live = live && ti[i] != 0x7fffffff;
+        }
       }
     }
   }

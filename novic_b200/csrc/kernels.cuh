@@ -771,11 +771,79 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
   }
   __syncwarp();
   const int per_row = ntiles * HCAP;
+  // Candidate lists: one per (live row h, 64-column slice), sorted, ending at the first unused slot.  The k-th best total is always
+  // the head of some list once the k-1 better ones have been popped, so the H winners are drawn by a tournament over the list heads:
+  // every lane owns the lists L = h * ntiles + slice with L % 32 == lane and caches their heads; per winner one warp arg-max and one
+  // pop.  (The first version rescanned all H * ntiles * HCAP entries for every winner: 10 x 17 280 entries per sample at H = 10.)
+  constexpr int kSelMaxLists = 64;                         // lists per lane the tournament can hold: H * ntiles <= 2048
+  const int nlists = H * ntiles;
+  const bool tournament = nlists <= 32 * kSelMaxLists;
+  float lraw[kSelMaxLists];
+  int lidx[kSelMaxLists];
+  unsigned char lpos[kSelMaxLists], lh[kSelMaxLists];
+  int nmine = 0;
+  unsigned fin_avail = 0;                                  // lane 0: finished / not yet existing rows, one end-token candidate each
+  if (tournament) {
+    for (int L = lane; L < nlists; L += 32) {
+      const int h = L / ntiles, sl = L - h * ntiles;
+      lpos[nmine] = 0; lh[nmine] = static_cast<unsigned char>(h); lidx[nmine] = -1; lraw[nmine] = -INFINITY;
+      if (!(fin[h] || h >= nrows)) {
+        const size_t e = (row0 + h) * per_row + static_cast<size_t>(sl) * HCAP;
+        const int idx = topi[e];
+        if (idx < V) { lidx[nmine] = idx; lraw[nmine] = base[h] + (topv[e] * inv_tau - lse[h]); }
+      }
+      ++nmine;
+    }
+    for (int h = 0; h < H; ++h) if (fin[h] || h >= nrows) fin_avail |= 1u << h;
+  }
   float prev_v = INFINITY;
   long long prev_f = -1;
   for (int k = 0; k < H; ++k) {
     float bv = -INFINITY, braw = -INFINITY;
     long long bf = 0x7fffffffffffffffLL;
+    if (tournament) {
+      int bm = -1;
+      for (int m = 0; m < nmine; ++m) {
+        if (lidx[m] < 0) continue;
+        const int h = lh[m];
+        const float raw = lraw[m];
+        const float v = (length_alpha != 0.f) ? raw * scale[h] : raw;
+        const long long f = static_cast<long long>(h) * V + lidx[m];
+        if (v > bv || (v == bv && f < bf)) { bv = v; bf = f; braw = raw; bm = m; }
+      }
+      if (lane == 0) {
+        for (int h = 0; h < H; ++h) {
+          if (!((fin_avail >> h) & 1u)) continue;
+          const float raw = base[h];
+          const float v = (length_alpha != 0.f) ? raw * scale[h] : raw;
+          const long long f = static_cast<long long>(h) * V;
+          if (v > bv || (v == bv && f < bf)) { bv = v; bf = f; braw = raw; bm = kSelMaxLists + h; }
+        }
+      }
+      int owner = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const float oraw = __shfl_xor_sync(0xffffffffu, braw, o);
+        const long long of = __shfl_xor_sync(0xffffffffu, bf, o);
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+        if (ov > bv || (ov == bv && of < bf)) { bv = ov; bf = of; braw = oraw; owner = oo; }
+      }
+      if (lane == owner && bm >= 0 && bf != 0x7fffffffffffffffLL) {   // pop the winner from its list
+        if (bm >= kSelMaxLists) {
+          fin_avail &= ~(1u << (bm - kSelMaxLists));
+        } else {
+          const int h = lh[bm], L = lane + 32 * bm, sl = L - h * ntiles;
+          const int pos = ++lpos[bm];
+          lidx[bm] = -1;
+          if (pos < HCAP) {
+            const size_t e = (row0 + h) * per_row + static_cast<size_t>(sl) * HCAP + pos;
+            const int idx = topi[e];
+            if (idx < V) { lidx[bm] = idx; lraw[bm] = base[h] + (topv[e] * inv_tau - lse[h]); }
+          }
+        }
+      }
+    } else {
     for (int h = 0; h < H; ++h) {
       if (fin[h] || h >= nrows) {
         // finished (or not yet existing) candidate: single continuation = end token at zero cost
@@ -790,14 +858,28 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
       }
       const float* tvp = topv + (row0 + h) * per_row;
       const int* tip = topi + (row0 + h) * per_row;
-      for (int e = lane; e < per_row; e += 32) {
-        const int idx = tip[e];
-        if (idx >= V) continue;  // unused slot
-        const float raw = base[h] + (tvp[e] * inv_tau - lse[h]);
-        const float v = (length_alpha != 0.f) ? raw * scale[h] : raw;
-        const long long f = static_cast<long long>(h) * V + idx;
-        const bool after_prev = (v < prev_v) || (v == prev_v && f > prev_f);
-        if (after_prev && (v > bv || (v == bv && f < bf))) { bv = v; bf = f; braw = raw; }
+      // one lane per 64-column slice; a slice's list is sorted and ends at its first unused slot (index >= V)
+      for (int sl = lane; sl < ntiles; sl += 32) {
+        const int4* ti4 = reinterpret_cast<const int4*>(tip + sl * HCAP);
+        const float4* tv4 = reinterpret_cast<const float4*>(tvp + sl * HCAP);
+        bool more = true;
+#pragma unroll 1
+        for (int q = 0; q < HCAP / 4 && more; ++q) {
+          const int4 i4 = ti4[q];
+          if (i4.x >= V) break;
+          const float4 v4 = tv4[q];
+          const int idx[4] = {i4.x, i4.y, i4.z, i4.w};
+          const float val[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (idx[j] >= V) { more = false; break; }
+            const float raw = base[h] + (val[j] * inv_tau - lse[h]);
+            const float v = (length_alpha != 0.f) ? raw * scale[h] : raw;
+            const long long f = static_cast<long long>(h) * V + idx[j];
+            const bool after_prev = (v < prev_v) || (v == prev_v && f > prev_f);
+            if (after_prev && (v > bv || (v == bv && f < bf))) { bv = v; bf = f; braw = raw; }
+          }
+        }
       }
     }
 #pragma unroll
@@ -806,6 +888,7 @@ select_beam_kernel(const LogitPartial* __restrict__ part, const float* __restric
       const float oraw = __shfl_xor_sync(0xffffffffu, braw, o);
       const long long of = __shfl_xor_sync(0xffffffffu, bf, o);
       if (ov > bv || (ov == bv && of < bf)) { bv = ov; bf = of; braw = oraw; }
+    }
     }
     prev_v = bv;
     prev_f = bf;
