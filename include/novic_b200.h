@@ -146,12 +146,17 @@ int novic_score_targets(NovicHandle* h, const float* embed, int64_t B, int32_t M
                         int32_t C, float temperature, const NovicGuide* guide, float* score, void* ws, size_t ws_bytes, void* stream);
 
 /* Replaces the forward + backward of one training batch (train.py:1270-1273: model(..., calc_loss=True, calc_correct=True,
- * only_pred=False) followed by loss.backward()) with dropout disabled.  Same inputs as novic_forward (C >= 2).
+ * only_pred=False) followed by loss.backward()); dropout as set by novic_set_dropout.  Same inputs as novic_forward (C >= 2).
  * Outputs (device): loss [2] = {loss_sum, loss_basis}; correct [A, C] u8 and pad_out [A, C] u8 (may be NULL); `grads`
  * holds fp32 device buffers shaped like the parameters of NovicWeights and receives d(loss_sum) / d(parameter)
  * (overwritten).  The caller applies the 1 / (loss_basis * accumulation) factor, gradient clipping and the optimizer,
  * exactly as train.py:1272-1286 does. */
 size_t novic_train_workspace_bytes(const NovicHandle* h, int64_t B, int32_t M, int32_t C);
+/* Dropout of the following novic_train_fwd_bwd calls (embedding_decoder.py:1290,:1297 input_dropout after the positional embedding;
+ * nn.TransformerEncoderLayer's layer_dropout on the attention probabilities, on both residual branches and on the activated
+ * feed-forward hidden rows).  Masks are a counter-based hash of (seed, layer, site, element) - the backward pass regenerates them.
+ * p = 0 switches a site off (the default); pass a fresh seed per step.  Inference entry points never apply dropout. */
+int novic_set_dropout(NovicHandle* h, float p_input, float p_layer, uint64_t seed);
 int novic_train_fwd_bwd(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
                         const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
                         void* ws, size_t ws_bytes, void* stream);

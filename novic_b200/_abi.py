@@ -70,6 +70,7 @@ SIGNATURES = {
     "novic_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "novic_train_fwd_bwd": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, _FP, _FP, _FP, C.POINTER(NovicWeights),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "novic_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_uint64]),
     "novic_noise_apply": (C.c_int, [C.POINTER(NovicNoiseCfg), _FP, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "novic_noise_apply_predrawn": (C.c_int, [C.POINTER(NovicNoiseCfg), _FP, C.c_int64, _FP, _FP, _FP, _FP, C.c_void_p]),
     "novic_debug_gemm": (C.c_int, [_FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

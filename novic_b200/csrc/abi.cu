@@ -155,6 +155,7 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(3, false)));
@@ -165,7 +166,8 @@ int set_rowln_attr() {
 // N must be a multiple of 512: every 4 consecutive 128-column tiles form one cluster = one full residual row.
 int launch_rowln(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const RowParams& ep) {
   dim3 grid(static_cast<unsigned>(N / kRowBN), static_cast<unsigned>(ceil_div(M, kBlockM)));
-  if (g_row_stages == 2) CUDA_TRY(launch_k(gemm_rowln_kernel<2, false>, grid, dim3(kRowThreads), rowln_smem_bytes(2, false), s, ta, tb, tb, M, K / kBlockK, ep));
+  if (ep.drop.thresh != 0u) CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, 0, true>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, false), s, ta, tb, tb, M, K / kBlockK, ep));
+  else if (g_row_stages == 2) CUDA_TRY(launch_k(gemm_rowln_kernel<2, false>, grid, dim3(kRowThreads), rowln_smem_bytes(2, false), s, ta, tb, tb, M, K / kBlockK, ep));
   else if (g_row_stages == 3) CUDA_TRY(launch_k(gemm_rowln_kernel<3, false>, grid, dim3(kRowThreads), rowln_smem_bytes(3, false), s, ta, tb, tb, M, K / kBlockK, ep));
   else CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, false>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, false), s, ta, tb, tb, M, K / kBlockK, ep));
   ++g_launches;
@@ -331,6 +333,7 @@ struct NovicHandle {
   cudaStream_t chain_streams[8] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
   int attn_smem_budget = 200 * 1024;
+  DropCfg drop_in{0u, 0u, 1.f}, drop_layer{0u, 0u, 1.f};   // training dropout (novic_set_dropout); thresh 0 = off
   WeightPtrs w;
   cudaStream_t capture_stream = nullptr;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -465,7 +468,7 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
     nstages = nstages / ncons * ncons;
     const int smem = nstages * stage_bytes + 2 * kAttnMaxStages * 8;
     const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, 2)));
-    CUDA_TRY(launch_k(attention_bulk_kernel, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
+    CUDA_TRY(launch_k(attention_bulk_kernel_t<false>, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
   }
   ++g_launches;
   return 0;
@@ -876,7 +879,8 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   h->num_sms = prop.multiProcessorCount;
   g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
-  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
+  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
+  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 3, 4)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<12, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(12, 2, 8)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));
@@ -932,6 +936,21 @@ int novic_debug_keep_classes(NovicHandle* h, uint32_t keep_mask) {
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);   // the launch set is baked into captured graphs
   h->graphs.clear();
   h->graph_nodes.clear();
+  return 0;
+}
+
+int novic_set_dropout(NovicHandle* h, float p_input, float p_layer, uint64_t seed) {
+  if (h == nullptr) return fail("null handle");
+  if (!(p_input >= 0.f && p_input < 1.f && p_layer >= 0.f && p_layer < 1.f)) return fail("dropout probabilities must be in [0, 1)");
+  auto mk = [&](float p, uint32_t salt) {
+    DropCfg d;
+    d.seed = static_cast<uint32_t>(seed ^ (seed >> 32)) + salt;
+    d.thresh = static_cast<uint32_t>(static_cast<double>(p) * 16777216.0 + 0.5);
+    d.scale = d.thresh != 0u ? 1.0f / (1.0f - p) : 1.0f;
+    return d;
+  };
+  h->drop_in = mk(p_input, 0u);
+  h->drop_layer = mk(p_layer, 0u);
   return 0;
 }
 

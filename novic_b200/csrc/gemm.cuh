@@ -635,6 +635,8 @@ struct RowParams {
   int remap_skip;         //   leading rows per sequence to drop,
   int remap_rows_out;     //   rows per sequence out
   float eps;
+  DropCfg drop;           // training: dropout on the GEMM result before the residual add (thresh 0 = off; not in prefix mode)
+  uint32_t drop_site;
 };
 
 __host__ __device__ constexpr int rowln_smem_bytes(int stages, bool fuse_ffn) {
@@ -650,7 +652,9 @@ __host__ __device__ constexpr int rowln_smem_bytes(int stages, bool fuse_ffn) {
 // applies GELU and stores the bf16 values into the h operand of all four CTAs through distributed shared memory; one cluster
 // barrier later every CTA holds the complete 128 x 128 hidden tile.  4x less GELU work, W1 traffic and FFN1 MMA per CTA
 // (the phase trace of the redundant variant shows 5.1 k cycles of GELU per CTA, profiles/r01_phase_trace_v6.txt).
-template <int STAGES, int FFN>
+// DROP (training only): dropout on the GEMM result before the residual add (a separate instantiation: the mask arithmetic in the
+// accumulation loop costs the inference kernels 0.5 ms per decode when it is merely branched around).
+template <int STAGES, int FFN, bool DROP = false>
 __global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kRowThreads, 1)
 gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_w1, int M, int num_k_blocks, RowParams ep) {
@@ -859,7 +863,9 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tmem_ld_32x16(acc + c * 16, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float t = r[c * 16 + j] + v[j];
+        float b = v[j];
+        if (DROP) b *= drop_factor(ep.drop, ep.drop_site, static_cast<uint32_t>(row) * kE + static_cast<uint32_t>(c0 + c * 16 + j));
+        const float t = r[c * 16 + j] + b;
         r[c * 16 + j] = t;
         sum += t;
         sumsq = fmaf(t, t, sumsq);

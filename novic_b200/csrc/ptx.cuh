@@ -90,6 +90,25 @@ __device__ __forceinline__ void trace_point(bool on, int idx) {
   if (on) g_trace[idx] = clock64();
 }
 
+// Dropout masks of the training step (nn.Dropout at embedding_decoder.py:1290,:1297 and inside nn.TransformerEncoderLayer): a
+// counter-based hash of (seed, site, element index) - reproducible in the backward pass and in the test oracle
+// (the tests' CPU checker replays them) without storing a mask.  site = layer * 8 + kind (0 input, 1 attention probabilities,
+// 2 attention branch, 3 feed-forward activation, 4 feed-forward branch).  Returns 1 / (1 - p) for kept elements, 0 for dropped.
+struct DropCfg {
+  uint32_t seed;
+  uint32_t thresh;   // round(p * 2^24); 0 = dropout off
+  float scale;       // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t site, uint32_t idx) {
+  uint32_t x = idx * 0x9E3779B1u + seed + site * 0x85EBCA77u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ float drop_factor(const DropCfg& d, uint32_t site, uint32_t idx) {
+  return (drop_hash(d.seed, site, idx) >> 8) >= d.thresh ? d.scale : 0.f;
+}
+constexpr uint32_t kDropInput = 0, kDropAttn = 1, kDropBranch1 = 2, kDropFfn = 3, kDropBranch2 = 4;
+
 // Programmatic dependent launch: pdl_trigger() lets the next kernel of the stream start its prologue while this one is
 // still running; pdl_wait() blocks until every kernel this one depends on has completed and its writes are visible.
 // Both are no-ops when the kernel was not launched with the programmatic-serialization attribute.

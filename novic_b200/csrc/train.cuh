@@ -133,6 +133,82 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const LnBwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Dropout helpers of the training step (elementwise, in place).
+//   drop_mask_bf16_kernel : a[r, c] *= factor(site, r * cols + c) on a row-major bf16 [rows, cols] matrix and, optionally, on its
+//                           transposed copy at[c, r] (leading dimension ld_t) - the bf16 operands of the backward GEMMs.
+//   drop_mask_blocked_kernel : the same on the blocked fp32 residual layout (gradient w.r.t. the input embedding rows).
+//   input_dropout_ln_kernel : x = dropout(x) in place, xn = LayerNorm(x) * gain (forward, input dropout embedding_decoder.py:1297).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) drop_mask_bf16_kernel(__nv_bfloat16* __restrict__ a, int rows, int cols, __nv_bfloat16* __restrict__ at, int ld_t,
+                                                             DropCfg d, uint32_t site) {
+  // blockIdx.y == 0: the row-major matrix, 8 consecutive columns per thread; blockIdx.y == 1: the transposed copy, 8 consecutive rows
+  // per thread - both coalesced.  cols and ld_t are multiples of 8.
+  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (blockIdx.y == 0) {
+    if (i >= static_cast<size_t>(rows) * cols) return;
+    uint4 v = *reinterpret_cast<const uint4*>(a + i);
+    float f[8];
+    bf16x8_to_f32(v, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] *= drop_factor(d, site, static_cast<uint32_t>(i) + k);
+    *reinterpret_cast<uint4*>(a + i) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  } else {
+    if (at == nullptr || i >= static_cast<size_t>(cols) * ld_t) return;
+    const int c = static_cast<int>(i / ld_t), r0 = static_cast<int>(i - static_cast<size_t>(c) * ld_t);
+    if (r0 >= rows) return;
+    uint4 v = *reinterpret_cast<const uint4*>(at + i);
+    float f[8];
+    bf16x8_to_f32(v, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = (r0 + k < rows) ? f[k] * drop_factor(d, site, static_cast<uint32_t>(r0 + k) * cols + c) : f[k];
+    *reinterpret_cast<uint4*>(at + i) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+inline void launch_drop_mask_bf16(cudaStream_t s, __nv_bfloat16* a, int rows, int cols, __nv_bfloat16* at, int ld_t, const DropCfg& d, uint32_t site) {
+  const size_t n = std::max(static_cast<size_t>(rows) * cols, at != nullptr ? static_cast<size_t>(cols) * ld_t : 0);
+  dim3 grid(static_cast<unsigned>((n / 8 + 255) / 256), at != nullptr ? 2 : 1);
+  drop_mask_bf16_kernel<<<grid, 256, 0, s>>>(a, rows, cols, at, ld_t, d, site);
+}
+
+__global__ void __launch_bounds__(256) drop_mask_blocked_kernel(float* __restrict__ x, int rows, DropCfg d, uint32_t site) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(rows) * kE) return;
+  const int r = static_cast<int>(i / kE), c = static_cast<int>(i - static_cast<size_t>(r) * kE);
+  float* e = x + xblk_off(r, c >> 2) + (c & 3);
+  *e *= drop_factor(d, site, static_cast<uint32_t>(i));
+}
+
+__global__ void __launch_bounds__(128) input_dropout_ln_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ xn, const float* __restrict__ gain, int rows,
+                                                               float eps, DropCfg d, uint32_t site) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = lane_id();
+  float v[16];
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 t = *reinterpret_cast<const float4*>(x + xblk_off(row, lane * 4 + q));
+    const uint32_t c = static_cast<uint32_t>(lane * 16 + q * 4), base = static_cast<uint32_t>(row) * kE + c;
+    t.x *= drop_factor(d, site, base); t.y *= drop_factor(d, site, base + 1); t.z *= drop_factor(d, site, base + 2); t.w *= drop_factor(d, site, base + 3);
+    *reinterpret_cast<float4*>(x + xblk_off(row, lane * 4 + q)) = t;
+    v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+    sum += t.x + t.y + t.z + t.w;
+    sumsq += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
+  sum = warp_sum(sum);
+  sumsq = warp_sum(sumsq);
+  const float mean = sum * (1.0f / kE);
+  const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + eps);
+  uint32_t o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    o[k] = pack_bf16x2((v[2 * k] - mean) * rstd * __ldg(gain + lane * 16 + 2 * k), (v[2 * k + 1] - mean) * rstd * __ldg(gain + lane * 16 + 2 * k + 1));
+  uint4* dst = reinterpret_cast<uint4*>(xn + static_cast<size_t>(row) * kE) + lane * 2;
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // GELU backward, elementwise on row-major bf16: dpre = dh * (Phi(pre) + pre * phi(pre))
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ pre,
@@ -177,6 +253,8 @@ struct AttnBwdParams {
   const unsigned char* keypad;  // optional [nseq, S]
   int nseq, S, smax, P, prefix_bidir;
   float scale;                  // 1 / sqrt(64)
+  DropCfg drop;                 // dropout on the attention probabilities, same masks as the forward pass
+  uint32_t drop_site;
 };
 
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
@@ -226,16 +304,21 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
       s = acc * p.scale;
       dp = accd;
     }
+    // out_i = sum_j p_ij m_ij v_j with m the dropout factor: d p_ij = m_ij (do_i . v_j), and dv_j receives p_ij m_ij do_i
+    float dm = 1.f;
+    if (p.drop.thresh != 0u && vis) dm = drop_factor(p.drop, p.drop_site, ((static_cast<uint32_t>(a) * kHeads + head) * S + i) * S + j);
+    dp *= dm;
     const float mx = warp_max(s);
     const float e = vis ? __expf(s - mx) : 0.f;
     const float pj = e / warp_sum(e);
+    const float pjd = pj * dm;
     const float dsum = warp_sum(pj * dp);
     const float ds = pj * (dp - dsum) * p.scale;   // gradient w.r.t. q_i . k_j
     // dq_i = sum_j ds_ij k_j ; dk_j += ds_ij q_i ; dv_j += p_ij do_i   (lanes now own channels c = lane, lane + 32)
     float dq0 = 0.f, dq1 = 0.f;
     for (int jj = 0; jj < nkeys; ++jj) {
       const float dsj = __shfl_sync(0xffffffffu, ds, jj);
-      const float pjj = __shfl_sync(0xffffffffu, pj, jj);
+      const float pjj = __shfl_sync(0xffffffffu, pjd, jj);
       dq0 = fmaf(dsj, sk[jj * HS + lane], dq0);
       dq1 = fmaf(dsj, sk[jj * HS + lane + 32], dq1);
       sdk[jj * HS + lane] = fmaf(dsj, sq[i * HS + lane], sdk[jj * HS + lane]);

@@ -48,8 +48,11 @@ class _SelfAttention(nn.Module):               # key names of nn.MultiheadAttent
 
 
 class _Layer(nn.Module):                       # key names of nn.TransformerEncoderLayer(bias=False)
-    def __init__(self, dim: int, ffn_dim: int):
+    def __init__(self, dim: int, ffn_dim: int, dropout_prob: float = 0.0):
         super().__init__()
+        # holder of the layer's dropout probability (attention probabilities, both residual branches, feed-forward activation all use
+        # layer_dropout in nn.TransformerEncoderLayer); an nn.Dropout so that utils.rescale_dropout (utils.py:177-192) reaches it
+        self.dropout = nn.Dropout(p=dropout_prob)
         self.self_attn = _SelfAttention(dim)
         self.linear1 = nn.Linear(dim, ffn_dim, bias=False)
         self.linear2 = nn.Linear(ffn_dim, dim, bias=False)
@@ -58,9 +61,9 @@ class _Layer(nn.Module):                       # key names of nn.TransformerEnco
 
 
 class _Stack(nn.Module):                       # key names of nn.TransformerEncoder(norm=LayerNorm)
-    def __init__(self, dim: int, ffn_dim: int, num_layers: int):
+    def __init__(self, dim: int, ffn_dim: int, num_layers: int, dropout_prob: float = 0.0):
         super().__init__()
-        self.layers = nn.ModuleList([_Layer(dim, ffn_dim) for _ in range(num_layers)])
+        self.layers = nn.ModuleList([_Layer(dim, ffn_dim, dropout_prob) for _ in range(num_layers)])
         self.norm = nn.LayerNorm(dim, bias=False)
 
 
@@ -199,7 +202,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         self.logits_linear = nn.Linear(E, self.vocab_size_quant, bias=False)
         self.token_embedding = None
         self.pos_embedding = _PositionTable(self.max_seq_len, E, input_dropout)
-        self.transformer = _Stack(E, self.feedfwd_dim, num_layers)
+        self.transformer = _Stack(E, self.feedfwd_dim, num_layers, layer_dropout)
         mask = torch.triu(torch.full((self.max_seq_len, self.max_seq_len), float('-inf'), dtype=self.embed_dtype), diagonal=1)
         if not strictly_causal:
             mask[:P, :P] = 0
@@ -422,14 +425,13 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     def _forward_train(self, embed, target, target_padding, target_weight, calc_loss, calc_correct, only_pred):
         """Training-mode forward with autograd (train.py:1270-1273).  One fused forward+backward library call; the logits are
         not materialised (the reference's training loop discards them, train.py:1271), so the first return value is None.
-        Dropout (input_dropout / layer_dropout) is NOT applied by the CUDA path."""
+        Dropout: input_dropout after the positional embedding (embedding_decoder.py:1297) and layer_dropout on the attention
+        probabilities, both residual branches and the activated feed-forward rows (nn.TransformerEncoderLayer), with masks from a
+        counter-based hash seeded from torch's CPU generator once per call (reproducible under torch.manual_seed; not torch's own
+        dropout stream).  The probabilities are read from the nn.Dropout holders so that utils.rescale_dropout applies."""
         from . import training
         if only_pred:
             raise NotImplementedError("only_pred=True is not supported in training mode")
-        if (self.input_dropout > 0 or self.layer_dropout > 0) and not getattr(self, '_warned_dropout', False):
-            import warnings
-            warnings.warn("novic_b200 training forward does not apply dropout (input_dropout / layer_dropout are ignored)")
-            self._warned_dropout = True
         B = embed.shape[0]
         multi = target.ndim == 3
         multi_first = bool(multi and getattr(self.data_config, 'multi_target', False) and getattr(self.data_config, 'multi_first', False))

@@ -4,7 +4,8 @@
 (`novic_train_fwd_bwd`) runs the teacher-forced forward *and* the full backward and leaves d(loss_sum)/d(parameter)
 for all parameters in fp32 buffers; the autograd Function hands them to torch scaled by the incoming gradient of
 loss_sum, so the reference's own `loss.backward()`, `clip_grad_norm_` and `torch.optim.AdamW.step()`
-(train.py:1273-1286) work unchanged on the module's parameters.  Dropout is not applied by the CUDA path.
+(train.py:1273-1286) work unchanged on the module's parameters.  Dropout (input + layer) is applied inside the library call with
+hash-generated masks (novic_set_dropout); the seed of each call is drawn from torch's CPU generator.
 """
 from __future__ import annotations
 
@@ -46,6 +47,10 @@ class TrainStep(torch.autograd.Function):
         correct = torch.empty((A, Ct), dtype=torch.uint8, device=dev)
         pad_out = torch.empty((A, Ct), dtype=torch.uint8, device=dev)
         gs = _grad_struct(model, grads)
+        p_in, p_layer = dropout_probs(model)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (p_in > 0 or p_layer > 0) else 0
+        _abi.check(lib.novic_set_dropout(st['handle'], float(p_in), float(p_layer), seed))
+        model._last_dropout = (p_in, p_layer, seed)      # tests replay the masks from this
         with torch.cuda.device(dev):
             _abi.check(lib.novic_train_fwd_bwd(
                 st['handle'], embed.data_ptr(), B, M, target.data_ptr(), None if padding is None else padding.data_ptr(),
@@ -63,6 +68,14 @@ class TrainStep(torch.autograd.Function):
             return (None,) * 6 + tuple(None for _ in grads)
         torch._foreach_mul_(grads, g_loss_sum)   # d(loss)/d(theta) = d(loss)/d(loss_sum) * d(loss_sum)/d(theta)
         return (None,) * 6 + tuple(grads)
+
+
+def dropout_probs(model) -> tuple[float, float]:
+    """(input, layer) dropout probabilities of a training step, from the nn.Dropout holders (utils.rescale_dropout mutates those)."""
+    if not model.training:
+        return 0.0, 0.0
+    layers = model.transformer.layers
+    return float(model.pos_embedding.dropout.p), float(layers[0].dropout.p) if len(layers) else 0.0
 
 
 def train_forward(model, embed: torch.Tensor, target: torch.Tensor, padding: Optional[torch.Tensor], weight: Optional[torch.Tensor], M: int):

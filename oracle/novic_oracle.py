@@ -22,6 +22,7 @@ import dataclasses
 import math
 from typing import Optional
 
+import numpy as np
 import torch
 
 NEG_INF = float("-inf")
@@ -121,13 +122,45 @@ def key_padding_bias(cfg: OracleCfg, padding: torch.Tensor, S: int, dtype: torch
     return bias, eff
 
 
-def transformer_stack(cfg: OracleCfg, sd: dict, x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+class DropMasks:
+    """The dropout masks of novic_b200's training step, replayed on the CPU (test infrastructure): the product draws them from a
+    counter-based hash of (seed, site, element index) - csrc/ptx.cuh:drop_hash - so that its backward pass can regenerate them; the
+    reference uses torch's dropout stream, which no other implementation can reproduce, so parity under dropout is defined as
+    "same function given the same masks".  site = layer * 8 + kind; kinds as in ptx.cuh."""
+    INPUT, ATTN, BRANCH1, FFN, BRANCH2 = 0, 1, 2, 3, 4
+
+    def __init__(self, p_input: float, p_layer: float, seed: int):
+        self.seed32 = np.uint32(((seed ^ (seed >> 32)) & 0xFFFFFFFF))
+        self.p = {"input": float(p_input), "layer": float(p_layer)}
+
+    def factor(self, which: str, layer: int, kind: int, shape: tuple) -> Optional[torch.Tensor]:
+        """1 / (1 - p) where the element is kept, 0 where it is dropped; element index = C-order position in `shape`."""
+        p = self.p[which]
+        thresh = np.uint32(int(p * 16777216.0 + 0.5))
+        if thresh == 0:
+            return None
+        n = int(np.prod(shape))
+        with np.errstate(over="ignore"):
+            x = np.arange(n, dtype=np.uint32) * np.uint32(0x9E3779B1) + self.seed32 + np.uint32(layer * 8 + kind) * np.uint32(0x85EBCA77)
+            x ^= x >> np.uint32(16); x *= np.uint32(0x7FEB352D); x ^= x >> np.uint32(15); x *= np.uint32(0x846CA68B); x ^= x >> np.uint32(16)
+        keep = (x >> np.uint32(8)) >= thresh
+        scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+        return torch.from_numpy(np.where(keep, scale, np.float32(0.0)).astype(np.float32).reshape(shape))
+
+
+def transformer_stack(cfg: OracleCfg, sd: dict, x: torch.Tensor, bias: torch.Tensor, drop: Optional[DropMasks] = None) -> torch.Tensor:
     """Pre-LN encoder stack + final LayerNorm (nn.TransformerEncoder built at embedding_decoder.py:309-327,
-    called at :714).  x: A x S x E, bias: broadcastable to A x 1 x S x S (additive)."""
+    called at :714).  x: A x S x E, bias: broadcastable to A x 1 x S x S (additive).  drop: training-mode dropout with
+    explicit masks (attention probabilities, both residual branches, the activated feed-forward rows)."""
     A, S, E = x.shape
     H = cfg.num_heads
     d = E // H
     scale = 1.0 / math.sqrt(d)
+
+    def dropped(t, layer, kind):
+        f = None if drop is None else drop.factor("layer", layer, kind, tuple(t.shape))
+        return t if f is None else t * f
+
     for l in range(cfg.num_layers):
         p = f"transformer.layers.{l}."
         h = _layer_norm(x, sd[p + "norm1.weight"], cfg.ln_eps)
@@ -136,21 +169,21 @@ def transformer_stack(cfg: OracleCfg, sd: dict, x: torch.Tensor, bias: torch.Ten
         q = q.view(A, S, H, d).transpose(1, 2)
         k = k.view(A, S, H, d).transpose(1, 2)
         v = v.view(A, S, H, d).transpose(1, 2)
-        if FUSED_OPS:
+        if FUSED_OPS and drop is None:
             o = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=bias.expand(A, 1, S, S) if bias.shape[0] != A else bias)
         else:
             att = torch.softmax((q @ k.transpose(-1, -2)) * scale + bias, dim=-1)
-            o = att @ v
+            o = dropped(att, l, DropMasks.ATTN) @ v
         o = o.transpose(1, 2).reshape(A, S, E)
-        x = x + o @ sd[p + "self_attn.out_proj.weight"].t()
+        x = x + dropped(o @ sd[p + "self_attn.out_proj.weight"].t(), l, DropMasks.BRANCH1)
         h = _layer_norm(x, sd[p + "norm2.weight"], cfg.ln_eps)
-        h = _gelu_erf(h @ sd[p + "linear1.weight"].t())
-        x = x + h @ sd[p + "linear2.weight"].t()
+        h = dropped(_gelu_erf(h @ sd[p + "linear1.weight"].t()), l, DropMasks.FFN)
+        x = x + dropped(h @ sd[p + "linear2.weight"].t(), l, DropMasks.BRANCH2)
     return _layer_norm(x, sd["transformer.norm.weight"], cfg.ln_eps)
 
 
 def forward_logits(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: Optional[torch.Tensor],
-                   padding: Optional[torch.Tensor], only_pred: bool) -> tuple[torch.Tensor, Optional[torch.Tensor]]:
+                   padding: Optional[torch.Tensor], only_pred: bool, drop: Optional[DropMasks] = None) -> tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Restates PrefixedIterDecoder.forward up to the logits (embedding_decoder.py:659-727).
     embed B x F; target A x C (A = B*M, sequences of one embedding adjacent, i.e. B-before-M) or None;
     padding A x C bool or None.  Returns (A x T x V logits, A x T effective padding or None)."""
@@ -168,12 +201,15 @@ def forward_logits(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: Option
             x = torch.cat((x, Wt[target[:, :-1]]), dim=1)  # tied token embedding, :692, utils.py:65-68
     S = x.shape[1]
     x = x + sd["pos_embedding.embedding.weight"][:S]  # :1297 (dropout is identity in eval)
+    if drop is not None:
+        f = drop.factor("input", 0, DropMasks.INPUT, tuple(x.shape))
+        x = x if f is None else x * f
     bias = attention_bias(cfg, S, dtype).view(1, 1, S, S)
     eff_pad = None
     if padding is not None:
         kb, eff_pad = key_padding_bias(cfg, padding, S, dtype)
         bias = bias + kb.view(-1, 1, 1, S)
-    x = transformer_stack(cfg, sd, x, bias)
+    x = transformer_stack(cfg, sd, x, bias, drop)
     if only_pred:
         x = x[:, -1:, :]
         if eff_pad is not None:
@@ -184,13 +220,13 @@ def forward_logits(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: Option
 
 
 def forward_loss(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: torch.Tensor, padding: Optional[torch.Tensor],
-                 weight: Optional[torch.Tensor], label_smoothing: float = 0.0):
+                 weight: Optional[torch.Tensor], label_smoothing: float = 0.0, drop: Optional[DropMasks] = None):
     """Teacher-forced forward with loss/correct (embedding_decoder.py:729-761), only_pred=False.
     Returns (logits A x C x V, loss_sum, loss_basis, correct A x C)."""
     if weight is not None:  # :681-685
         wpad = (weight == 0).unsqueeze(1)
         padding = wpad.expand_as(target) if padding is None else (padding | wpad)
-    logits, eff_pad = forward_logits(cfg, sd, embed, target, padding, only_pred=False)
+    logits, eff_pad = forward_logits(cfg, sd, embed, target, padding, only_pred=False, drop=drop)
     A, C, V = logits.shape
     tgt = target if eff_pad is None else target.masked_fill(eff_pad, -1)
     logp = torch.log_softmax(logits, dim=-1)

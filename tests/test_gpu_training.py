@@ -14,11 +14,11 @@ REL_TOL = 0.05      # ||g_cuda - g_ref|| / ||g_ref|| per parameter tensor
 COS_TOL = 0.998
 
 
-def _oracle_grads(sd, embed, tgt, pad, weight, M):
+def _oracle_grads(sd, embed, tgt, pad, weight, M, drop=None):
     cfg = orc.cfg_from_state_dict(sd)
     leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "causality_mask"}
     A = tgt.shape[0]
-    _, loss_sum, loss_basis, correct = orc.forward_loss(cfg, leaf, embed, tgt, pad, weight)
+    _, loss_sum, loss_basis, correct = orc.forward_loss(cfg, leaf, embed, tgt, pad, weight, drop=drop)
     loss_sum.backward()
     return loss_sum.item(), float(loss_basis), correct, {k: v.grad for k, v in leaf.items()}
 
@@ -93,3 +93,70 @@ def test_reference_style_optimizer_step_runs():
     with torch.inference_mode():
         out = model(embed, tgt, pad, None, True, True, False, None)
     assert abs((out[2] / out[3]).item() - losses[-1]) < 1.0   # inference forward sees the updated weights (re-packed automatically)
+
+
+@pytest.mark.parametrize("p_in,p_layer", [(0.1, 0.1), (0.0, 0.25), (0.3, 0.0)])
+def test_dropout_matches_oracle_with_replayed_masks(p_in, p_layer):
+    """Training with dropout (the reference's default: input_dropout = layer_dropout = 0.1, train.yaml; sites listed in SURVEY.md
+    section 8 "numerical contract").  torch's dropout stream cannot be reproduced, so the masks are the product's own hash-generated
+    ones, replayed on the CPU by the oracle (oracle.DropMasks): same masks -> loss and every gradient must agree as without dropout."""
+    dims = synth.DecoderDims()
+    sd = weight_case("eos")
+    B = 24
+    embed = synth.synth_embeddings(B, seed=21)
+    tgt, pad = synth.synth_targets(B, dims, seed=5)
+    model = default_decoder(dims, sd, input_dropout=p_in, layer_dropout=p_layer).to(DEV).train()
+    torch.manual_seed(123)
+    _, _, loss_sum, loss_basis, _ = model(embed.to(DEV), tgt.to(DEV), pad.to(DEV), None, True, True, False, None)
+    (loss_sum / loss_basis).backward()
+    got_p_in, got_p_layer, seed = model._last_dropout
+    assert (got_p_in, got_p_layer) == (p_in, p_layer) and seed != 0
+    drop = orc.DropMasks(p_in, p_layer, seed)
+    ref_loss, ref_basis, _, ref = _oracle_grads(sd, embed, tgt, pad, None, 1, drop=drop)
+    assert abs(loss_sum.item() - ref_loss) <= 0.12 * ref_basis + 1e-3
+    got = dict(model.named_parameters())
+    bad = {}
+    for k, g_ref in ref.items():
+        g = got[k].grad.detach().cpu().double()
+        r = (g_ref / ref_basis).double()
+        rel = (g - r).norm().item() / max(r.norm().item(), 1e-12)
+        cos = torch.nn.functional.cosine_similarity(g.flatten(), r.flatten(), dim=0).item()
+        if rel > REL_TOL or cos < COS_TOL:
+            bad[k] = (rel, cos)
+    assert not bad, bad
+    # and the masks matter: against the same batch WITHOUT dropout the gradients are clearly off (the test discriminates)
+    _, plain_basis, _, plain = _oracle_grads(sd, embed, tgt, pad, None, 1)
+    off = 0
+    for k, g_ref in plain.items():
+        g = got[k].grad.detach().cpu().double()
+        r = (g_ref / plain_basis).double()
+        off += (g - r).norm().item() / max(r.norm().item(), 1e-12) > 4 * REL_TOL
+    assert off >= len(plain) // 2
+
+
+def test_dropout_controls():
+    """Fresh masks per call, reproducible under torch.manual_seed, off in eval mode, and utils.rescale_dropout-style mutation of the
+    nn.Dropout holders (utils.py:177-192) is honoured."""
+    dims = synth.DecoderDims()
+    sd = weight_case("lively")
+    embed = synth.synth_embeddings(16, seed=3).to(DEV)
+    tgt, pad = synth.synth_targets(16, dims, seed=5)
+    tgt, pad = tgt.to(DEV), pad.to(DEV)
+    model = default_decoder(dims, sd).to(DEV).train()                      # reference defaults: 0.1 / 0.1
+
+    def loss():
+        out = model(embed, tgt, pad, None, True, True, False, None)
+        return out[2].item()
+    torch.manual_seed(7); a = loss()
+    b = loss()
+    torch.manual_seed(7); c = loss()
+    assert a != b and a == c
+    for m in model.modules():                                              # what utils.rescale_dropout(model, 0) does
+        if isinstance(m, torch.nn.modules.dropout._DropoutNd):
+            m.p *= 0.0
+    d, e = loss(), loss()
+    assert d == e and model._last_dropout[:2] == (0.0, 0.0)
+    model.eval()
+    with torch.inference_mode():
+        f = model(embed, tgt, pad, None, True, True, False, None)[2].item()
+    assert abs(f - d) <= 1e-3 * abs(d)

@@ -18,7 +18,7 @@ if world > 1:
 from novic_b200 import synth, default_decoder, EmbeddingNoise
 from novic_b200.dist import train_step
 dims = synth.DecoderDims()
-model = default_decoder(dims, synth.synth_state_dict(dims, seed=1), input_dropout=0.0, layer_dropout=0.0).to(dev).train()
+model = default_decoder(dims, synth.synth_state_dict(dims, seed=1)).to(dev).train()   # input / layer dropout 0.1 (train.yaml defaults)
 decay = [p for p in model.parameters() if p.dim() >= 2]; no_decay = [p for p in model.parameters() if p.dim() < 2]
 opt = torch.optim.AdamW([{'params': no_decay, 'weight_decay': 0.0}, {'params': decay, 'weight_decay': 0.1}], lr=1.5e-3, betas=(0.9, 0.95), fused=True)
 noise = EmbeddingNoise.create("GaussElemUniformAngle", 1024, 3.25, 45.0, 75.0, 0.0, 0.15)
@@ -39,5 +39,5 @@ if world > 1: dist.barrier()
 dt = (time.perf_counter() - t0) / args.steps
 if rank == 0:
     print(json.dumps({"metric": "training samples/sec (teacher-forced step, noise + fwd + bwd + allreduce + clip + AdamW)", "value": B * world / dt, "unit": "samples/s",
-                      "n_gpus": world, "ms_per_step": dt * 1e3, "batch_per_gpu": B, "loss_first": losses[0].item(), "loss_last": losses[-1].item(), "dropout": "not applied"}))
+                      "n_gpus": world, "ms_per_step": dt * 1e3, "batch_per_gpu": B, "loss_first": losses[0].item(), "loss_last": losses[-1].item(), "dropout": "input 0.1, layer 0.1"}))
 if world > 1: dist.destroy_process_group()
