@@ -355,7 +355,7 @@ int plan_workspace(const NovicHandle* h, int64_t B, int H, int rps, char* base, 
   w.rows = tf ? w.nseq * rps : std::max<int64_t>(B * P, w.nseq);
   w.logit_rows = tf ? w.nseq * c.token_length : w.nseq;
   w.ntiles = 2 * static_cast<int>(ceil_div(c.vocab_size, kTileN));  // 64-column partial slices
-  w.hcap = tf ? 0 : (H <= 1 ? 0 : (H <= 4 ? 4 : 16));
+  w.hcap = tf ? 0 : (H <= 1 ? 0 : (H <= 4 ? 4 : (H <= 12 ? 12 : 16)));   // per-slice candidate list length >= beam width
   const int64_t rows32 = ceil_div(w.rows, 32) * 32;
   Bump b;
   auto P_ = [&](size_t bytes) { return base + b.take(bytes); };
@@ -616,18 +616,21 @@ int run_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, int 
                const long long* target, float inv_tau, int ban_eos, cudaStream_t s, const GuideCfg* g = nullptr, int allow_mod = 0) {
   if (g != nullptr && g->on && g->bias != nullptr) {
     if (ws.hcap == 4) return launch_logits<4, true, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s, g->bias);
+    if (ws.hcap == 12) return launch_logits<12, true, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s, g->bias);
     return launch_logits<16, true, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s, g->bias);
   }
   if (g != nullptr && g->on) {
     switch (ws.hcap) {
       case 0: return launch_logits<0, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
       case 4: return launch_logits<4, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
+      case 12: return launch_logits<12, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
       default: return launch_logits<16, true>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, g->renorm, allow_mod, s);
     }
   }
   switch (ws.hcap) {
     case 0: return launch_logits<0, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
     case 4: return launch_logits<4, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
+    case 12: return launch_logits<12, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
     default: return launch_logits<16, false>(h, ws, a, M, logits, ld_logits, target, inv_tau, ban_eos, false, 0, s);
   }
 }
@@ -716,6 +719,7 @@ int enqueue_beam(NovicHandle* h, const Workspace& ws, float tau, float alpha, co
                  guide.on ? ws.b_node[in] : static_cast<const int*>(nullptr), guide.on ? ws.b_node[out] : static_cast<int*>(nullptr)};
     const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
     if (ws.hcap == 4) launch_select_beam<4>(ws, h, step, inv_tau, alpha, st, pos_next, guide, s);
+    else if (ws.hcap == 12) launch_select_beam<12>(ws, h, step, inv_tau, alpha, st, pos_next, guide, s);
     else launch_select_beam<16>(ws, h, step, inv_tau, alpha, st, pos_next, guide, s);
     if (step < G) {
       PassCfg dec{A, A, 1, P + step - 1, 1, H, nullptr, 0, ws.b_anc[out], G, 0, 0, 0};
@@ -857,6 +861,9 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
+      set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<0>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<4>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<16>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<0, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<4, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<16, true>, kWideStages, kWideKbs>() ||
