@@ -280,7 +280,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from novic_b200 import _abi, default_decoder, synth
-    from novic_b200.dist import gather_generation
+    from novic_b200.dist import gather_generation_async
     dims = synth.DecoderDims()
     model = default_decoder(dims, synth.synth_state_dict(dims, seed=1)).to(dev)
     B = args.batch
@@ -290,13 +290,16 @@ def main():
     lib = _abi.lib()
 
     def step_device():
-        tok, pad, _, _, _, score = model.generate(embed, False, True, 1.0, 0.0, None, None, False)
-        if world > 1:
-            tok, pad, score = gather_generation(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world, gen_len=dims.token_length - 1)
-        return tok, pad, score
+        if world == 1:
+            tok, pad, _, _, _, score = model.generate(embed, False, True, 1.0, 0.0, None, None, False)
+            return tok, pad, score
+        # sharded: decode and gather are enqueued without a host synchronisation; the one sync of the step reads the global early-exit length
+        tok, pad, score, T = model.generate_async(embed, 1.0, 0.0)
+        tok, pad, score, T = gather_generation_async(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world, dims.token_length - 1, T)
+        t = int(T.item())
+        return tok[:, :, :t], pad[:, :, :t], score
 
     from novic_b200.serve import GenerationPipeline
-    from novic_b200.dist import gather_generation_async
     gather = (lambda t, p, sc, T: gather_generation_async(t, p, sc, B * world, dims.token_length - 1, T)) if world > 1 else None
     pipeline = GenerationPipeline(model, "greedy", post=gather, emit=(rank == 0))
 

@@ -49,11 +49,13 @@ def gather_generation_async(tok: torch.Tensor, pad: torch.Tensor, score: torch.T
     o_hdr = (o_pad + rows * G + 7) // 8 * 8
     nbytes = o_hdr + 8
     dev = tok.device
-    buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    full = n_local == n_max and T_have == G                  # every byte of the payload gets written below: no need to clear it first
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev) if full else torch.zeros(nbytes, dtype=torch.uint8, device=dev)
     buf[o_ids:o_score].view(torch.int64).view(n_max, K, G)[:n_local, :, :T_have] = tok
     buf[o_score:o_pad].view(torch.float32).view(n_max, K)[:n_local] = score
     pd = buf[o_pad:o_pad + rows * G].view(n_max, K, G)
-    pd[:n_local, :, T_have:] = 1
+    if not full:
+        pd[:n_local, :, T_have:] = 1
     pd[:n_local, :, :T_have] = pad.view(torch.uint8) if pad.dtype == torch.bool else pad
     hdr = buf[o_hdr:].view(torch.int64)
     if T_local is None:
