@@ -230,6 +230,8 @@ def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict
     work = algorithmic_work(embed.shape[0], dims, fused=cnt[names.index('layer_stack')] > 0)
     if cnt[names.index('ffn1_gemm')] == 0:      # fused feed-forward kernel: its launches do both GEMMs of the block
         work["ffn2_gemm"] = ("tensor", work["ffn1_gemm"][1] + work["ffn2_gemm"][1])
+    if cnt[names.index('outproj_gemm')] == 0:   # fused block kernel (out-proj + LN2 + feed-forward + LN): timed as class ffn2_gemm
+        work["ffn2_gemm"] = ("tensor", work["ffn2_gemm"][1] + work["outproj_gemm"][1])
     total = sum(max(v, 0.0) for v in in_graph.values()) or 1.0
     out = {}
     for i, name in enumerate(names):

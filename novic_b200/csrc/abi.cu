@@ -102,6 +102,7 @@ int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, i
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
+bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
 int g_attn_hint = 1;                           // NOVIC_ATTN_HINT bit 0: evict-first L2 policy on the streamed K/V rows; bit 1: evict-last on new K/V rows
 int g_row_stages = 4;                          // NOVIC_ROW_STAGES=2|3: shallower row-kernel pipelines (tuning: co-residency with the next kernel)
 bool g_split_ffn = true;                       // NOVIC_SPLIT_FFN=0: every CTA of a cluster recomputes the whole hidden tile
@@ -155,6 +156,7 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
+  CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
@@ -183,6 +185,17 @@ int launch_ffn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw1, co
   else if (split_h && g_row_stages == 3) CUDA_TRY(launch_k(gemm_rowln_kernel<3, 2>, grid, dim3(kRowThreads), rowln_smem_bytes(3, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
   else if (split_h) CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, 2>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
   else CUDA_TRY(launch_k(gemm_rowln_kernel<kStagesRow, true>, grid, dim3(kRowThreads), rowln_smem_bytes(kStagesRow, true), s, ta, tw2, tw1, M, kE / kBlockK, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Attention output -> next LayerNorm rows in one cluster kernel (out-proj + LN2 + feed-forward + LN), decode path.
+int launch_outproj_ffn(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1q, const CUtensorMap& tw2, int M,
+                       const FusedBlockParams& ep) {
+  static_assert(outproj_ffn_smem_bytes() <= 227 * 1024, "fused block kernel does not fit in shared memory");
+  dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kBlockM)));
+  CUDA_TRY(launch_k(outproj_ffn_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1q, tw2, M, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -540,6 +553,20 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
     }
     if (launch_attention(h, ws, pc, l, s)) return 1;
+    if (g_fuse_block && h->fuse_ffn && c.ffn_dim == kFfnDim) {
+      FusedBlockParams fb{};
+      fb.x = ws.x; fb.gain_mid = h->w.norm2[l]; fb.eps = c.ln_eps;
+      if (l + 1 < L) {
+        fb.xn = ws.xn; fb.gain_out = h->w.norm1[l + 1];
+      } else {
+        fb.gain_out = h->w.final_norm;
+        fb.xn = pc.remap_in > 0 ? ws.xfin : ws.xn;
+        fb.remap_rows_in = pc.remap_in; fb.remap_skip = pc.remap_skip; fb.remap_rows_out = pc.remap_out;
+      }
+      KSpan t(kKFfn2, s);
+      if (launch_outproj_ffn(s, tm_ao, h->w.tm_out_proj[l], h->w.tm_linear1_q[l], h->w.tm_linear2[l], M, fb)) return 1;
+      continue;
+    }
     RowParams po{};
     po.x = ws.x; po.xn = ws.xn; po.gain = h->w.norm2[l]; po.pos = nullptr; po.eps = c.ln_eps;
     { KSpan t(kKOutProj, s); if (launch_rowln(s, tm_ao, h->w.tm_out_proj[l], M, kE, kE, po)) return 1; }
@@ -903,6 +930,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e16 = getenv("NOVIC_SPLIT_FFN")) g_split_ffn = e16[0] != '0';
   if (const char* e17 = getenv("NOVIC_ROW_STAGES")) g_row_stages = atoi(e17);
   if (const char* e18 = getenv("NOVIC_ATTN_HINT")) g_attn_hint = atoi(e18);
+  if (const char* e22 = getenv("NOVIC_FUSE_BLOCK")) g_fuse_block = e22[0] != '0';
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';

@@ -950,4 +950,329 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Attention output -> next layer's LayerNorm rows in ONE cluster kernel (decode path): out-proj + residual + LN2, then the whole
+// feed-forward block + residual + LN, without the round trip of x_mid (fp32) and LN2(x_mid) (bf16) through L2 that the two separate
+// row kernels need - 12 MB of stores at the L2's ~5 TB/s write rate plus a 128 KB TMA reload per CTA and one kernel ramp per layer.
+//   phase A  acc0 = ao * Wo^T (this CTA's 128 columns, pipelined over K = 512);  r = x + acc0;  LN2 statistics over the cluster
+//   hand-over  y = LN2(r) in bf16: the thread's 64 columns are exactly one 128-byte row of k-block (2 * rank + half) of the K-major
+//            swizzled A operand of FFN1, and are stored into the operand buffer of all four CTAs through DSMEM.  The buffer is the
+//            out-proj ring itself (dead once every CTA's phase-A MMAs have completed, which the statistics barrier guarantees).
+//   phase B  acc1 = y * W1[32 r : 32 r + 32]^T (UMMA N = 32, A resident);  GELU;  hidden columns broadcast through DSMEM
+//   phase C  acc2 = h * W2^T;  r += acc2;  LN statistics over the cluster;  store x (fp32) and LayerNorm(x) (bf16)
+// The residual values r never leave the registers between the two LayerNorms.  Results are bit-identical to the separate kernels.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFbStages = 4;
+__host__ __device__ constexpr int outproj_ffn_smem_bytes() {
+  return kFbStages * kStageBytes /*ring = FFN1 A operand*/ + (kFfnDim / kRowCluster) * kE * 2 /*W1 slice*/ + 2 * kBBytes /*W2*/ + 2 * kABytes /*h*/ +
+         1024 /*align*/ + 256 /*barriers*/ + 2 * kRowBN * 4 /*gains*/;
+}
+struct FusedBlockParams {
+  float* x;                 // blocked fp32 residual stream, in and out (in place)
+  __nv_bfloat16* xn;        // [rows, 512] LayerNorm output of the block (next layer's LN1 / final LN)
+  const float* gain_mid;    // LN2 weight
+  const float* gain_out;    // weight of the LayerNorm that follows the block
+  int remap_rows_in, remap_skip, remap_rows_out;   // xn row remap of the last layer (0 = identity)
+  float eps;
+};
+
+__global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kRowThreads, 1)
+outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1q,
+                   const __grid_constant__ CUtensorMap tmap_w2, int M, FusedBlockParams ep) {
+  constexpr int BN = kRowBN;
+  constexpr int kHSplit = kFfnDim / kRowCluster;              // 32 hidden columns per CTA
+  constexpr int kW1kb = kHSplit * kBlockK * 2;                // bytes of one k-block of the W1 slice: 4 KB
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
+  constexpr uint32_t kIdescH = umma_idesc_bf16_f32(kBlockM, kHSplit);
+  constexpr int kNkb = kE / kBlockK;                          // 8
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;                                       // phase A pipeline; afterwards the 8 k-block tiles of LN2(x_mid)
+  uint8_t* w1_smem = ring + kFbStages * kStageBytes;
+  uint8_t* w2_smem = w1_smem + kNkb * kW1kb;
+  uint8_t* h_smem = w2_smem + 2 * kBBytes;
+  uint8_t* after = h_smem + 2 * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
+  uint64_t* empty_bar = full_bar + kFbStages;
+  uint64_t* tmem_full0 = empty_bar + kFbStages;
+  uint64_t* w1_full = tmem_full0 + 1;
+  uint64_t* w2_full = tmem_full0 + 2;
+  uint64_t* tmem_full1 = tmem_full0 + 3;
+  uint64_t* tmem_full2 = tmem_full0 + 4;
+  uint64_t* affn_full = tmem_full0 + 5;                       // the three peers' LN2 slices have landed in this CTA's FFN1 operand
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 6);
+  float* s_gain_mid = reinterpret_cast<float*>(after + 256);
+  float* s_gain_out = s_gain_mid + BN;
+  float2* s_stats = reinterpret_cast<float2*>(h_smem);        // [2 halves][128 rows]; h is written after the first exchange and dead before the second
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = static_cast<int>(lane_id());
+  const int m0 = blockIdx.y * kBlockM;
+  const uint32_t crank = cluster_ctarank();
+  const int coff = static_cast<int>(crank) * BN;
+  const int n0 = coff;
+  __shared__ int s_trace;
+  pdl_trigger();
+  if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
+
+  GemmSmemView sv;
+  sv.stages = ring; sv.full_bar = full_bar; sv.empty_bar = empty_bar; sv.tmem_full_bar = tmem_full0; sv.tmem_slot = tmem_slot; sv.scratch = nullptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1q); tma_prefetch_desc(&tmap_w2);
+      for (int st = 0; st < kFbStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
+      mbar_init(tmem_full0, 1); mbar_init(w1_full, 1); mbar_init(w2_full, 1); mbar_init(tmem_full1, 1); mbar_init(tmem_full2, 1);
+      mbar_init(affn_full, 1);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(affn_full, (kRowCluster - 1) * 2 * kABytes);   // the peers' copies can only start after cluster barrier #1
+      // all weights first (they do not depend on the previous kernel), then wait, then the activation tiles
+      for (int kb = 0; kb < kFbStages; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
+        tma_load_2d(ring + kb * kStageBytes + kABytes, &tmap_wo, &full_bar[kb], kb * kBlockK, n0, kEvictLast);
+      }
+      mbar_arrive_expect_tx(w1_full, kNkb * kW1kb);
+      for (int kb = 0; kb < kNkb; ++kb) tma_load_2d(w1_smem + kb * kW1kb, &tmap_w1q, w1_full, kb * kBlockK, static_cast<int>(crank) * kHSplit, kEvictLast);
+      mbar_arrive_expect_tx(w2_full, 2 * kBBytes);
+      tma_load_2d(w2_smem, &tmap_w2, w2_full, 0, n0, kEvictLast);
+      tma_load_2d(w2_smem + kBBytes, &tmap_w2, w2_full, kBlockK, n0, kEvictLast);
+      pdl_wait();
+      for (int kb = 0; kb < kFbStages; ++kb)
+        tma_load_2d(ring + kb * kStageBytes, &tmap_ao, &full_bar[kb], kb * kBlockK, m0, kEvictNormal);
+    }
+  } else if (warp == 1) {
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool tr = s_trace != 0;
+  pdl_wait();
+  if (threadIdx.x == 0) trace_point(tr, 1);
+
+  if (warp == 0) {
+    if (elect_one()) producer_rest<kFbStages>(sv, &tmap_ao, &tmap_wo, kNkb, m0, n0);
+  } else if (warp == 1) {
+    if (elect_one()) mma_mainloop<kFbStages>(sv, tmem_base, kNkb, false);      // acc0 -> TMEM columns [0, 128)
+  }
+
+  // ---- phase A epilogue: residual + accumulator, LN2 statistics
+  const bool is_epi = warp >= 2;
+  const int ew = warp - 2;
+  const int quad = warp & 3;
+  const int half = ew >> 2;
+  const int row_in_tile = quad * 32 + lane;
+  const int row = m0 + row_in_tile;
+  const int c0 = coff + half * kRowCols;
+  const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  float r[kRowCols];
+  auto add_acc_and_stats = [&](uint32_t acc_col) {
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRowCols / 16; ++c) {
+      float v[16];
+      tmem_ld_32x16(tmem_lane + acc_col + half * kRowCols + c * 16, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float t = r[c * 16 + j] + v[j];
+        r[c * 16 + j] = t;
+        sum += t;
+        sumsq = fmaf(t, t, sumsq);
+      }
+    }
+    s_stats[half * 128 + row_in_tile] = make_float2(sum, sumsq);
+  };
+  auto gather_stats = [&](float& mean, float& rstd) {
+    float2 part[kRowCluster * 2];
+#pragma unroll
+    for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) part[pr * 2 + hh] = dsmem_ld_f32x2_addr(dsmem_addr(&s_stats[hh * 128 + row_in_tile], pr));
+    }
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowCluster * 2; ++i) { sum += part[i].x; sumsq += part[i].y; }
+    mean = sum * (1.0f / kE);
+    rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
+  };
+  if (is_epi) {
+    if (ew < 4) {
+      s_gain_mid[threadIdx.x - 64] = __ldg(ep.gain_mid + coff + (threadIdx.x - 64));
+      s_gain_out[threadIdx.x - 64] = __ldg(ep.gain_out + coff + (threadIdx.x - 64));
+    }
+    if (row < M) {
+#pragma unroll
+      for (int q = 0; q < kRowCols / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (c0 >> 2) + q));
+        r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRowCols; ++i) r[i] = 0.f;
+    }
+    mbar_wait(tmem_full0, 0, 3);
+    if (threadIdx.x == 64) trace_point(tr, 2);
+    tc_fence_after_sync();
+    add_acc_and_stats(0);
+    if (threadIdx.x == 64) trace_point(tr, 3);
+  }
+  __syncthreads();          // s_gain visible to all epilogue warps
+  cluster_sync_all();       // #1: LN2 partials visible; every CTA's phase-A MMAs have completed (their accumulators were read)
+  if (threadIdx.x == 64) trace_point(tr, 4);
+
+  // ---- hand-over: LN2 rows -> FFN1 operand of all four CTAs.  Every thread writes its 128-byte row into the LOCAL operand buffer; one
+  // thread then pushes the CTA's two k-block tiles (32 KB) to each peer with a TMA shared->shared bulk copy that completes on the peer's
+  // mbarrier (per-thread st.shared::cluster stores took 11 k cycles for the same bytes).
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    if (row < M) gather_stats(mean, rstd);
+    const int kb = static_cast<int>(crank) * 2 + half;                       // this thread's 64 columns = one row of that k-block
+    uint8_t* arow = ring + kb * kABytes + row_in_tile * 128;
+#pragma unroll
+    for (int q = 0; q < kRowCols / 8; ++q) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain_mid[half * kRowCols + q * 8 + i];
+      *reinterpret_cast<uint4*>(arow + ((q ^ (row_in_tile & 7)) << 4)) =
+          make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    }
+    fence_proxy_async_smem();      // generic-proxy writes -> visible to the async proxy (the bulk copies and this CTA's own MMAs)
+    if (threadIdx.x == 64) trace_point(tr, 5);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint8_t* src = ring + static_cast<int>(crank) * 2 * kABytes;
+#pragma unroll
+      for (uint32_t d = 1; d < kRowCluster; ++d) {
+        const uint32_t pr = (crank + d) % kRowCluster;
+        dsmem_bulk_copy(dsmem_addr(src, pr), src, 2 * kABytes, dsmem_addr(affn_full, pr));
+      }
+    }
+  }
+  __syncwarp();
+  if (threadIdx.x == 64) trace_point(tr, 6);
+
+  // ---- phase B: this CTA's 32 hidden columns
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(affn_full, 0, 5);
+      trace_point(tr, 15);
+      mbar_wait(w1_full, 0, 6);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(ring), sb = smem_u32(w1_smem);
+#pragma unroll
+      for (int kb = 0; kb < kNkb; ++kb)
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base + 128, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
+                       umma_desc_sw128_kmajor(sb + kb * kW1kb + k * (kUmmaK * 2)), kIdescH, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full1);
+    }
+  }
+  __syncwarp();
+  if (is_epi) {
+    mbar_wait(tmem_full1, 0, 7);
+    if (threadIdx.x == 64) trace_point(tr, 7);
+    tc_fence_after_sync();
+    float v[16];
+    tmem_ld_32x16(tmem_lane + 128 + half * 16, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+    const int hcol = static_cast<int>(crank) * kHSplit + half * 16;
+    uint8_t* hrow = h_smem + (hcol >> 6) * kABytes + row_in_tile * 128;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int chunk = ((hcol & 63) >> 3) + q;
+      const uint4 pk = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                                  pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+      uint8_t* dst = hrow + ((chunk ^ (row_in_tile & 7)) << 4);
+#pragma unroll
+      for (uint32_t pr = 0; pr < kRowCluster; ++pr) dsmem_st_v4(dsmem_addr(dst, pr), pk);
+    }
+    fence_proxy_async_any();
+    tc_fence_before_sync();
+  }
+  if (threadIdx.x == 64) trace_point(tr, 8);
+  __syncwarp();
+  cluster_sync_all();       // #3: the whole hidden tile sits in every CTA's h operand
+  if (threadIdx.x == 64) trace_point(tr, 9);
+
+  // ---- phase C: second feed-forward GEMM, residual, LayerNorm
+  if (warp == 1) {
+    if (elect_one()) {
+      fence_proxy_async_any();
+      mbar_wait(w2_full, 0, 8);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(h_smem), sb = smem_u32(w2_smem);
+#pragma unroll
+      for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base + 256, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
+                       umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full2);
+    }
+  }
+  __syncwarp();
+  if (is_epi) {
+    mbar_wait(tmem_full2, 0, 9);     // the MMAs have read h: its first 2 KB can hold the statistics again
+    if (threadIdx.x == 64) trace_point(tr, 10);
+    tc_fence_after_sync();
+    add_acc_and_stats(256);
+    if (threadIdx.x == 64) trace_point(tr, 11);
+  }
+  __syncwarp();
+  cluster_sync_all();       // #4
+  if (threadIdx.x == 64) trace_point(tr, 12);
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    if (row < M) gather_stats(mean, rstd);
+    uint8_t* stage = ring + ew * (32 * kRowStagePitch);      // the FFN1 operand is dead: every CTA's phase-B MMAs completed before #3
+    {
+      uint4* d = reinterpret_cast<uint4*>(stage + lane * kRowStagePitch);
+#pragma unroll
+      for (int q = 0; q < kRowCols / 8; ++q) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain_out[half * kRowCols + q * 8 + i];
+        d[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+    }
+    if (row < M) {
+#pragma unroll
+      for (int q = 0; q < kRowCols / 4; ++q)
+        *reinterpret_cast<float4*>(ep.x + xblk_off(row, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+    }
+    __syncwarp();
+    const int warp_row0 = m0 + quad * 32;
+    const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 4
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + sub;
+      const int grow = warp_row0 + rr;
+      if (grow < M) {
+        int nrow = grow;
+        bool keep = true;
+        if (ep.remap_rows_in > 0) {
+          const int seq = grow / ep.remap_rows_in;
+          const int k = grow - seq * ep.remap_rows_in;
+          keep = k >= ep.remap_skip;
+          nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+        }
+        if (keep)
+          *reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + c0 + chunk * 8) =
+              *reinterpret_cast<const uint4*>(stage + rr * kRowStagePitch + chunk * 16);
+      }
+    }
+  }
+  if (threadIdx.x == 64) trace_point(tr, 13);
+  tc_fence_before_sync();
+  __syncwarp();
+  cluster_sync_relaxed();   // peers may still be reading this CTA's statistics
+  if (threadIdx.x == 0) trace_point(tr, 14);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace novic

@@ -312,6 +312,13 @@ __device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint3
   return raddr;
 }
 // Non-volatile so that several independent remote loads can be in flight at once (each costs ~200+ cycles).
+// Bulk copy from this CTA's shared memory into a peer CTA's (TMA engine, asynchronous): `bytes` (multiple of 16) from local_src to the
+// peer address dst_cluster (dsmem_addr), completion signalled as complete_tx on the PEER's mbarrier bar_cluster (dsmem_addr of it).
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, const void* local_src, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_cluster),
+               "r"(smem_u32(local_src)), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
 // 16-byte store into a peer CTA's shared memory (address from dsmem_addr)
 __device__ __forceinline__ void dsmem_st_v4(uint32_t raddr, const uint4& v) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
