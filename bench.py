@@ -252,6 +252,9 @@ def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict
                 entry.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"],
                              isolated_frac=amount / (ms[i] / steps * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"])
         out[name] = entry
+    if cnt[names.index('outproj_gemm')] == 0 and 'ffn2_gemm' in out:
+        # decode path with the fused block kernel (out-proj + LN2 + feed-forward + LN in one cluster kernel): name it for what it is
+        out['block_outproj_ffn'] = out.pop('ffn2_gemm')
     return out
 
 
@@ -378,7 +381,7 @@ def main():
         if os.path.isfile(tpath) and d.get("bound") == "hbm":
             entry = json.load(open(tpath)).get(dom)
             if entry:  # ncu-measured DRAM bytes of one launch / that launch's algorithmic bytes, applied to the average launch
-                work = algorithmic_work(B, dims, fused='layer_stack' in kernels)[dom][1]
+                work = algorithmic_work(B, dims, fused='layer_stack' in kernels).get(dom, (None, 0))[1]
                 traffic = entry["ratio_to_algorithmic"] * work / max(1, d["launches_per_step"])
         roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
                     "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],
