@@ -962,11 +962,14 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 //   phase C  acc2 = h * W2^T;  r += acc2;  LN statistics over the cluster;  store x (fp32) and LayerNorm(x) (bf16)
 // The residual values r never leave the registers between the two LayerNorms.  Results are bit-identical to the separate kernels.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kFbStages = 4;
+constexpr int kFbRing = 4;      // 32 KB stages that later hold the FFN1 A operand (128 KB)
+constexpr int kFbStages = 7;    // phase-A pipeline depth: the W1 / W2 / h regions (3 x 32 KB) are idle during phase A and serve as stages 4..6,
+                                // so 7 of the 8 k-block loads are in flight at once; W1 and W2 are loaded once stages 4 and 5 have been consumed
 __host__ __device__ constexpr int outproj_ffn_smem_bytes() {
-  return kFbStages * kStageBytes /*ring = FFN1 A operand*/ + (kFfnDim / kRowCluster) * kE * 2 /*W1 slice*/ + 2 * kBBytes /*W2*/ + 2 * kABytes /*h*/ +
+  return kFbRing * kStageBytes /*ring = FFN1 A operand*/ + (kFfnDim / kRowCluster) * kE * 2 /*W1 slice*/ + 2 * kBBytes /*W2*/ + 2 * kABytes /*h*/ +
          1024 /*align*/ + 256 /*barriers*/ + 2 * kRowBN * 4 /*gains*/;
 }
+static_assert((kFfnDim / kRowCluster) * kE * 2 == kStageBytes && 2 * kBBytes == kStageBytes && 2 * kABytes == kStageBytes, "regions double as pipeline stages");
 struct FusedBlockParams {
   float* x;                 // blocked fp32 residual stream, in and out (in place)
   __nv_bfloat16* xn;        // [rows, 512] LayerNorm output of the block (next layer's LN1 / final LN)
@@ -988,7 +991,7 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;                                       // phase A pipeline; afterwards the 8 k-block tiles of LN2(x_mid)
-  uint8_t* w1_smem = ring + kFbStages * kStageBytes;
+  uint8_t* w1_smem = ring + kFbRing * kStageBytes;
   uint8_t* w2_smem = w1_smem + kNkb * kW1kb;
   uint8_t* h_smem = w2_smem + 2 * kBBytes;
   uint8_t* after = h_smem + 2 * kABytes;
@@ -1001,6 +1004,7 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   uint64_t* tmem_full2 = tmem_full0 + 4;
   uint64_t* affn_full = tmem_full0 + 5;                       // the three peers' LN2 slices have landed in this CTA's FFN1 operand
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 6);
+  static_assert((2 * kFbStages + 6) * 8 + 4 <= 256, "barrier area");
   float* s_gain_mid = reinterpret_cast<float*>(after + 256);
   float* s_gain_out = s_gain_mid + BN;
   float2* s_stats = reinterpret_cast<float2*>(h_smem);        // [2 halves][128 rows]; h is written after the first exchange and dead before the second
@@ -1031,11 +1035,6 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
         mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
         tma_load_2d(ring + kb * kStageBytes + kABytes, &tmap_wo, &full_bar[kb], kb * kBlockK, n0, kEvictLast);
       }
-      mbar_arrive_expect_tx(w1_full, kNkb * kW1kb);
-      for (int kb = 0; kb < kNkb; ++kb) tma_load_2d(w1_smem + kb * kW1kb, &tmap_w1q, w1_full, kb * kBlockK, static_cast<int>(crank) * kHSplit, kEvictLast);
-      mbar_arrive_expect_tx(w2_full, 2 * kBBytes);
-      tma_load_2d(w2_smem, &tmap_w2, w2_full, 0, n0, kEvictLast);
-      tma_load_2d(w2_smem + kBBytes, &tmap_w2, w2_full, kBlockK, n0, kEvictLast);
       pdl_wait();
       for (int kb = 0; kb < kFbStages; ++kb)
         tma_load_2d(ring + kb * kStageBytes, &tmap_ao, &full_bar[kb], kb * kBlockK, m0, kEvictNormal);
@@ -1052,7 +1051,17 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   if (threadIdx.x == 0) trace_point(tr, 1);
 
   if (warp == 0) {
-    if (elect_one()) producer_rest<kFbStages>(sv, &tmap_ao, &tmap_wo, kNkb, m0, n0);
+    if (elect_one()) {
+      producer_rest<kFbStages>(sv, &tmap_ao, &tmap_wo, kNkb, m0, n0);
+      // stages 4 and 5 are the W1 / W2 regions: load the feed-forward weights as soon as the out-proj MMAs have read them
+      mbar_wait(&empty_bar[kFbRing], 0, 1);
+      mbar_arrive_expect_tx(w1_full, kNkb * kW1kb);
+      for (int kb = 0; kb < kNkb; ++kb) tma_load_2d(w1_smem + kb * kW1kb, &tmap_w1q, w1_full, kb * kBlockK, static_cast<int>(crank) * kHSplit, kEvictLast);
+      mbar_wait(&empty_bar[kFbRing + 1], 0, 1);
+      mbar_arrive_expect_tx(w2_full, 2 * kBBytes);
+      tma_load_2d(w2_smem, &tmap_w2, w2_full, 0, n0, kEvictLast);
+      tma_load_2d(w2_smem + kBBytes, &tmap_w2, w2_full, kBlockK, n0, kEvictLast);
+    }
   } else if (warp == 1) {
     if (elect_one()) mma_mainloop<kFbStages>(sv, tmem_base, kNkb, false);      // acc0 -> TMEM columns [0, 128)
   }
