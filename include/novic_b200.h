@@ -135,6 +135,15 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
                   const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
                   uint8_t* pad_out, float* loss, uint8_t* correct, void* ws, size_t ws_bytes, void* stream);
 
+/* novic_forward with the guided correctness evaluation of embedding_decoder.py:754-760: `correct` compares the target with the arg-max
+ * over the ids that continue a guide target matching the sequence's own prefix (trie built over the first C columns of guide_targets);
+ * logits, padding and loss are those of the unguided forward.  only_pred is not available (the reference asserts the same).
+ * mask_scratch: caller-owned device memory of at least A * C * ceil(V / 32) * 4 bytes (A = B * M). */
+int novic_forward_guided(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
+                         const uint8_t* padding, const float* weight, int32_t C, float* logits, uint8_t* pad_out, float* loss,
+                         uint8_t* correct, const NovicGuide* guide, void* mask_scratch, size_t mask_bytes, void* ws, size_t ws_bytes,
+                         void* stream);
+
 /* Replaces the scoring loop of PrefixedIterDecoder.generate_all (embedding_decoder.py:1063-1072): the teacher-forced
  * log-probability of M given token sequences for each of B embeddings, without materialising logits.
  *   target [A, C] int64 and padding [A, C] u8 (may be NULL) with A = B * M, the M sequences of an embedding adjacent.

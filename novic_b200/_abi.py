@@ -65,6 +65,8 @@ SIGNATURES = {
                                       C.POINTER(C.c_int32), C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_forward": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, C.c_int32, _FP, _FP, _FP,
                                 _FP, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "novic_forward_guided": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, _FP, _FP, _FP, _FP,
+                                       C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_score_targets": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, C.c_int32, C.c_float, C.POINTER(NovicGuide), _FP,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),

@@ -1235,10 +1235,16 @@ int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H
   return 0;
 }
 
-int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
-                  const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
-                  uint8_t* pad_out, float* loss, uint8_t* correct, void* wsbuf, size_t ws_bytes, void* stream) {
+static int forward_impl(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
+                        const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
+                        uint8_t* pad_out, float* loss, uint8_t* correct, const NovicGuide* guide, void* allow_buf, size_t allow_bytes,
+                        void* wsbuf, size_t ws_bytes, void* stream) {
   if (check_ready(h)) return 1;
+  GuideCfg gcfg;
+  if (make_guide(guide, h, &gcfg)) return 1;
+  if (gcfg.bias != nullptr) return fail("child_bias (vocabulary prior) applies to novic_generate_beam only");
+  if (gcfg.on && only_pred) return fail("guided correctness evaluation needs only_pred = 0 (embedding_decoder.py:755)");
+  gcfg.renorm = false;   // the guide restricts the predicted id only; logits and loss are those of the unguided forward
   const NovicCfg& c = h->cfg;
   if (B < 1 || M < 1 || C < 1 || C > c.token_length) return fail("bad B / M / C (C must be in [1, token_length])");
   if (target == nullptr) return fail("target is required (embedding-only forward is not part of the hot path)");
@@ -1268,6 +1274,18 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
              S, only_pred ? S - 1 : P - 1, T};
   if (run_layers(h, ws, pc, s)) return 1;
   const bool need_stats = loss != nullptr || correct != nullptr;
+  if (gcfg.on && correct != nullptr) {
+    // allowed ids of position t of sequence a = the continuations of the guide targets that match target[a, :t] (embedding_decoder.py:754-760)
+    ws.allow_words = static_cast<int>(ceil_div(c.vocab_size, 32));
+    const size_t need = sizeof(uint32_t) * static_cast<size_t>(A) * T * ws.allow_words;
+    if (allow_buf == nullptr || allow_bytes < need) return fail("guided forward: mask scratch too small: %zu < %zu", allow_bytes, need);
+    ws.allow = static_cast<uint32_t*>(allow_buf);
+    const size_t smem = sizeof(uint32_t) * kWarpsPerBlock * ws.allow_words;
+    guide_path_mask_kernel<<<static_cast<unsigned>(ceil_div(A, kWarpsPerBlock)), kWarpsPerBlock * 32, smem, s>>>(
+        gcfg.trie, reinterpret_cast<const long long*>(target), C, static_cast<int>(A), T, ws.allow_words, ws.allow);
+    ++g_launches;
+    if (run_logits(h, ws, ws.xfin, static_cast<int>(A * T), logits, c.vocab_size, ws.tgt_masked, 1.0f, 0, s, &gcfg, 0)) return 1;
+  } else
   if (run_logits(h, ws, ws.xfin, static_cast<int>(A * T), logits, c.vocab_size, need_stats ? ws.tgt_masked : nullptr, 1.0f, 0, s)) return 1;
   if (need_stats) {
     loss_rows_kernel<<<static_cast<unsigned>(ceil_div(A * T, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(
@@ -1283,6 +1301,20 @@ int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, cons
   if (pad_out != nullptr) CUDA_TRY(cudaMemcpyAsync(pad_out, ws.effpad, A * T, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+int novic_forward(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
+                  const uint8_t* padding, const float* weight, int32_t C, int32_t only_pred, float* logits,
+                  uint8_t* pad_out, float* loss, uint8_t* correct, void* wsbuf, size_t ws_bytes, void* stream) {
+  return forward_impl(h, embed, B, M, target, padding, weight, C, only_pred, logits, pad_out, loss, correct, nullptr, nullptr, 0, wsbuf, ws_bytes, stream);
+}
+
+int novic_forward_guided(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target,
+                         const uint8_t* padding, const float* weight, int32_t C, float* logits, uint8_t* pad_out, float* loss,
+                         uint8_t* correct, const NovicGuide* guide, void* mask_scratch, size_t mask_bytes, void* wsbuf, size_t ws_bytes,
+                         void* stream) {
+  if (guide == nullptr) return fail("novic_forward_guided needs a guide");
+  return forward_impl(h, embed, B, M, target, padding, weight, C, 0, logits, pad_out, loss, correct, guide, mask_scratch, mask_bytes, wsbuf, ws_bytes, stream);
 }
 
 int novic_score_targets(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,

@@ -358,11 +358,13 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     # forward (embedding_decoder.py:659-777)
     # ------------------------------------------------------------------------------------------------------
     def forward(self, embed, target, target_padding, target_weight, calc_loss, calc_correct, only_pred, guide_targets):
-        if guide_targets is not None:
-            raise NotImplementedError("guided correctness evaluation (embedding_decoder.py:754-760) is not implemented in novic_b200 yet")
         embed = self._check_embed(embed)
         if self.training and torch.is_grad_enabled() and target is not None:
+            if guide_targets is not None:
+                raise NotImplementedError("guided correctness evaluation is available in evaluation mode only (the training loop never uses it)")
             return self._forward_train(embed, target, target_padding, target_weight, calc_loss, calc_correct, only_pred)
+        if guide_targets is not None and calc_correct:
+            assert not only_pred  # embedding_decoder.py:755
         if target is None:
             raise NotImplementedError("forward without targets (prefix-only logits) is not part of the accelerated path")
         B = embed.shape[0]
@@ -402,9 +404,19 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         correct = torch.empty((A, T), dtype=torch.uint8, device=dev) if calc_correct else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            _abi.check(_abi.lib().novic_forward(st['handle'], embed.data_ptr(), B, M, target_c.data_ptr(), _ptr(pad_c), _ptr(w_c), Ct,
-                                                int(bool(only_pred)), logits.data_ptr(), _ptr(pad_out), _ptr(loss), _ptr(correct),
-                                                ws.data_ptr(), ws.numel(), stream))
+            if guide_targets is not None and calc_correct:
+                # guided correctness evaluation (embedding_decoder.py:754-760): the trie spans the first Ct columns of the guide targets
+                if not hasattr(self, "_trie_cache"):
+                    self._trie_cache = guide.TrieCache()
+                trie = self._trie_cache.get(guide_targets, Ct, V, dev)
+                masks = torch.empty(A * Ct * ((V + 31) // 32), dtype=torch.int32, device=dev)
+                _abi.check(_abi.lib().novic_forward_guided(st['handle'], embed.data_ptr(), B, M, target_c.data_ptr(), _ptr(pad_c), _ptr(w_c), Ct,
+                                                           logits.data_ptr(), _ptr(pad_out), _ptr(loss), _ptr(correct), guide.guide_arg(trie, False),
+                                                           masks.data_ptr(), masks.numel() * 4, ws.data_ptr(), ws.numel(), stream))
+            else:
+                _abi.check(_abi.lib().novic_forward(st['handle'], embed.data_ptr(), B, M, target_c.data_ptr(), _ptr(pad_c), _ptr(w_c), Ct,
+                                                    int(bool(only_pred)), logits.data_ptr(), _ptr(pad_out), _ptr(loss), _ptr(correct),
+                                                    ws.data_ptr(), ws.numel(), stream))
         out_pad = None if pad_out is None else pad_out.view(torch.bool)
         out_correct = None if correct is None else correct.view(torch.bool)
         loss_sum = loss_basis = None

@@ -66,6 +66,20 @@ def main():
             out[f"{tag}/tf/loss"] = np.array([ls.item(), float(lb)], dtype=np.float64)
             out[f"{tag}/tf/correct"] = cor.numpy()
             out[f"{tag}/tf/effpad"] = epad.numpy()
+            # guided correctness evaluation (embedding_decoder.py:754-760): targets drawn from a guide set, one of them corrupted
+            ggt = synth.synth_guide_targets(300, dims, seed=21, first_pool=24)
+            gidx = torch.randint(0, 300, (B_GOLD,), generator=torch.Generator().manual_seed(1))
+            gtgt = ggt[gidx].clone()
+            gtgt[5, 2] = 77
+            gpad = torch.zeros_like(gtgt, dtype=torch.bool)
+            gpad[:, 1:] = (gtgt[:, :-1] == 0).cummax(dim=1).values
+            glog, _, _, _, gcor = model(embed, gtgt, gpad, None, True, True, False, ggt)
+            out[f"{tag}/tfg/correct"] = gcor.numpy()
+            gT = ggt.t()
+            mism = torch.cat((torch.zeros(B_GOLD, 1, 300, dtype=torch.bool), (gtgt[:, :-1, None] != gT[None, :-1, :]).cummax(dim=1).values), dim=1)
+            gs = torch.full((B_GOLD, gtgt.shape[1], dims.vocab_size + 1), float("-inf")).scatter_(2, gT[None].expand(B_GOLD, -1, -1).masked_fill(mism, dims.vocab_size), 0.0)[:, :, :-1]
+            top2 = (gs + glog).topk(2, dim=-1).values
+            out[f"{tag}/tfg/margin"] = (top2[..., 0] - top2[..., 1]).nan_to_num(nan=float("inf"), posinf=float("inf")).numpy()
             # multi-target weighted forward
             tgt3, pad3 = synth.synth_targets(8, dims, seed=6, multi=3)
             w3 = torch.from_numpy(np.random.default_rng(8).random((8, 3)).astype(np.float32))

@@ -220,7 +220,8 @@ def forward_logits(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: Option
 
 
 def forward_loss(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: torch.Tensor, padding: Optional[torch.Tensor],
-                 weight: Optional[torch.Tensor], label_smoothing: float = 0.0, drop: Optional[DropMasks] = None):
+                 weight: Optional[torch.Tensor], label_smoothing: float = 0.0, drop: Optional[DropMasks] = None,
+                 guide_targets: Optional[torch.Tensor] = None):
     """Teacher-forced forward with loss/correct (embedding_decoder.py:729-761), only_pred=False.
     Returns (logits A x C x V, loss_sum, loss_basis, correct A x C)."""
     if weight is not None:  # :681-685
@@ -243,7 +244,16 @@ def forward_loss(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: torch.Te
         loss_sum = (weight * nll.sum(dim=1)).sum()
         n = valid.sum(dim=1) if eff_pad is not None else torch.full((A,), C)
         loss_basis = (weight * n.to(weight.dtype)).sum()
-    correct = (logits.argmax(dim=2) == tgt)
+    if guide_targets is None:
+        pred = logits.argmax(dim=2)
+    else:                                                                       # embedding_decoder.py:754-760
+        W = guide_targets.shape[0]
+        gT = guide_targets.t()                                                  # Cmax x W
+        mism = torch.cat((torch.zeros(A, 1, W, dtype=torch.bool),
+                          (target[:, :C - 1, None] != gT[None, :C - 1, :]).cummax(dim=1).values), dim=1)   # A x C x W
+        gs = torch.full((A, C, V + 1), NEG_INF, dtype=logits.dtype).scatter_(2, gT[None, :C, :].expand(A, -1, -1).masked_fill(mism, V), 0.0)[:, :, :-1]
+        pred = (gs + logits).argmax(dim=2)
+    correct = (pred == tgt)
     return logits, loss_sum, loss_basis, correct
 
 

@@ -34,3 +34,14 @@ def weight_case(tag: str, dims: synth.DecoderDims = synth.DecoderDims()) -> dict
 
 def gold_embed() -> torch.Tensor:
     return synth.synth_embeddings(B_GOLD, seed=1234)
+
+
+def guided_eval_case(dims: synth.DecoderDims = synth.DecoderDims()):
+    """Guide set, targets drawn from it (one corrupted) and their padding - the inputs of the `tfg/*` fixtures (oracle/make_golden.py)."""
+    gt = synth.synth_guide_targets(300, dims, seed=21, first_pool=24)
+    idx = torch.randint(0, 300, (B_GOLD,), generator=torch.Generator().manual_seed(1))
+    tgt = gt[idx].clone()
+    tgt[5, 2] = 77
+    pad = torch.zeros_like(tgt, dtype=torch.bool)
+    pad[:, 1:] = (tgt[:, :-1] == 0).cummax(dim=1).values
+    return gt, tgt, pad

@@ -308,3 +308,23 @@ def test_noise_statistics_and_in_place_contract():
     assert EmbeddingNoise.create("", 1024, 1, 0, 0, 0, 0) is None
     with pytest.raises(ValueError):
         EmbeddingNoise.create("nope", 1024, 1, 0, 0, 0, 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ("lively", "eos", "eosall"))
+def test_guided_correctness_evaluation_vs_reference_outputs(gold, models, tag):
+    """forward(..., guide_targets) in evaluation mode (embedding_decoder.py:754-760): `correct` must equal the reference's wherever the
+    guided top-2 margin exceeds the logit tolerance; logits / loss are those of the unguided forward."""
+    from tests.golden_util import guided_eval_case
+    gt, tgt, pad = guided_eval_case()
+    m = models(tag)
+    with torch.inference_mode():
+        lg, opad, ls, lb, cor = m(gold_embed().to(DEV), tgt.to(DEV), pad.to(DEV), None, True, True, False, gt.to(DEV))
+        lg0, _, ls0, lb0, cor0 = m(gold_embed().to(DEV), tgt.to(DEV), pad.to(DEV), None, True, True, False, None)
+    assert torch.equal(lg, lg0) and ls.item() == ls0.item() and int(lb) == int(lb0)
+    ref_cor, margin = gold[f"{tag}/tfg/correct"], gold[f"{tag}/tfg/margin"]
+    decided = (margin > 0.12) & ~pad
+    assert torch.equal(cor.cpu()[decided], ref_cor[decided])
+    assert not cor.cpu()[pad].any() and cor.sum() > cor0.sum()
+    with pytest.raises(AssertionError):
+        m(gold_embed().to(DEV), tgt.to(DEV), pad.to(DEV), None, True, True, True, gt.to(DEV))      # only_pred is incompatible (embedding_decoder.py:755)

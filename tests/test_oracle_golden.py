@@ -5,7 +5,7 @@ import torch
 
 from novic_b200 import synth
 from oracle import novic_oracle as orc
-from tests.golden_util import B_GOLD, Golden, gold_embed, weight_case
+from tests.golden_util import guided_eval_case, B_GOLD, Golden, gold_embed, weight_case
 
 TAGS = ("lively", "eos", "eosall")
 
@@ -114,3 +114,17 @@ def test_fused_and_spelled_out_maths_agree(monkeypatch):
         monkeypatch.setattr(orc, "FUSED_OPS", False)
         b, _ = orc.forward_logits(cfg, sd, e, tgt, pad, False)
     assert (a - b)[~pad].abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("tag", ("lively", "eos", "eosall"))
+def test_guided_correctness_evaluation(gold, tag):
+    """forward(..., guide_targets=...) (embedding_decoder.py:754-760): `correct` compares the target with the arg-max over the ids that
+    continue a guide target matching the sequence's own prefix."""
+    dims = synth.DecoderDims()
+    sd = weight_case(tag)
+    cfg = orc.cfg_from_state_dict(sd)
+    gt, tgt, pad = guided_eval_case(dims)
+    with torch.inference_mode():
+        _, _, _, correct = orc.forward_loss(cfg, sd, gold_embed(), tgt, pad, None, guide_targets=gt)
+    assert torch.equal(correct, gold[f"{tag}/tfg/correct"])
+    assert correct.sum() > gold[f"{tag}/tf/correct"].sum()          # the guide makes the evaluation far more lenient than the plain arg-max
