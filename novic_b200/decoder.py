@@ -366,7 +366,12 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         if guide_targets is not None and calc_correct:
             assert not only_pred  # embedding_decoder.py:755
         if target is None:
-            raise NotImplementedError("forward without targets (prefix-only logits) is not part of the accelerated path")
+            # embedding-only forward (embedding_decoder.py:690-693 with no token positions): logits of the first generated position.
+            # A one-column target contributes no token embedding (target[:, :-1] is empty), so the same call computes it.
+            assert target_padding is None and target_weight is None
+            dummy = torch.zeros((embed.shape[0], 1), dtype=self.target_config.token_dtype, device=embed.device)
+            logits, _, _, _, _ = self.forward(embed, dummy, None, None, False, False, only_pred, None)
+            return logits, None, None, None, None
         B = embed.shape[0]
         multi = target.ndim == 3
         multi_first = bool(multi and getattr(self.data_config, 'multi_target', False) and getattr(self.data_config, 'multi_first', False))

@@ -328,3 +328,19 @@ def test_guided_correctness_evaluation_vs_reference_outputs(gold, models, tag):
     assert not cor.cpu()[pad].any() and cor.sum() > cor0.sum()
     with pytest.raises(AssertionError):
         m(gold_embed().to(DEV), tgt.to(DEV), pad.to(DEV), None, True, True, True, gt.to(DEV))      # only_pred is incompatible (embedding_decoder.py:755)
+
+
+@pytest.mark.gpu
+def test_forward_without_targets_is_the_first_step(models):
+    """forward(embed, target=None, ...) returns the logits of the first generated position (B x 1 x V), i.e. step 1 of generate."""
+    m = models("lively")
+    sd = weight_case("lively")
+    cfg = orc.cfg_from_state_dict(sd)
+    e = gold_embed()[:12]
+    with torch.inference_mode():
+        lg, pad, ls, lb, cor = m(e.to(DEV), None, None, None, False, False, False, None)
+        o, _ = orc.forward_logits(cfg, sd, e, None, None, only_pred=False)
+        g = m.generate(e.to(DEV), True, False, 1.0, 0.0, None, None, False)
+    assert lg.shape == (12, 1, cfg.vocab_size) and pad is None and ls is None and lb is None and cor is None
+    assert (lg.cpu() - o).abs().max().item() <= 0.06
+    assert (lg[:, 0] - g[2][:, 0]).abs().max().item() <= 1e-3          # same kernels, prefill path vs decode path
