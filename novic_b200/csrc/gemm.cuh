@@ -958,7 +958,8 @@ gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 //   hand-over  y = LN2(r) in bf16: the thread's 64 columns are exactly one 128-byte row of k-block (2 * rank + half) of the K-major
 //            swizzled A operand of FFN1, and are stored into the operand buffer of all four CTAs through DSMEM.  The buffer is the
 //            out-proj ring itself (dead once every CTA's phase-A MMAs have completed, which the statistics barrier guarantees).
-//   phase B  acc1 = y * W1[32 r : 32 r + 32]^T (UMMA N = 32, A resident);  GELU;  hidden columns broadcast through DSMEM
+//   phase B  acc1 = y * W1[32 r : 32 r + 32]^T (UMMA N = 32, A resident);  GELU;  the CTA's 8 KB of hidden columns go to the peers as bulk
+//            copies too, and every CTA assembles the swizzled FFN2 operand locally (in the W1 region, dead by then)
 //   phase C  acc2 = h * W2^T;  r += acc2;  LN statistics over the cluster;  store x (fp32) and LayerNorm(x) (bf16)
 // The residual values r never leave the registers between the two LayerNorms.  Results are bit-identical to the separate kernels.
 // ---------------------------------------------------------------------------------------------------------
@@ -1003,11 +1004,16 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   uint64_t* tmem_full1 = tmem_full0 + 3;
   uint64_t* tmem_full2 = tmem_full0 + 4;
   uint64_t* affn_full = tmem_full0 + 5;                       // the three peers' LN2 slices have landed in this CTA's FFN1 operand
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 6);
-  static_assert((2 * kFbStages + 6) * 8 + 4 <= 256, "barrier area");
+  uint64_t* hx_full = tmem_full0 + 6;                         // the three peers' hidden-column slices have landed in the h region
+  uint64_t* hop_ready = tmem_full0 + 7;                       // the epilogue warps have assembled the FFN2 A operand
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 8);
+  static_assert((2 * kFbStages + 8) * 8 + 4 <= 256, "barrier area");
+  constexpr int kHSlice = kBlockM * kHSplit * 2;              // one CTA's hidden columns: 128 rows x 64 B = 8 KB
   float* s_gain_mid = reinterpret_cast<float*>(after + 256);
   float* s_gain_out = s_gain_mid + BN;
-  float2* s_stats = reinterpret_cast<float2*>(h_smem);        // [2 halves][128 rows]; h is written after the first exchange and dead before the second
+  // LayerNorm partials [2 halves][128 rows]: the first exchange uses the start of the h region (no hidden slice exists yet), the second
+  // the start of the W2 region (FFN2 has read it; the h region may still be the source of this CTA's outgoing slice copies)
+  float2* s_stats = reinterpret_cast<float2*>(h_smem);
 
   const int warp = threadIdx.x >> 5;
   const int lane = static_cast<int>(lane_id());
@@ -1027,9 +1033,10 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
       tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1q); tma_prefetch_desc(&tmap_w2);
       for (int st = 0; st < kFbStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
       mbar_init(tmem_full0, 1); mbar_init(w1_full, 1); mbar_init(w2_full, 1); mbar_init(tmem_full1, 1); mbar_init(tmem_full2, 1);
-      mbar_init(affn_full, 1);
+      mbar_init(affn_full, 1); mbar_init(hx_full, 1); mbar_init(hop_ready, kRowEpiWarps);
       fence_mbar_init();
       mbar_arrive_expect_tx(affn_full, (kRowCluster - 1) * 2 * kABytes);   // the peers' copies can only start after cluster barrier #1
+      mbar_arrive_expect_tx(hx_full, (kRowCluster - 1) * kHSlice);
       // all weights first (they do not depend on the previous kernel), then wait, then the activation tiles
       for (int kb = 0; kb < kFbStages; ++kb) {
         mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
@@ -1189,32 +1196,56 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
     tmem_ld_32x16(tmem_lane + 128 + half * 16, v);
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
-    const int hcol = static_cast<int>(crank) * kHSplit + half * 16;
-    uint8_t* hrow = h_smem + (hcol >> 6) * kABytes + row_in_tile * 128;
+    // hidden-column exchange: the h region holds four 8 KB slices [source CTA][128 rows][64 B]; this thread's 16 columns go into the
+    // local slice, which one thread then pushes to the peers with bulk copies (per-thread st.shared::cluster stores: 4.2 k cycles)
+    uint4* mine = reinterpret_cast<uint4*>(h_smem + static_cast<int>(crank) * kHSlice + row_in_tile * 64 + half * 32);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int chunk = ((hcol & 63) >> 3) + q;
-      const uint4 pk = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
-                                  pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-      uint8_t* dst = hrow + ((chunk ^ (row_in_tile & 7)) << 4);
-#pragma unroll
-      for (uint32_t pr = 0; pr < kRowCluster; ++pr) dsmem_st_v4(dsmem_addr(dst, pr), pk);
-    }
-    fence_proxy_async_any();
-    tc_fence_before_sync();
+    for (int q = 0; q < 2; ++q)
+      mine[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+    fence_proxy_async_smem();
   }
-  if (threadIdx.x == 64) trace_point(tr, 8);
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint8_t* src = h_smem + static_cast<int>(crank) * kHSlice;
+#pragma unroll
+      for (uint32_t d = 1; d < kRowCluster; ++d) {
+        const uint32_t pr = (crank + d) % kRowCluster;
+        dsmem_bulk_copy(dsmem_addr(src, pr), src, kHSlice, dsmem_addr(hx_full, pr));
+      }
+    }
+  }
   __syncwarp();
-  cluster_sync_all();       // #3: the whole hidden tile sits in every CTA's h operand
+  if (threadIdx.x == 64) trace_point(tr, 8);
+  if (is_epi) {
+    // assemble the K-major swizzled A operand of FFN2 in the (now dead) W1 region: this thread's row, k-block `half` = the slices of
+    // source CTAs 2 * half and 2 * half + 1
+    mbar_wait(hx_full, 0, 10);
+    uint8_t* hrow = w1_smem + half * kABytes + row_in_tile * 128;
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const uint4* src = reinterpret_cast<const uint4*>(h_smem + (2 * half + sidx) * kHSlice + row_in_tile * 64);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int chunk = sidx * 4 + c;
+        *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row_in_tile & 7)) << 4)) = src[c];
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(hop_ready);
+  }
   if (threadIdx.x == 64) trace_point(tr, 9);
 
   // ---- phase C: second feed-forward GEMM, residual, LayerNorm
   if (warp == 1) {
     if (elect_one()) {
-      fence_proxy_async_any();
+      mbar_wait(hop_ready, 0, 11);
       mbar_wait(w2_full, 0, 8);
       tc_fence_after_sync();
-      const uint32_t sa = smem_u32(h_smem), sb = smem_u32(w2_smem);
+      const uint32_t sa = smem_u32(w1_smem), sb = smem_u32(w2_smem);
 #pragma unroll
       for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
 #pragma unroll
@@ -1226,9 +1257,10 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   }
   __syncwarp();
   if (is_epi) {
-    mbar_wait(tmem_full2, 0, 9);     // the MMAs have read h: its first 2 KB can hold the statistics again
+    mbar_wait(tmem_full2, 0, 9);     // FFN2 has read W2: its first 2 KB hold the second round of statistics
     if (threadIdx.x == 64) trace_point(tr, 10);
     tc_fence_after_sync();
+    s_stats = reinterpret_cast<float2*>(w2_smem);
     add_acc_and_stats(256);
     if (threadIdx.x == 64) trace_point(tr, 11);
   }
@@ -1237,6 +1269,7 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   if (threadIdx.x == 64) trace_point(tr, 12);
   if (is_epi) {
     float mean = 0.f, rstd = 0.f;
+    s_stats = reinterpret_cast<float2*>(w2_smem);
     if (row < M) gather_stats(mean, rstd);
     uint8_t* stage = ring + ew * (32 * kRowStagePitch);      // the FFN1 operand is dead: every CTA's phase-B MMAs completed before #3
     {
