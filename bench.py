@@ -239,7 +239,8 @@ def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict
             continue
         # classes of a few microseconds per decode drown in the run-to-run noise of the subtraction: never report less than
         # 40 % of the isolated time (the largest in-graph gain seen on any class is 45 %)
-        g_ms = max(in_graph[name], 0.4 * ms[i] / steps)
+        iso_ms = ms[i] / steps
+        g_ms = iso_ms if iso_ms < 0.1 else max(in_graph[name], 0.4 * iso_ms)   # (below 0.1 ms per decode the subtraction is all noise: keep the isolated time)
         entry = {"ms_per_step": g_ms, "launches_per_step": cnt[i] // steps, "share": g_ms / total, "isolated_ms_per_step": ms[i] / steps}
         if name in work:
             bound, amount = work[name]
