@@ -897,7 +897,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<4, true, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<16, true, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
       set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
     return 1;
-  CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 6 * kAttnBwdMaxS * kAttnBwdStride * 4));
+  CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes(kAttnBwdMaxS)));
   if (g_wd_host == nullptr) {
     CUDA_TRY(cudaHostAlloc(&g_wd_host, sizeof(unsigned int), cudaHostAllocMapped));
     *g_wd_host = 0;

@@ -58,40 +58,56 @@ struct LnBwdParams {
   float eps;
 };
 
+// One CTA = 32 rows; warp w owns columns [128 w, 128 w + 128) of them, the row reductions go through shared memory.  (The first version
+// gave a whole row to one thread: 608 warps for 19 456 rows = one warp per scheduler, 1536 dependent-latency loads each - 225 us per launch.)
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const LnBwdParams p) {
   __shared__ float s_gain[kE];
+  __shared__ float s_red[4][4][32];                     // [quantity][warp][row]
   __shared__ __align__(16) uint8_t s_stage[4][32 * kEpiStagePitch];
   for (int i = threadIdx.x; i < kE; i += 128) s_gain[i] = p.gain[i];
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int row0 = (blockIdx.x * 4 + warp) * 32;
+  const int row0 = blockIdx.x * 32;
   const int row = row0 + lane;
   const bool ok = row < p.R;
-  // pass 1: statistics of x and the two row reductions
+  const int q0 = warp * (kE / 16);                      // first float4 group of this warp's 128 columns
+  constexpr int NQ = kE / 16;                           // 32 float4 groups per warp
+  // pass 1: statistics of x
   float sum = 0.f, sumsq = 0.f;
   if (ok) {
-    for (int q = 0; q < kE / 4; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q));
+#pragma unroll 8
+    for (int q = 0; q < NQ; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q0 + q));
       sum += (v.x + v.y) + (v.z + v.w);
       sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
   }
+  s_red[0][warp][lane] = sum;
+  s_red[1][warp][lane] = sumsq;
+  __syncthreads();
+  sum = (s_red[0][0][lane] + s_red[0][1][lane]) + (s_red[0][2][lane] + s_red[0][3][lane]);
+  sumsq = (s_red[1][0][lane] + s_red[1][1][lane]) + (s_red[1][2][lane] + s_red[1][3][lane]);
   const float mean = sum * (1.0f / kE);
   const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + p.eps);
   float s1 = 0.f, s2 = 0.f;
   if (ok) {
-    for (int q = 0; q < kE / 4; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q));
-      const float4 d = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, q));
-      const float4 g = *reinterpret_cast<const float4*>(&s_gain[q * 4]);
+#pragma unroll 4
+    for (int q = 0; q < NQ; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q0 + q));
+      const float4 d = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, q0 + q));
+      const float4 g = *reinterpret_cast<const float4*>(&s_gain[(q0 + q) * 4]);
       const float a0 = d.x * g.x, a1 = d.y * g.y, a2 = d.z * g.z, a3 = d.w * g.w;
       s1 += (a0 + a1) + (a2 + a3);
       s2 += a0 * (v.x - mean) * rstd + a1 * (v.y - mean) * rstd + a2 * (v.z - mean) * rstd + a3 * (v.w - mean) * rstd;
     }
   }
+  s_red[2][warp][lane] = s1;
+  s_red[3][warp][lane] = s2;
+  __syncthreads();
+  s1 = (s_red[2][0][lane] + s_red[2][1][lane]) + (s_red[2][2][lane] + s_red[2][3][lane]);
+  s2 = (s_red[3][0][lane] + s_red[3][1][lane]) + (s_red[3][2][lane] + s_red[3][3][lane]);
   const float m1 = s1 * (1.0f / kE), m2 = s2 * (1.0f / kE);
   // pass 2: dx, outputs, dgain.  64 columns at a time so the bf16 row-major copy can go through the warp's staging tile.
-  for (int c0 = 0; c0 < kE; c0 += kEpiCols) {
+  for (int c0 = warp * (kE / 4); c0 < (warp + 1) * (kE / 4); c0 += kEpiCols) {
     float o[kEpiCols];
 #pragma unroll
     for (int q = 0; q < kEpiCols / 4; ++q) {
@@ -242,7 +258,10 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
 //   P = softmax(Q K^T / 8 + mask)   dV = P^T dO   dP = dO V^T   dS = P o (dP - rowsum(dP o P))   dQ = dS K / 8   dK = dS^T Q / 8
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAttnBwdMaxS = 32;
-constexpr int kAttnBwdStride = kHeadDim + 1;   // padded row stride: lanes that own different key rows hit different banks
+constexpr int kAttnBwdWarps = 2;                  // warps (items) per CTA
+constexpr int kAttnBwdPk = kHeadDim / 2 + 1;      // q / k / v / dout rows as packed bf16 pairs: 32 words + 1 pad (key-owning lanes hit different banks)
+constexpr int kAttnBwdAcc = kHeadDim + 2;         // dk / dv accumulator rows (fp32), even so that a lane's channel pair is one 8-byte access
+__host__ __device__ constexpr int attn_bwd_smem_bytes(int S) { return kAttnBwdWarps * S * (4 * kAttnBwdPk + 2 * kAttnBwdAcc) * 4; }
 
 struct AttnBwdParams {
   const __nv_bfloat16* q;       // [nseq * S, 512]
@@ -257,35 +276,33 @@ struct AttnBwdParams {
   uint32_t drop_site;
 };
 
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
-  extern __shared__ float sm_attn[];
+// One warp per (sequence, head).  The operands stay in shared memory as the packed bf16 pairs they are in global memory (the first
+// version expanded them to fp32: 30 KB per warp, one warp per scheduler, every dependent shared-memory load exposed - 702 us per launch).
+__global__ void __launch_bounds__(kAttnBwdWarps * 32) attn_bwd_kernel(const AttnBwdParams p) {
+  extern __shared__ uint32_t sm_attn_u[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int item = blockIdx.x * 4 + warp;
+  const int item = blockIdx.x * kAttnBwdWarps + warp;
   if (item >= p.nseq * kHeads) return;
   const int a = item / kHeads, head = item - a * kHeads;
   const int S = p.S;
-  constexpr int HS = kAttnBwdStride;
-  float* base = sm_attn + static_cast<size_t>(warp) * (6 * S * HS);
-  float* sq = base;                       // [S][65]
-  float* sk = sq + S * HS;
-  float* sv = sk + S * HS;
-  float* sdo = sv + S * HS;
-  float* sdk = sdo + S * HS;
-  float* sdv = sdk + S * HS;
+  constexpr int PK = kAttnBwdPk, AC = kAttnBwdAcc;
+  uint32_t* base = sm_attn_u + static_cast<size_t>(warp) * (S * (4 * PK + 2 * AC));
+  uint32_t* sq = base;                       // [S][33] packed bf16 pairs
+  uint32_t* sk = sq + S * PK;
+  uint32_t* sv = sk + S * PK;
+  uint32_t* sdo = sv + S * PK;
+  float* sdk = reinterpret_cast<float*>(sdo + S * PK);   // [S][66] fp32
+  float* sdv = sdk + S * AC;
   for (int i = lane; i < S * (kHeadDim / 2); i += 32) {
-    const int s = i / (kHeadDim / 2), c = (i - s * (kHeadDim / 2)) * 2;
-    const size_t rq = (static_cast<size_t>(a) * S + s) * kE + head * kHeadDim + c;
-    const size_t rk = (static_cast<size_t>(a) * p.smax + s) * kE + head * kHeadDim + c;
-    const float2 fq = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.q + rq));
-    const float2 fk = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.kcache + rk));
-    const float2 fv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.vcache + rk));
-    const float2 fd = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.dout + rq));
-    sq[s * HS + c] = fq.x; sq[s * HS + c + 1] = fq.y;
-    sk[s * HS + c] = fk.x; sk[s * HS + c + 1] = fk.y;
-    sv[s * HS + c] = fv.x; sv[s * HS + c + 1] = fv.y;
-    sdo[s * HS + c] = fd.x; sdo[s * HS + c + 1] = fd.y;
-    sdk[s * HS + c] = 0.f; sdk[s * HS + c + 1] = 0.f;
-    sdv[s * HS + c] = 0.f; sdv[s * HS + c + 1] = 0.f;
+    const int s = i / (kHeadDim / 2), c2 = i - s * (kHeadDim / 2);
+    const size_t rq = (static_cast<size_t>(a) * S + s) * kE + head * kHeadDim + 2 * c2;
+    const size_t rk = (static_cast<size_t>(a) * p.smax + s) * kE + head * kHeadDim + 2 * c2;
+    sq[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.q + rq);
+    sk[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.kcache + rk);
+    sv[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.vcache + rk);
+    sdo[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.dout + rq);
+    *reinterpret_cast<float2*>(&sdk[s * AC + 2 * c2]) = make_float2(0.f, 0.f);
+    *reinterpret_cast<float2*>(&sdv[s * AC + 2 * c2]) = make_float2(0.f, 0.f);
   }
   __syncwarp();
   const int j = lane;  // key position owned by this lane
@@ -295,14 +312,16 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
     const bool vis = key_ok && j < nkeys;
     float s = -INFINITY, dp = 0.f;
     if (vis) {
-      float acc = 0.f, accd = 0.f;
+      float acc0 = 0.f, acc1 = 0.f, accd0 = 0.f, accd1 = 0.f;
 #pragma unroll 8
-      for (int c = 0; c < kHeadDim; ++c) {
-        acc = fmaf(sq[i * HS + c], sk[j * HS + c], acc);
-        accd = fmaf(sdo[i * HS + c], sv[j * HS + c], accd);
+      for (int c2 = 0; c2 < kHeadDim / 2; ++c2) {
+        const float2 qf = unpack_bf16x2(sq[i * PK + c2]), kf = unpack_bf16x2(sk[j * PK + c2]);
+        const float2 df = unpack_bf16x2(sdo[i * PK + c2]), vf = unpack_bf16x2(sv[j * PK + c2]);
+        acc0 = fmaf(qf.x, kf.x, acc0); acc1 = fmaf(qf.y, kf.y, acc1);
+        accd0 = fmaf(df.x, vf.x, accd0); accd1 = fmaf(df.y, vf.y, accd1);
       }
-      s = acc * p.scale;
-      dp = accd;
+      s = (acc0 + acc1) * p.scale;
+      dp = accd0 + accd1;
     }
     // out_i = sum_j p_ij m_ij v_j with m the dropout factor: d p_ij = m_ij (do_i . v_j), and dv_j receives p_ij m_ij do_i
     float dm = 1.f;
@@ -314,28 +333,33 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnBwdParams p) {
     const float pjd = pj * dm;
     const float dsum = warp_sum(pj * dp);
     const float ds = pj * (dp - dsum) * p.scale;   // gradient w.r.t. q_i . k_j
-    // dq_i = sum_j ds_ij k_j ; dk_j += ds_ij q_i ; dv_j += p_ij do_i   (lanes now own channels c = lane, lane + 32)
+    // dq_i = sum_j ds_ij k_j ; dk_j += ds_ij q_i ; dv_j += p_ij do_i   (lanes now own the channel pair 2 * lane, 2 * lane + 1)
+    const float2 qi = unpack_bf16x2(sq[i * PK + lane]), doi = unpack_bf16x2(sdo[i * PK + lane]);
     float dq0 = 0.f, dq1 = 0.f;
     for (int jj = 0; jj < nkeys; ++jj) {
       const float dsj = __shfl_sync(0xffffffffu, ds, jj);
       const float pjj = __shfl_sync(0xffffffffu, pjd, jj);
-      dq0 = fmaf(dsj, sk[jj * HS + lane], dq0);
-      dq1 = fmaf(dsj, sk[jj * HS + lane + 32], dq1);
-      sdk[jj * HS + lane] = fmaf(dsj, sq[i * HS + lane], sdk[jj * HS + lane]);
-      sdk[jj * HS + lane + 32] = fmaf(dsj, sq[i * HS + lane + 32], sdk[jj * HS + lane + 32]);
-      sdv[jj * HS + lane] = fmaf(pjj, sdo[i * HS + lane], sdv[jj * HS + lane]);
-      sdv[jj * HS + lane + 32] = fmaf(pjj, sdo[i * HS + lane + 32], sdv[jj * HS + lane + 32]);
+      const float2 kf = unpack_bf16x2(sk[jj * PK + lane]);
+      dq0 = fmaf(dsj, kf.x, dq0);
+      dq1 = fmaf(dsj, kf.y, dq1);
+      float2* dk = reinterpret_cast<float2*>(&sdk[jj * AC + 2 * lane]);
+      float2* dv = reinterpret_cast<float2*>(&sdv[jj * AC + 2 * lane]);
+      float2 tk = *dk, tv = *dv;
+      tk.x = fmaf(dsj, qi.x, tk.x); tk.y = fmaf(dsj, qi.y, tk.y);
+      tv.x = fmaf(pjj, doi.x, tv.x); tv.y = fmaf(pjj, doi.y, tv.y);
+      *dk = tk; *dv = tv;
     }
     __nv_bfloat16* dq = p.dqkv + (static_cast<size_t>(a) * S + i) * (3 * kE) + head * kHeadDim;
-    dq[lane] = __float2bfloat16_rn(dq0);
-    dq[lane + 32] = __float2bfloat16_rn(dq1);
+    *reinterpret_cast<uint32_t*>(dq + 2 * lane) = pack_bf16x2(dq0, dq1);
   }
   __syncwarp();
-  for (int i = lane; i < S * kHeadDim; i += 32) {
-    const int s = i / kHeadDim, c = i - s * kHeadDim;
-    __nv_bfloat16* row = p.dqkv + (static_cast<size_t>(a) * S + s) * (3 * kE) + head * kHeadDim + c;
-    row[kE] = __float2bfloat16_rn(sdk[s * HS + c]);
-    row[2 * kE] = __float2bfloat16_rn(sdv[s * HS + c]);
+  for (int i = lane; i < S * (kHeadDim / 2); i += 32) {
+    const int s = i / (kHeadDim / 2), c2 = i - s * (kHeadDim / 2);
+    __nv_bfloat16* row = p.dqkv + (static_cast<size_t>(a) * S + s) * (3 * kE) + head * kHeadDim + 2 * c2;
+    const float2 tk = *reinterpret_cast<const float2*>(&sdk[s * AC + 2 * c2]);
+    const float2 tv = *reinterpret_cast<const float2*>(&sdv[s * AC + 2 * c2]);
+    *reinterpret_cast<uint32_t*>(row + kE) = pack_bf16x2(tk.x, tk.y);
+    *reinterpret_cast<uint32_t*>(row + 2 * kE) = pack_bf16x2(tv.x, tv.y);
   }
 }
 
