@@ -15,26 +15,58 @@ namespace novic {
 // ---------------------------------------------------------------------------------------------------------
 // bf16 transpose: dst[c, r] = src[r, c]   (src row-major [R, C] with leading dimension ld_src; dst [C, ld_dst])
 // ---------------------------------------------------------------------------------------------------------
+// 64 x 64 tile per CTA.  Two source rows x 8 columns per thread (two 16-byte loads), stored to shared memory as (row, row + 1) pairs
+// in transposed position; read back as 16 bytes = 8 consecutive source rows of one column.  Pitch 33 words: both sides conflict-free
+// or 2-way.  Unaligned or ragged edges take the element-wise path.  (The first version moved single bf16 values: 15.6 us per
+// [19 456, 512] matrix against 5.4 us of HBM time.)
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int R, int C, int ld_src,
                                                              __nv_bfloat16* __restrict__ dst, int ld_dst) {
-  __shared__ __nv_bfloat16 tile[64][66];
+  __shared__ uint32_t tile[64 * 33];                       // [column][row pair]
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int i = ty; i < 64; i += 8) {
-    const int r = r0 + i;
+  const int t = threadIdx.x;
+  {
+    const int chunk = t & 7, rp = t >> 3;                  // columns [8 chunk, 8 chunk + 8), rows 2 rp and 2 rp + 1
+    const int c = c0 + chunk * 8;
+    uint4 v[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int c = c0 + tx * 2 + h;
-      tile[i][tx * 2 + h] = (r < R && c < C) ? src[static_cast<size_t>(r) * ld_src + c] : __float2bfloat16(0.f);
+      const int r = r0 + 2 * rp + h;
+      const __nv_bfloat16* row = src + static_cast<size_t>(r) * ld_src + c;
+      v[h] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < R) {
+        if (c + 8 <= C && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+          v[h] = *reinterpret_cast<const uint4*>(row);
+        } else {
+          uint16_t e[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = (c + j < C) ? reinterpret_cast<const uint16_t*>(row)[j] : uint16_t(0);
+          v[h] = make_uint4(e[0] | (uint32_t(e[1]) << 16), e[2] | (uint32_t(e[3]) << 16), e[4] | (uint32_t(e[5]) << 16), e[6] | (uint32_t(e[7]) << 16));
+        }
+      }
+    }
+    const uint32_t lo[4] = {v[0].x, v[0].y, v[0].z, v[0].w}, hi[4] = {v[1].x, v[1].y, v[1].z, v[1].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tile[(chunk * 8 + 2 * j) * 33 + rp] = __byte_perm(lo[j], hi[j], 0x5410);       // column 2j: (row, row + 1)
+      tile[(chunk * 8 + 2 * j + 1) * 33 + rp] = __byte_perm(lo[j], hi[j], 0x7632);   // column 2j + 1
     }
   }
   __syncthreads();
-  for (int i = ty; i < 64; i += 8) {
-    const int c = c0 + i;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = r0 + tx * 2 + h;
-      if (c < C && r < R) dst[static_cast<size_t>(c) * ld_dst + r] = tile[tx * 2 + h][i];
+  for (int h = 0; h < 2; ++h) {
+    const int cl = (t >> 3) + 32 * h, rch = t & 7;         // output row (source column) cl, source rows [8 rch, 8 rch + 8)
+    const int c = c0 + cl, r = r0 + rch * 8;
+    if (c >= C || r >= R) continue;
+    const uint32_t* w = &tile[cl * 33 + rch * 4];
+    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+    __nv_bfloat16* out = dst + static_cast<size_t>(c) * ld_dst + r;
+    if (r + 8 <= R && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      *reinterpret_cast<uint4*>(out) = v;
+    } else {
+      const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (r + j < R) reinterpret_cast<uint16_t*>(out)[j] = static_cast<uint16_t>(e[j >> 1] >> ((j & 1) * 16));
     }
   }
 }
@@ -58,94 +90,108 @@ struct LnBwdParams {
   float eps;
 };
 
-// One CTA = 32 rows; warp w owns columns [128 w, 128 w + 128) of them, the row reductions go through shared memory.  (The first version
-// gave a whole row to one thread: 608 warps for 19 456 rows = one warp per scheduler, 1536 dependent-latency loads each - 225 us per launch.)
-__global__ void __launch_bounds__(128) ln_bwd_kernel(const LnBwdParams p) {
-  __shared__ float s_gain[kE];
-  __shared__ float s_red[4][4][32];                     // [quantity][warp][row]
-  __shared__ __align__(16) uint8_t s_stage[4][32 * kEpiStagePitch];
-  for (int i = threadIdx.x; i < kE; i += 128) s_gain[i] = p.gain[i];
+// One CTA = 32 rows x 8 warps; warp w owns columns [64 w, 64 w + 64) of them and keeps its x and dy values in registers, so every tensor
+// is read exactly once and all of a thread's loads are in flight together; the row reductions go through shared memory.  (The first
+// version gave a whole row to one thread - 225 us per launch; the second re-read x three times from four warps - 157 us.)
+// 32 column sums of 32 rows by recursive halving: 62 shuffles per 64 values; lane l ends up holding columns 2l and 2l + 1 in v[0], v[1].
+__device__ __forceinline__ void warp_column_sums64(float (&v)[kEpiCols], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off > 0; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float keep = upper ? v[i + n] : v[i];
+      const float send = upper ? v[i] : v[i + n];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const LnBwdParams p) {
+  __shared__ float s_red[4][8][32];                     // [quantity][warp][row]
+  __shared__ __align__(16) uint8_t s_stage[8][kEpiStageBytes];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int row0 = blockIdx.x * 32;
   const int row = row0 + lane;
   const bool ok = row < p.R;
-  const int q0 = warp * (kE / 16);                      // first float4 group of this warp's 128 columns
-  constexpr int NQ = kE / 16;                           // 32 float4 groups per warp
-  // pass 1: statistics of x
-  float sum = 0.f, sumsq = 0.f;
-  if (ok) {
-#pragma unroll 8
-    for (int q = 0; q < NQ; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q0 + q));
-      sum += (v.x + v.y) + (v.z + v.w);
-      sumsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  const int c0 = warp * kEpiCols;
+  constexpr int NQ = kEpiCols / 4;                      // 16 float4 groups per thread
+  float x[kEpiCols], d[kEpiCols];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = v;
+    if (ok) {
+      v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, (c0 >> 2) + q));
+      w = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, (c0 >> 2) + q));
     }
+    x[q * 4] = v.x, x[q * 4 + 1] = v.y, x[q * 4 + 2] = v.z, x[q * 4 + 3] = v.w;
+    d[q * 4] = w.x, d[q * 4 + 1] = w.y, d[q * 4 + 2] = w.z, d[q * 4 + 3] = w.w;
   }
+  float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEpiCols; ++i) sum += x[i], sumsq += x[i] * x[i];
   s_red[0][warp][lane] = sum;
   s_red[1][warp][lane] = sumsq;
   __syncthreads();
-  sum = (s_red[0][0][lane] + s_red[0][1][lane]) + (s_red[0][2][lane] + s_red[0][3][lane]);
-  sumsq = (s_red[1][0][lane] + s_red[1][1][lane]) + (s_red[1][2][lane] + s_red[1][3][lane]);
+  sum = 0.f, sumsq = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += s_red[0][w][lane], sumsq += s_red[1][w][lane];
   const float mean = sum * (1.0f / kE);
   const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + p.eps);
   float s1 = 0.f, s2 = 0.f;
-  if (ok) {
-#pragma unroll 4
-    for (int q = 0; q < NQ; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, q0 + q));
-      const float4 d = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, q0 + q));
-      const float4 g = *reinterpret_cast<const float4*>(&s_gain[(q0 + q) * 4]);
-      const float a0 = d.x * g.x, a1 = d.y * g.y, a2 = d.z * g.z, a3 = d.w * g.w;
-      s1 += (a0 + a1) + (a2 + a3);
-      s2 += a0 * (v.x - mean) * rstd + a1 * (v.y - mean) * rstd + a2 * (v.z - mean) * rstd + a3 * (v.w - mean) * rstd;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float4 g = *reinterpret_cast<const float4*>(p.gain + c0 + q * 4);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float xhat = (x[q * 4 + i] - mean) * rstd;
+      const float a = d[q * 4 + i] * gv[i];
+      x[q * 4 + i] = xhat;                              // x now holds xhat
+      s1 += a;
+      s2 += a * xhat;
     }
   }
   s_red[2][warp][lane] = s1;
   s_red[3][warp][lane] = s2;
   __syncthreads();
-  s1 = (s_red[2][0][lane] + s_red[2][1][lane]) + (s_red[2][2][lane] + s_red[2][3][lane]);
-  s2 = (s_red[3][0][lane] + s_red[3][1][lane]) + (s_red[3][2][lane] + s_red[3][3][lane]);
+  s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s1 += s_red[2][w][lane], s2 += s_red[3][w][lane];
   const float m1 = s1 * (1.0f / kE), m2 = s2 * (1.0f / kE);
-  // pass 2: dx, outputs, dgain.  64 columns at a time so the bf16 row-major copy can go through the warp's staging tile.
-  for (int c0 = warp * (kE / 4); c0 < (warp + 1) * (kE / 4); c0 += kEpiCols) {
-    float o[kEpiCols];
+  uint8_t* stage = s_stage[warp];
 #pragma unroll
-    for (int q = 0; q < kEpiCols / 4; ++q) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), d = v, r = v;
-      if (ok) {
-        v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, (c0 >> 2) + q));
-        d = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, (c0 >> 2) + q));
-        if (p.resid != nullptr) r = *reinterpret_cast<const float4*>(p.resid + xblk_off(row, (c0 >> 2) + q));
-      }
-      const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w}, rv[4] = {r.x, r.y, r.z, r.w};
+  for (int q = 0; q < NQ; ++q) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && p.resid != nullptr) r = *reinterpret_cast<const float4*>(p.resid + xblk_off(row, (c0 >> 2) + q));
+    const float4 g = *reinterpret_cast<const float4*>(p.gain + c0 + q * 4);
+    const float gv[4] = {g.x, g.y, g.z, g.w}, rv[4] = {r.x, r.y, r.z, r.w};
+    float o[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c0 + q * 4 + i;
-        const float xhat = (xv[i] - mean) * rstd;
-        const float dx = ok ? rstd * (dv[i] * s_gain[c] - m1 - xhat * m2) : 0.f;
-        o[q * 4 + i] = dx + rv[i];
-        float dg = ok ? dv[i] * xhat : 0.f;   // column reduction over the warp's 32 rows
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) dg += __shfl_xor_sync(0xffffffffu, dg, off);
-        if (lane == 0) atomicAdd(p.dgain + c, dg);
-      }
-      if (ok) *reinterpret_cast<float4*>(p.out + xblk_off(row, (c0 >> 2) + q)) = make_float4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+    for (int i = 0; i < 4; ++i) {
+      const float xhat = x[q * 4 + i], dv = d[q * 4 + i];
+      o[i] = (ok ? rstd * (dv * gv[i] - m1 - xhat * m2) : 0.f) + rv[i];
+      x[q * 4 + i] = ok ? dv * xhat : 0.f;              // x now holds this row's dgain terms
+      d[q * 4 + i] = o[i];                              // d now holds the output row
     }
-    if (p.out_t != nullptr && ok) {
-#pragma unroll
-      for (int i = 0; i < kEpiCols; ++i) p.out_t[static_cast<size_t>(c0 + i) * p.ld_t + row] = __float2bfloat16_rn(o[i]);
-    }
-    if (p.out_bf != nullptr) {
-      uint8_t* stage = s_stage[warp];
-#pragma unroll
-      for (int q = 0; q < kEpiCols / 8; ++q)
-        *stage_chunk(stage, lane, q) = make_uint4(pack_bf16x2(o[q * 8], o[q * 8 + 1]), pack_bf16x2(o[q * 8 + 2], o[q * 8 + 3]), pack_bf16x2(o[q * 8 + 4], o[q * 8 + 5]),
-                          pack_bf16x2(o[q * 8 + 6], o[q * 8 + 7]));
-      stage_copy_out(stage, lane, [&](int r) -> __nv_bfloat16* {
-        return row0 + r < p.R ? p.out_bf + static_cast<size_t>(row0 + r) * kE + c0 : nullptr;
-      });
-    }
+    if (ok) *reinterpret_cast<float4*>(p.out + xblk_off(row, (c0 >> 2) + q)) = make_float4(o[0], o[1], o[2], o[3]);
   }
+  if (p.out_t != nullptr && ok) {
+#pragma unroll
+    for (int i = 0; i < kEpiCols; ++i) p.out_t[static_cast<size_t>(c0 + i) * p.ld_t + row] = __float2bfloat16_rn(d[i]);
+  }
+  if (p.out_bf != nullptr) {
+#pragma unroll
+    for (int q = 0; q < kEpiCols / 8; ++q)
+      *stage_chunk(stage, lane, q) = make_uint4(pack_bf16x2(d[q * 8], d[q * 8 + 1]), pack_bf16x2(d[q * 8 + 2], d[q * 8 + 3]), pack_bf16x2(d[q * 8 + 4], d[q * 8 + 5]),
+                        pack_bf16x2(d[q * 8 + 6], d[q * 8 + 7]));
+    stage_copy_out(stage, lane, [&](int r) -> __nv_bfloat16* {
+      return row0 + r < p.R ? p.out_bf + static_cast<size_t>(row0 + r) * kE + c0 : nullptr;
+    });
+  }
+  warp_column_sums64(x, lane);
+  atomicAdd(p.dgain + c0 + 2 * lane, x[0]);
+  atomicAdd(p.dgain + c0 + 2 * lane + 1, x[1]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -368,31 +414,69 @@ __global__ void __launch_bounds__(kAttnBwdWarps * 32) attn_bwd_kernel(const Attn
 //   dpos[s] += sum_a dx0[a, s]                      (learned positions, embedding_decoder.py:1297)
 //   dtok[target[a, i]] += dx0[a, P + i]             (tied token embedding, :692)
 //   dprefix_t[(p, e), b] = sum_j dx0[(b * M + j), p][e]   bf16, the A operand of the prefix-projection wgrad
-// Warp per row; lane owns 16 channels.
+// Two kernels.  (One warp-per-row kernel with scalar atomics for everything took 600 us: 18 M atomics, a thousand per address.)
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// dpos: row block b (32 rows, lane = row) holds position (32 b + lane) mod S in lane `lane`, so the row blocks b0, b0 + S, b0 + 2 S, ...
+// give every lane the same position each time: blockIdx.y = b0 accumulates them in registers and adds once at the end.
+// blockIdx.x * 4 + warp selects four of the 128 float4 column groups.
+constexpr int kPosGradGroups = 4;
+__global__ void __launch_bounds__(128) pos_grad_kernel(const float* __restrict__ dx0, int R, int S, float* __restrict__ dpos) {
+  const int lane = lane_id();
+  const int g0 = (blockIdx.x * 4 + (threadIdx.x >> 5)) * kPosGradGroups;
+  const int b0 = blockIdx.y;
+  const int nblk = (R + 31) >> 5;
+  float4 acc[kPosGradGroups];
+#pragma unroll
+  for (int q = 0; q < kPosGradGroups; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = b0; b < nblk; b += S) {
+    const int row = b * 32 + lane;
+    if (row < R) {
+#pragma unroll
+      for (int q = 0; q < kPosGradGroups; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(dx0 + xblk_off(row, g0 + q));
+        acc[q].x += t.x; acc[q].y += t.y; acc[q].z += t.z; acc[q].w += t.w;
+      }
+    }
+  }
+  const int s = (b0 * 32 + lane) % S;
+#pragma unroll
+  for (int q = 0; q < kPosGradGroups; ++q) red_add_v4(dpos + static_cast<size_t>(s) * kE + (g0 + q) * 4, acc[q].x, acc[q].y, acc[q].z, acc[q].w);
+}
+
+// dtok / dprefix_t: warp per row; lane owns the float4 column groups lane, lane + 32, lane + 64, lane + 96 (512-byte vector reductions).
+// Rows whose gradient is exactly zero (every position after a sequence's EOS) are skipped.
 __global__ void __launch_bounds__(128) embed_bwd_kernel(const float* __restrict__ dx0, const long long* __restrict__ target, int ld_target,
-                                                        int nseq, int S, int P, int V, int Mrep, int B, float* __restrict__ dpos,
+                                                        int nseq, int S, int P, int V, int Mrep, int B,
                                                         float* __restrict__ dtok, __nv_bfloat16* __restrict__ dprefix_t, int ld_pt) {
   const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (w >= nseq * S) return;
   const int lane = lane_id();
   const int a = w / S, s = w - a * S;
-  float v[16];
+  if (s < P && Mrep != 1) return;
+  float4 v[4];
+  bool nz = false;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 t = *reinterpret_cast<const float4*>(dx0 + xblk_off(w, lane * 4 + q));
-    v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+    v[q] = *reinterpret_cast<const float4*>(dx0 + xblk_off(w, q * 32 + lane));
+    nz = nz || v[q].x != 0.f || v[q].y != 0.f || v[q].z != 0.f || v[q].w != 0.f;
   }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) atomicAdd(dpos + static_cast<size_t>(s) * kE + lane * 16 + i, v[i]);
   if (s >= P) {
+    if (!__any_sync(0xffffffffu, nz)) return;
     long long tok = target[static_cast<size_t>(a) * ld_target + (s - P)];
     tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) atomicAdd(dtok + static_cast<size_t>(tok) * kE + lane * 16 + i, v[i]);
-  } else if (Mrep == 1) {
+    for (int q = 0; q < 4; ++q) red_add_v4(dtok + static_cast<size_t>(tok) * kE + (q * 32 + lane) * 4, v[q].x, v[q].y, v[q].z, v[q].w);
+  } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) dprefix_t[static_cast<size_t>(s * kE + lane * 16 + i) * ld_pt + a] = __float2bfloat16_rn(v[i]);
+    for (int q = 0; q < 4; ++q) {
+      const float e[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dprefix_t[static_cast<size_t>(s * kE + (q * 32 + lane) * 4 + i) * ld_pt + a] = __float2bfloat16_rn(e[i]);
+    }
   }
 }
 
