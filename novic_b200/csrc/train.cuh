@@ -299,15 +299,19 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
 
 // ---------------------------------------------------------------------------------------------------------
 // Attention backward for the teacher-forced pass (S <= 32 positions per sequence, 8 heads x 64).
-// One warp per (sequence, head): q, k, v, dO rows of the head are staged in shared memory (fp32), probabilities are
-// recomputed, lanes own key positions for the score work and channels for the dQ / dK / dV accumulation.
 //   P = softmax(Q K^T / 8 + mask)   dV = P^T dO   dP = dO V^T   dS = P o (dP - rowsum(dP o P))   dQ = dS K / 8   dK = dS^T Q / 8
+// One warp per (sequence, head).  The five products are 32 x 32 x 64 or 32 x 64 x 32: they run on mma.sync m16n8k16 (bf16 in, fp32
+// accumulate) from ldmatrix fragments - they are far too small for a tcgen05 tile, and far too many instructions as scalar FMAs:
+// the scalar version, lanes owning keys for the scores and channels for the accumulation, issued ~15 k instructions per item and took
+// 273 us per launch (702 us with fp32 shared-memory operands) against ~20 us of HBM time.  P (with the dropout factor) and dS pass
+// through shared memory as bf16 to become the A operands of the second group of products.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAttnBwdMaxS = 32;
 constexpr int kAttnBwdWarps = 2;                  // warps (items) per CTA
-constexpr int kAttnBwdPk = kHeadDim / 2 + 1;      // q / k / v / dout rows as packed bf16 pairs: 32 words + 1 pad (key-owning lanes hit different banks)
-constexpr int kAttnBwdAcc = kHeadDim + 2;         // dk / dv accumulator rows (fp32), even so that a lane's channel pair is one 8-byte access
-__host__ __device__ constexpr int attn_bwd_smem_bytes(int S) { return kAttnBwdWarps * S * (4 * kAttnBwdPk + 2 * kAttnBwdAcc) * 4; }
+constexpr int kAbPitch = kHeadDim + 8;            // q / k / v / dout rows: 64 bf16 + 16 B pad (ldmatrix rows land in distinct bank groups)
+constexpr int kAbPPitch = kAttnBwdMaxS + 8;       // P / dS rows: 32 bf16 + 16 B pad
+constexpr int kAbWarpBytes = (4 * kAttnBwdMaxS * kAbPitch + 2 * kAttnBwdMaxS * kAbPPitch) * 2;   // 23 552 B
+__host__ __device__ constexpr int attn_bwd_smem_bytes(int /*S*/) { return kAttnBwdWarps * kAbWarpBytes; }
 
 struct AttnBwdParams {
   const __nv_bfloat16* q;       // [nseq * S, 512]
@@ -322,91 +326,199 @@ struct AttnBwdParams {
   uint32_t drop_site;
 };
 
-// One warp per (sequence, head).  The operands stay in shared memory as the packed bf16 pairs they are in global memory (the first
-// version expanded them to fp32: 30 KB per warp, one warp per scheduler, every dependent shared-memory load exposed - 702 us per launch).
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// out[32, 64] = A' B with the contraction over 32: A' = A (A_TRANS = false, sa is [m][k], pitch kAbPPitch) or A^T (sa is [k][m]);
+// B is [k][64] row-major (pitch kAbPitch).  The result goes to `stage` (bf16, pitch kAbPitch) and from there, rows < S, to
+// dst + row * 3 * kE as 16-byte stores.
+template <bool A_TRANS>
+__device__ __forceinline__ void attn_bwd_product(const __nv_bfloat16* sa, const __nv_bfloat16* sb, __nv_bfloat16* stage, __nv_bfloat16* dst, int S, int lane) {
+  const int lm = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3;
+  float acc[2][8][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+#pragma unroll
+  for (int ki = 0; ki < 2; ++ki) {
+    uint32_t a[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      if (A_TRANS) ldsm_x4_t(a[mi], sa + (ki * 16 + (lm >> 1) * 8 + lr) * kAbPPitch + mi * 16 + (lm & 1) * 8);
+      else ldsm_x4(a[mi], sa + (mi * 16 + (lm & 1) * 8 + lr) * kAbPPitch + ki * 16 + (lm >> 1) * 8);
+    }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, sb + (ki * 16 + (lm & 1) * 8 + lr) * kAbPitch + np * 16 + (lm >> 1) * 8);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        mma_bf16_16816(acc[mi][np * 2], a[mi], b[0], b[1]);
+        mma_bf16_16816(acc[mi][np * 2 + 1], a[mi], b[2], b[3]);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        *reinterpret_cast<uint32_t*>(stage + (mi * 16 + h * 8 + g) * kAbPitch + ni * 8 + 2 * t) = pack_bf16x2(acc[mi][ni][h * 2], acc[mi][ni][h * 2 + 1]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + lm, ch = lr;
+    if (r < S) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(r) * (3 * kE) + ch * 8) = *reinterpret_cast<const uint4*>(stage + r * kAbPitch + ch * 8);
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kAttnBwdWarps * 32) attn_bwd_kernel(const AttnBwdParams p) {
-  extern __shared__ uint32_t sm_attn_u[];
+  extern __shared__ __align__(16) uint8_t sm_attn_b[];
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int item = blockIdx.x * kAttnBwdWarps + warp;
   if (item >= p.nseq * kHeads) return;
   const int a = item / kHeads, head = item - a * kHeads;
   const int S = p.S;
-  constexpr int PK = kAttnBwdPk, AC = kAttnBwdAcc;
-  uint32_t* base = sm_attn_u + static_cast<size_t>(warp) * (S * (4 * PK + 2 * AC));
-  uint32_t* sq = base;                       // [S][33] packed bf16 pairs
-  uint32_t* sk = sq + S * PK;
-  uint32_t* sv = sk + S * PK;
-  uint32_t* sdo = sv + S * PK;
-  float* sdk = reinterpret_cast<float*>(sdo + S * PK);   // [S][66] fp32
-  float* sdv = sdk + S * AC;
-  for (int i = lane; i < S * (kHeadDim / 2); i += 32) {
-    const int s = i / (kHeadDim / 2), c2 = i - s * (kHeadDim / 2);
-    const size_t rq = (static_cast<size_t>(a) * S + s) * kE + head * kHeadDim + 2 * c2;
-    const size_t rk = (static_cast<size_t>(a) * p.smax + s) * kE + head * kHeadDim + 2 * c2;
-    sq[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.q + rq);
-    sk[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.kcache + rk);
-    sv[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.vcache + rk);
-    sdo[s * PK + c2] = *reinterpret_cast<const uint32_t*>(p.dout + rq);
-    *reinterpret_cast<float2*>(&sdk[s * AC + 2 * c2]) = make_float2(0.f, 0.f);
-    *reinterpret_cast<float2*>(&sdv[s * AC + 2 * c2]) = make_float2(0.f, 0.f);
+  constexpr int PT = kAbPitch, PP = kAbPPitch;
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_attn_b + static_cast<size_t>(warp) * kAbWarpBytes);
+  __nv_bfloat16* sk = sq + kAttnBwdMaxS * PT;
+  __nv_bfloat16* sv = sk + kAttnBwdMaxS * PT;     // after the score products: staging for the outputs
+  __nv_bfloat16* sdo = sv + kAttnBwdMaxS * PT;
+  __nv_bfloat16* sp = sdo + kAttnBwdMaxS * PT;    // P o dropout, [i][j]
+  __nv_bfloat16* sds = sp + kAttnBwdMaxS * PP;    // dS, [i][j]
+  const int lm = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int s = it * 4 + lm;
+    uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = vq, vv = vq, vd = vq;
+    if (s < S) {
+      const size_t rq = (static_cast<size_t>(a) * S + s) * kE + head * kHeadDim + lr * 8;
+      const size_t rk = (static_cast<size_t>(a) * p.smax + s) * kE + head * kHeadDim + lr * 8;
+      vq = *reinterpret_cast<const uint4*>(p.q + rq);
+      vk = *reinterpret_cast<const uint4*>(p.kcache + rk);
+      vv = *reinterpret_cast<const uint4*>(p.vcache + rk);
+      vd = *reinterpret_cast<const uint4*>(p.dout + rq);
+    }
+    *reinterpret_cast<uint4*>(sq + s * PT + lr * 8) = vq;
+    *reinterpret_cast<uint4*>(sk + s * PT + lr * 8) = vk;
+    *reinterpret_cast<uint4*>(sv + s * PT + lr * 8) = vv;
+    *reinterpret_cast<uint4*>(sdo + s * PT + lr * 8) = vd;
   }
+  const bool key_ok = lane < S && !(p.keypad != nullptr && lane > 0 && p.keypad[static_cast<size_t>(a) * S + lane]);
+  const uint32_t kmask = __ballot_sync(0xffffffffu, key_ok);
   __syncwarp();
-  const int j = lane;  // key position owned by this lane
-  const bool key_ok = j < S && !(p.keypad != nullptr && j > 0 && p.keypad[static_cast<size_t>(a) * S + j]);
-  for (int i = 0; i < S; ++i) {
-    const int nkeys = (p.prefix_bidir && i < p.P) ? p.P : i + 1;
-    const bool vis = key_ok && j < nkeys;
-    float s = -INFINITY, dp = 0.f;
-    if (vis) {
-      float acc0 = 0.f, acc1 = 0.f, accd0 = 0.f, accd1 = 0.f;
-#pragma unroll 8
-      for (int c2 = 0; c2 < kHeadDim / 2; ++c2) {
-        const float2 qf = unpack_bf16x2(sq[i * PK + c2]), kf = unpack_bf16x2(sk[j * PK + c2]);
-        const float2 df = unpack_bf16x2(sdo[i * PK + c2]), vf = unpack_bf16x2(sv[j * PK + c2]);
-        acc0 = fmaf(qf.x, kf.x, acc0); acc1 = fmaf(qf.y, kf.y, acc1);
-        accd0 = fmaf(df.x, vf.x, accd0); accd1 = fmaf(df.y, vf.y, accd1);
+  // scores Q K^T and dP = dO V^T: [32 queries] x [32 keys], contraction over the 64 channels
+  float sc[2][4][4], dp[2][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[mi][ni][e] = 0.f, dp[mi][ni][e] = 0.f;
+#pragma unroll
+  for (int ki = 0; ki < 4; ++ki) {
+    uint32_t aq[2][4], ad[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      ldsm_x4(aq[mi], sq + (mi * 16 + (lm & 1) * 8 + lr) * PT + ki * 16 + (lm >> 1) * 8);
+      ldsm_x4(ad[mi], sdo + (mi * 16 + (lm & 1) * 8 + lr) * PT + ki * 16 + (lm >> 1) * 8);
+    }
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bk[4], bv[4];
+      ldsm_x4(bk, sk + (np * 16 + (lm >> 1) * 8 + lr) * PT + ki * 16 + (lm & 1) * 8);
+      ldsm_x4(bv, sv + (np * 16 + (lm >> 1) * 8 + lr) * PT + ki * 16 + (lm & 1) * 8);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        mma_bf16_16816(sc[mi][np * 2], aq[mi], bk[0], bk[1]);
+        mma_bf16_16816(sc[mi][np * 2 + 1], aq[mi], bk[2], bk[3]);
+        mma_bf16_16816(dp[mi][np * 2], ad[mi], bv[0], bv[1]);
+        mma_bf16_16816(dp[mi][np * 2 + 1], ad[mi], bv[2], bv[3]);
       }
-      s = (acc0 + acc1) * p.scale;
-      dp = accd0 + accd1;
     }
-    // out_i = sum_j p_ij m_ij v_j with m the dropout factor: d p_ij = m_ij (do_i . v_j), and dv_j receives p_ij m_ij do_i
-    float dm = 1.f;
-    if (p.drop.thresh != 0u && vis) dm = drop_factor(p.drop, p.drop_site, ((static_cast<uint32_t>(a) * kHeads + head) * S + i) * S + j);
-    dp *= dm;
-    const float mx = warp_max(s);
-    const float e = vis ? __expf(s - mx) : 0.f;
-    const float pj = e / warp_sum(e);
-    const float pjd = pj * dm;
-    const float dsum = warp_sum(pj * dp);
-    const float ds = pj * (dp - dsum) * p.scale;   // gradient w.r.t. q_i . k_j
-    // dq_i = sum_j ds_ij k_j ; dk_j += ds_ij q_i ; dv_j += p_ij do_i   (lanes now own the channel pair 2 * lane, 2 * lane + 1)
-    const float2 qi = unpack_bf16x2(sq[i * PK + lane]), doi = unpack_bf16x2(sdo[i * PK + lane]);
-    float dq0 = 0.f, dq1 = 0.f;
-    for (int jj = 0; jj < nkeys; ++jj) {
-      const float dsj = __shfl_sync(0xffffffffu, ds, jj);
-      const float pjj = __shfl_sync(0xffffffffu, pjd, jj);
-      const float2 kf = unpack_bf16x2(sk[jj * PK + lane]);
-      dq0 = fmaf(dsj, kf.x, dq0);
-      dq1 = fmaf(dsj, kf.y, dq1);
-      float2* dk = reinterpret_cast<float2*>(&sdk[jj * AC + 2 * lane]);
-      float2* dv = reinterpret_cast<float2*>(&sdv[jj * AC + 2 * lane]);
-      float2 tk = *dk, tv = *dv;
-      tk.x = fmaf(dsj, qi.x, tk.x); tk.y = fmaf(dsj, qi.y, tk.y);
-      tv.x = fmaf(pjj, doi.x, tv.x); tv.y = fmaf(pjj, doi.y, tv.y);
-      *dk = tk; *dv = tv;
+  }
+  // softmax, dropout and dS per query row: thread (g, t) holds keys ni * 8 + 2 t + {0, 1} of rows mi * 16 + h * 8 + g
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = mi * 16 + h * 8 + g;
+      int nkeys = (p.prefix_bidir && i < p.P) ? p.P : i + 1;
+      if (i >= S) nkeys = 0;
+      const uint32_t rowmask = kmask & (nkeys >= 32 ? 0xffffffffu : ((1u << nkeys) - 1u));
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ni * 8 + 2 * t + e;
+          const float v = ((rowmask >> j) & 1u) ? sc[mi][ni][h * 2 + e] * p.scale : -INFINITY;
+          sc[mi][ni][h * 2 + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ni * 8 + 2 * t + e;
+          const float ex = ((rowmask >> j) & 1u) ? __expf(sc[mi][ni][h * 2 + e] - mx) : 0.f;
+          sc[mi][ni][h * 2 + e] = ex;
+          sum += ex;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      // out_i = sum_j p_ij m_ij v_j with m the dropout factor: d p_ij = m_ij (do_i . v_j), and dv_j receives p_ij m_ij do_i
+      float dsum = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        float pd[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ni * 8 + 2 * t + e;
+          const float pj = sc[mi][ni][h * 2 + e] * inv;
+          float dm = 1.f;
+          if (p.drop.thresh != 0u && ((rowmask >> j) & 1u)) dm = drop_factor(p.drop, p.drop_site, ((static_cast<uint32_t>(a) * kHeads + head) * S + i) * S + j);
+          const float dpv = dp[mi][ni][h * 2 + e] * dm;
+          sc[mi][ni][h * 2 + e] = pj;
+          dp[mi][ni][h * 2 + e] = dpv;
+          dsum += pj * dpv;
+          pd[e] = pj * dm;
+        }
+        *reinterpret_cast<uint32_t*>(sp + i * PP + ni * 8 + 2 * t) = pack_bf16x2(pd[0], pd[1]);
+      }
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const float d0 = sc[mi][ni][h * 2] * (dp[mi][ni][h * 2] - dsum) * p.scale;       // gradient w.r.t. q_i . k_j
+        const float d1 = sc[mi][ni][h * 2 + 1] * (dp[mi][ni][h * 2 + 1] - dsum) * p.scale;
+        *reinterpret_cast<uint32_t*>(sds + i * PP + ni * 8 + 2 * t) = pack_bf16x2(d0, d1);
+      }
     }
-    __nv_bfloat16* dq = p.dqkv + (static_cast<size_t>(a) * S + i) * (3 * kE) + head * kHeadDim;
-    *reinterpret_cast<uint32_t*>(dq + 2 * lane) = pack_bf16x2(dq0, dq1);
   }
   __syncwarp();
-  for (int i = lane; i < S * (kHeadDim / 2); i += 32) {
-    const int s = i / (kHeadDim / 2), c2 = i - s * (kHeadDim / 2);
-    __nv_bfloat16* row = p.dqkv + (static_cast<size_t>(a) * S + s) * (3 * kE) + head * kHeadDim + 2 * c2;
-    const float2 tk = *reinterpret_cast<const float2*>(&sdk[s * AC + 2 * c2]);
-    const float2 tv = *reinterpret_cast<const float2*>(&sdv[s * AC + 2 * c2]);
-    *reinterpret_cast<uint32_t*>(row + kE) = pack_bf16x2(tk.x, tk.y);
-    *reinterpret_cast<uint32_t*>(row + 2 * kE) = pack_bf16x2(tv.x, tv.y);
-  }
+  __nv_bfloat16* out = p.dqkv + static_cast<size_t>(a) * S * (3 * kE) + head * kHeadDim;
+  attn_bwd_product<true>(sp, sdo, sv, out + 2 * kE, S, lane);    // dv_j = sum_i (p m)_ij do_i
+  attn_bwd_product<true>(sds, sq, sv, out + kE, S, lane);        // dk_j = sum_i ds_ij q_i
+  attn_bwd_product<false>(sds, sk, sv, out, S, lane);            // dq_i = sum_j ds_ij k_j
 }
 
 // ---------------------------------------------------------------------------------------------------------
