@@ -522,6 +522,159 @@ __global__ void __launch_bounds__(kAttnBwdWarps * 32) attn_bwd_kernel(const Attn
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Attention forward of the teacher-forced pass, same tiling as the backward kernel above: one warp per (sequence, head), all S <= 32
+// queries at once, Q K^T and P V on mma.sync tiles; the probabilities go from the score accumulators straight into the A fragments of
+// the second product.  Replaces the key-by-key online-softmax kernel (attention_bulk_kernel_t, 138 us per launch) in the training step.
+// Requires q0 = 0, one beam, no ancestor mask.  Dropout masks the numerator only (torch applies it to the normalised probabilities).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAttnTfWarps = 2;
+constexpr int kAttnTfWarpBytes = 3 * kAttnBwdMaxS * kAbPitch * 2;   // 13 824 B
+constexpr int kAttnTfSmemBytes = kAttnTfWarps * kAttnTfWarpBytes;
+
+template <bool DROP>
+__global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) uint8_t sm_attn_f[];
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  const int item = blockIdx.x * kAttnTfWarps + warp;
+  if (item >= p.nseq * kHeads) return;
+  const int a = item / kHeads, head = item - a * kHeads;
+  const int S = p.nq;
+  constexpr int PT = kAbPitch;
+  __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_attn_f + static_cast<size_t>(warp) * kAttnTfWarpBytes);   // later: output staging
+  __nv_bfloat16* sk = sq + kAttnBwdMaxS * PT;
+  __nv_bfloat16* sv = sk + kAttnBwdMaxS * PT;
+  const int lm = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int s = it * 4 + lm;
+    uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = vq, vv = vq;
+    if (s < S) {
+      const size_t rq = (static_cast<size_t>(a) * S + s) * kE + head * kHeadDim + lr * 8;
+      const size_t rk = (static_cast<size_t>(a) * p.smax + s) * kE + head * kHeadDim + lr * 8;
+      vq = *reinterpret_cast<const uint4*>(p.q + rq);
+      vk = *reinterpret_cast<const uint4*>(p.kcache + rk);
+      vv = *reinterpret_cast<const uint4*>(p.vcache + rk);
+    }
+    *reinterpret_cast<uint4*>(sq + s * PT + lr * 8) = vq;
+    *reinterpret_cast<uint4*>(sk + s * PT + lr * 8) = vk;
+    *reinterpret_cast<uint4*>(sv + s * PT + lr * 8) = vv;
+  }
+  const bool key_ok = lane < S && !(p.keypad != nullptr && lane > 0 && p.keypad[static_cast<size_t>(a) * p.keypad_ld + lane]);
+  const uint32_t kmask = __ballot_sync(0xffffffffu, key_ok);
+  __syncwarp();
+  float sc[2][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[mi][ni][e] = 0.f;
+#pragma unroll
+  for (int ki = 0; ki < 4; ++ki) {
+    uint32_t aq[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) ldsm_x4(aq[mi], sq + (mi * 16 + (lm & 1) * 8 + lr) * PT + ki * 16 + (lm >> 1) * 8);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bk[4];
+      ldsm_x4(bk, sk + (np * 16 + (lm >> 1) * 8 + lr) * PT + ki * 16 + (lm & 1) * 8);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        mma_bf16_16816(sc[mi][np * 2], aq[mi], bk[0], bk[1]);
+        mma_bf16_16816(sc[mi][np * 2 + 1], aq[mi], bk[2], bk[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = mi * 16 + h * 8 + g;
+      int nkeys = (p.prefix_bidir && i < p.P) ? p.P : i + 1;
+      if (i >= S) nkeys = 0;
+      const uint32_t rowmask = kmask & (nkeys >= 32 ? 0xffffffffu : ((1u << nkeys) - 1u));
+      float mx = -INFINITY;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ni * 8 + 2 * t + e;
+          const float v = ((rowmask >> j) & 1u) ? sc[mi][ni][h * 2 + e] * p.scale_log2e : -INFINITY;
+          sc[mi][ni][h * 2 + e] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ni * 8 + 2 * t + e;
+          const float ex = ((rowmask >> j) & 1u) ? exp2f(sc[mi][ni][h * 2 + e] - mx) : 0.f;
+          sc[mi][ni][h * 2 + e] = ex;
+          sum += ex;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = ni * 8 + 2 * t + e;
+          float pj = sc[mi][ni][h * 2 + e] * inv;
+          if (DROP && ((rowmask >> j) & 1u)) pj *= drop_factor(p.drop, p.drop_site, ((static_cast<uint32_t>(a) * kHeads + head) * S + i) * S + j);
+          sc[mi][ni][h * 2 + e] = pj;
+        }
+    }
+  }
+  float acc[2][8][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+#pragma unroll
+  for (int ki = 0; ki < 2; ++ki) {
+    uint32_t ap[2][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      ap[mi][0] = pack_bf16x2(sc[mi][2 * ki][0], sc[mi][2 * ki][1]);
+      ap[mi][1] = pack_bf16x2(sc[mi][2 * ki][2], sc[mi][2 * ki][3]);
+      ap[mi][2] = pack_bf16x2(sc[mi][2 * ki + 1][0], sc[mi][2 * ki + 1][1]);
+      ap[mi][3] = pack_bf16x2(sc[mi][2 * ki + 1][2], sc[mi][2 * ki + 1][3]);
+    }
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, sv + (ki * 16 + (lm & 1) * 8 + lr) * PT + np * 16 + (lm >> 1) * 8);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        mma_bf16_16816(acc[mi][np * 2], ap[mi], b[0], b[1]);
+        mma_bf16_16816(acc[mi][np * 2 + 1], ap[mi], b[2], b[3]);
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        *reinterpret_cast<uint32_t*>(sq + (mi * 16 + h * 8 + g) * PT + ni * 8 + 2 * t) = pack_bf16x2(acc[mi][ni][h * 2], acc[mi][ni][h * 2 + 1]);
+  __syncwarp();
+  __nv_bfloat16* out = p.out + static_cast<size_t>(a) * S * kE + head * kHeadDim;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + lm;
+    if (r < S) *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * kE + lr * 8) = *reinterpret_cast<const uint4*>(sq + r * PT + lr * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Input-embedding backward: dx0 (blocked fp32, rows a * S + s) ->
 //   dpos[s] += sum_a dx0[a, s]                      (learned positions, embedding_decoder.py:1297)
 //   dtok[target[a, i]] += dx0[a, P + i]             (tied token embedding, :692)
