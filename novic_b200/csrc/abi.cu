@@ -103,6 +103,7 @@ int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, i
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
+bool g_attn_tf = true;                         // NOVIC_ATTN_TF=0: teacher-forced passes use the key-by-key bulk kernel instead of attention_tf_kernel
 int g_attn_hint = 1;                           // NOVIC_ATTN_HINT bit 0: evict-first L2 policy on the streamed K/V rows; bit 1: evict-last on new K/V rows
 int g_row_stages = 4;                          // NOVIC_ROW_STAGES=2|3: shallower row-kernel pipelines (tuning: co-residency with the next kernel)
 bool g_split_ffn = true;                       // NOVIC_SPLIT_FFN=0: every CTA of a cluster recomputes the whole hidden tile
@@ -470,6 +471,11 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
       case 8: CUDA_TRY(go(attention_stream_kernel_t<16, 2, 4>, 16, 2, 4)); break;   // 128 KB: can share an SM with a 2-stage row kernel
       default: CUDA_TRY(go(attention_stream_kernel_t<16, 3, 4>, 16, 3, 4)); break;
     }
+  } else if (g_attn_tf && pc.q0 == 0 && pc.nq > c.prefix_len && pc.nq <= kAttnBwdMaxS && pc.beams == 1 && pc.slot_mul == 1 && pc.anc == nullptr) {
+    // teacher-forced passes (forward, score_targets): all positions of a sequence at once on tensor-core tiles
+    const unsigned grid = static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * kHeads, kAttnTfWarps));
+    attention_tf_kernel<false><<<grid, kAttnTfWarps * 32, kAttnTfSmemBytes, s>>>(pa);
+    CUDA_TRY(cudaGetLastError());
   } else if (h->attn_v1) {
     attention_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * pc.nq, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, s>>>(pa);
   } else {
@@ -930,6 +936,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e16 = getenv("NOVIC_SPLIT_FFN")) g_split_ffn = e16[0] != '0';
   if (const char* e17 = getenv("NOVIC_ROW_STAGES")) g_row_stages = atoi(e17);
   if (const char* e18 = getenv("NOVIC_ATTN_HINT")) g_attn_hint = atoi(e18);
+  if (const char* e19 = getenv("NOVIC_ATTN_TF")) g_attn_tf = atoi(e19) != 0;
   if (const char* e22 = getenv("NOVIC_FUSE_BLOCK")) g_fuse_block = e22[0] != '0';
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';

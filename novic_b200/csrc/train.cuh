@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
   if (item >= p.nseq * kHeads) return;
   const int a = item / kHeads, head = item - a * kHeads;
   const int S = p.nq;
+  const bool small = S <= 16;                      // one 16-row query tile and one 16-key tile are enough (warp-uniform)
   constexpr int PT = kAbPitch;
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_attn_f + static_cast<size_t>(warp) * kAttnTfWarpBytes);   // later: output staging
   __nv_bfloat16* sk = sq + kAttnBwdMaxS * PT;
@@ -546,6 +547,7 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
   const int lm = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
+    if (it >= 4 && small) continue;
     const int s = it * 4 + lm;
     uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = vq, vv = vq;
     if (s < S) {
@@ -573,13 +575,16 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
   for (int ki = 0; ki < 4; ++ki) {
     uint32_t aq[2][4];
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) ldsm_x4(aq[mi], sq + (mi * 16 + (lm & 1) * 8 + lr) * PT + ki * 16 + (lm >> 1) * 8);
+    for (int mi = 0; mi < 2; ++mi)
+      if (mi == 0 || !small) ldsm_x4(aq[mi], sq + (mi * 16 + (lm & 1) * 8 + lr) * PT + ki * 16 + (lm >> 1) * 8);
 #pragma unroll
     for (int np = 0; np < 2; ++np) {
+      if (np == 1 && small) continue;
       uint32_t bk[4];
       ldsm_x4(bk, sk + (np * 16 + (lm >> 1) * 8 + lr) * PT + ki * 16 + (lm & 1) * 8);
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
+        if (mi == 1 && small) continue;
         mma_bf16_16816(sc[mi][np * 2], aq[mi], bk[0], bk[1]);
         mma_bf16_16816(sc[mi][np * 2 + 1], aq[mi], bk[2], bk[3]);
       }
@@ -587,6 +592,7 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
   }
 #pragma unroll
   for (int mi = 0; mi < 2; ++mi) {
+    if (mi == 1 && small) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int i = mi * 16 + h * 8 + g;
@@ -638,6 +644,7 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
       for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
 #pragma unroll
   for (int ki = 0; ki < 2; ++ki) {
+    if (ki == 1 && small) continue;
     uint32_t ap[2][4];
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
@@ -652,6 +659,7 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
       ldsm_x4_t(b, sv + (ki * 16 + (lm & 1) * 8 + lr) * PT + np * 16 + (lm >> 1) * 8);
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
+        if (mi == 1 && small) continue;
         mma_bf16_16816(acc[mi][np * 2], ap[mi], b[0], b[1]);
         mma_bf16_16816(acc[mi][np * 2 + 1], ap[mi], b[2], b[3]);
       }
@@ -664,7 +672,7 @@ __global__ void __launch_bounds__(kAttnTfWarps * 32) attention_tf_kernel(const A
     for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
       for (int h = 0; h < 2; ++h)
-        *reinterpret_cast<uint32_t*>(sq + (mi * 16 + h * 8 + g) * PT + ni * 8 + 2 * t) = pack_bf16x2(acc[mi][ni][h * 2], acc[mi][ni][h * 2 + 1]);
+        if (mi == 0 || !small) *reinterpret_cast<uint32_t*>(sq + (mi * 16 + h * 8 + g) * PT + ni * 8 + 2 * t) = pack_bf16x2(acc[mi][ni][h * 2], acc[mi][ni][h * 2 + 1]);
   __syncwarp();
   __nv_bfloat16* out = p.out + static_cast<size_t>(a) * S * kE + head * kHeadDim;
 #pragma unroll

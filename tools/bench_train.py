@@ -16,6 +16,7 @@ if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
 from novic_b200 import synth, default_decoder, EmbeddingNoise
+torch.manual_seed(1234 + rank)   # noise and dropout seeds; the loss trajectory at lr 1.5e-3 from random weights is still sensitive to fp32 atomic order
 from novic_b200.dist import train_step
 dims = synth.DecoderDims()
 model = default_decoder(dims, synth.synth_state_dict(dims, seed=1)).to(dev).train()   # input / layer dropout 0.1 (train.yaml defaults)
