@@ -88,54 +88,62 @@ struct LnBwdParams {
   float* dgain;          // [512] accumulated with atomics
   int R, ld_t;
   float eps;
+  DropCfg drop;          // thresh != 0: the bf16 copies are multiplied by the dropout mask of the branch they feed (site drop_site, element
+  uint32_t drop_site;    // index row * 512 + column); the fp32 residual gradient `out` is never masked
 };
 
-// One CTA = 32 rows x 8 warps; warp w owns columns [64 w, 64 w + 64) of them and keeps its x and dy values in registers, so every tensor
-// is read exactly once and all of a thread's loads are in flight together; the row reductions go through shared memory.  (The first
-// version gave a whole row to one thread - 225 us per launch; the second re-read x three times from four warps - 157 us.)
-// 32 column sums of 32 rows by recursive halving: 62 shuffles per 64 values; lane l ends up holding columns 2l and 2l + 1 in v[0], v[1].
-__device__ __forceinline__ void warp_column_sums64(float (&v)[kEpiCols], int lane) {
+// One CTA = 32 rows x 16 warps; warp w owns columns [32 w, 32 w + 32) of them and loads its x, dy and residual values into registers
+// up front, so every tensor is read exactly once and all of a CTA's loads are in flight together; the row reductions go through
+// shared memory.  (The first version gave a whole row to one thread - 225 us per launch; the second re-read x three times from four
+// warps - 157 us; 8 warps x 64 columns with the residual loaded late - 73 us.)
+// Column sums of the warp's 32 rows by recursive halving: 31 shuffles for 32 columns; lane l ends up holding column l in v[0].
+__device__ __forceinline__ void warp_column_sums32(float (&v)[32], int lane) {
 #pragma unroll
-  for (int off = 16, n = 32; off > 0; off >>= 1, n >>= 1) {
+  for (int off = 16; off > 0; off >>= 1) {
     const bool upper = (lane & off) != 0;
 #pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float keep = upper ? v[i + n] : v[i];
-      const float send = upper ? v[i] : v[i + n];
+    for (int i = 0; i < off; ++i) {
+      const float keep = upper ? v[i + off] : v[i];
+      const float send = upper ? v[i] : v[i + off];
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
 }
 
-__global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const LnBwdParams p) {
-  __shared__ float s_red[4][8][32];                     // [quantity][warp][row]
-  __shared__ __align__(16) uint8_t s_stage[8][kEpiStageBytes];
+constexpr int kLnBwdWarps = 16;
+constexpr int kLnBwdCols = kE / kLnBwdWarps;            // 32
+
+__global__ void __launch_bounds__(kLnBwdWarps * 32, 1) ln_bwd_kernel(const LnBwdParams p) {
+  __shared__ float s_red[4][kLnBwdWarps][32];           // [quantity][warp][row]
+  __shared__ __align__(16) uint8_t s_stage[kLnBwdWarps][32 * kLnBwdCols * 2];   // bf16 rows of 64 B, 16-byte chunks swizzled by the row pair
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int row0 = blockIdx.x * 32;
   const int row = row0 + lane;
   const bool ok = row < p.R;
-  const int c0 = warp * kEpiCols;
-  constexpr int NQ = kEpiCols / 4;                      // 16 float4 groups per thread
-  float x[kEpiCols], d[kEpiCols];
+  const int c0 = warp * kLnBwdCols;
+  constexpr int NC = kLnBwdCols, NQ = NC / 4;
+  float x[NC], d[NC], r[NC];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = v;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = v, u = v;
     if (ok) {
       v = *reinterpret_cast<const float4*>(p.x + xblk_off(row, (c0 >> 2) + q));
       w = *reinterpret_cast<const float4*>(p.dy + xblk_off(row, (c0 >> 2) + q));
+      if (p.resid != nullptr) u = *reinterpret_cast<const float4*>(p.resid + xblk_off(row, (c0 >> 2) + q));
     }
     x[q * 4] = v.x, x[q * 4 + 1] = v.y, x[q * 4 + 2] = v.z, x[q * 4 + 3] = v.w;
     d[q * 4] = w.x, d[q * 4 + 1] = w.y, d[q * 4 + 2] = w.z, d[q * 4 + 3] = w.w;
+    r[q * 4] = u.x, r[q * 4 + 1] = u.y, r[q * 4 + 2] = u.z, r[q * 4 + 3] = u.w;
   }
   float sum = 0.f, sumsq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kEpiCols; ++i) sum += x[i], sumsq += x[i] * x[i];
+  for (int i = 0; i < NC; ++i) sum += x[i], sumsq += x[i] * x[i];
   s_red[0][warp][lane] = sum;
   s_red[1][warp][lane] = sumsq;
   __syncthreads();
   sum = 0.f, sumsq = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) sum += s_red[0][w][lane], sumsq += s_red[1][w][lane];
+  for (int w = 0; w < kLnBwdWarps; ++w) sum += s_red[0][w][lane], sumsq += s_red[1][w][lane];
   const float mean = sum * (1.0f / kE);
   const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + p.eps);
   float s1 = 0.f, s2 = 0.f;
@@ -157,81 +165,53 @@ __global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const LnBwdParams p) {
   __syncthreads();
   s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) s1 += s_red[2][w][lane], s2 += s_red[3][w][lane];
+  for (int w = 0; w < kLnBwdWarps; ++w) s1 += s_red[2][w][lane], s2 += s_red[3][w][lane];
   const float m1 = s1 * (1.0f / kE), m2 = s2 * (1.0f / kE);
-  uint8_t* stage = s_stage[warp];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok && p.resid != nullptr) r = *reinterpret_cast<const float4*>(p.resid + xblk_off(row, (c0 >> 2) + q));
     const float4 g = *reinterpret_cast<const float4*>(p.gain + c0 + q * 4);
-    const float gv[4] = {g.x, g.y, g.z, g.w}, rv[4] = {r.x, r.y, r.z, r.w};
-    float o[4];
+    const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float xhat = x[q * 4 + i], dv = d[q * 4 + i];
-      o[i] = (ok ? rstd * (dv * gv[i] - m1 - xhat * m2) : 0.f) + rv[i];
-      x[q * 4 + i] = ok ? dv * xhat : 0.f;              // x now holds this row's dgain terms
-      d[q * 4 + i] = o[i];                              // d now holds the output row
+      d[q * 4 + i] = (ok ? rstd * (dv * gv[i] - m1 - xhat * m2) : 0.f) + r[q * 4 + i];   // d now holds the output row
+      x[q * 4 + i] = ok ? dv * xhat : 0.f;                                              // x now holds this row's dgain terms
     }
-    if (ok) *reinterpret_cast<float4*>(p.out + xblk_off(row, (c0 >> 2) + q)) = make_float4(o[0], o[1], o[2], o[3]);
+    if (ok) *reinterpret_cast<float4*>(p.out + xblk_off(row, (c0 >> 2) + q)) = make_float4(d[q * 4], d[q * 4 + 1], d[q * 4 + 2], d[q * 4 + 3]);
+  }
+  if (p.drop.thresh != 0u) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) d[i] *= drop_factor(p.drop, p.drop_site, static_cast<uint32_t>(row) * kE + c0 + i);
   }
   if (p.out_t != nullptr && ok) {
 #pragma unroll
-    for (int i = 0; i < kEpiCols; ++i) p.out_t[static_cast<size_t>(c0 + i) * p.ld_t + row] = __float2bfloat16_rn(d[i]);
+    for (int i = 0; i < NC; ++i) p.out_t[static_cast<size_t>(c0 + i) * p.ld_t + row] = __float2bfloat16_rn(d[i]);
   }
   if (p.out_bf != nullptr) {
+    uint8_t* stage = s_stage[warp];
 #pragma unroll
-    for (int q = 0; q < kEpiCols / 8; ++q)
-      *stage_chunk(stage, lane, q) = make_uint4(pack_bf16x2(d[q * 8], d[q * 8 + 1]), pack_bf16x2(d[q * 8 + 2], d[q * 8 + 3]), pack_bf16x2(d[q * 8 + 4], d[q * 8 + 5]),
-                        pack_bf16x2(d[q * 8 + 6], d[q * 8 + 7]));
-    stage_copy_out(stage, lane, [&](int r) -> __nv_bfloat16* {
-      return row0 + r < p.R ? p.out_bf + static_cast<size_t>(row0 + r) * kE + c0 : nullptr;
-    });
+    for (int q = 0; q < NC / 8; ++q)
+      *reinterpret_cast<uint4*>(stage + lane * (NC * 2) + ((q ^ ((lane >> 1) & 3)) << 4)) =
+          make_uint4(pack_bf16x2(d[q * 8], d[q * 8 + 1]), pack_bf16x2(d[q * 8 + 2], d[q * 8 + 3]), pack_bf16x2(d[q * 8 + 4], d[q * 8 + 5]), pack_bf16x2(d[q * 8 + 6], d[q * 8 + 7]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = i * 8 + (lane >> 2), ch = lane & 3;
+      const uint4 v = *reinterpret_cast<const uint4*>(stage + rr * (NC * 2) + ((ch ^ ((rr >> 1) & 3)) << 4));
+      if (row0 + rr < p.R) *reinterpret_cast<uint4*>(p.out_bf + static_cast<size_t>(row0 + rr) * kE + c0 + ch * 8) = v;
+    }
   }
-  warp_column_sums64(x, lane);
-  atomicAdd(p.dgain + c0 + 2 * lane, x[0]);
-  atomicAdd(p.dgain + c0 + 2 * lane + 1, x[1]);
+  warp_column_sums32(x, lane);
+  atomicAdd(p.dgain + c0 + lane, x[0]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Dropout helpers of the training step (elementwise, in place).
-//   drop_mask_bf16_kernel : a[r, c] *= factor(site, r * cols + c) on a row-major bf16 [rows, cols] matrix and, optionally, on its
-//                           transposed copy at[c, r] (leading dimension ld_t) - the bf16 operands of the backward GEMMs.
-//   drop_mask_blocked_kernel : the same on the blocked fp32 residual layout (gradient w.r.t. the input embedding rows).
+// Dropout helpers of the training step (elementwise, in place).  The masks of the residual branches and of the activated feed-forward
+// rows are applied where the masked tensor is produced (ln_bwd_kernel, gelu_bwd_kernel, EpiGeluTrain, the row kernel's DROP instantiation);
+// separate masking passes over the bf16 GEMM operands cost 24 launches and 0.3 ms per step.
+//   drop_mask_blocked_kernel : x[r, c] *= factor(site, r * 512 + c) on the blocked fp32 residual layout (gradient w.r.t. the input embedding rows).
 //   input_dropout_ln_kernel : x = dropout(x) in place, xn = LayerNorm(x) * gain (forward, input dropout embedding_decoder.py:1297).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) drop_mask_bf16_kernel(__nv_bfloat16* __restrict__ a, int rows, int cols, __nv_bfloat16* __restrict__ at, int ld_t,
-                                                             DropCfg d, uint32_t site) {
-  // blockIdx.y == 0: the row-major matrix, 8 consecutive columns per thread; blockIdx.y == 1: the transposed copy, 8 consecutive rows
-  // per thread - both coalesced.  cols and ld_t are multiples of 8.
-  const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-  if (blockIdx.y == 0) {
-    if (i >= static_cast<size_t>(rows) * cols) return;
-    uint4 v = *reinterpret_cast<const uint4*>(a + i);
-    float f[8];
-    bf16x8_to_f32(v, f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] *= drop_factor(d, site, static_cast<uint32_t>(i) + k);
-    *reinterpret_cast<uint4*>(a + i) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-  } else {
-    if (at == nullptr || i >= static_cast<size_t>(cols) * ld_t) return;
-    const int c = static_cast<int>(i / ld_t), r0 = static_cast<int>(i - static_cast<size_t>(c) * ld_t);
-    if (r0 >= rows) return;
-    uint4 v = *reinterpret_cast<const uint4*>(at + i);
-    float f[8];
-    bf16x8_to_f32(v, f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = (r0 + k < rows) ? f[k] * drop_factor(d, site, static_cast<uint32_t>(r0 + k) * cols + c) : f[k];
-    *reinterpret_cast<uint4*>(at + i) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-  }
-}
-inline void launch_drop_mask_bf16(cudaStream_t s, __nv_bfloat16* a, int rows, int cols, __nv_bfloat16* at, int ld_t, const DropCfg& d, uint32_t site) {
-  const size_t n = std::max(static_cast<size_t>(rows) * cols, at != nullptr ? static_cast<size_t>(cols) * ld_t : 0);
-  dim3 grid(static_cast<unsigned>((n / 8 + 255) / 256), at != nullptr ? 2 : 1);
-  drop_mask_bf16_kernel<<<grid, 256, 0, s>>>(a, rows, cols, at, ld_t, d, site);
-}
-
 __global__ void __launch_bounds__(256) drop_mask_blocked_kernel(float* __restrict__ x, int rows, DropCfg d, uint32_t site) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(rows) * kE) return;
@@ -273,14 +253,19 @@ __global__ void __launch_bounds__(128) input_dropout_ln_kernel(float* __restrict
 // ---------------------------------------------------------------------------------------------------------
 // GELU backward, elementwise on row-major bf16: dpre = dh * (Phi(pre) + pre * phi(pre))
 // ---------------------------------------------------------------------------------------------------------
+// drop.thresh != 0: the activated rows were dropped in the forward pass (site drop_site, element index = flat index): dh is masked first.
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ pre,
-                                                       __nv_bfloat16* __restrict__ dpre, size_t n) {
+                                                       __nv_bfloat16* __restrict__ dpre, size_t n, DropCfg drop, uint32_t drop_site) {
   const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   const uint4 a = *reinterpret_cast<const uint4*>(dh + i), b = *reinterpret_cast<const uint4*>(pre + i);
   float d[8], x[8];
   bf16x8_to_f32(a, d);
   bf16x8_to_f32(b, x);
+  if (drop.thresh != 0u) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] *= drop_factor(drop, drop_site, static_cast<uint32_t>(i) + k);
+  }
   uint32_t o[4];
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
@@ -816,6 +801,8 @@ struct EpiGeluTrain {
     __nv_bfloat16* pre;
     __nv_bfloat16* h;
     int ldh;
+    DropCfg drop;        // thresh != 0: dropout on the activated rows h (element index row * ldh + column); pre stays unmasked
+    uint32_t drop_site;
   };
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
@@ -839,6 +826,10 @@ struct EpiGeluTrain {
       float t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] = gelu_fast(__bfloat162float(__float2bfloat16_rn(v[ch * 32 + j])));  // from the stored pre-activation
+      if (p.drop.thresh != 0u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t[j] *= drop_factor(p.drop, p.drop_site, static_cast<uint32_t>(c.row) * p.ldh + c.n0 + ch * 32 + j);
+      }
       stage_put32(c.stage, lane, ch * 32, t);
     }
     stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {

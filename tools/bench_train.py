@@ -38,7 +38,18 @@ for _ in range(args.steps): losses.append(step())
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 dt = (time.perf_counter() - t0) / args.steps
+# device time of forward + backward alone (one C-ABI call), the part this repo's kernels own; the rest of the step is torch
+# (noise, clip_grad_norm_ with its host sync, fused AdamW) and NCCL
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+model.zero_grad(set_to_none=True)
+ev[0].record()
+for _ in range(args.steps):
+    _, _, ls, lb, _ = model(embed0, tgt, pad, None, True, True, False, None)
+    ls.backward()
+    model.zero_grad(set_to_none=True)
+ev[1].record(); torch.cuda.synchronize()
+fwd_bwd_ms = ev[0].elapsed_time(ev[1]) / args.steps
 if rank == 0:
-    print(json.dumps({"metric": "training samples/sec (teacher-forced step, noise + fwd + bwd + allreduce + clip + AdamW)", "value": B * world / dt, "unit": "samples/s",
+    print(json.dumps({"fwd_bwd_ms": fwd_bwd_ms, "metric": "training samples/sec (teacher-forced step, noise + fwd + bwd + allreduce + clip + AdamW)", "value": B * world / dt, "unit": "samples/s",
                       "n_gpus": world, "ms_per_step": dt * 1e3, "batch_per_gpu": B, "loss_first": losses[0].item(), "loss_last": losses[-1].item(), "dropout": "input 0.1, layer 0.1"}))
 if world > 1: dist.destroy_process_group()
