@@ -182,6 +182,16 @@ int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B
 int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,
                      int32_t block_n, void* stream);
 
+/* Building blocks of the training step's backward pass, exported for the test-suite (ragged and unaligned shapes):
+ *   novic_debug_transpose_bf16: dst[c, r] = src[r, c] for a row-major bf16 [rows, cols] matrix (leading dimensions in elements);
+ *   novic_debug_wgrad: dw[Mo, No] (fp32, accumulated into) += a_t[Mo, K] * b_t[No, K]^T, both operands bf16 with the contraction
+ *     index contiguous and leading dimension ld (a multiple of 8) - the split-K weight-gradient GEMM;
+ *   novic_debug_wgrad_splits: the split-K factor that GEMM picks for `tiles` output tiles, `kblocks` 64-wide k-blocks and `sms`
+ *     CTAs (pure host arithmetic; -1 on bad arguments). */
+int novic_debug_transpose_bf16(const void* src, int64_t rows, int32_t cols, int32_t ld_src, void* dst, int32_t ld_dst, void* stream);
+int novic_debug_wgrad(const void* a_t, int32_t Mo, const void* b_t, int32_t No, int64_t K, int32_t ld, float* dw, void* stream);
+int32_t novic_debug_wgrad_splits(int64_t tiles, int64_t kblocks, int32_t sms);
+
 /* Per-kernel-class device timing for roofline reports.  novic_kernel_timing(1) makes every subsequent direct
  * (non-graph) launch record a CUDA-event pair on its stream; novic_kernel_times() synchronises and returns the
  * accumulated milliseconds and launch counts per class, then clears.  Classes, in order: embed-prep, prefix GEMM,

@@ -1531,4 +1531,21 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
   return rc;
 }
 
+int32_t novic_debug_wgrad_splits(int64_t tiles, int64_t kblocks, int32_t sms) {
+  if (tiles < 1 || kblocks < 1 || sms < 1) return -1;
+  return choose_wgrad_splits(tiles, kblocks, sms);
+}
+
+int novic_debug_transpose_bf16(const void* src, int64_t rows, int32_t cols, int32_t ld_src, void* dst, int32_t ld_dst, void* stream) {
+  if (rows < 1 || cols < 1 || ld_src < cols || ld_dst < rows) return fail("bad transpose shape");
+  return launch_transpose(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(src), rows, cols, ld_src,
+                          static_cast<__nv_bfloat16*>(dst), ld_dst);
+}
+
+int novic_debug_wgrad(const void* a_t, int32_t Mo, const void* b_t, int32_t No, int64_t K, int32_t ld, float* dw, void* stream) {
+  if (Mo < 1 || No < 1 || K < 1 || ld < K || ld % 8 != 0) return fail("bad wgrad shape (ld must be a multiple of 8 and >= K)");
+  if (set_gemm_attr<EpiAtomicF32, kStagesQKV>()) return 1;
+  return launch_wgrad(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a_t), Mo, static_cast<const __nv_bfloat16*>(b_t), No, K, ld, dw);
+}
+
 }  // extern "C"

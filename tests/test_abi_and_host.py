@@ -150,3 +150,26 @@ def test_drop_in_through_the_reference_loader():
 def test_oracle_matches_live_reference():
     from oracle import validate_vs_reference
     assert validate_vs_reference.run()
+
+
+def test_wgrad_split_factor_properties(built_lib):
+    """novic_debug_wgrad_splits (pure host arithmetic): no split may be empty, the work fits the round count it was chosen for,
+    and the known shapes of the default decoder avoid a ragged extra round on 148 SMs."""
+    lib = _abi.lib()
+    ceil = lambda a, b: -(-a // b)
+    for tiles in (1, 2, 4, 16, 48, 216, 300):
+        for kblocks in (1, 2, 7, 8, 64, 240, 304, 1000):
+            for sms in (1, 132, 148):
+                sp = lib.novic_debug_wgrad_splits(tiles, kblocks, sms)
+                assert 1 <= sp <= max(1, kblocks // 4)
+                per = ceil(kblocks, sp)
+                assert (sp - 1) * per < kblocks, (tiles, kblocks, sms, sp)          # last split not empty
+    # linear1 / linear2 wgrad of the default decoder at 19 456 rows: 4 tiles x 304 k-blocks -> one round on 148 SMs
+    sp = lib.novic_debug_wgrad_splits(4, 304, 148)
+    assert 4 * sp <= 148 and sp >= 30
+    # in_proj: 48 tiles; out_proj: 16 tiles -> whole rounds (at most 4 idle CTAs per round)
+    for tiles in (16, 48):
+        sp = lib.novic_debug_wgrad_splits(tiles, 304, 148)
+        items = tiles * sp
+        assert items % 148 == 0 or items % 148 >= 140, (tiles, sp)
+    assert lib.novic_debug_wgrad_splits(0, 10, 148) == -1

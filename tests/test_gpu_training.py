@@ -23,11 +23,11 @@ def _oracle_grads(sd, embed, tgt, pad, weight, M, drop=None):
     return loss_sum.item(), float(loss_basis), correct, {k: v.grad for k, v in leaf.items()}
 
 
-@pytest.mark.parametrize("case", ["plain", "padded", "multi_weighted"])
+@pytest.mark.parametrize("case", ["plain", "padded", "multi_weighted", "ragged"])
 def test_gradients_match_autograd_oracle(case):
     dims = synth.DecoderDims()
     sd = weight_case("eos")
-    B = 24
+    B = 5 if case == "ragged" else 24     # ragged: 95 rows - not a multiple of 8, 32 or 64 (edge paths of the row-blocked kernels and transposes)
     embed = synth.synth_embeddings(B, seed=21)
     if case == "multi_weighted":
         tgt, pad = synth.synth_targets(B, dims, seed=6, multi=3)
@@ -160,3 +160,37 @@ def test_dropout_controls():
     with torch.inference_mode():
         f = model(embed, tgt, pad, None, True, True, False, None)[2].item()
     assert abs(f - d) <= 1e-3 * abs(d)
+
+
+@pytest.mark.parametrize("R,Cc,ld_src,ld_dst,off", [(456, 512, 512, 456, 0), (95, 128, 128, 96, 0), (57, 72, 80, 64, 0), (130, 64, 192, 136, 64), (33, 8, 8, 40, 0)])
+def test_transpose_kernel_on_ragged_and_strided_shapes(R, Cc, ld_src, ld_dst, off):
+    """dst[c, r] = src[r, c]: aligned 16-byte path and the element-wise edges, bit-exact (it only moves bf16 values)."""
+    from novic_b200 import _abi
+    lib = _abi.lib()
+    g = torch.Generator().manual_seed(R * 1000 + Cc)
+    full = torch.randn(R, ld_src + off, generator=g).to(torch.bfloat16).to(DEV)
+    src = full[:, off:]                                   # column offset: rows start 128 B into the allocation's rows
+    dst = torch.full((Cc, ld_dst), 7.0, dtype=torch.bfloat16, device=DEV)
+    _abi.check(lib.novic_debug_transpose_bf16(src.data_ptr(), R, Cc, ld_src + off, dst.data_ptr(), ld_dst, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, :R].cpu(), src[:, :Cc].t().cpu())
+    assert bool((dst[:, R:] == 7.0).all())                # nothing written past the valid rows
+
+
+@pytest.mark.parametrize("Mo,No,K", [(128, 512, 19456), (512, 128, 456), (1536, 512, 95), (200, 72, 1000), (6912, 512, 360)])
+def test_wgrad_gemm_accumulates_into_fp32(Mo, No, K):
+    """dw += a_t b_t^T with split-K vector reductions: against an fp64 product of the same bf16 operands, on top of a non-zero dw."""
+    from novic_b200 import _abi
+    lib = _abi.lib()
+    ld = (K + 63) // 64 * 64
+    g = torch.Generator().manual_seed(Mo + No + K)
+    a = torch.zeros(Mo, ld, dtype=torch.bfloat16); a[:, :K] = (torch.randn(Mo, K, generator=g) * 0.5).to(torch.bfloat16)
+    b = torch.zeros(No, ld, dtype=torch.bfloat16); b[:, :K] = (torch.randn(No, K, generator=g) * 0.5).to(torch.bfloat16)
+    dw0 = torch.randn(Mo, No, generator=g)
+    dw = dw0.clone().to(DEV)
+    ad, bd = a.to(DEV), b.to(DEV)
+    _abi.check(lib.novic_debug_wgrad(ad.data_ptr(), Mo, bd.data_ptr(), No, K, ld, dw.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = dw0.double() + a[:, :K].double() @ b[:, :K].double().t()
+    err = (dw.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, K ** 0.5), err          # fp32 accumulation of K products of O(0.25) values
