@@ -119,10 +119,46 @@ def generate_sharded(model, embed_full: torch.Tensor, method: str = "greedy", to
 # Data-parallel training: gradients of the 40 parameter tensors are summed over ranks as one flat
 # bucket (12.73 M fp32 = 50.9 MB, a single NCCL all-reduce over NVLink), together with the two loss scalars.
 # ----------------------------------------------------------------------------------------------------------------
-def allreduce_gradients(params, extra: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None) -> Optional[torch.Tensor]:
+class GradBucket:
+    """The flat fp32 buffer the training step's gradients are views of (novic_b200/training.py allocates one per step; autograd hands
+    the views to `.grad` without copying).  `spare` trailing floats carry the loss scalars through the same collective."""
+    SPARE = 8
+    in_place_reductions = 0      # how many all-reduces ran directly on a bucket (diagnostics: tools/bench_train.py prints it)
+
+    def __init__(self, flat: torch.Tensor, views):
+        self.flat = flat
+        self.total = sum(v.numel() for v in views)
+        self.ptrs = {v.data_ptr(): v.numel() for v in views}
+
+    def covers(self, grads) -> bool:
+        """True when `grads` are exactly this bucket's views (same memory, every element accounted for once)."""
+        if len(grads) != len(self.ptrs) or sum(g.numel() for g in grads) != self.total:
+            return False
+        seen = set()
+        for g in grads:
+            ptr = g.data_ptr()
+            if g.dtype != torch.float32 or not g.is_contiguous() or self.ptrs.get(ptr) != g.numel() or ptr in seen:
+                return False
+            seen.add(ptr)
+        return True
+
+
+def allreduce_gradients(params, extra: Optional[torch.Tensor] = None, group: Optional[dist.ProcessGroup] = None,
+                        bucket: Optional[GradBucket] = None) -> Optional[torch.Tensor]:
     """Sum `.grad` of `params` (and the optional small tensor `extra`, e.g. [loss_sum, loss_basis]) over all ranks, in
-    place.  One flat bucket -> one collective."""
+    place.  One flat bucket -> one collective.  When the gradients already live in `bucket` (the training step's own flat buffer)
+    the collective runs on that buffer directly: no gather / scatter copies."""
     grads = [p.grad for p in params if p.grad is not None]
+    if bucket is not None and bucket.covers(grads) and (extra is None or extra.numel() <= GradBucket.SPARE):
+        flat = bucket.flat
+        n = 0 if extra is None else extra.numel()
+        tail = flat[bucket.total:bucket.total + GradBucket.SPARE]
+        tail.zero_()
+        if n:
+            tail[:n].copy_(extra.reshape(-1).to(torch.float32))
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        GradBucket.in_place_reductions += 1
+        return tail[:n].clone().view_as(extra).to(extra.dtype) if n else None
     pieces = grads + ([extra] if extra is not None else [])
     flat = torch.cat([t.reshape(-1).to(torch.float32) for t in pieces])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
@@ -151,7 +187,7 @@ def train_step(model, optimizer, embed: torch.Tensor, target: torch.Tensor, mask
     stats = torch.stack((loss_sum.detach().float(), loss_basis.detach().float(), correct.sum().float()))
     params = [p for p in model.parameters() if p.requires_grad]
     if world > 1:
-        stats = allreduce_gradients(params, stats, group)
+        stats = allreduce_gradients(params, stats, group, bucket=getattr(model, "_grad_bucket", None))
     inv_basis = 1.0 / stats[1].clamp(min=1.0)
     torch._foreach_mul_([p.grad for p in params if p.grad is not None], inv_basis)
     norm = torch.nn.utils.clip_grad_norm_(params, max_norm=gradient_clip, error_if_nonfinite=True) if gradient_clip > 0 else None

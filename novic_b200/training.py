@@ -42,7 +42,16 @@ class TrainStep(torch.autograd.Function):
         if ws is None or ws.numel() < need:
             st['train_ws'] = None
             st['train_ws'] = ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
+        # one flat buffer, the gradients are views of it: autograd passes the views on to `.grad` as they are, so the data-parallel
+        # all-reduce (dist.allreduce_gradients) can run on the buffer in place
+        from .dist import GradBucket
+        sizes = [p.numel() for p in params]
+        flat = torch.empty(sum(sizes) + GradBucket.SPARE, dtype=torch.float32, device=dev)
+        grads, off = [], 0
+        for p, n in zip(params, sizes):
+            grads.append(flat[off:off + n].view(p.shape))
+            off += n
+        model._grad_bucket = GradBucket(flat, grads)
         loss = torch.empty(2, dtype=torch.float32, device=dev)
         correct = torch.empty((A, Ct), dtype=torch.uint8, device=dev)
         pad_out = torch.empty((A, Ct), dtype=torch.uint8, device=dev)

@@ -85,8 +85,23 @@ def _grad_worker(rank, world, port, results):
         params[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
         params[2].grad = None                                   # parameters without a gradient are skipped consistently
         extra = allreduce_gradients(params, torch.tensor([10.0 * (rank + 1), 1.0]))
+        # the same sums when the gradients are views of one flat bucket (the training step's layout): the collective runs in place
+        from novic_b200.dist import GradBucket
+        flat = torch.zeros(15 + 7 + GradBucket.SPARE)
+        views = [flat[:15].view(5, 3), flat[15:22]]
+        views[0].fill_(float(rank + 1)); views[1].copy_(torch.arange(7, dtype=torch.float32) * (rank + 1))
+        bparams = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+        bparams[0].grad, bparams[1].grad = views[0], views[1]
+        bucket = GradBucket(flat, views)
+        assert bucket.covers([p.grad for p in bparams if p.grad is not None])
+        bextra = allreduce_gradients(bparams, torch.tensor([10.0 * (rank + 1), 1.0]), bucket=bucket)
+        in_place = bparams[0].grad.data_ptr() == flat.data_ptr() and torch.equal(flat[:15].view(5, 3), bparams[0].grad)
+        # a gradient that is not the bucket's view (e.g. accumulated twice by autograd) must fall back to the copying path
+        bparams[1].grad = bparams[1].grad.clone()
+        assert not bucket.covers([p.grad for p in bparams if p.grad is not None])
+        allreduce_gradients(bparams, None, bucket=bucket)
         if rank == 0:
-            results.put((params[0].grad.clone(), params[1].grad.clone(), extra))
+            results.put((params[0].grad.clone(), params[1].grad.clone(), extra, bparams[0].grad.clone(), bparams[1].grad.clone(), bextra, in_place))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -101,10 +116,13 @@ def test_two_rank_gradient_allreduce():
     procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, results)) for r in range(2)]
     for p in procs:
         p.start()
-    g0, g1, extra = results.get(timeout=120)
+    g0, g1, extra, b0, b1, bextra, in_place = results.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert torch.equal(g0, torch.full((5, 3), 3.0))
     assert torch.equal(g1, torch.arange(7, dtype=torch.float32) * 3)
     assert torch.equal(extra, torch.tensor([30.0, 2.0]))
+    assert in_place and torch.equal(bextra, torch.tensor([30.0, 2.0]))
+    assert torch.equal(b0, torch.full((5, 3), 6.0))                          # summed twice: bucket path (1 + 2), then the fallback path (3 + 3)
+    assert torch.equal(b1, torch.arange(7, dtype=torch.float32) * 3 * 2)

@@ -50,6 +50,7 @@ for _ in range(args.steps):
 ev[1].record(); torch.cuda.synchronize()
 fwd_bwd_ms = ev[0].elapsed_time(ev[1]) / args.steps
 if rank == 0:
-    print(json.dumps({"fwd_bwd_ms": fwd_bwd_ms, "metric": "training samples/sec (teacher-forced step, noise + fwd + bwd + allreduce + clip + AdamW)", "value": B * world / dt, "unit": "samples/s",
+    from novic_b200.dist import GradBucket
+    print(json.dumps({"fwd_bwd_ms": fwd_bwd_ms, "in_place_allreduces": GradBucket.in_place_reductions, "metric": "training samples/sec (teacher-forced step, noise + fwd + bwd + allreduce + clip + AdamW)", "value": B * world / dt, "unit": "samples/s",
                       "n_gpus": world, "ms_per_step": dt * 1e3, "batch_per_gpu": B, "loss_first": losses[0].item(), "loss_last": losses[-1].item(), "dropout": "input 0.1, layer 0.1"}))
 if world > 1: dist.destroy_process_group()
