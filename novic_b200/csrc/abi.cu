@@ -487,7 +487,7 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
     nstages = nstages / ncons * ncons;
     const int smem = nstages * stage_bytes + 2 * kAttnMaxStages * 8;
     const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, 2)));
-    CUDA_TRY(launch_k(attention_bulk_kernel_t<false>, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
+    CUDA_TRY(launch_k(attention_bulk_kernel, dim3(grid), dim3(kAttnThreads), smem, s, pa, nstages, stage_bytes, ncons));
   }
   ++g_launches;
   return 0;
@@ -919,8 +919,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   h->num_sms = prop.multiProcessorCount;
   g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
-  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
-  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
+  CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 3, 4)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<12, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(12, 2, 8)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));

@@ -114,7 +114,7 @@ struct AttnParams {
   int nseq, nq, q0, smax, P, beams, slot_mul, prefix_bidir, keypad_ld, anc_ld;
   int early_loads;              // stream kernel: request chunks of older rows before griddepcontrol.wait
   int stream_hint;              // stream kernel: K/V rows are requested with an evict-first L2 policy (NOVIC_ATTN_HINT)
-  DropCfg drop;                 // bulk kernel, training: dropout on the attention probabilities (thresh 0 = off)
+  DropCfg drop;                 // attention_tf_kernel<true> (training): dropout on the attention probabilities (thresh 0 = off)
   uint32_t drop_site;
   float scale_log2e;            // (1/sqrt(head_dim)) * log2(e)
 };
@@ -218,8 +218,7 @@ constexpr int kAttnMaxStages = 16;
 // `ncons` consumer warps are active and nstages is a multiple of ncons: consumer c then owns ring stages c, c+ncons, ...
 // and visits them in order, so it observes every phase of their mbarriers (a parity wait can only tell the current
 // phase from the previous one - a waiter must never be a whole phase ahead).
-template <bool DROP>
-__global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel_t(const AttnParams p, int nstages, int stage_bytes, int ncons) {
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel(const AttnParams p, int nstages, int stage_bytes, int ncons) {
   extern __shared__ __align__(128) uint8_t attn_smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(attn_smem);
   uint64_t* empty_bar = full_bar + kAttnMaxStages;
@@ -320,11 +319,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_bulk_kernel_t(const
           float vf[16];
           bf16x8_to_f32(v4[0], vf);
           bf16x8_to_f32(v4[1], vf + 8);
-          float pd = pj;   // dropout acts on the normalised probabilities: the numerator is masked, the normaliser l is not
-          if (DROP)
-            pd *= drop_factor(p.drop, p.drop_site, ((static_cast<uint32_t>(a) * kHeads + (lane >> 2)) * p.nq + qi) * p.nq + j);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], corr, pd * vf[i]);
+          for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], corr, pj * vf[i]);
           m = m_new;
         }
         const float inv = 1.0f / l;

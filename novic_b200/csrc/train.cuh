@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(kAttnBwdWarps * 32) attn_bwd_kernel(const Attn
 // ---------------------------------------------------------------------------------------------------------
 // Attention forward of the teacher-forced pass, same tiling as the backward kernel above: one warp per (sequence, head), all S <= 32
 // queries at once, Q K^T and P V on mma.sync tiles; the probabilities go from the score accumulators straight into the A fragments of
-// the second product.  Replaces the key-by-key online-softmax kernel (attention_bulk_kernel_t, 138 us per launch) in the training step.
+// the second product.  Replaces the key-by-key online-softmax kernel (attention_bulk_kernel, 138 us per launch; it carried the dropout too until then) in the training step.
 // Requires q0 = 0, one beam, no ancestor mask.  Dropout masks the numerator only (torch applies it to the normalised probabilities).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAttnTfWarps = 2;
