@@ -117,3 +117,19 @@ def test_cache_file_round_trip(N, F, R1, C, M, with_weights, id_dtype):
     finally:
         if os.path.exists(path):
             os.remove(path)
+
+
+def test_grad_bucket_recognises_only_its_own_views():
+    """dist.GradBucket.covers: the in-place all-reduce may only run when the gradients are exactly the bucket's views."""
+    from novic_b200.dist import GradBucket
+    flat = torch.zeros(12 + 5 + GradBucket.SPARE)
+    views = [flat[:12].view(3, 4), flat[12:17]]
+    b = GradBucket(flat, views)
+    assert b.total == 17 and b.covers(views) and b.covers(list(reversed(views)))          # order does not matter, memory does
+    assert b.covers([v.detach() for v in views])                                            # autograd hands over detached aliases
+    assert not b.covers(views[:1])                                                          # a gradient is missing
+    assert not b.covers([views[0], views[0]])                                               # one view twice
+    assert not b.covers([views[0], views[1].clone()])                                       # a copy lives elsewhere
+    assert not b.covers([views[0], flat[12:16]])                                            # right address, wrong extent
+    assert not b.covers([views[0].double(), views[1]])                                      # cast gradients
+    assert not b.covers([flat[:12].view(4, 3).t(), views[1]])                               # same memory, not contiguous
