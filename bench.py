@@ -171,6 +171,46 @@ def algorithmic_work(B: int, dims, fused: bool = True) -> dict:
     }
 
 
+def gemm_hbm_bytes(B: int, dims) -> dict:
+    """Algorithmic HBM bytes per decode of the GEMM classes: activation rows read and written once (bf16 operands 2 B, fp32 residual
+    stream 4 B per element); weights (25 MB in all) stay L2-resident across the launches of a decode and are not counted.  A GEMM
+    class is reported against whichever roof - tensor or HBM - takes longer for its algorithmic work (roof_entry)."""
+    F, E, K, L, P, V, G = dims.embed_dim, dims.hidden_dim, dims.ffn_dim, dims.num_layers, dims.prefix_len, dims.vocab_size, dims.token_length - 1
+    rows = B * (P + G - 1)
+    return {
+        "prefix_gemm": B * F * 2 + B * P * E * (4 + 2),                 # bf16 embedding in; fp32 residual rows + their LayerNorm-ed bf16 copy out
+        "qkv_gemm": rows * L * (2 * E + 3 * 2 * E),                     # xn in; q, k, v out
+        "outproj_gemm": rows * L * (2 * E + 4 * E + 4 * E + 2 * E),     # attention rows + residual in; residual + LN2 rows out
+        "ffn1_gemm": rows * L * (2 * E + 2 * K),
+        "ffn2_gemm": rows * L * (2 * K + 4 * E + 4 * E + 2 * E),
+        "logits_gemm": B * G * (2 * E + -(-V // 64) * 32),              # final rows in; one 32-byte partial record per 64 vocabulary columns out
+        # fused kernels keep their intermediates on chip: attention rows + residual in, residual + next LayerNorm rows out
+        "fused_block": rows * L * (2 * E + 4 * E + 4 * E + 2 * E),
+    }
+
+
+def roof_entry(bound: str, amount: float, hbm_bytes, ms: float, iso_ms: float, peaks: dict) -> dict:
+    """Roofline fields of one kernel class from its algorithmic work and its measured time per decode (ms in graph, iso_ms isolated).
+    bound 'hbm': amount = bytes.  bound 'tensor': amount = FLOPs and, when hbm_bytes is given, the class is reported against the roof
+    that takes longer for that work (the binding one); both fractions are kept as tensor_frac / hbm_frac."""
+    def hbm(nbytes, t_ms):
+        return nbytes / (t_ms * 1e-3) / 1e9
+    def tensor(flops, t_ms):
+        return flops / (t_ms * 1e-3) / 1e12
+    if bound == "hbm":
+        ach = hbm(amount, ms)
+        return {"bound": "hbm", "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "isolated_frac": hbm(amount, iso_ms) / peaks["hbm_gbs"]}
+    t_frac = tensor(amount, ms) / peaks["bf16_tflops_sustained"]
+    out = {"bound": "tensor", "achieved": tensor(amount, ms), "unit": "TFLOP/s", "frac": t_frac,
+           "isolated_frac": tensor(amount, iso_ms) / peaks["bf16_tflops_sustained"]}
+    if hbm_bytes:
+        h_frac = hbm(hbm_bytes, ms) / peaks["hbm_gbs"]
+        out.update(tensor_frac=t_frac, hbm_frac=h_frac)
+        if h_frac > t_frac:   # the HBM roof binds: moving the rows takes longer than the math
+            out.update(bound="hbm", achieved=hbm(hbm_bytes, ms), unit="GB/s", frac=h_frac, isolated_frac=hbm(hbm_bytes, iso_ms) / peaks["hbm_gbs"])
+    return out
+
+
 def _timed_decodes(model, embed, flush, n):
     """Mean device time (CUDA events on the launching stream, L2 flushed before each) of n greedy decodes."""
     total = 0.0
@@ -232,6 +272,9 @@ def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict
         work["ffn2_gemm"] = ("tensor", work["ffn1_gemm"][1] + work["ffn2_gemm"][1])
     if cnt[names.index('outproj_gemm')] == 0:   # fused block kernel (out-proj + LN2 + feed-forward + LN): timed as class ffn2_gemm
         work["ffn2_gemm"] = ("tensor", work["ffn2_gemm"][1] + work["outproj_gemm"][1])
+    gbytes = gemm_hbm_bytes(embed.shape[0], dims)
+    if cnt[names.index('ffn1_gemm')] == 0 or cnt[names.index('outproj_gemm')] == 0:
+        gbytes["ffn2_gemm"] = gbytes["fused_block"]
     total = sum(max(v, 0.0) for v in in_graph.values()) or 1.0
     out = {}
     for i, name in enumerate(names):
@@ -244,14 +287,7 @@ def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict
         entry = {"ms_per_step": g_ms, "launches_per_step": cnt[i] // steps, "share": g_ms / total, "isolated_ms_per_step": ms[i] / steps}
         if name in work:
             bound, amount = work[name]
-            if bound == "hbm":
-                ach = amount / (g_ms * 1e-3) / 1e9
-                entry.update(bound="hbm", achieved=ach, unit="GB/s", frac=ach / peaks["hbm_gbs"],
-                             isolated_frac=amount / (ms[i] / steps * 1e-3) / 1e9 / peaks["hbm_gbs"])
-            else:
-                ach = amount / (g_ms * 1e-3) / 1e12
-                entry.update(bound="tensor", achieved=ach, unit="TFLOP/s", frac=ach / peaks["bf16_tflops_sustained"],
-                             isolated_frac=amount / (ms[i] / steps * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"])
+            entry.update(roof_entry(bound, amount, gbytes.get(name), g_ms, iso_ms, peaks))
         out[name] = entry
     if cnt[names.index('outproj_gemm')] == 0 and 'ffn2_gemm' in out:
         # decode path with the fused block kernel (out-proj + LN2 + feed-forward + LN in one cluster kernel): name it for what it is
