@@ -6,7 +6,7 @@ import torch
 
 from novic_b200 import default_decoder, synth
 from oracle import novic_oracle as orc
-from tests.golden_util import gold_embed, weight_case
+from tests.golden_util import weight_case
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from novic_b200.dist import gather_generation, generate_sharded, shard_bounds
+from novic_b200.dist import generate_sharded, shard_bounds
 
 
 def test_shard_bounds_partition():

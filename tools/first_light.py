@@ -72,7 +72,6 @@ def _deblock(xb: torch.Tensor, rows: int) -> torch.Tensor:
 
 
 def _fwd(num_layers, B, Cc, pad_mode, dump=False):
-    import math
     from novic_b200 import synth
     _abi, lib = _lib()
     dims, sd, cfg, orc, model = _oracle_setup(num_layers)
