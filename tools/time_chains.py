@@ -1,3 +1,4 @@
+"""Wall-clock time of greedy and beam-3 decodes (B from argv) with output checksums - to compare NOVIC_* switches for speed AND equal results."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
