@@ -1,7 +1,7 @@
 """GPU bring-up diagnostics: each stage runs in its own process (a device trap must not hide later stages).
 
-    python tools/first_light.py            # run every stage, each under `timeout`
-    python tools/first_light.py gemm       # one stage in-process
+    python tests/first_light.py            # run every stage, each under `timeout`
+    python tests/first_light.py gemm       # one stage in-process
 """
 from __future__ import annotations
 
