@@ -155,3 +155,31 @@ def test_formats_match_committed_reference_vectors(name):
             assert np.array_equal(out.numpy(), z[f"{key}__b{bi}__ids"]), (sw, batch)
             assert (mask is None) == (f"{key}__b{bi}__mask" not in z.files) and (mask is None or np.array_equal(mask.numpy(), z[f"{key}__b{bi}__mask"])), (sw, batch)
             assert np.array_equal(decode_targets(out, tok, fmt).numpy(), z[f"{key}__b{bi}__raw"]), (sw, batch)
+
+
+def test_random_vocabularies_match_the_reference_embedder(ref):
+    """Seeded random noun lists (1-12 letters from random alphabets, duplicates of letters, single-noun lists) and random switch
+    choices against the live reference."""
+    import random
+    rng = random.Random(1234)
+    for trial in range(25):
+        name = rng.choice(sorted(TOKENIZERS))
+        spec = TOKENIZERS[name]
+        tok = _tok(spec)
+        alphabet = rng.sample("abcdefghijklmnopqrstuvwxyz", rng.randint(1, 26))
+        nouns = tuple(dict.fromkeys("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 12))) for _ in range(rng.randint(1, 30))))
+        emb = _toy_embedder(ref, spec)
+        all_ids, all_attn = _raw(nouns, spec["start"], spec["end"], spec["pad"])
+        for sw in rng.sample(SWITCHES, 6):
+            cfg = emb.create_target_config(nouns, **sw)
+            fmt = make_target_format(all_ids, all_attn, tok, **sw)
+            assert (fmt.vocab_size, fmt.start_token_id, fmt.end_token_id, fmt.pad_token_id, fmt.token_length) == \
+                   (cfg.vocab_size, cfg.start_token_id, cfg.end_token_id, cfg.pad_token_id, cfg.token_length), (trial, sw)
+            if cfg.compact_ids:
+                assert torch.equal(fmt.compact_map, cfg.compact_map) and torch.equal(fmt.compact_unmap, cfg.compact_unmap), (trial, sw)
+            emb.configure_target(cfg, nouns)
+            batch = tuple(rng.sample(nouns, rng.randint(1, len(nouns))))
+            want_ids, want_mask = emb.tokenize_target(batch)
+            got_ids, got_mask = encode_targets(*_raw(batch, spec["start"], spec["end"], spec["pad"]), tok, fmt)
+            assert torch.equal(got_ids, want_ids) and ((got_mask is None and want_mask is None) or torch.equal(got_mask, want_mask)), (trial, sw)
+            assert torch.equal(decode_targets(got_ids, tok, fmt), emb.detokenize_target(want_ids)), (trial, sw)
