@@ -149,7 +149,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # algorithmic work per kernel class for one greedy decode of B embeddings
 # ----------------------------------------------------------------------------------------------------------------
-def algorithmic_work(B: int, dims, fused: bool = True) -> dict:
+def algorithmic_work(B: int, dims) -> dict:
     F, E, K, L, P, V, G = dims.embed_dim, dims.hidden_dim, dims.ffn_dim, dims.num_layers, dims.prefix_len, dims.vocab_size, dims.token_length - 1
     rows = B * (P + G - 1)                       # residual rows that pass through the layers (prefill P + G-1 decode steps)
     attn_bytes = 0
@@ -159,15 +159,13 @@ def algorithmic_work(B: int, dims, fused: bool = True) -> dict:
     return {
         "embed_prep": ("hbm", B * F * (4 + 2)),
         "prefix_gemm": ("tensor", 2 * B * F * P * E),
-        "qkv_gemm": ("tensor", 2 * rows * E * 3 * E * (1 if fused else L)),
+        "qkv_gemm": ("tensor", 2 * rows * E * 3 * E * L),
         "attention": ("hbm", attn_bytes),
         "outproj_gemm": ("tensor", 2 * rows * E * E * L),
         "ffn1_gemm": ("tensor", 2 * rows * E * K * L),
         "ffn2_gemm": ("tensor", 2 * rows * K * E * L),
         "logits_gemm": ("tensor", 2 * B * G * E * V),
         "select": ("hbm", B * G * (-(-V // 64) * 32 + E * (4 + 4 + 2))),
-        # fused cluster kernel: out-proj + FFN of layer l + QKV of layer l+1 (the first layer's QKV is timed as qkv_gemm)
-        "layer_stack": ("tensor", 2 * rows * E * (E + 2 * K) * L + 2 * rows * E * 3 * E * (L - 1)),
     }
 
 
@@ -267,7 +265,7 @@ def kernel_breakdown(model, embed, flush, steps: int, peaks: dict, dims) -> dict
         finally:
             _abi.check(lib.novic_debug_keep_classes(st["handle"], 0))
         model.generate(embed, False, True, 1.0, 0.0, None, None, False)          # re-capture the full graph
-    work = algorithmic_work(embed.shape[0], dims, fused=cnt[names.index('layer_stack')] > 0)
+    work = algorithmic_work(embed.shape[0], dims)
     if cnt[names.index('ffn1_gemm')] == 0:      # fused feed-forward kernel: its launches do both GEMMs of the block
         work["ffn2_gemm"] = ("tensor", work["ffn1_gemm"][1] + work["ffn2_gemm"][1])
     if cnt[names.index('outproj_gemm')] == 0:   # fused block kernel (out-proj + LN2 + feed-forward + LN): timed as class ffn2_gemm
@@ -418,7 +416,7 @@ def main():
         if os.path.isfile(tpath) and d.get("bound") == "hbm":
             entry = json.load(open(tpath)).get(dom)
             if entry:  # ncu-measured DRAM bytes of one launch / that launch's algorithmic bytes, applied to the average launch
-                work = algorithmic_work(B, dims, fused='layer_stack' in kernels).get(dom, (None, 0))[1]
+                work = algorithmic_work(B, dims).get(dom, (None, 0))[1]
                 traffic = entry["ratio_to_algorithmic"] * work / max(1, d["launches_per_step"])
         roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
                     "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],

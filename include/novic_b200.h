@@ -119,6 +119,12 @@ int novic_generate_greedy_async(NovicHandle* h, const float* embed, int64_t B, f
                                 int64_t* tok, uint8_t* pad, float* score, float* nll, float* len, int32_t* T_dev,
                                 const NovicGuide* guide, void* ws, size_t ws_bytes, void* stream);
 
+/* Tail of PrefixedIterDecoder.generate (embedding_decoder.py:838-846): loss_sum = sum_b w_b * nll_b and loss_basis = sum_b w_b * len_b over
+ * the per-sample vectors novic_generate_greedy returns (weight = sample_weight, NULL = 1), as one deterministic single-block reduction.
+ *   out_f32x2 [2] fp32 device = {loss_sum, loss_basis}; out_i64 [1] int64 device (may be NULL) = loss_basis rounded to an integer
+ *   (what the reference returns without sample weights). */
+int novic_loss_totals(const float* nll, const float* len, const float* weight, int64_t n, float* out_f32x2, int64_t* out_i64, void* stream);
+
 /* Replaces PrefixedIterDecoder.generate_beam (embedding_decoder.py:852-984); guide = NULL: unguided, no vocabulary prior.
  * With a vocabulary prior and no guide_targets the caller passes the vocabulary trie as the guide (renorm = 0) with child_bias set.
  *   Outputs (device): tok [B, H, G] int64, pad [B, H, G] u8, score [B, H] fp32 sorted descending. */
@@ -195,8 +201,8 @@ int32_t novic_debug_wgrad_splits(int64_t tiles, int64_t kblocks, int32_t sms);
 /* Per-kernel-class device timing for roofline reports.  novic_kernel_timing(1) makes every subsequent direct
  * (non-graph) launch record a CUDA-event pair on its stream; novic_kernel_times() synchronises and returns the
  * accumulated milliseconds and launch counts per class, then clears.  Classes, in order: embed-prep, prefix GEMM,
- * QKV GEMM, attention, out-proj GEMM, FFN1 GEMM, FFN2 GEMM, logits GEMM, selection, other, fused layer stack (out-proj +
- * FFN + next layer's QKV in one cluster kernel) (n_classes >= 11). */
+ * QKV GEMM, attention, out-proj GEMM, FFN1 GEMM, FFN2 GEMM (also the fused out-proj + feed-forward block kernel), logits GEMM,
+ * selection, other (n_classes >= 10). */
 int novic_kernel_timing(int32_t enable);
 int novic_kernel_times(double* ms_out, int64_t* count_out, int32_t n_classes);
 

@@ -63,6 +63,7 @@ SIGNATURES = {
                                               C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_generate_beam": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, C.c_float, C.c_float, _FP, _FP, _FP,
                                       C.POINTER(C.c_int32), C.POINTER(NovicGuide), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "novic_loss_totals": (C.c_int, [_FP, _FP, _FP, C.c_int64, _FP, _FP, C.c_void_p]),
     "novic_forward": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, C.c_int32, _FP, _FP, _FP,
                                 _FP, C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_forward_guided": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, _FP, _FP, _FP, _FP,
@@ -90,7 +91,7 @@ SIGNATURES = {
 }
 
 KERNEL_CLASSES = ("embed_prep", "prefix_gemm", "qkv_gemm", "attention", "outproj_gemm", "ffn1_gemm", "ffn2_gemm", "logits_gemm",
-                  "select", "other", "layer_stack")
+                  "select", "other")
 
 _lib = None
 

@@ -12,7 +12,6 @@
 
 #include "../../include/novic_b200.h"
 #include "train.cuh"
-#include "stack.cuh"
 
 using namespace novic;
 
@@ -202,15 +201,6 @@ int launch_outproj_ffn(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap
   return 0;
 }
 
-// The fused layer-stack kernel (stack.cuh): one 4-CTA cluster per 128 residual rows.
-int launch_stack(cudaStream_t s, const StackMaps& maps, const StackArgs& a) {
-  dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(a.M, kBlockM)));
-  CUDA_TRY(launch_k(layer_stack_kernel, grid, dim3(kStkThreads), kStkSmemBytes, s, maps, a));
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
 __global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
@@ -251,7 +241,7 @@ __global__ void tf_mask_kernel(const long long* __restrict__ target, const unsig
 }
 
 // Optional per-kernel-class CUDA-event timing (bench.py's roofline numbers): only in direct-launch mode.
-enum KClass : int { kKPrep = 0, kKPrefix, kKQkv, kKAttn, kKOutProj, kKFfn1, kKFfn2, kKLogits, kKSelect, kKMisc, kKStack, kKNumClasses };
+enum KClass : int { kKPrep = 0, kKPrefix, kKQkv, kKAttn, kKOutProj, kKFfn1, kKFfn2, kKLogits, kKSelect, kKMisc, kKNumClasses };
 struct KTiming {
   bool enabled = false;
   std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> spans;
@@ -321,11 +311,14 @@ struct Workspace {
 
 struct GraphKey {
   int mode; int64_t B; int H; float tau, alpha; void* ws;
-  const void* guide = nullptr; int guide_flags = 0;   // trie identity (child_off pointer) and renorm flag baked into the graph
-  const void* bias = nullptr;                         // vocabulary-prior edge scores baked into the graph
+  // everything of the guide that a captured graph bakes in: the three trie arrays, their sizes, the renorm flag and the
+  // vocabulary-prior edge scores (the arrays' CONTENTS are read at replay time, so a key match is sufficient for correctness)
+  const void* guide = nullptr; int guide_flags = 0;
+  const void* bias = nullptr;
+  const void* guide_tok = nullptr; const void* guide_node = nullptr; int num_nodes = 0, num_edges = 0;
   bool operator<(const GraphKey& o) const {
-    return std::tie(mode, B, H, tau, alpha, ws, guide, guide_flags, bias) <
-           std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws, o.guide, o.guide_flags, o.bias);
+    return std::tie(mode, B, H, tau, alpha, ws, guide, guide_flags, bias, guide_tok, guide_node, num_nodes, num_edges) <
+           std::tie(o.mode, o.B, o.H, o.tau, o.alpha, o.ws, o.guide, o.guide_flags, o.bias, o.guide_tok, o.guide_node, o.num_nodes, o.num_edges);
   }
 };
 
@@ -339,8 +332,6 @@ struct NovicHandle {
   int attn_cfg = 0;                   // stream-attention shape (tuning): 0 = 16 warps x 3 slots x 4 keys
   bool attn_stream = true;            // decode steps use attention_stream_kernel (NOVIC_ATTN_STREAM=0: the bulk-ring kernel)
   bool fuse_ffn = true;
-  bool stack_attn = true;             // decode steps run attention inside the stack kernel (NOVIC_STACK_ATTN=0: separate launches)
-  bool fuse_stack = false;            // experimental (NOVIC_STACK=1): whole layer stack as one cluster kernel, stack.cuh - measured slower, see DESIGN.md
   bool split_sms = true;
   int num_sms = 148;
   int max_chains = 1;                 // concurrent sub-batch chains per decode (NOVIC_CHAINS); measured: no gain for greedy on B200
@@ -451,7 +442,7 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   pa.nseq = pc.nseq; pa.nq = pc.nq; pa.q0 = pc.q0; pa.smax = S; pa.P = c.prefix_len; pa.beams = pc.beams;
   pa.prefix_bidir = c.strictly_causal ? 0 : 1; pa.keypad_ld = pc.keypad_ld; pa.anc_ld = pc.anc_ld;
   pa.slot_mul = pc.slot_mul;
-  pa.early_loads = h->fuse_stack ? 0 : h->attn_early;   // early bulk loads next to the stack kernel fault under graphs + PDL (unexplained)
+  pa.early_loads = h->attn_early;
   pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
   pa.stream_hint = g_attn_hint;
   KSpan t(kKAttn, s);
@@ -493,53 +484,9 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   return 0;
 }
 
-// Fused schedule: QKV_0 | attention_0 | OUT_0 FFN_0 QKV_1 | attention_1 | ... | OUT_{L-1} FFN_{L-1}
-int run_layers_stack(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStream_t s) {
-  const NovicCfg& c = h->cfg;
-  const int L = c.num_layers, S = h->S(), M = pc.M;
-  StackMaps maps;
-  if (make_tmap(&maps.xn, ws.xn, M, kE, kBlockM)) return 1;
-  if (make_tmap(&maps.ao, ws.ao, M, kE, kBlockM)) return 1;
-  StackArgs a{};
-  a.M = M; a.num_layers = L; a.x = ws.x; a.xn = ws.xn; a.q = ws.q; a.kv = ws.kv;
-  a.xfin = pc.remap_in > 0 ? ws.xfin : nullptr;
-  a.kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
-  a.rows_per_seq = pc.nq; a.pos0 = pc.q0; a.slot_mul = pc.slot_mul; a.smax = S;
-  a.remap_in = pc.remap_in; a.remap_skip = pc.remap_skip; a.remap_out = pc.remap_out;
-  a.eps = c.ln_eps;
-  for (int l = 0; l < L; ++l) {
-    maps.w[l].in_proj = h->w.tm_in_proj[l]; maps.w[l].out_proj = h->w.tm_out_proj[l];
-    maps.w[l].linear1 = h->w.tm_linear1[l]; maps.w[l].linear2 = h->w.tm_linear2[l];
-    a.gain_out[l] = h->w.norm2[l];
-    a.gain_ffn[l] = l + 1 < L ? h->w.norm1[l + 1] : h->w.final_norm;
-  }
-  for (int l = L; l < kStkMaxLayers; ++l) maps.w[l] = maps.w[0];
-  a.ao = ws.ao; a.anc = pc.anc; a.anc_ld = pc.anc_ld; a.beams = pc.beams; a.prefix_len = c.prefix_len;
-  a.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
-  if (h->stack_attn && pc.nq == 1 && pc.keypad == nullptr && pc.q0 >= c.prefix_len) {
-    // decode step: the whole stack, attention included, is one launch
-    a.ph_begin = 0; a.ph_end = 4 * L; a.load_x = 1; a.store_x = 0;
-    KSpan t(kKStack, s);
-    return launch_stack(s, maps, a);
-  }
-  a.ph_begin = 0; a.ph_end = 1; a.load_x = 0; a.store_x = 0;
-  { KSpan t(kKQkv, s); if (launch_stack(s, maps, a)) return 1; }
-  for (int l = 0; l < L; ++l) {
-    if (launch_attention(h, ws, pc, l, s)) return 1;
-    a.ph_begin = 4 * l + kPhOut;
-    a.ph_end = l + 1 < L ? 4 * (l + 1) + kPhQkv + 1 : 4 * l + kPhFfn + 1;
-    a.load_x = 1; a.store_x = l + 1 < L ? 1 : 0;
-    KSpan t(kKStack, s);
-    if (launch_stack(s, maps, a)) return 1;
-  }
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
 int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStream_t s) {
   const NovicCfg& c = h->cfg;
   const int L = c.num_layers, S = h->S(), M = pc.M;
-  if (h->fuse_stack && h->fuse_ffn && L <= kStkMaxLayers) return run_layers_stack(h, ws, pc, s);
   CUtensorMap tm_xn, tm_ao, tm_hb;
   if (make_tmap(&tm_xn, ws.xn, M, kE, kBlockM)) return 1;
   if (make_tmap(&tm_ao, ws.ao, M, kE, kBlockM)) return 1;
@@ -944,10 +891,6 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e6 = getenv("NOVIC_NO_PDL")) g_use_pdl = e6[0] != '1';
   if (const char* e5 = getenv("NOVIC_NO_SM_SPLIT")) h->split_sms = e5[0] != '1';
   if (const char* e4 = getenv("NOVIC_NO_FFN_FUSION")) h->fuse_ffn = e4[0] != '1';
-  if (const char* e8 = getenv("NOVIC_STACK")) h->fuse_stack = e8[0] == '1';
-  if (const char* e10 = getenv("NOVIC_STACK_ATTN")) h->stack_attn = e10[0] != '0';
-  if (const char* e11 = getenv("NOVIC_STACK_FENCE")) { const int mode = atoi(e11); CUDA_TRY(cudaMemcpyToSymbol(g_stk_fence_mode, &mode, sizeof(int))); }
-  CUDA_TRY(cudaFuncSetAttribute(layer_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStkSmemBytes));
   if (const char* e3 = getenv("NOVIC_CHAINS")) h->max_chains = std::max(1, std::min(8, atoi(e3)));
   for (int i = 0; i < 8; ++i) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->chain_streams[i], cudaStreamNonBlocking));
@@ -1148,6 +1091,7 @@ static int greedy_impl(NovicHandle* h, const float* embed, int64_t B, float temp
     CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
   GraphKey key{0, B, cp.n, temperature, length_alpha, wsbuf, gcfg.on ? static_cast<const void*>(gcfg.trie.child_off) : nullptr,
                (gcfg.on ? 1 : 0) | (gcfg.renorm ? 2 : 0)};
+  if (gcfg.on) { key.guide_tok = gcfg.trie.child_tok; key.guide_node = gcfg.trie.child_node; key.num_nodes = guide->num_nodes; key.num_edges = guide->num_edges; }
   if (run_maybe_graph(h, key, logits == nullptr, s, [&](cudaStream_t cs) {
         return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) {
           float* lg = logits != nullptr ? logits + static_cast<size_t>(cp.b0[i]) * G * V : nullptr;
@@ -1217,6 +1161,7 @@ int novic_generate_beam(NovicHandle* h, const float* embed, int64_t B, int32_t H
     CUDA_TRY(cudaMemcpyAsync(cp.ws[i].ein, embed + cp.b0[i] * F, sizeof(float) * cp.nb[i] * F, cudaMemcpyDeviceToDevice, s));
   GraphKey key{1, B, H * 16 + cp.n, temperature, length_alpha, wsbuf, gcfg.on ? static_cast<const void*>(gcfg.trie.child_off) : nullptr,
                (gcfg.on ? 1 : 0) | (gcfg.renorm ? 2 : 0), gcfg.bias};
+  if (gcfg.on) { key.guide_tok = gcfg.trie.child_tok; key.guide_node = gcfg.trie.child_node; key.num_nodes = guide->num_nodes; key.num_edges = guide->num_edges; }
   if (run_maybe_graph(h, key, true, s, [&](cudaStream_t cs) {
         return run_chains(h, cs, cp.n, [&](int i, cudaStream_t st) { return enqueue_beam(h, cp.ws[i], temperature, length_alpha, gcfg, st); });
       }))
@@ -1445,6 +1390,15 @@ int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B
                                const float* normals_b, const float* row_a, const float* row_b, void* stream) {
   if (normals_a == nullptr) return fail("normals_a is required");
   return noise_launch(cfg, embed, B, normals_a, normals_b, row_a, row_b, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int novic_loss_totals(const float* nll, const float* len, const float* weight, int64_t n, float* out_f32x2, int64_t* out_i64, void* stream) {
+  if (nll == nullptr || len == nullptr || out_f32x2 == nullptr || n < 1) return fail("novic_loss_totals: nll, len, out and n >= 1 are required");
+  pair_reduce_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(nll, len, weight, static_cast<long long>(n), out_f32x2,
+                                                                      reinterpret_cast<long long*>(out_i64));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 int novic_kernel_timing(int32_t enable) {

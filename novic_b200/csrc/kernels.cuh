@@ -1021,6 +1021,41 @@ loss_reduce_kernel(const float* __restrict__ nll, const long long* __restrict__ 
   }
 }
 
+// Deterministic single-block reduction of two per-sample vectors (the tail of generate(), embedding_decoder.py:838-846):
+// out_f[0] = sum_b w_b * a_b, out_f[1] = sum_b w_b * b_b (w = 1 without weights); out_i[0] = round(out_f[1]) as int64.
+__global__ void __launch_bounds__(1024)
+pair_reduce_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ weight, long long n,
+                   float* __restrict__ out_f /*[2]*/, long long* __restrict__ out_i /*[1] or nullptr*/) {
+  __shared__ double s_a[32], s_b[32];
+  double sa = 0.0, sb = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const double w = weight != nullptr ? static_cast<double>(weight[i]) : 1.0;
+    sa += w * a[i];
+    sb += w * b[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if (lane_id() == 0) { s_a[threadIdx.x >> 5] = sa; s_b[threadIdx.x >> 5] = sb; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    sa = threadIdx.x < (blockDim.x >> 5) ? s_a[threadIdx.x] : 0.0;
+    sb = threadIdx.x < (blockDim.x >> 5) ? s_b[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (threadIdx.x == 0) {
+      out_f[0] = static_cast<float>(sa);
+      out_f[1] = static_cast<float>(sb);
+      if (out_i != nullptr) out_i[0] = llrint(sb);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Embedding noise (embedding_noise.py), fused draw + perturb + renormalise, in place.  Warp per row.
 // With `pre` pointers given the random draws are read instead of generated (deterministic parity mode).

@@ -208,6 +208,8 @@ class PrefixedIterDecoder(EmbeddingDecoder):
             mask[:P, :P] = 0
         self.register_buffer('causality_mask', mask)
         self.reset_parameters()
+        # a checkpoint's vocab_quant rows (V .. ceil64(V)) must be zero, as the reference's loader demands (embedding_decoder.py:437-441)
+        self.register_load_state_dict_post_hook(self._verify_unused)
 
         self._handles: dict[int, dict] = {}  # per CUDA device: library handle, packed weights, workspace
 
@@ -255,6 +257,11 @@ class PrefixedIterDecoder(EmbeddingDecoder):
             nn.init.constant_(layer.norm1.weight, norm_scale)
             nn.init.constant_(layer.norm2.weight, norm_scale)
         nn.init.constant_(self.transformer.norm.weight, f if ic['init_tfrm_unit_postnorm'] else 1.0)
+
+    def _verify_unused(self, *args, **kwargs):
+        V = self.target_config.vocab_size
+        if self.vocab_size_quant > V and bool(torch.any(self.logits_linear.weight[V:] != 0)):
+            raise ValueError("Unexpected values in the unused portion of a parameter tensor")
 
     def get_num_params(self):
         unused = (self.vocab_size_quant - self.target_config.vocab_size) * self.hidden_dim
@@ -411,9 +418,10 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         with torch.cuda.device(dev):
             if guide_targets is not None and calc_correct:
                 # guided correctness evaluation (embedding_decoder.py:754-760): the trie spans the first Ct columns of the guide targets
-                if not hasattr(self, "_trie_cache"):
-                    self._trie_cache = guide.TrieCache()
-                trie = self._trie_cache.get(guide_targets, Ct, V, dev)
+                # its own cache (one trie per trimmed target width Ct of an evaluation batch): the decode paths' tries are not evicted
+                if not hasattr(self, "_trie_cache_fwd"):
+                    self._trie_cache_fwd = guide.TrieCache(max_entries=max(8, tc.token_length))
+                trie = self._trie_cache_fwd.get(guide_targets, Ct, V, dev)
                 masks = torch.empty(A * Ct * ((V + 31) // 32), dtype=torch.int32, device=dev)
                 _abi.check(_abi.lib().novic_forward_guided(st['handle'], embed.data_ptr(), B, M, target_c.data_ptr(), _ptr(pad_c), _ptr(w_c), Ct,
                                                            logits.data_ptr(), _ptr(pad_out), _ptr(loss), _ptr(correct), guide.guide_arg(trie, False),
@@ -485,14 +493,14 @@ class PrefixedIterDecoder(EmbeddingDecoder):
     # ------------------------------------------------------------------------------------------------------
     # generate (embedding_decoder.py:779-850)
     # ------------------------------------------------------------------------------------------------------
-    def _guide_trie(self, guide_targets, device):
+    def _guide_trie(self, guide_targets, device, check_content: bool = True):
         """W x Cmax guide targets -> cached device trie (novic_b200/guide.py), or None when unguided."""
         if guide_targets is None:
             return None
         assert guide_targets.ndim == 2 and guide_targets.dtype == self.target_config.token_dtype
         if not hasattr(self, "_trie_cache"):
             self._trie_cache = guide.TrieCache()
-        return self._trie_cache.get(guide_targets, self.target_config.token_length - 1, self.target_config.vocab_size, device)
+        return self._trie_cache.get(guide_targets, self.target_config.token_length - 1, self.target_config.vocab_size, device, check_content)
 
     def _vocab_prior(self, guide_targets, vocab_targets, per_token, scaler, device):
         """(trie, per-edge prior scores) of a beam search with a vocabulary prior (embedding_decoder.py:881-891, :924-936), cached
@@ -500,9 +508,13 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         assert vocab_targets.ndim == 2 and vocab_targets.dtype == self.target_config.token_dtype
         if not hasattr(self, "_prior_cache"):
             self._prior_cache = []
-        ident = lambda t: None if t is None else (t.data_ptr(), tuple(t.shape), guide.tensor_version(t), str(t.device))  # noqa: E731
+        def ident(t):   # identity + version, and the content where no version counter exists (inference tensors)
+            if t is None:
+                return None
+            ver = guide.tensor_version(t)
+            return (t.data_ptr(), tuple(t.shape), ver, str(t.device), guide.content_checksum(t) if ver < 0 else None)
         key = (ident(guide_targets), ident(vocab_targets), per_token, scaler, str(device))
-        for k, v in self._prior_cache:
+        for k, _, v in self._prior_cache:
             if k == key:
                 return v
         G, V = self.target_config.token_length - 1, self.target_config.vocab_size
@@ -511,7 +523,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         gtrie = None if guide_targets is None else guide.build_trie(guide_targets, G, V)
         trie, bias = guide.prior_bias(gtrie, vocab_targets, is_guide, per_token, scaler, G, V)
         value = (trie.to(device), bias.to(device))
-        self._prior_cache.append((key, value))
+        self._prior_cache.append((key, (guide_targets, vocab_targets), value))   # the sources stay alive: their addresses cannot be reused
         if len(self._prior_cache) > 4:
             self._prior_cache.pop(0)
         return value
@@ -552,12 +564,16 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         seq_logits = None if logits is None else logits[:, :T, :]
         if not calc_loss:
             return target, target_padding, seq_logits, None, None, None
-        if sample_weight is None:
-            loss_sum = nll.sum()
-            loss_basis = length.sum().round().to(torch.int64)
-        else:
-            loss_sum = sample_weight.dot(nll)
-            loss_basis = sample_weight.dot(length)
+        # loss_sum / loss_basis (:838-846): one deterministic reduction kernel of the library, no eager torch arithmetic
+        totals = torch.empty(2, dtype=torch.float32, device=dev)
+        basis_i = torch.empty(1, dtype=torch.int64, device=dev) if sample_weight is None else None
+        if sample_weight is not None:
+            assert sample_weight.dtype == torch.float32 and sample_weight.shape == (B,)
+            sample_weight = sample_weight.contiguous()
+        with torch.cuda.device(dev):
+            _abi.check(lib.novic_loss_totals(nll.data_ptr(), length.data_ptr(), _ptr(sample_weight), B, totals.data_ptr(), _ptr(basis_i), stream))
+        loss_sum = totals[0]
+        loss_basis = basis_i[0] if sample_weight is None else totals[1]
         return target, target_padding, seq_logits, loss_sum, loss_basis, score
 
     def generate_async(self, embed, temperature=1.0, length_alpha=0.0, guide_targets=None, guide_renorm=False):
@@ -579,7 +595,7 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         score = torch.empty(B, dtype=torch.float32, device=dev)
         T = torch.empty(1, dtype=torch.int32, device=dev)
         ws = self._workspace(st, dev, B, 1, 0)
-        trie = self._guide_trie(guide_targets, dev)
+        trie = self._guide_trie(guide_targets, dev, check_content=False)     # no host synchronisation on this path
         garg = guide.guide_arg(trie, bool(guide_renorm))
         with torch.cuda.device(dev):
             _abi.check(_abi.lib().novic_generate_greedy_async(
@@ -603,6 +619,10 @@ class PrefixedIterDecoder(EmbeddingDecoder):
         G = self.target_config.token_length - 1
         if H == 1 and vocab_on:
             raise NotImplementedError("a beam of one with a vocabulary prior is not implemented in novic_b200 (use topk >= 2)")
+        if self.num_end_loss != 1:
+            # with N > 1 the reference's effective padding lags the end token by N - 1 positions (embedding_decoder.py:700-707), so a
+            # finished candidate grows N - 1 more tokens whose log-probabilities enter its score before being zeroed (:913, :980)
+            raise NotImplementedError("generate_beam with num_end_loss != 1 is not implemented in novic_b200")
         if H == 1:
             # a beam of one is the greedy path; scores coincide (sum of log-probs, length-normalised)
             t, p, _, _, _, s = self.generate(embed, False, True, temperature, length_alpha, None, guide_targets, guide_renorm)

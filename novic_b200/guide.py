@@ -177,28 +177,49 @@ def prior_bias(guide_trie, vocab_targets: torch.Tensor, vocab_is_guide: bool, pe
 def tensor_version(t: torch.Tensor) -> int:
     try:
         return t._version
-    except RuntimeError:                # inference tensors do not track versions; they cannot be modified in place either
+    except RuntimeError:                # inference tensors do not track versions
         return -1
 
 
-class TrieCache:
-    """Tries keyed by the identity and version of the guide tensor (infer.py hands the same tensor to every batch)."""
+def content_checksum(t: torch.Tensor) -> int:
+    """Position-weighted 64-bit checksum of an integer tensor (wrap-around arithmetic on the tensor's device, one scalar read
+    back).  Used where a version counter cannot tell whether a guide tensor changed: inference tensors have none, yet they can be
+    written in place inside torch.inference_mode()."""
+    flat = t.reshape(-1).to(torch.int64)
+    w = torch.arange(1, flat.numel() + 1, device=flat.device, dtype=torch.int64) * 0x9E3779B1
+    return int(((flat + 1) * w).sum().item())
 
-    def __init__(self, max_entries: int = 4):
-        self.entries: list[tuple[tuple, GuideTrie]] = []
+
+class TrieCache:
+    """Tries keyed by identity, version and (for tensors without a version counter) content of the guide tensor - infer.py hands the
+    same tensor to every batch.  An entry keeps a strong reference to its source tensor: while the entry lives the tensor's
+    storage cannot be freed, so a different tensor can never appear at the cached address (address-only keys return a
+    stale trie after the allocator reuses a freed guide tensor's block)."""
+
+    def __init__(self, max_entries: int = 8):
+        self.entries: list[tuple[tuple, torch.Tensor, GuideTrie]] = []
         self.max_entries = max_entries
 
-    def get(self, guide_targets: torch.Tensor, gen_len: int, vocab_size: int, device) -> GuideTrie:
+    def get(self, guide_targets: torch.Tensor, gen_len: int, vocab_size: int, device, check_content: bool = True) -> GuideTrie:
         version = tensor_version(guide_targets)
-        key = (guide_targets.data_ptr(), tuple(guide_targets.shape), version, str(guide_targets.device), str(device), gen_len, vocab_size)
-        for k, trie in self.entries:
-            if k == key:
+        ident = (guide_targets.data_ptr(), tuple(guide_targets.shape), tuple(guide_targets.stride()), version, str(guide_targets.device),
+                 str(device), gen_len, vocab_size)
+        # a version of -1 says nothing: compare contents instead (skipped only by callers that must not synchronise)
+        checksum = content_checksum(guide_targets) if (version < 0 and check_content) else None
+        for i, (k, src, trie) in enumerate(self.entries):
+            if k[0] == ident and (checksum is None or k[1] is None or k[1] == checksum):
+                if i != len(self.entries) - 1:                      # most recently used last
+                    self.entries.append(self.entries.pop(i))
                 return trie
         trie = build_trie(guide_targets, gen_len, vocab_size).to(device)
-        self.entries.append((key, trie))
+        self.entries = [e for e in self.entries if e[0][0] != ident]   # same tensor, new content: drop the stale entry
+        self.entries.append(((ident, checksum), guide_targets, trie))
         if len(self.entries) > self.max_entries:
             self.entries.pop(0)
         return trie
+
+    def clear(self) -> None:
+        self.entries.clear()
 
 
 def guide_arg(trie, renorm: bool, bias: torch.Tensor = None):

@@ -52,6 +52,11 @@ class TrainStep(torch.autograd.Function):
             grads.append(flat[off:off + n].view(p.shape))
             off += n
         model._grad_bucket = GradBucket(flat, grads)
+        V = model.target_config.vocab_size
+        if grads[1].shape[0] > V:
+            grads[1][V:].zero_()    # vocab_quant rows never receive a gradient (the library writes the V used rows only)
+        if GradBucket.SPARE:
+            flat[off:].zero_()
         loss = torch.empty(2, dtype=torch.float32, device=dev)
         correct = torch.empty((A, Ct), dtype=torch.uint8, device=dev)
         pad_out = torch.empty((A, Ct), dtype=torch.uint8, device=dev)

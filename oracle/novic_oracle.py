@@ -41,6 +41,7 @@ class OracleCfg:
     token_length: int = 16     # Cmax (includes the trailing end token)
     ln_eps: float = 1e-5
     num_end_loss: int = 1
+    strictly_causal: bool = False   # embedding_decoder.py:652: without it the P x P prefix block is bidirectional
 
     @property
     def max_seq_len(self) -> int:  # embedding_decoder.py:648
@@ -51,9 +52,11 @@ class OracleCfg:
         return self.token_length - 1
 
 
-def cfg_from_state_dict(sd: dict, token_length: Optional[int] = None, num_heads: int = 8) -> OracleCfg:
+def cfg_from_state_dict(sd: dict, token_length: Optional[int] = None, num_heads: int = 8, vocab_size: Optional[int] = None,
+                        num_end_loss: int = 1, strictly_causal: bool = False) -> OracleCfg:
+    """vocab_size: pass the real V when the tied matrix carries vocab_quant rows (embedding_decoder.py:642-645, :726-727)."""
     E = sd["logits_linear.weight"].shape[1]
-    V = sd["logits_linear.weight"].shape[0]
+    V = sd["logits_linear.weight"].shape[0] if vocab_size is None else vocab_size
     F = sd["embed_mlp.mlp.0.weight"].shape[1]
     P = sd["embed_mlp.mlp.0.weight"].shape[0] // E
     L = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
@@ -61,7 +64,7 @@ def cfg_from_state_dict(sd: dict, token_length: Optional[int] = None, num_heads:
     S = sd["pos_embedding.embedding.weight"].shape[0]
     Cmax = S - P + 1 if token_length is None else token_length
     return OracleCfg(embed_dim=F, hidden_dim=E, ffn_dim=K, num_layers=L, num_heads=num_heads, prefix_len=P,
-                     vocab_size=V, token_length=Cmax)
+                     vocab_size=V, token_length=Cmax, num_end_loss=num_end_loss, strictly_causal=strictly_causal)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -95,7 +98,7 @@ def attention_bias(cfg: OracleCfg, S: int, dtype: torch.dtype) -> torch.Tensor:
     (embedding_decoder.py:651-654)."""
     q = torch.arange(S).unsqueeze(1)
     k = torch.arange(S).unsqueeze(0)
-    visible = (k <= q) | ((q < cfg.prefix_len) & (k < cfg.prefix_len))
+    visible = (k <= q) if cfg.strictly_causal else ((k <= q) | ((q < cfg.prefix_len) & (k < cfg.prefix_len)))
     bias = torch.zeros(S, S, dtype=dtype)
     bias.masked_fill_(~visible, NEG_INF)
     return bias
@@ -216,7 +219,7 @@ def forward_logits(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: Option
             eff_pad = eff_pad[:, -1:]
     else:
         x = x[:, P - 1:, :]
-    return x @ Wt.t(), eff_pad
+    return x @ Wt[:cfg.vocab_size].t(), eff_pad    # vocab_quant rows (if any) are sliced away, :726-727
 
 
 def forward_loss(cfg: OracleCfg, sd: dict, embed: torch.Tensor, target: torch.Tensor, padding: Optional[torch.Tensor],
@@ -271,7 +274,7 @@ def guide_score_dense(guide_tok: torch.Tensor, guide_mask: torch.Tensor, V: int,
 
 def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: float = 1.0, length_alpha: float = 0.0,
                     sample_weight: Optional[torch.Tensor] = None, early_exit: bool = True,
-                    guide_targets: Optional[torch.Tensor] = None, guide_renorm: bool = False):
+                    guide_targets: Optional[torch.Tensor] = None, guide_renorm: bool = False, label_smoothing: float = 0.0):
     """Returns dict(target B x T int64, padding B x T bool, logits B x T x V, loss_sum, loss_basis, score B).
     guide_targets (W x Cmax, :802-813): the generated ids must spell one of the guide targets."""
     B = embed.shape[0]
@@ -316,7 +319,11 @@ def generate_greedy(cfg: OracleCfg, sd: dict, embed: torch.Tensor, temperature: 
     length = (T - pad.sum(dim=1)).to(score.dtype)
     if length_alpha != 0:
         score = score * length.clamp(min=1).pow(-length_alpha)  # :836
-    nll = -torch.log_softmax(seq_logits, dim=2).gather(2, tok.unsqueeze(2)).squeeze(2).masked_fill(pad, 0.0)
+    logp = torch.log_softmax(seq_logits, dim=2)
+    nll = -logp.gather(2, tok.unsqueeze(2)).squeeze(2)
+    if label_smoothing != 0.0:                                           # F.cross_entropy(label_smoothing=...), :840 / :844
+        nll = (1.0 - label_smoothing) * nll + label_smoothing * (-logp.mean(dim=-1))
+    nll = nll.masked_fill(pad, 0.0)
     if sample_weight is None:
         loss_sum = nll.sum()
         loss_basis = (~pad).sum()

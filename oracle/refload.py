@@ -1,10 +1,10 @@
-"""Import the *unmodified* reference (pallgeuer/novic at /root/reference) in the build container.
+"""Import the *unmodified* reference (pallgeuer/novic): from /root/reference in the build container, else from the
+byte-for-byte staged copy oracle/_ref/ (oracle/build_ref.py; a git-ignored build output that travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box, so nothing that runs there
-(-m gpu tests, smoke(), bench.py) may call this; the CPU test-suite skips when it is absent.  The only
-shims are a stub `unidecode` module (utils.py:19 imports it, only utils.get_canon uses it) and a
-SimpleNamespace standing in for the CLIP embedder, of which the decoder reads four attributes
-(embedding_decoder.py:77-86).  No reference source is copied.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY: tests/, bench.py's CPU legs and __graft_entry__.smoke() are the only callers; nothing
+under novic_b200/ imports it.  The only shims are a stub `unidecode` module (utils.py:19 imports it, only utils.get_canon uses
+it) and a SimpleNamespace standing in for the CLIP embedder, of which the decoder reads four attributes
+(embedding_decoder.py:77-86).
 """
 from __future__ import annotations
 
@@ -14,11 +14,27 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("NOVIC_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py: byte-for-byte copies, git-ignored
+
+
+def _default_root() -> str:
+    if "NOVIC_REFERENCE_ROOT" in os.environ:
+        return os.environ["NOVIC_REFERENCE_ROOT"]
+    if os.path.isfile("/root/reference/embedding_decoder.py"):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "embedding_decoder.py"))
+
+
+def full_tree() -> bool:
+    """True in the build container (the whole reference tree, e.g. embedding_cache.py); the staged copy holds the hot path only."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "embedding_cache.py"))
 
 
 def import_reference():

@@ -128,3 +128,65 @@ def test_guided_correctness_evaluation(gold, tag):
         _, _, _, correct = orc.forward_loss(cfg, sd, gold_embed(), tgt, pad, None, guide_targets=gt)
     assert torch.equal(correct, gold[f"{tag}/tfg/correct"])
     assert correct.sum() > gold[f"{tag}/tf/correct"].sum()          # the guide makes the evaluation far more lenient than the plain arg-max
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Constructor variants (tests/golden/reference_variants.npz): the oracle restates them too
+# ----------------------------------------------------------------------------------------------------------------------
+from tests.golden_util import GRAD_CASES, VARIANTS, VARIANTS_PATH, grad_case_inputs, grad_probe, probe_columns, variant_state_dict  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def vgold():
+    return Golden(VARIANTS_PATH)
+
+
+def _variant_cfg(sd, dims, overrides):
+    return orc.cfg_from_state_dict(sd, token_length=dims.token_length, vocab_size=dims.vocab_size,
+                                   num_end_loss=overrides.get("num_end_loss", 1), strictly_causal=overrides.get("strictly_causal", False))
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_variant_forward_and_greedy(vgold, name):
+    dims, overrides = VARIANTS[name]
+    sd = variant_state_dict(dims, overrides)
+    cfg = _variant_cfg(sd, dims, overrides)
+    ls_eps = overrides.get("label_smoothing", 0.0)
+    probes = probe_columns(dims.vocab_size)
+    embed = synth.synth_embeddings(B_GOLD, dims.embed_dim, seed=1234)
+    tgt, pad = synth.synth_targets(B_GOLD, dims, seed=5)
+    with torch.inference_mode():
+        logits, ls, lb, cor = orc.forward_loss(cfg, sd, embed, tgt, pad, None, label_smoothing=ls_eps)
+        o = orc.generate_greedy(cfg, sd, embed, 1.0, 0.0, label_smoothing=ls_eps)
+    valid = ~vgold[f"{name}/tf/effpad"]
+    assert logits.shape[-1] == dims.vocab_size
+    assert (logits[..., probes] - vgold[f"{name}/tf/probes"])[valid].abs().max() < 2e-4
+    assert (logits[..., -8:] - vgold[f"{name}/tf/last_cols"])[valid].abs().max() < 2e-4
+    assert torch.equal(cor, vgold[f"{name}/tf/correct"])
+    assert abs(ls.item() - vgold[f"{name}/tf/loss"][0].item()) < 1e-3 * abs(ls.item())
+    assert int(lb) == int(vgold[f"{name}/tf/loss"][1].item())
+    assert torch.equal(o["target"], vgold[f"{name}/g10/tok"]) and torch.equal(o["padding"], vgold[f"{name}/g10/pad"])
+    assert (o["score"] - vgold[f"{name}/g10/score"]).abs().max() < 2e-4
+    assert abs(o["loss_sum"].item() - vgold[f"{name}/g10/loss"][0].item()) < 1e-3 * abs(o["loss_sum"].item())
+
+
+@pytest.mark.parametrize("name", ["grad_default", "grad_ls01", "grad_multi"])
+def test_variant_gradients_of_the_oracle(vgold, name):
+    """torch autograd through the oracle reproduces the reference's gradients (which pins the gradient checks of tests/test_gpu_training.py)."""
+    dims, overrides, multi = GRAD_CASES[name]
+    sd = variant_state_dict(dims, overrides)
+    cfg = _variant_cfg(sd, dims, overrides)
+    embed, tgt, pad, w = grad_case_inputs(dims, multi)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k != "causality_mask"}
+    A = tgt.shape[0] * max(multi, 1)
+    _, loss_sum, _, _ = orc.forward_loss(cfg, leaf, embed, tgt.view(A, -1), pad.view(A, -1), None if w is None else w.view(-1),
+                                         label_smoothing=overrides.get("label_smoothing", 0.0))
+    loss_sum.backward()
+    assert abs(loss_sum.item() - vgold[f"{name}/loss"][0].item()) < 1e-3 * abs(loss_sum.item())
+    for i, k in enumerate(sorted(leaf)):
+        g = leaf[k].grad.double().flatten()
+        idx, proj = grad_probe(i, g.numel())
+        r_norm = float(vgold[f"{name}/{k}/norm"])
+        assert abs(g.norm().item() - r_norm) <= 1e-3 * r_norm, k
+        assert (g[torch.from_numpy(idx)] - vgold[f"{name}/{k}/probe"].double()).abs().max().item() <= 1e-3 * max(vgold[f"{name}/{k}/probe"].abs().max().item(), 1e-9), k
+        assert ((torch.from_numpy(proj).double() @ g) - vgold[f"{name}/{k}/proj"].double()).abs().max().item() <= 1e-3 * r_norm, k

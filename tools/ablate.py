@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASSES = ["prep", "prefix", "qkv", "attn", "outproj", "ffn1", "ffn2", "logits", "select", "misc", "stack"]
+CLASSES = ["prep", "prefix", "qkv", "attn", "outproj", "ffn1", "ffn2", "logits", "select", "misc"]
 CHILD = r"""
 import sys, torch
 sys.path.insert(0, %r)
