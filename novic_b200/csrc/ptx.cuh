@@ -95,17 +95,19 @@ __device__ __forceinline__ void trace_point(bool on, int idx) {
 // (the tests' CPU checker replays them) without storing a mask.  site = layer * 8 + kind (0 input, 1 attention probabilities,
 // 2 attention branch, 3 feed-forward activation, 4 feed-forward branch).  Returns 1 / (1 - p) for kept elements, 0 for dropped.
 struct DropCfg {
-  uint32_t seed;
-  uint32_t thresh;   // round(p * 2^24); 0 = dropout off
-  float scale;       // 1 / (1 - p)
+  const uint32_t* seed;   // device word holding the step's seed: the value changes every step, the pointer does not, so a captured graph of the
+                          // training step replays with fresh masks (the host rewrites the word before each launch)
+  uint32_t thresh;        // round(p * 2^24); 0 = dropout off (seed is not read)
+  float scale;            // 1 / (1 - p)
 };
 __host__ __device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t site, uint32_t idx) {
   uint32_t x = idx * 0x9E3779B1u + seed + site * 0x85EBCA77u;
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
   return x;
 }
-__host__ __device__ __forceinline__ float drop_factor(const DropCfg& d, uint32_t site, uint32_t idx) {
-  return (drop_hash(d.seed, site, idx) >> 8) >= d.thresh ? d.scale : 0.f;
+__device__ __forceinline__ float drop_factor(const DropCfg& d, uint32_t site, uint32_t idx) {
+  if (d.thresh == 0u) return 1.0f;
+  return (drop_hash(__ldg(d.seed), site, idx) >> 8) >= d.thresh ? d.scale : 0.f;
 }
 constexpr uint32_t kDropInput = 0, kDropAttn = 1, kDropBranch1 = 2, kDropFfn = 3, kDropBranch2 = 4;
 

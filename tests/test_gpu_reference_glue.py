@@ -115,8 +115,14 @@ def test_reference_decoder_on_the_host_agrees_with_the_cuda_class(ref, loaded):
     first = rl[:, 0, 1:].topk(2, dim=-1).values
     margin[:, 0] = first[:, 0] - first[:, 1]
     n = min(t.shape[1], rt.shape[1])
-    decided = ((margin[:, :n] > 0.12) | rp[:, :n]).cummin(dim=1).values & ~rp[:, :n]
-    assert torch.equal(t[:, :n][decided], rt[:, :n][decided])
-    live = decided & ~rp[:, :n]
+    diff = t[:, :n] != rt[:, :n]
+    first = torch.where(diff.any(dim=1), diff.float().argmax(dim=1), torch.full((24,), n))
+    clean = first >= n
+    for b in (~clean).nonzero().flatten().tolist():      # a row may leave the reference's path only where the reference was undecided
+        assert margin[b, first[b]] <= 0.12, f"row {b} diverged at step {first[b]} with margin {margin[b, first[b]]:.3f}"
+    assert clean.float().mean() >= 0.9
+    assert torch.equal(p[clean, :n], rp[clean, :n])
+    live = (~rp[:, :n]) & clean.unsqueeze(1)
     assert (lg[:, :n] - rl[:, :n])[live].abs().max() <= 0.06
-    assert decided.float().mean() > 0.3
+    n_tok = (~rp).sum(dim=1).float()
+    assert ((s - rs).abs()[clean] <= 2 * 0.06 * n_tok[clean].clamp(min=1) + 1e-3).all()
