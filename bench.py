@@ -6,8 +6,15 @@
 
 A step = one greedy decode (prefix prefill + 15 autoregressive steps, KV-cached) of one batch of 4096 synthetic
 unit-norm 1024-d embeddings per GPU through novic_b200.PrefixedIterDecoder (random-init default decoder,
-config/train.yaml:224-308).  Rank 0 prints ONE JSON line (see the keys below).  `--impl reference` times the CPU
-port of the reference's own algorithm (oracle/, re-forward schedule without KV cache) on the host cores instead.
+config/train.yaml:224-308).  Rank 0 prints ONE JSON line:
+  value / e2e      weak scaling, 4096 embeddings per GPU (device-timed / through the public serving loop from pinned host memory)
+  strong           (N > 1) the metric's own global batch of 4096 split N ways: 4096 / N embeddings per GPU
+  secondary        BASELINE configs #3 (beam k = 3, 65 536 embeddings over 8 GPUs = 8192 per GPU) and #4 (training step, global
+                   batch 8192 over 8 GPUs = 1024 per GPU, embedding noise, NCCL gradient all-reduce, fused clip + AdamW) at this N
+  roofline         per kernel class, against MEASURED_PEAKS.json, with ncu DRAM traffic from profiles/traffic.json
+  cpu_baseline     (N = 1) the reference's own PrefixedIterDecoder.generate on the host cores over a bounded sample
+`--impl reference` times the reference's CPU implementation alone: the unmodified reference staged in oracle/_ref (oracle/build_ref.py),
+else the oracle port of its algorithm (re-forward schedule without KV cache).
 """
 from __future__ import annotations
 
@@ -39,6 +46,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="embeddings per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=256, help="embeddings in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (beam k=3, training step)")
     return ap.parse_args()
 
 
@@ -52,25 +60,47 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle's restatement of the reference algorithm (no KV cache, re-forward every step), all host threads
+# CPU arm: the reference's own greedy path on the host cores (staged copy oracle/_ref), else the oracle's restatement of it
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_greedy_rate(sample: int, repeats: int = 1, warmup: int = 1):
+    """Times `repeats` greedy decodes of `sample` embeddings on all host threads.  Returns (times [s], threads, kind, description).
+    kind 'reference': embedding_decoder.PrefixedIterDecoder.generate of the unmodified reference, called exactly as infer.py:567-576
+    does (collect_logits=False, calc_loss=True, tau=1, alpha=0); kind 'port': oracle.generate_greedy (same schedule: the whole
+    sequence is re-forwarded every step, no KV cache)."""
+    import contextlib
     from novic_b200 import synth
-    from oracle import novic_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     dims = synth.DecoderDims()
     sd = synth.synth_state_dict(dims, seed=1)
-    cfg = orc.cfg_from_state_dict(sd)
     embed = synth.synth_embeddings(sample, seed=1234)
+    os.environ["NOVIC_REFERENCE_ROOT"] = os.path.join(ROOT, "oracle", "_ref")     # never /root/reference at run time: it does not exist on the GPU box
+    from oracle import refload
+    kind = "port"
+    fn = None
+    if refload.available():
+        try:
+            with contextlib.redirect_stdout(sys.stderr):                            # the reference's logger writes to stdout; ours is one JSON line
+                ref = refload.import_reference()
+                model = refload.build_reference_decoder(ref, sd)
+            fn = lambda e: model.generate(e, False, True, 1.0, 0.0, None, None, False)   # noqa: E731
+            kind = "reference"
+        except Exception as exc:                                                    # fall back to the port, say why
+            print(f"bench.py: staged reference unusable ({type(exc).__name__}: {exc}); timing the oracle port", file=sys.stderr)
+    if fn is None:
+        from oracle import novic_oracle as orc
+        cfg = orc.cfg_from_state_dict(sd)
+        fn = lambda e: orc.generate_greedy(cfg, sd, e, 1.0, 0.0)                   # noqa: E731
     times = []
     with torch.inference_mode():
         for _ in range(warmup):
-            orc.generate_greedy(cfg, sd, embed[: min(16, sample)], 1.0, 0.0)
+            fn(embed[: min(16, sample)])
         for _ in range(repeats):
             t0 = time.perf_counter()
-            orc.generate_greedy(cfg, sd, embed, 1.0, 0.0)
+            fn(embed)
             times.append(time.perf_counter() - t0)
-    return times, torch.get_num_threads()
+    what = ("unmodified reference PrefixedIterDecoder.generate (oracle/_ref)" if kind == "reference" else "oracle port of the reference greedy path")
+    desc = f"{what}, no KV cache, {sample} of the {BATCH_PER_GPU} embeddings per step (bounded sample), fp32, {torch.get_num_threads()} torch threads"
+    return times, torch.get_num_threads(), kind, desc
 
 
 def run_reference_arm(args):
@@ -78,15 +108,19 @@ def run_reference_arm(args):
     if rank != 0:
         return  # the CPU arm runs on rank 0 only
     sample = args.cpu_sample
-    times, cores = cpu_greedy_rate(sample, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    times, cores, kind, desc = cpu_greedy_rate(sample, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
     ms = statistics.mean(times) * 1e3
     value = sample / (ms / 1e3)
-    desc = f"greedy decode of {sample} embeddings per step (bounded sample of the 4096-embedding workload), fp32, torch CPU ops, {cores} threads"
+    cfg = workload_config(args, max(1, args.gpus))
+    cfg["workload"] = (f"BASELINE configs[1] on the host cores: random-init default EmbeddingDecoder (E=512, FFN 128, L=6, 8 heads, P=4, V=6912, Cmax=16), greedy decode "
+                       f"(15 steps, tau=1, alpha=0) of a bounded sample of {sample} of the 4096 synthetic unit-norm 1024-d embeddings per step, fp32, the reference's "
+                       "own schedule (whole sequence re-forwarded every step)")
+    cfg.update(batch_per_gpu=None, global_batch=sample, parallelism=f"{cores} host threads", l2="n/a (CPU)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, max(1, args.gpus)),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -104,7 +138,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -209,6 +243,18 @@ def roof_entry(bound: str, amount: float, hbm_bytes, ms: float, iso_ms: float, p
     return out
 
 
+def whole_decode_roofline(B: int, dims, ms_per_step: float, peaks: dict) -> dict:
+    """The whole decode against both roofs: algorithmic GEMM FLOPs vs the measured cuBLAS rate, algorithmic KV / row bytes of
+    the attention vs the measured copy bandwidth, and the time the two would take back to back."""
+    work = algorithmic_work(B, dims)
+    flops = sum(v for k, (b, v) in work.items() if b == "tensor")
+    nbytes = sum(v for k, (b, v) in work.items() if b == "hbm")
+    t_tensor = flops / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3
+    t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    return {"gemm_flops": flops, "hbm_bytes": nbytes, "tensor_ms": t_tensor, "hbm_ms": t_hbm, "frac_of_tensor_bound": t_tensor / ms_per_step,
+            "frac_of_hbm_bound": t_hbm / ms_per_step, "frac_of_non_overlapped_bound": (t_tensor + t_hbm) / ms_per_step}
+
+
 def _timed_decodes(model, embed, flush, n):
     """Mean device time (CUDA events on the launching stream, L2 flushed before each) of n greedy decodes."""
     total = 0.0
@@ -301,6 +347,15 @@ def load_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def traffic_entry(name: str):
+    """ncu-measured DRAM traffic of one launch of a kernel class (profiles/traffic.json, written from `ncu --set full` captures by
+    tools/ncu_traffic.py): {dram_bytes, algorithmic_bytes, ratio_to_algorithmic, tensor_pipe_pct, ...} or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(path):
+        return None
+    return json.load(open(path)).get(name)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -312,6 +367,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA (sm_100a) device: novic_b200 has no CPU fallback. Use --impl reference for the CPU arm.")
+    # CPU leg first, on rank 0 of the single-GPU run only, before any other rank or collective exists (a rank spinning in a barrier
+    # while rank 0 times the host cores would falsify it)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, cores, kind, desc = cpu_greedy_rate(args.cpu_sample, repeats=1, warmup=1)
+        cpu_baseline = {"value": args.cpu_sample / times[0], "unit": UNIT, "cores": cores, "kind": kind, "sample": desc + ", 1 run after warm-up"}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -319,125 +380,220 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from novic_b200 import _abi, default_decoder, synth
-    from novic_b200.dist import gather_generation_async
+    from novic_b200 import EmbeddingNoise, _abi, default_decoder, synth
+    from novic_b200.dist import gather_generation_async, gather_generation, train_step
+    from novic_b200.optim import FusedAdamW
+    from novic_b200.serve import GenerationPipeline
     dims = synth.DecoderDims()
+    G = dims.token_length - 1
     model = default_decoder(dims, synth.synth_state_dict(dims, seed=1)).to(dev)
-    B = args.batch
-    embed_host = synth.synth_embeddings(B, seed=1234 + rank).pin_memory()
-    embed = embed_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _abi.lib()
 
-    def step_device():
-        if world == 1:
-            tok, pad, _, _, _, score = model.generate(embed, False, True, 1.0, 0.0, None, None, False)
-            return tok, pad, score
-        # sharded: decode and gather are enqueued without a host synchronisation; the one sync of the step reads the global early-exit length
-        tok, pad, score, T = model.generate_async(embed, 1.0, 0.0)
-        tok, pad, score, T = gather_generation_async(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world, dims.token_length - 1, T)
-        t = int(T.item())
-        return tok[:, :, :t], pad[:, :, :t], score
-
-    from novic_b200.serve import GenerationPipeline
-    gather = (lambda t, p, sc, T: gather_generation_async(t, p, sc, B * world, dims.token_length - 1, T)) if world > 1 else None
-    pipeline = GenerationPipeline(model, "greedy", post=gather, emit=(rank == 0))
-
-    def run_e2e(steps):
-        """The public serving loop (novic_b200.serve.GenerationPipeline): every step copies its batch from pinned host memory to the
-        device, decodes it (and gathers across ranks), and rank 0 reads ids / padding / scores back to the host; the copies of
-        neighbouring steps overlap the decode.  Timed as a whole: K steps between two synchronised CUDA events."""
+    def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = None
-        for res in pipeline.run(embed_host for _ in range(steps)):
-            out = res if res is not None else out
-        b.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+
+    def max_over_ranks(ms: float) -> float:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item(), out
+        return t.item()
+
+    def greedy_workload(B: int):
+        """(step_device, run_e2e, embed) for B embeddings per GPU."""
+        embed_host = synth.synth_embeddings(B, seed=1234 + rank).pin_memory()
+        embed = embed_host.to(dev)
+
+        def step_device():
+            if world == 1:
+                tok, pad, _, _, _, score = model.generate(embed, False, True, 1.0, 0.0, None, None, False)
+                return tok, pad, score
+            # sharded: decode and gather are enqueued without a host synchronisation; the one sync of the step reads the global early-exit length
+            tok, pad, score, T = model.generate_async(embed, 1.0, 0.0)
+            tok, pad, score, T = gather_generation_async(tok.unsqueeze(1), pad.unsqueeze(1), score.unsqueeze(1), B * world, G, T)
+            t = int(T.item())
+            return tok[:, :, :t], pad[:, :, :t], score
+
+        gather = (lambda t, p, sc, T: gather_generation_async(t, p, sc, B * world, G, T)) if world > 1 else None
+        pipeline = GenerationPipeline(model, "greedy", post=gather, emit=(rank == 0))
+
+        def run_e2e(steps):
+            """The public serving loop (novic_b200.serve.GenerationPipeline): every step copies its batch from pinned host memory to the
+            device, decodes it (and gathers across ranks), and rank 0 reads ids / padding / scores back to the host; the copies of
+            neighbouring steps overlap the decode.  Timed as a whole: K steps between two synchronised CUDA events."""
+            barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = None
+            for res in pipeline.run(embed_host for _ in range(steps)):
+                out = res if res is not None else out
+            b.record()
+            torch.cuda.synchronize()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)), out
+        return step_device, run_e2e, embed
 
     def timed(fn, steps):
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-        if world > 1:
-            dist.barrier()
+        barrier()
         torch.cuda.synchronize()
         n0 = lib.novic_launch_count()
+        out = None
         for i in range(steps):
             flush.zero_()                      # L2 flush, outside the timed span
             starts[i].record()
             out = fn()
             ends[i].record()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        barrier()
         launches = lib.novic_launch_count() - n0
         per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-        total_ms = sum(per_step)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        timed.last_per_step = per_step
-        return t.item(), launches, out
+        return max_over_ranks(sum(per_step)), launches, out, per_step
 
+    W = max(args.warmup, 3)
+    B = args.batch
     with torch.inference_mode():
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        for _ in range(max(args.warmup, 3)):
+        step_device, run_e2e, embed = greedy_workload(B)
+        for _ in range(W):
             step_device()
-        run_e2e(max(args.warmup, 3))
+        run_e2e(W)
         if sampler:
             sampler.wait_started()
             sampler.mark()
-        total_ms, launches, out = timed(step_device, args.steps)
-        dev_steps = list(timed.last_per_step)
+        total_ms, launches, out, dev_steps = timed(step_device, args.steps)
         e2e_ms, out_host = run_e2e(args.steps)
         clocks = sampler.stop() if sampler else None
-    tok = out[0]
-    assert tok.shape[0] == B * world and tok.shape[-1] == dims.token_length - 1
+        tok = out[0]
+        assert tok.shape[0] == B * world and tok.shape[-1] == G
+
+        # ---- strong scaling on the metric's own batch: global 4096 embeddings, 4096 / N per GPU (SURVEY.md 8d)
+        strong = None
+        if world > 1 and B % world == 0:
+            sd_step, sd_e2e, _ = greedy_workload(B // world)
+            for _ in range(W):
+                sd_step()
+            sd_e2e(W)
+            s_ms, _, s_out, _ = timed(sd_step, args.steps)
+            s_e2e_ms, _ = sd_e2e(args.steps)
+            assert s_out[0].shape[0] == B
+            strong = {"scaling": "strong", "global_batch": B, "batch_per_gpu": B // world, "value": B * args.steps / (s_ms / 1e3), "unit": UNIT,
+                      "ms_per_step": s_ms / args.steps, "e2e": {"value": B * args.steps / (s_e2e_ms / 1e3), "unit": UNIT, "ms_per_step": s_e2e_ms / args.steps}}
+
+        # ---- BASELINE config #3: beam k = 3 over 65 536 embeddings sharded over 8 GPUs = 8192 per GPU (kept per GPU at every N)
+        secondary = {}
+        if not args.no_secondary:
+            nb = 8192
+            e_beam = synth.synth_embeddings(nb, seed=4321 + rank).to(dev)
+
+            def beam_step():
+                t, p, sc = model.generate_beam(e_beam, 3, 1.0, 0.0, None, False, 0.0, None, False)
+                if world > 1:
+                    t, p, sc = gather_generation(t, p, sc, nb * world, gen_len=G)
+                return t
+            beam_step()
+            k_beam = max(2, min(args.steps, 5))
+            b_ms, b_launches, b_out, _ = timed(beam_step, k_beam)
+            assert b_out.shape[0] == nb * world and b_out.shape[1] == 3
+            secondary["beam3"] = {"workload": f"BASELINE configs[2]: beam search k=3, tau=1, alpha=0, {nb} embeddings per GPU ({nb * world} in all; 65 536 at 8 GPUs), final gather of ids / padding / scores",
+                                  "metric": "labels/sec (beam k=3)", "value": nb * world * k_beam / (b_ms / 1e3), "unit": UNIT, "ms_per_step": b_ms / k_beam, "steps": k_beam,
+                                  "collective": "one all-gather of the packed results per step (none inside the decode loop)" if world > 1 else None}
+            del e_beam
+
+    # ---- BASELINE config #4: teacher-forced training step, 1024 samples per GPU (global 8192 at 8 GPUs), noise, all-reduce, clip + AdamW
+    if not args.no_secondary:
+        tb = 1024
+        torch.manual_seed(1234)
+        tmodel = default_decoder(dims, synth.synth_state_dict(dims, seed=1)).to(dev).train()        # input / layer dropout 0.1 (train.yaml defaults)
+        opt = FusedAdamW(tmodel, lr=1.5e-3, betas=(0.9, 0.95), weight_decay=0.1)                     # train.yaml:427-441
+        noise = EmbeddingNoise.create("GaussElemUniformAngle", 1024, 3.25, 45.0, 75.0, 0.0, 0.15)
+        e_tr = synth.synth_embeddings(tb, seed=100 + rank).to(dev)
+        tgt, pad = synth.synth_targets(tb, dims, seed=200 + rank)
+        tgt, pad = tgt.to(dev), pad.to(dev)
+        e_work = torch.empty_like(e_tr)
+
+        def tr_step():
+            e_work.copy_(e_tr)                 # the noise is applied in place (embedding_noise.py:50)
+            return train_step(tmodel, opt, e_work, tgt, pad, None, noise=noise, gradient_clip=1.0)
+        for _ in range(3):
+            tr_step()
+        k_tr = max(5, min(args.steps, 20))
+        barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.novic_launch_count()
+        a.record()
+        losses = [tr_step()[0] for _ in range(k_tr)]
+        b.record()
+        torch.cuda.synchronize()
+        barrier()
+        t_ms = max_over_ranks(a.elapsed_time(b))
+        t_launches = lib.novic_launch_count() - n0
+        coll_ms = None
+        if world > 1:   # the gradient all-reduce on its own (50.9 MB fp32), for the record of what the overlap has to hide
+            gb = tmodel._grad_bucket.flat
+            for _ in range(2):
+                dist.all_reduce(gb)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(5):
+                dist.all_reduce(gb)
+            b.record()
+            torch.cuda.synchronize()
+            coll_ms = max_over_ranks(a.elapsed_time(b)) / 5
+        secondary["train_step"] = {
+            "workload": f"BASELINE configs[3]: teacher-forced training step, {tb} samples per GPU ({tb * world} in all; 8192 at 8 GPUs), C=16 random targets, "
+                        "GaussElemUniformAngle noise 3.25 / 45-75 deg / 0.15, dropout 0.1 / 0.1, forward + backward (CUDA graphs), NCCL all-reduce of the flat "
+                        "gradient bucket in two parts (the first overlapping the backward pass), fused global-norm clip + AdamW, no host synchronisation",
+            "metric": "training samples/sec", "value": tb * world * k_tr / (t_ms / 1e3), "unit": "samples/s", "ms_per_step": t_ms / k_tr, "steps": k_tr,
+            "gpu_launches_per_step": t_launches / k_tr, "loss_first": losses[0].item(), "loss_last": losses[-1].item(),
+            "collective": None if world == 1 else {"what": "ncclAllReduce of the 50.9 MB fp32 gradient bucket, timed alone", "ms": coll_ms},
+        }
+        del tmodel, opt
 
     if rank == 0:
         peaks = load_peaks()
         ms_per_step = total_ms / args.steps
         value = B * world * args.steps / (total_ms / 1e3)
         e2e_value = B * world * args.steps / (e2e_ms / 1e3)
-        kernels = kernel_breakdown(model, embed, flush, min(args.steps, 5), peaks, dims)
+        with torch.inference_mode():
+            kernels = kernel_breakdown(model, embed, flush, min(args.steps, 5), peaks, dims)
+        for name, entry in kernels.items():
+            tr = traffic_entry(name)
+            if tr:   # per-launch DRAM bytes from ncu beside the per-launch algorithmic bytes: traffic well below the algorithm's means L2 hits
+                entry["traffic"] = {k: tr.get(k) for k in ("dram_bytes", "algorithmic_bytes", "ratio_to_algorithmic", "tensor_pipe_pct", "dram_pct", "capture")}
+                if tr.get("ratio_to_algorithmic") is not None and tr["ratio_to_algorithmic"] < 0.6 and (tr.get("tensor_pipe_pct") or 0) < 30:
+                    entry["regime"] = "latency-bound: neither DRAM traffic nor the tensor pipe is near its roof (dependent phases per tile)"
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
         d = kernels[dom]
-        if os.path.isfile(tpath) and d.get("bound") == "hbm":
-            entry = json.load(open(tpath)).get(dom)
-            if entry:  # ncu-measured DRAM bytes of one launch / that launch's algorithmic bytes, applied to the average launch
-                work = algorithmic_work(B, dims).get(dom, (None, 0))[1]
-                traffic = entry["ratio_to_algorithmic"] * work / max(1, d["launches_per_step"])
+        tr = traffic_entry(dom)
         roofline = {"kernel": dom, "bound": d.get("bound"), "achieved": d.get("achieved"), "peak": peaks["hbm_gbs"] if d.get("bound") == "hbm" else peaks["bf16_tflops_sustained"],
-                    "unit": d.get("unit"), "frac": d.get("frac"), "traffic": traffic, "peak_source": peaks["source"],
+                    "unit": d.get("unit"), "frac": d.get("frac"), "traffic": tr.get("dram_bytes") if tr else None, "regime": d.get("regime"), "peak_source": peaks["source"],
                     "how": "CUDA events on the launching stream around the captured decode graph with only this kernel class's launches kept (real arguments, PDL, L2 flushed "
                            "before each decode), minus the same graph with no kernels; achieved = algorithmic work of the class's launches / that duration, i.e. per-launch work / average "
-                           "launch duration.  isolated_* = event pair around every direct launch (adds a launch gap per kernel; comparable to ncu's serialised times in profiles/)",
+                           "launch duration.  isolated_* = event pair around every direct launch (adds a launch gap per kernel; comparable to ncu's serialised times in profiles/).  "
+                           "traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch from an ncu --set full capture (profiles/traffic.json)",
+                    "whole_decode": whole_decode_roofline(B, dims, ms_per_step, peaks),
                     "kernels": kernels}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": B * dims.embed_dim * 4, "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host)),
                     "api": "novic_b200.serve.GenerationPipeline.run (double-buffered H2D / D2H around PrefixedIterDecoder.generate; per-rank H2D, rank 0 reads the gathered result)"},
             "gpu_launches": int(launches), "roofline": roofline,
-            "step_ms": {"device_median": statistics.median(dev_steps), "device_max": max(dev_steps)},
+            "step_ms": {"device_median": statistics.median(dev_steps), "device_max": max(dev_steps), "device_min": min(dev_steps)},
         }
-        if not args.no_cpu_baseline:
-            times, cores = cpu_greedy_rate(args.cpu_sample, repeats=1, warmup=1)
-            line["cpu_baseline"] = {"value": args.cpu_sample / times[0], "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle port of the reference greedy path (no KV cache), {args.cpu_sample} of the {B} embeddings, fp32, {cores} torch threads, 1 run after warm-up"}
+        if strong is not None:
+            line["strong"] = strong
+        if secondary:
+            line["secondary"] = secondary
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -176,6 +176,33 @@ int novic_train_fwd_bwd(NovicHandle* h, const float* embed, int64_t B, int32_t M
                         const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
                         void* ws, size_t ws_bytes, void* stream);
 
+/* novic_train_fwd_bwd with a completion point inside the backward pass: once the gradients of layers >= split_layer are final (layers are
+ * walked from the last to the first), `split_event` (a cudaEvent_t passed as void*) is recorded on `stream`; the rest of the call only writes
+ * the gradients of layers < split_layer, of the embeddings, the positions and the prefix projection.  A data-parallel step starts the
+ * all-reduce of the finished part of the gradient bucket on another stream there (novic_b200/dist.py).  split_layer <= 0: no event.
+ * Both entry points replay the ~280 launches of a step as CUDA graphs (two when split) cached per shape / flags / workspace / gradient
+ * addresses; inputs are staged inside the workspace and the dropout seed lives in a device word, so the graphs stay valid across steps. */
+int novic_train_fwd_bwd_ex(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                           const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
+                           void* ws, size_t ws_bytes, void* stream, int32_t split_layer, void* split_event);
+
+/* Replaces the optimizer tail of a training step (train.py:1281-1286: clip_grad_norm_(max_norm, error_if_nonfinite) + torch.optim.AdamW.step(),
+ * parameter groups of train.py:1108-1119) over ONE flat fp32 buffer each for parameters, gradients and the two moments - three launches,
+ * no host synchronisation.
+ *   grads: d(loss_sum) / d(parameter), n elements (n a multiple of 512), in the parameters' order.
+ *   stats: device [loss_sum, loss_basis, ...] or NULL: the gradients are divided by max(loss_basis, 1) first (train.py:1272).
+ *   decay_flags [n / 512] u8: chunk c receives weight decay (tensors with >= 2 dimensions).
+ *   out4 (device fp32): [0] gradient norm (after the 1 / basis factor), [1] clip coefficient min(1, max_norm / (norm + 1e-6)), [2] factor
+ *   applied to the raw gradients, [3] 1.0 if the norm was not finite - the update is then skipped (the reference raises at that point).
+ *   max_grad_norm <= 0: no clipping (train.py:1281). */
+typedef struct NovicAdamW {
+  float lr, beta1, beta2, eps, weight_decay, max_grad_norm;
+  int64_t step;   /* 1-based: bias corrections 1 - beta^step */
+} NovicAdamW;
+size_t novic_adamw_scratch_bytes(void);
+int novic_adamw_step(const NovicAdamW* cfg, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const uint8_t* decay_flags, const float* stats, void* scratch, size_t scratch_bytes, float* out4, void* stream);
+
 /* Replaces EmbeddingNoise.forward (embedding_noise.py:72-75, :90-95, :105-112, :169-172): in place on
  * embed [B, F] fp32 device; random draws come from Philox (seed, offset). */
 int novic_noise_apply(const NovicNoiseCfg* cfg, float* embed, int64_t B, uint64_t seed, uint64_t offset, void* stream);

@@ -43,6 +43,11 @@ class NovicNoiseCfg(C.Structure):
     ]
 
 
+class NovicAdamW(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("max_grad_norm", C.c_float), ("step", C.c_int64)]
+
+
 class NovicGuide(C.Structure):
     _fields_ = [("child_off", _FP), ("child_tok", _FP), ("child_node", _FP), ("num_nodes", C.c_int32), ("num_edges", C.c_int32),
                 ("renorm", C.c_int32), ("child_bias", _FP)]
@@ -73,6 +78,10 @@ SIGNATURES = {
     "novic_train_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
     "novic_train_fwd_bwd": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, _FP, _FP, _FP, C.POINTER(NovicWeights),
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "novic_train_fwd_bwd_ex": (C.c_int, [C.c_void_p, _FP, C.c_int64, C.c_int32, _FP, _FP, _FP, C.c_int32, _FP, _FP, _FP, C.POINTER(NovicWeights),
+                                         C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_void_p]),
+    "novic_adamw_scratch_bytes": (C.c_size_t, []),
+    "novic_adamw_step": (C.c_int, [C.POINTER(NovicAdamW), _FP, _FP, _FP, _FP, C.c_int64, _FP, _FP, C.c_void_p, C.c_size_t, _FP, C.c_void_p]),
     "novic_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_uint64]),
     "novic_noise_apply": (C.c_int, [C.POINTER(NovicNoiseCfg), _FP, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "novic_noise_apply_predrawn": (C.c_int, [C.POINTER(NovicNoiseCfg), _FP, C.c_int64, _FP, _FP, _FP, _FP, C.c_void_p]),

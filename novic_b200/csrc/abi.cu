@@ -12,6 +12,7 @@
 
 #include "../../include/novic_b200.h"
 #include "train.cuh"
+#include "optim.cuh"
 
 using namespace novic;
 
@@ -338,7 +339,13 @@ struct NovicHandle {
   cudaStream_t chain_streams[8] = {};
   cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
   int attn_smem_budget = 200 * 1024;
-  DropCfg drop_in{0u, 0u, 1.f}, drop_layer{0u, 0u, 1.f};   // training dropout (novic_set_dropout); thresh 0 = off
+  DropCfg drop_in{nullptr, 0u, 1.f}, drop_layer{nullptr, 0u, 1.f};   // training dropout (novic_set_dropout); thresh 0 = off
+  uint32_t* d_drop_seed = nullptr;    // device word both DropCfg point at (rewritten before every training step)
+  uint32_t drop_seed = 0;
+  const void* wbuf_seen = nullptr;    // weight buffer of the last novic_set_weights
+  bool train_graphs = true;           // NOVIC_TRAIN_GRAPHS=0: enqueue the ~280 launches of a training step directly
+  std::map<std::vector<uint64_t>, std::pair<cudaGraphExec_t, cudaGraphExec_t>> train_graph_cache;   // key -> (part 1, part 2 or nullptr)
+  std::map<std::vector<uint64_t>, int64_t> train_graph_nodes;
   WeightPtrs w;
   cudaStream_t capture_stream = nullptr;
   std::map<GraphKey, cudaGraphExec_t> graphs;
@@ -863,6 +870,9 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   h->device = dev;
   CUDA_TRY(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaMallocHost(&h->h_flags, sizeof(int) * 8 * (cfg->token_length + 2)));
+  CUDA_TRY(cudaMalloc(&h->d_drop_seed, 16));
+  CUDA_TRY(cudaMemset(h->d_drop_seed, 0, 16));
+  if (const char* e20 = getenv("NOVIC_TRAIN_GRAPHS")) h->train_graphs = e20[0] != '0';
   h->num_sms = prop.multiProcessorCount;
   g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
@@ -906,6 +916,8 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
 int novic_destroy(NovicHandle* h) {
   if (h == nullptr) return 0;
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : h->train_graph_cache) { cudaGraphExecDestroy(kv.second.first); if (kv.second.second) cudaGraphExecDestroy(kv.second.second); }
+  if (h->d_drop_seed) cudaFree(h->d_drop_seed);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   for (int i = 0; i < 8; ++i) { if (h->chain_streams[i]) cudaStreamDestroy(h->chain_streams[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
@@ -926,15 +938,16 @@ int novic_debug_keep_classes(NovicHandle* h, uint32_t keep_mask) {
 int novic_set_dropout(NovicHandle* h, float p_input, float p_layer, uint64_t seed) {
   if (h == nullptr) return fail("null handle");
   if (!(p_input >= 0.f && p_input < 1.f && p_layer >= 0.f && p_layer < 1.f)) return fail("dropout probabilities must be in [0, 1)");
-  auto mk = [&](float p, uint32_t salt) {
+  auto mk = [&](float p) {
     DropCfg d;
-    d.seed = static_cast<uint32_t>(seed ^ (seed >> 32)) + salt;
+    d.seed = h->d_drop_seed;
     d.thresh = static_cast<uint32_t>(static_cast<double>(p) * 16777216.0 + 0.5);
     d.scale = d.thresh != 0u ? 1.0f / (1.0f - p) : 1.0f;
     return d;
   };
-  h->drop_in = mk(p_input, 0u);
-  h->drop_layer = mk(p_layer, 0u);
+  h->drop_seed = static_cast<uint32_t>(seed ^ (seed >> 32));   // written to the device word on the stream of the next training call
+  h->drop_in = mk(p_input);
+  h->drop_layer = mk(p_layer);
   return 0;
 }
 
@@ -1033,10 +1046,17 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
     if (make_tmap(&o.tm_linear1_q[l], o.linear1[l], K, E, kFfnDim / kRowCluster)) return 1;
     if (make_tmap(&o.tm_linear2[l], o.linear2[l], E, K, kRowBN)) return 1;
   }
-  // the weight pointers are baked into captured graphs
+  // the weight pointers are baked into captured graphs (the training step's graphs only bake addresses inside wbuf, which a
+  // re-pack into the same buffer leaves valid: they are dropped only when the buffer moved)
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   h->graphs.clear();
   h->graph_nodes.clear();
+  if (h->wbuf_seen != wbuf) {
+    for (auto& kv : h->train_graph_cache) { cudaGraphExecDestroy(kv.second.first); if (kv.second.second) cudaGraphExecDestroy(kv.second.second); }
+    h->train_graph_cache.clear();
+    h->train_graph_nodes.clear();
+    h->wbuf_seen = wbuf;
+  }
   h->weights_set = true;
   return 0;
 }
@@ -1322,43 +1342,148 @@ size_t novic_train_workspace_bytes(const NovicHandle* h, int64_t B, int32_t M, i
   return t.bytes;
 }
 
-int novic_train_fwd_bwd(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
-                        const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
-                        void* wsbuf, size_t ws_bytes, void* stream) {
+__global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
+
+int novic_train_fwd_bwd_ex(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                           const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
+                           void* wsbuf, size_t ws_bytes, void* stream, int32_t split_layer, void* split_event) {
   if (check_ready(h)) return 1;
   const NovicCfg& c = h->cfg;
   if (B < 1 || M < 1 || C < 2 || C > c.token_length) return fail("bad B / M / C (C must be in [2, token_length])");
   if (target == nullptr || grads == nullptr || loss == nullptr) return fail("target, grads and loss are required");
   if (B * M * static_cast<int64_t>(c.prefix_len + C - 1) > (1LL << 24)) return fail("too many rows for one training call; split the batch");
   if (c.prefix_len + C - 1 > kAttnBwdMaxS) return fail("sequence too long for the attention backward kernel");
+  if (split_layer >= c.num_layers) return fail("split_layer must be below num_layers");
+  if (split_layer > 0 && split_event == nullptr) return fail("split_layer needs an event to record");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   TrainPlan t;
   plan_train(h, B, M, C, static_cast<char*>(wsbuf), &t);
   if (ws_bytes < t.bytes) return fail("workspace too small: %zu < %zu", ws_bytes, t.bytes);
   t.has_pad = padding != nullptr || weight != nullptr;
   const size_t E = kE, K = c.ffn_dim, F = c.embed_dim, P = c.prefix_len, V = c.vocab_size, L = c.num_layers, S = c.prefix_len + c.token_length - 1;
-  TrainGrads g;
-  auto zero = [&](const float* p, size_t n) -> float* { cudaMemsetAsync(const_cast<float*>(p), 0, 4 * n, s); return const_cast<float*>(p); };
-  g.embed_mlp = zero(grads->embed_mlp, P * E * F);
-  g.tok = zero(grads->tok_embed, V * E);
-  g.pos = zero(grads->pos_embed, S * E);
-  g.final_norm = zero(grads->final_norm, E);
-  for (size_t l = 0; l < L; ++l) {
-    g.in_proj[l] = zero(grads->in_proj[l], 3 * E * E); g.out_proj[l] = zero(grads->out_proj[l], E * E);
-    g.linear1[l] = zero(grads->linear1[l], K * E); g.linear2[l] = zero(grads->linear2[l], E * K);
-    g.norm1[l] = zero(grads->norm1[l], E); g.norm2[l] = zero(grads->norm2[l], E);
-  }
+  // inputs -> stable addresses inside the workspace (a captured graph replays with these), dropout seed -> the handle's device word
   CUDA_TRY(cudaMemcpyAsync(t.ein, embed, sizeof(float) * B * F, cudaMemcpyDeviceToDevice, s));
-  g_grid_div = 1;
-  const bool pdl = g_use_pdl;
-  g_use_pdl = false;   // the training path mixes in plainly launched kernels; keep ordinary stream ordering
-  int rc = train_forward(h, t, reinterpret_cast<const long long*>(target), padding, weight, s);
-  if (!rc) rc = train_backward(h, t, reinterpret_cast<const long long*>(target), weight, g, s);
-  g_use_pdl = pdl;
-  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(t.tgt_stage, target, 8 * t.Rt, cudaMemcpyDeviceToDevice, s));
+  if (padding != nullptr) CUDA_TRY(cudaMemcpyAsync(t.pad_stage, padding, t.Rt, cudaMemcpyDeviceToDevice, s));
+  if (weight != nullptr) CUDA_TRY(cudaMemcpyAsync(t.w_stage, weight, 4 * t.A, cudaMemcpyDeviceToDevice, s));
+  if (h->drop_in.thresh != 0u || h->drop_layer.thresh != 0u) {
+    set_u32_kernel<<<1, 1, 0, s>>>(h->d_drop_seed, h->drop_seed);
+    ++g_launches;
+  }
+  const long long* tgt_p = t.tgt_stage;
+  const unsigned char* pad_p = padding != nullptr ? t.pad_stage : nullptr;
+  const float* w_p = weight != nullptr ? t.w_stage : nullptr;
+  auto enqueue = [&](cudaStream_t cs, auto&& at_split) -> int {
+    TrainGrads g;
+    auto zero = [&](const float* p, size_t n) -> float* { cudaMemsetAsync(const_cast<float*>(p), 0, 4 * n, cs); return const_cast<float*>(p); };
+    g.embed_mlp = zero(grads->embed_mlp, P * E * F);
+    g.tok = zero(grads->tok_embed, V * E);
+    g.pos = zero(grads->pos_embed, S * E);
+    g.final_norm = zero(grads->final_norm, E);
+    for (size_t l = 0; l < L; ++l) {
+      g.in_proj[l] = zero(grads->in_proj[l], 3 * E * E); g.out_proj[l] = zero(grads->out_proj[l], E * E);
+      g.linear1[l] = zero(grads->linear1[l], K * E); g.linear2[l] = zero(grads->linear2[l], E * K);
+      g.norm1[l] = zero(grads->norm1[l], E); g.norm2[l] = zero(grads->norm2[l], E);
+    }
+    g_grid_div = 1;
+    const bool pdl = g_use_pdl;
+    g_use_pdl = false;   // the training path mixes in plainly launched kernels; keep ordinary stream ordering
+    int rc = train_forward(h, t, tgt_p, pad_p, w_p, cs);
+    if (!rc) rc = train_backward(h, t, tgt_p, w_p, g, cs, split_layer, at_split);
+    g_use_pdl = pdl;
+    return rc;
+  };
+  cudaEvent_t ev = static_cast<cudaEvent_t>(split_event);
+  if (!h->train_graphs || !h->use_graphs) {
+    if (enqueue(s, [&]() -> int { CUDA_TRY(cudaEventRecord(ev, s)); return 0; })) return 1;
+  } else {
+    // everything a captured step bakes in: shape, flags, dropout thresholds, workspace and gradient addresses
+    std::vector<uint64_t> key{static_cast<uint64_t>(B), static_cast<uint64_t>(M), static_cast<uint64_t>(C), static_cast<uint64_t>(padding != nullptr),
+                              static_cast<uint64_t>(weight != nullptr), h->drop_in.thresh, h->drop_layer.thresh,
+                              static_cast<uint64_t>(reinterpret_cast<uintptr_t>(wsbuf)), static_cast<uint64_t>(split_layer + 1)};
+    const uint64_t* gp = reinterpret_cast<const uint64_t*>(grads);
+    for (size_t i = 0; i < sizeof(NovicWeights) / 8; ++i) key.push_back(gp[i]);
+    auto it = h->train_graph_cache.find(key);
+    if (it == h->train_graph_cache.end()) {
+      cudaGraph_t g1 = nullptr, g2 = nullptr;
+      cudaStream_t cs = h->capture_stream;
+      const int64_t before = g_launches;
+      CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      bool split_done = false;
+      int rc = enqueue(cs, [&]() -> int {
+        cudaError_t e = cudaStreamEndCapture(cs, &g1);
+        if (e != cudaSuccess) return fail("cudaStreamEndCapture (training step, part 1) failed: %s", cudaGetErrorString(e));
+        split_done = true;
+        CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        return 0;
+      });
+      cudaGraph_t last = nullptr;
+      cudaError_t e = cudaStreamEndCapture(cs, &last);
+      const int64_t nodes = g_launches - before;
+      g_launches = before;
+      if (split_done) g2 = last; else g1 = last;
+      if (rc || e != cudaSuccess) {
+        if (g1) cudaGraphDestroy(g1);
+        if (g2) cudaGraphDestroy(g2);
+        return rc ? rc : fail("cudaStreamEndCapture (training step) failed: %s", cudaGetErrorString(e));
+      }
+      cudaGraphExec_t x1 = nullptr, x2 = nullptr;
+      e = cudaGraphInstantiate(&x1, g1, 0);
+      if (e == cudaSuccess && g2 != nullptr) e = cudaGraphInstantiate(&x2, g2, 0);
+      cudaGraphDestroy(g1);
+      if (g2) cudaGraphDestroy(g2);
+      if (e != cudaSuccess) return fail("cudaGraphInstantiate (training step) failed: %s", cudaGetErrorString(e));
+      if (h->train_graph_cache.size() >= 8) {
+        for (auto& kv : h->train_graph_cache) { cudaGraphExecDestroy(kv.second.first); if (kv.second.second) cudaGraphExecDestroy(kv.second.second); }
+        h->train_graph_cache.clear();
+        h->train_graph_nodes.clear();
+      }
+      h->train_graph_cache[key] = {x1, x2};
+      h->train_graph_nodes[key] = nodes;
+      it = h->train_graph_cache.find(key);
+    }
+    CUDA_TRY(cudaGraphLaunch(it->second.first, s));
+    if (it->second.second != nullptr) {
+      CUDA_TRY(cudaEventRecord(ev, s));
+      CUDA_TRY(cudaGraphLaunch(it->second.second, s));
+    } else if (split_layer > 0) {
+      CUDA_TRY(cudaEventRecord(ev, s));   // (single-layer models: nothing left to overlap)
+    }
+    g_launches += h->train_graph_nodes[it->first];
+  }
   CUDA_TRY(cudaMemcpyAsync(loss, t.loss, 8, cudaMemcpyDeviceToDevice, s));
   if (correct != nullptr) CUDA_TRY(cudaMemcpyAsync(correct, t.correct, t.Rt, cudaMemcpyDeviceToDevice, s));
   if (pad_out != nullptr) CUDA_TRY(cudaMemcpyAsync(pad_out, t.effpad, t.Rt, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int novic_train_fwd_bwd(NovicHandle* h, const float* embed, int64_t B, int32_t M, const int64_t* target, const uint8_t* padding,
+                        const float* weight, int32_t C, float* loss, uint8_t* correct, uint8_t* pad_out, const NovicWeights* grads,
+                        void* wsbuf, size_t ws_bytes, void* stream) {
+  return novic_train_fwd_bwd_ex(h, embed, B, M, target, padding, weight, C, loss, correct, pad_out, grads, wsbuf, ws_bytes, stream, -1, nullptr);
+}
+
+size_t novic_adamw_scratch_bytes(void) { return sizeof(double) * kOptBlocks + 256; }
+
+int novic_adamw_step(const NovicAdamW* cfg, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const uint8_t* decay_flags, const float* stats, void* scratch, size_t scratch_bytes, float* out4, void* stream) {
+  if (cfg == nullptr || params == nullptr || grads == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || decay_flags == nullptr || out4 == nullptr)
+    return fail("novic_adamw_step: null argument");
+  if (n < kOptChunk || n % kOptChunk != 0) return fail("novic_adamw_step: the flat parameter count must be a positive multiple of %d (got %lld)", kOptChunk, (long long)n);
+  if (scratch == nullptr || scratch_bytes < novic_adamw_scratch_bytes()) return fail("novic_adamw_step: scratch too small");
+  if (cfg->step < 1 || !(cfg->beta1 >= 0.f && cfg->beta1 < 1.f) || !(cfg->beta2 >= 0.f && cfg->beta2 < 1.f) || !(cfg->eps > 0.f))
+    return fail("novic_adamw_step: bad step / betas / eps");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* partial = static_cast<double*>(scratch);
+  OptHyper hp;
+  hp.lr = cfg->lr; hp.beta1 = cfg->beta1; hp.beta2 = cfg->beta2; hp.eps = cfg->eps; hp.weight_decay = cfg->weight_decay; hp.max_norm = cfg->max_grad_norm;
+  hp.bias_correction1 = static_cast<float>(1.0 - std::pow(static_cast<double>(cfg->beta1), static_cast<double>(cfg->step)));
+  hp.bias_correction2_sqrt = static_cast<float>(std::sqrt(1.0 - std::pow(static_cast<double>(cfg->beta2), static_cast<double>(cfg->step))));
+  grad_sqnorm_kernel<<<kOptBlocks, kOptThreads, 0, s>>>(grads, static_cast<long long>(n), partial);
+  clip_coef_kernel<<<1, 32, 0, s>>>(partial, kOptBlocks, stats, cfg->max_grad_norm, out4);
+  adamw_kernel<<<kOptBlocks, kOptThreads, 0, s>>>(params, grads, exp_avg, exp_avg_sq, static_cast<long long>(n), decay_flags, hp, out4);
+  g_launches += 3;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

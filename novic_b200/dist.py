@@ -130,6 +130,11 @@ class GradBucket:
         self.total = sum(v.numel() for v in views)
         self.ptrs = {v.data_ptr(): v.numel() for v in views}
 
+    def in_parameter_order(self, grads) -> bool:
+        """True when `grads` lie in the buffer in the order given (the fused optimizer addresses parameters and gradients by one index)."""
+        ptrs = [g.data_ptr() for g in grads]
+        return all(a < b for a, b in zip(ptrs, ptrs[1:])) and (not ptrs or ptrs[0] == self.flat.data_ptr())
+
     def covers(self, grads) -> bool:
         """True when `grads` are exactly this bucket's views (same memory, every element accounted for once)."""
         if len(grads) != len(self.ptrs) or sum(g.numel() for g in grads) != self.total:
@@ -172,15 +177,88 @@ def allreduce_gradients(params, extra: Optional[torch.Tensor] = None, group: Opt
     return None
 
 
+_COMM = {}   # per device: (side stream, split event) of the overlapped gradient all-reduce
+
+
+def _comm_objects(dev: torch.device):
+    key = (dev.type, dev.index)
+    if key not in _COMM:
+        stream = torch.cuda.Stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))      # creates the underlying cudaEvent_t (torch makes it lazily)
+        _COMM[key] = (stream, ev)
+    return _COMM[key]
+
+
+def _flatten_multi(model, target, mask, weight):
+    """B x M x C (or M x B x C with multi_first) -> A x C with the sequences of one embedding adjacent, as forward() does."""
+    if target.ndim != 3:
+        return target, mask, weight, 1
+    dc = model.data_config
+    if bool(getattr(dc, 'multi_target', False) and getattr(dc, 'multi_first', False)):
+        target = target.transpose(0, 1)
+        mask = None if mask is None else mask.transpose(0, 1)
+        weight = None if weight is None else weight.transpose(0, 1)
+    B, M = target.shape[:2]
+    return (target.reshape(B * M, -1), None if mask is None else mask.reshape(B * M, -1), None if weight is None else weight.reshape(B * M), M)
+
+
+def _train_step_fused(model, optimizer, embed, target, mask, weight, noise, gradient_clip, group):
+    """The whole step on the device without a host synchronisation: noise -> forward + backward (one library call, CUDA graphs) ->
+    all-reduce of the flat gradient bucket in two parts, the first one (layers >= split, final early in the backward pass) overlapping
+    the rest of the backward pass on a side stream -> global-norm clip + AdamW (three kernels, optim.FusedAdamW)."""
+    from . import training
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    if noise is not None:
+        noise.stream_offset = rank
+        embed = noise(embed)
+    model.dropout_seed_offset = rank * 0x51ED2701      # per-rank dropout masks under one torch.manual_seed
+    tgt, pad, w, M = _flatten_multi(model, target, mask, weight)
+    pad_u8 = None if pad is None else pad.contiguous().view(torch.uint8)
+    dev = embed.device
+    L = len(model.transformer.layers)
+    split = max(1, L // 3) if (world > 1 and L >= 2) else -1
+    side, ev = _comm_objects(dev) if split > 0 else (None, None)
+    loss, correct, pad_out, bucket = training.fwd_bwd(model, embed.contiguous(), tgt.contiguous(), pad_u8, None if w is None else w.contiguous(), M,
+                                                     split_layer=split, split_event=ev)
+    flat = bucket.flat
+    stats = flat[bucket.total:bucket.total + 3]
+    stats[:2].copy_(loss)
+    stats[2:3].copy_(correct.sum(dtype=torch.float32).reshape(1))
+    if world > 1:
+        # flat = [prefix projection | tied matrix | positions | final norm | layer 0 .. layer L-1 | spare]: layers >= split are a contiguous tail
+        views = bucket.views
+        off_split = (views[4 + 6 * split].data_ptr() - flat.data_ptr()) // 4
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            early = dist.all_reduce(flat[off_split:bucket.total], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        dist.all_reduce(flat[:off_split], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(flat[bucket.total:bucket.total + GradBucket.SPARE], op=dist.ReduceOp.SUM, group=group)
+        early.wait()
+        GradBucket.in_place_reductions += 1
+    optimizer.max_grad_norm = float(gradient_clip)
+    out = optimizer.step(flat_grads=flat, stats=stats)
+    stats = stats.clone()
+    return stats[0] / stats[1].clamp(min=1.0), stats[2], stats[1], out[0]
+
+
 def train_step(model, optimizer, embed: torch.Tensor, target: torch.Tensor, mask: Optional[torch.Tensor], weight: Optional[torch.Tensor],
                noise=None, gradient_clip: float = 1.0, group: Optional[dist.ProcessGroup] = None):
     """One optimizer step on this rank's shard of the batch, mirroring train.py:1263-1286 with accum_factor folded into
     data parallelism: noise -> forward (loss_sum, loss_basis, correct) -> backward of loss_sum -> all-reduce of
     (gradients, loss_sum, loss_basis) -> normalise by the GLOBAL loss basis -> clip -> AdamW.step().
-    Returns (global mean loss, global correct count, global token count, gradient norm)."""
+    Returns (global mean loss, global correct count, global token count, gradient norm).
+    With a novic_b200.optim.FusedAdamW the step never synchronises with the host and overlaps the all-reduce with the backward pass;
+    with a torch optimizer the reference's own sequence (autograd, clip_grad_norm_, optimizer.step) runs on the module's parameters."""
+    from .optim import FusedAdamW
+    if isinstance(optimizer, FusedAdamW):
+        return _train_step_fused(model, optimizer, embed, target, mask, weight, noise, gradient_clip, group)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     if noise is not None:
+        noise.stream_offset = dist.get_rank(group) if world > 1 else 0
         embed = noise(embed)
+    model.dropout_seed_offset = (dist.get_rank(group) if world > 1 else 0) * 0x51ED2701
     optimizer.zero_grad(set_to_none=True)
     _, padding, loss_sum, loss_basis, correct = model(embed, target, mask, weight, True, True, False, None)
     loss_sum.backward()                                   # gradients of the local loss SUM (additive across shards)

@@ -47,6 +47,18 @@ class EmbeddingNoise(torch.nn.Module):
         self._cfg = _abi.NovicNoiseCfg(scheme=_SCHEMES[scheme.lower()], embed_dim=embed_dim, vec_norm=vec_norm, angle_min=angle_min,
                                        angle_max=angle_max, angle_std=angle_std, mix_ratio=mix_ratio)
         self._calls = 0
+        # Philox stream = (torch.initial_seed() + stream_offset, call counter).  Data-parallel training sets stream_offset to the rank
+        # (novic_b200/dist.py) so that shards do not draw identical noise; a resumed run sets `call_counter` to its global step so that it
+        # continues the sequence instead of replaying it (the module has no state-dict entries, like the reference's).
+        self.stream_offset = 0
+
+    @property
+    def call_counter(self) -> int:
+        return self._calls
+
+    @call_counter.setter
+    def call_counter(self, value: int) -> None:
+        self._calls = int(value)
 
     def _check(self, embed: torch.Tensor) -> None:
         if embed.device.type != 'cuda':
@@ -60,7 +72,7 @@ class EmbeddingNoise(torch.nn.Module):
         self._calls += 1
         with torch.cuda.device(embed.device):
             _abi.check(_abi.lib().novic_noise_apply(C.byref(self._cfg), embed.data_ptr(), embed.shape[0],
-                                                    torch.initial_seed() & 0xFFFFFFFFFFFFFFFF, self._calls,
+                                                    (torch.initial_seed() + 0x9E3779B97F4A7C15 * int(self.stream_offset)) & 0xFFFFFFFFFFFFFFFF, self._calls,
                                                     torch.cuda.current_stream(embed.device).cuda_stream))
         return embed
 

@@ -105,13 +105,16 @@ class GenerationPipeline:
             return
         pending = None           # (pinned views, event) of the previous batch's results
         i = 0
-        with torch.inference_mode():
-            while nxt is not None:
-                dev, ev = nxt
-                try:
-                    nxt = self._upload(next(it))          # batch i + 1 travels while batch i decodes
-                except StopIteration:
-                    nxt = None
+        # inference mode is entered around the library work only and left before every yield: a generator that yields inside
+        # `with torch.inference_mode()` would leak the thread-local mode into the consumer's loop body
+        while nxt is not None:
+            dev, ev = nxt
+            try:
+                nxt = self._upload(next(it))          # batch i + 1 travels while batch i decodes
+            except StopIteration:
+                nxt = None
+            ready = None
+            with torch.inference_mode():
                 cur_stream.wait_event(ev)
                 dev.record_stream(cur_stream)
                 res = self._decode(dev)
@@ -120,14 +123,16 @@ class GenerationPipeline:
                 if pending is not None:                   # hand out batch i - 1 (its copies finished during this decode)
                     outs, dev_ev = pending
                     dev_ev.synchronize()
-                    yield self._cut(outs)
-                if self.emit:
-                    pending = self._download(i & 1, res, done)
-                else:
-                    pending = None
-                    yield None
-                i += 1
+                    ready = self._cut(outs)
+                pending = self._download(i & 1, res, done) if self.emit else None
+            if ready is not None:
+                yield ready
+            if not self.emit:
+                yield None
+            i += 1
         if pending is not None:
             outs, dev_ev = pending
             dev_ev.synchronize()
-            yield self._cut(outs)
+            with torch.inference_mode():
+                last = self._cut(outs)
+            yield last
