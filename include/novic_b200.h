@@ -210,6 +210,56 @@ int novic_noise_apply(const NovicNoiseCfg* cfg, float* embed, int64_t B, uint64_
 int novic_noise_apply_predrawn(const NovicNoiseCfg* cfg, float* embed, int64_t B, const float* normals_a,
                                const float* normals_b, const float* row_a, const float* row_b, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------------------
+ * Image encoder in front of the decoder (BASELINE config #5).  Replaces the call
+ * `self.model_encode_image(images, normalize=False)` + fp32 normalise of embedders.py:759-764 for an open_clip VisionTransformer
+ * (un-vendored dependency open_clip_torch==2.23, requirements.txt:8; the architecture is an assumption documented in DESIGN.md):
+ * conv patch embedding without bias, class token, learned positions, ln_pre, `layers` pre-LN blocks (MultiheadAttention with biases,
+ * heads of 80 channels; MLP width -> mlp_dim -> width with QuickGELU), ln_post on the class token, bias-free projection to out_dim.
+ * All parameters fp32 device pointers named after open_clip's state dict (`visual.*`). */
+#define NOVIC_VIT_MAX_LAYERS 48
+typedef struct NovicVitCfg {
+  int32_t image_size;   /* 378 */
+  int32_t patch_size;   /* 14  */
+  int32_t width;        /* 1280 = heads * 80 */
+  int32_t layers;       /* 32 */
+  int32_t heads;        /* 16 */
+  int32_t mlp_dim;      /* 5120 */
+  int32_t out_dim;      /* 1024 = the decoder's embed_dim */
+  float ln_eps;         /* 1e-5 */
+} NovicVitCfg;
+typedef struct NovicVitWeights {
+  const float* conv1;                 /* visual.conv1.weight                         [width, 3, patch, patch] */
+  const float* class_embedding;       /* visual.class_embedding                      [width] */
+  const float* positional_embedding;  /* visual.positional_embedding                 [tokens, width] */
+  const float *ln_pre_w, *ln_pre_b;   /* visual.ln_pre.{weight,bias} */
+  const float *ln_post_w, *ln_post_b; /* visual.ln_post.{weight,bias} */
+  const float* proj;                  /* visual.proj                                 [width, out_dim] (x @ proj) */
+  const float* ln1_w[NOVIC_VIT_MAX_LAYERS];      /* visual.transformer.resblocks.i.ln_1.weight */
+  const float* ln1_b[NOVIC_VIT_MAX_LAYERS];
+  const float* in_proj_w[NOVIC_VIT_MAX_LAYERS];  /* ...attn.in_proj_weight   [3 width, width] */
+  const float* in_proj_b[NOVIC_VIT_MAX_LAYERS];  /* ...attn.in_proj_bias     [3 width] */
+  const float* out_proj_w[NOVIC_VIT_MAX_LAYERS]; /* ...attn.out_proj.weight  [width, width] */
+  const float* out_proj_b[NOVIC_VIT_MAX_LAYERS];
+  const float* ln2_w[NOVIC_VIT_MAX_LAYERS];      /* ...ln_2.weight */
+  const float* ln2_b[NOVIC_VIT_MAX_LAYERS];
+  const float* fc_w[NOVIC_VIT_MAX_LAYERS];       /* ...mlp.c_fc.weight       [mlp_dim, width] */
+  const float* fc_b[NOVIC_VIT_MAX_LAYERS];
+  const float* cproj_w[NOVIC_VIT_MAX_LAYERS];    /* ...mlp.c_proj.weight     [width, mlp_dim] */
+  const float* cproj_b[NOVIC_VIT_MAX_LAYERS];
+} NovicVitWeights;
+typedef struct NovicVitHandle NovicVitHandle;
+int novic_vit_create(const NovicVitCfg* cfg, NovicVitHandle** out);
+int novic_vit_destroy(NovicVitHandle* h);
+size_t novic_vit_weight_bytes(const NovicVitHandle* h);
+int novic_vit_set_weights(NovicVitHandle* h, const NovicVitWeights* w, void* wbuf, size_t wbuf_bytes, void* stream);
+/* Workspace of one chunk of `images_per_chunk` images (the encoder walks a batch chunk by chunk). */
+size_t novic_vit_workspace_bytes(const NovicVitHandle* h, int64_t images_per_chunk);
+/* images [B, 3, image_size, image_size] fp32 device (already preprocessed) -> embed_out [B, out_dim] fp32 device, L2-normalised when
+ * normalize != 0 (embedders.py:764).  The result can be handed to novic_generate_* without leaving the device. */
+int novic_vit_encode(NovicVitHandle* h, const float* images, int64_t B, float* embed_out, int32_t normalize, int64_t images_per_chunk,
+                     void* ws, size_t ws_bytes, void* stream);
+
 /* Building-block check used by the test-suite: out[M, N] fp32 = A[M, K] (bf16) * W[N, K]^T (bf16) through the
  * same tcgen05 / TMA kernel the decoder uses.  K % 64 == 0. */
 int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,

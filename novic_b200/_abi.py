@@ -43,6 +43,21 @@ class NovicNoiseCfg(C.Structure):
     ]
 
 
+NOVIC_VIT_MAX_LAYERS = 48
+
+
+class NovicVitCfg(C.Structure):
+    _fields_ = [("image_size", C.c_int32), ("patch_size", C.c_int32), ("width", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
+                ("mlp_dim", C.c_int32), ("out_dim", C.c_int32), ("ln_eps", C.c_float)]
+
+
+class NovicVitWeights(C.Structure):
+    _fields_ = [("conv1", _FP), ("class_embedding", _FP), ("positional_embedding", _FP), ("ln_pre_w", _FP), ("ln_pre_b", _FP),
+                ("ln_post_w", _FP), ("ln_post_b", _FP), ("proj", _FP)] + [
+        (name, _FP * NOVIC_VIT_MAX_LAYERS) for name in ("ln1_w", "ln1_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "ln2_w", "ln2_b",
+                                                        "fc_w", "fc_b", "cproj_w", "cproj_b")]
+
+
 class NovicAdamW(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
                 ("max_grad_norm", C.c_float), ("step", C.c_int64)]
@@ -82,6 +97,12 @@ SIGNATURES = {
                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_int32, C.c_void_p]),
     "novic_adamw_scratch_bytes": (C.c_size_t, []),
     "novic_adamw_step": (C.c_int, [C.POINTER(NovicAdamW), _FP, _FP, _FP, _FP, C.c_int64, _FP, _FP, C.c_void_p, C.c_size_t, _FP, C.c_void_p]),
+    "novic_vit_create": (C.c_int, [C.POINTER(NovicVitCfg), C.POINTER(C.c_void_p)]),
+    "novic_vit_destroy": (C.c_int, [C.c_void_p]),
+    "novic_vit_weight_bytes": (C.c_size_t, [C.c_void_p]),
+    "novic_vit_set_weights": (C.c_int, [C.c_void_p, C.POINTER(NovicVitWeights), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "novic_vit_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64]),
+    "novic_vit_encode": (C.c_int, [C.c_void_p, _FP, C.c_int64, _FP, C.c_int32, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "novic_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_uint64]),
     "novic_noise_apply": (C.c_int, [C.POINTER(NovicNoiseCfg), _FP, C.c_int64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "novic_noise_apply_predrawn": (C.c_int, [C.POINTER(NovicNoiseCfg), _FP, C.c_int64, _FP, _FP, _FP, _FP, C.c_void_p]),

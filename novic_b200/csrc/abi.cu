@@ -13,6 +13,7 @@
 #include "../../include/novic_b200.h"
 #include "train.cuh"
 #include "optim.cuh"
+#include "vit.cuh"
 
 using namespace novic;
 
@@ -1627,3 +1628,5 @@ int novic_debug_wgrad(const void* a_t, int32_t Mo, const void* b_t, int32_t No, 
 }
 
 }  // extern "C"
+
+#include "vit_host.inc"
