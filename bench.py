@@ -9,8 +9,9 @@ unit-norm 1024-d embeddings per GPU through novic_b200.PrefixedIterDecoder (rand
 config/train.yaml:224-308).  Rank 0 prints ONE JSON line:
   value / e2e      weak scaling, 4096 embeddings per GPU (device-timed / through the public serving loop from pinned host memory)
   strong           (N > 1) the metric's own global batch of 4096 split N ways: 4096 / N embeddings per GPU
-  secondary        BASELINE configs #3 (beam k = 3, 65 536 embeddings over 8 GPUs = 8192 per GPU) and #4 (training step, global
-                   batch 8192 over 8 GPUs = 1024 per GPU, embedding noise, NCCL gradient all-reduce, fused clip + AdamW) at this N
+  secondary        BASELINE configs #3 (beam k = 3, 65 536 embeddings over 8 GPUs = 8192 per GPU), #4 (training step, global
+                   batch 8192 over 8 GPUs = 1024 per GPU, embedding noise, NCCL gradient all-reduce, fused clip + AdamW) and #5
+                   (CLIP ViT-H/14-378 image encoder + decoder, 1024 images per GPU) at this N
   roofline         per kernel class, against MEASURED_PEAKS.json, with ncu DRAM traffic from profiles/traffic.json
   cpu_baseline     (N = 1) the reference's own PrefixedIterDecoder.generate on the host cores over a bounded sample
 `--impl reference` times the reference's CPU implementation alone: the unmodified reference staged in oracle/_ref (oracle/build_ref.py),
@@ -46,7 +47,8 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="embeddings per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=256, help="embeddings in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (beam k=3, training step)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (beam k=3, training step, image encoder + decoder)")
+    ap.add_argument("--encoder-images", type=int, default=1024, help="images per GPU of the encoder + decoder workload (BASELINE config #5)")
     return ap.parse_args()
 
 
@@ -553,6 +555,46 @@ def main():
             "collective": None if world == 1 else {"what": "ncclAllReduce of the 50.9 MB fp32 gradient bucket, timed alone", "ms": coll_ms},
         }
         del tmodel, opt
+
+    # ---- BASELINE config #5: random-init CLIP ViT-H/14-378 image encoder + decoder end to end, 1024 synthetic 378 x 378 images per GPU
+    if not args.no_secondary:
+        from novic_b200.encoder import EncoderDecoder, ImageEncoder, VitDims, synth_images, synth_vit_state_dict
+        vd = VitDims()
+        enc = ImageEncoder(vd, images_per_chunk=64)
+        enc.load_state_dict(synth_vit_state_dict(vd, seed=7))
+        enc = enc.to(dev).eval()
+        both = EncoderDecoder(enc, model)
+        n_img = args.encoder_images
+        base_img = synth_images(64, vd, seed=11 + rank).to(dev)
+        images = base_img.repeat((n_img + 63) // 64, 1, 1, 1)[:n_img].contiguous()       # 64 distinct synthetic images, tiled to the batch
+        Tk, Wd, Ly, Ml = vd.tokens, vd.width, vd.layers, vd.mlp_dim
+        flops_img = 2 * Tk * Ly * (4 * Wd * Wd + 2 * Wd * Ml) + 4 * Tk * Tk * Wd * Ly + 2 * (Tk - 1) * 588 * Wd
+        with torch.inference_mode():
+            both.generate(images[:128])
+            barrier()
+            torch.cuda.synchronize()
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            n0 = lib.novic_launch_count()
+            a.record()
+            emb = both.embed(images)
+            b.record()
+            t5, p5, _, _, _, s5 = model.generate(emb, False, True, 1.0, 0.0, None, None, False)
+            if world > 1:
+                t5, p5, s5 = gather_generation(t5.unsqueeze(1), p5.unsqueeze(1), s5.unsqueeze(1), n_img * world, gen_len=G)
+            c.record()
+            torch.cuda.synchronize()
+            barrier()
+        e_ms, all_ms = max_over_ranks(a.elapsed_time(b)), max_over_ranks(a.elapsed_time(c))
+        assert t5.shape[0] == n_img * world
+        secondary["encoder_decoder"] = {
+            "workload": f"BASELINE configs[4]: random-init CLIP ViT-H/14-378 image encoder (open_clip VisionTransformer as assumed in DESIGN.md: 730 tokens, width 1280, "
+                        f"32 blocks, 16 heads x 80, MLP 5120, QuickGELU) + default decoder, {n_img} synthetic 378 x 378 images per GPU ({n_img * world} in all), images resident "
+                        "in HBM, embeddings handed to the greedy decode on the device, final gather of ids",
+            "metric": "images/sec (encode + greedy decode)", "value": n_img * world / (all_ms / 1e3), "unit": "images/s", "ms_per_step": all_ms, "steps": 1,
+            "encoder_ms": e_ms, "encoder_tflops_per_gpu": flops_img * n_img / e_ms / 1e9, "encoder_frac_of_tensor_peak": flops_img * n_img / e_ms / 1e9 / load_peaks()["bf16_tflops_sustained"],
+            "gflop_per_image": flops_img / 1e9, "gpu_launches": int(lib.novic_launch_count() - n0), "parity": "unpinned (un-vendored open_clip; oracle/vit_oracle.py restates the architecture)",
+        }
+        del enc, both, images, base_img
 
     if rank == 0:
         peaks = load_peaks()

@@ -43,11 +43,15 @@ class VitCfg:
         return (self.image_size // self.patch_size) ** 2 + 1
 
 
-def encode_image(cfg: VitCfg, sd: dict, images: torch.Tensor, normalize: bool = False) -> torch.Tensor:
-    """images [B, 3, S, S] fp32 -> [B, out_dim] fp32."""
+def encode_image(cfg: VitCfg, sd: dict, images: torch.Tensor, normalize: bool = False, bf16_operands: bool = False) -> torch.Tensor:
+    """images [B, 3, S, S] fp32 -> [B, out_dim] fp32.
+    bf16_operands: round every matrix-product operand (weights, LayerNorm outputs, q / k / v, attention probabilities and outputs, the MLP
+    hidden rows) to bf16 first, as a kernel with bf16 tensor-core operands and fp32 accumulation sees them: a CUDA path must then agree to
+    accumulation-order level, which separates a wrong kernel from honest rounding."""
+    r = (lambda t: t.bfloat16().float()) if bf16_operands else (lambda t: t)
     B = images.shape[0]
     W, H = cfg.width, cfg.heads
-    x = F.conv2d(images, sd["visual.conv1.weight"], stride=cfg.patch_size)                       # B x W x np x np
+    x = F.conv2d(r(images), r(sd["visual.conv1.weight"]), stride=cfg.patch_size)                 # B x W x np x np
     x = x.reshape(B, W, -1).permute(0, 2, 1)                                                      # B x np^2 x W
     cls = sd["visual.class_embedding"].to(x.dtype).expand(B, 1, W)
     x = torch.cat((cls, x), dim=1) + sd["visual.positional_embedding"]
@@ -55,16 +59,21 @@ def encode_image(cfg: VitCfg, sd: dict, images: torch.Tensor, normalize: bool = 
     T = x.shape[1]
     for i in range(cfg.layers):
         p = f"visual.transformer.resblocks.{i}."
-        y = F.layer_norm(x, (W,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], cfg.ln_eps)
-        qkv = F.linear(y, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"])
+        y = r(F.layer_norm(x, (W,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], cfg.ln_eps))
+        qkv = r(F.linear(y, r(sd[p + "attn.in_proj_weight"]), sd[p + "attn.in_proj_bias"]))
         q, k, v = (t.reshape(B, T, H, W // H).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
-        att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(W // H), dim=-1) @ v
-        att = att.transpose(1, 2).reshape(B, T, W)
-        x = x + F.linear(att, sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"])
-        y = F.layer_norm(x, (W,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], cfg.ln_eps)
-        h = F.linear(y, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"])
-        h = h * torch.sigmoid(1.702 * h)
-        x = x + F.linear(h, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
-    pooled = F.layer_norm(x[:, 0], (W,), sd["visual.ln_post.weight"], sd["visual.ln_post.bias"], cfg.ln_eps)
-    out = pooled @ sd["visual.proj"]
+        sc = q @ k.transpose(-1, -2) / math.sqrt(W // H)
+        if bf16_operands:   # the kernel rounds the un-normalised exponentials to bf16 and divides by their fp32 sum afterwards
+            e = torch.exp(sc - sc.amax(dim=-1, keepdim=True))
+            att = (r(e) @ v) / e.sum(dim=-1, keepdim=True)
+        else:
+            att = torch.softmax(sc, dim=-1) @ v
+        att = r(att.transpose(1, 2).reshape(B, T, W))
+        x = x + F.linear(att, r(sd[p + "attn.out_proj.weight"]), sd[p + "attn.out_proj.bias"])
+        y = r(F.layer_norm(x, (W,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], cfg.ln_eps))
+        h = F.linear(y, r(sd[p + "mlp.c_fc.weight"]), sd[p + "mlp.c_fc.bias"])
+        h = r(h * torch.sigmoid(1.702 * h))
+        x = x + F.linear(h, r(sd[p + "mlp.c_proj.weight"]), sd[p + "mlp.c_proj.bias"])
+    pooled = r(F.layer_norm(x[:, 0], (W,), sd["visual.ln_post.weight"], sd["visual.ln_post.bias"], cfg.ln_eps))
+    out = pooled @ r(sd["visual.proj"])
     return F.normalize(out, dim=-1) if normalize else out
