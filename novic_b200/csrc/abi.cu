@@ -133,22 +133,22 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-template <class Epi, int STAGES, int KBS = 1>
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN>
 int set_gemm_attr() {
-  static_assert(gemm_persistent_smem_bytes(STAGES, KBS) <= 227 * 1024, "GEMM pipeline does not fit in shared memory");
-  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES, KBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES, KBS)));
+  static_assert(gemm_persistent_smem_bytes(STAGES, KBS, BN) <= 227 * 1024, "GEMM pipeline does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES, KBS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES, KBS, BN)));
   return 0;
 }
 
 // KBS > 1: ta / tb are 3-D maps (make_tmap3 with kbs = KBS), K a multiple of 64 * KBS, no split-K.
-template <class Epi, int STAGES, int KBS = 1>
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN>
 int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                 const typename Epi::Params& ep, int k_splits = 1, bool b_is_static = false) {
-  const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
+  const int n_tiles = static_cast<int>(ceil_div(N, BN));
   const int64_t total = n_tiles * ceil_div(M, kBlockM) * k_splits;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
   if (KBS > 1 && (k_splits != 1 || K % (kBlockK * KBS) != 0)) return fail("wide-stage GEMM needs K %% %d == 0 and no split-K", kBlockK * KBS);
-  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, KBS>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES, KBS), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, b_is_static ? 1 : 0, ep));
+  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, KBS, BN>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES, KBS, BN), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, b_is_static ? 1 : 0, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;

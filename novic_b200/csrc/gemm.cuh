@@ -42,7 +42,8 @@ struct EpiCtx {
   uint32_t tmem_row;   // TMEM address of this thread's lane, first column of the thread's column range
   int row;             // global output row of this thread
   int warp_row0;       // global output row of lane 0 of this warp
-  int n0;              // first output column of this thread's 64-column range
+  int n0;              // first output column of this thread's column range
+  int ncols;           // columns per thread: 64 (128-column tiles; what every decoder epilogue assumes) or 128 (256-column tiles)
   int M;
   int part;            // partial index: tile * 2 + half
   uint8_t* stage;      // warp-private staging memory (kEpiStageBytes)
@@ -443,8 +444,8 @@ __device__ __forceinline__ void mma_mainloop(const GemmSmemView& sv, uint32_t tm
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kAccStages = 2;                       // TMEM accumulator double buffering: 2 x 128 columns
 
-__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs = 1) {
-  return stages * kbs * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs = 1, int bn = kTileN) {
+  return stages * kbs * (kABytes + bn * kBlockK * 2) + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 // Persistent: grid = min(#tiles, #SMs); CTA b walks tiles b, b + grid, ... (n fastest, so neighbouring CTAs share A).
@@ -453,11 +454,18 @@ __host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs
 // KBS = k-blocks per pipeline stage.  KBS > 1 takes 3-D tensor maps (make_tmap3): one TMA request then brings KBS k-block tiles of
 // an operand.  The TMA unit serves ~2 requests at a time at ~0.4-0.5 k cycles each regardless of their size (tools/tmabench.cu),
 // so with 16 KB requests a 128 x 128 x 512 tile takes ~6 k cycles to load against 2 k cycles of MMA; 32 KB requests halve that.
-template <class Epi, int STAGES, int KBS = 1>
+// BN = output columns per tile: 128, or 256 (one UMMA of N = 256 per k-slice: 48 KB of operands per 128 x 256 x 64 block instead of 64 KB for
+// two 128 x 128 ones, i.e. 0.75 of the L2 -> SM traffic per FLOP - the large GEMMs of the image encoder are bound by exactly that; the
+// two accumulator stages then fill all 512 TMEM columns and every epilogue thread owns 128 columns).  Only epilogues that honour
+// EpiCtx::ncols may be instantiated with BN = 256.
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles,
             int num_k_blocks, int k_splits, int b_is_static, typename Epi::Params ep) {
-  constexpr int kStageBytes = KBS * novic::kStageBytes;   // this kernel's stage: [A: KBS k-blocks][B: KBS k-blocks]
+  static_assert(BN == 128 || BN == 256, "tile width");
+  constexpr int kTileN = BN;                               // shadows the namespace constant inside this kernel
+  constexpr int kBBytes = BN * kBlockK * 2;
+  constexpr int kStageBytes = KBS * (kABytes + kBBytes);   // this kernel's stage: [A: KBS k-blocks][B: KBS k-blocks]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -581,10 +589,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (i < 8 && threadIdx.x == 64) trace_point(tr, 16 + 2 * i);   // per-tile: accumulator ready / epilogue done
       tc_fence_after_sync();
       EpiCtx c;
-      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * kEpiCols;
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * (kTileN / 2);
       c.warp_row0 = m0 + quad * 32;
       c.row = c.warp_row0 + lane;
-      c.n0 = nt * kTileN + half * kEpiCols;
+      c.n0 = nt * kTileN + half * (kTileN / 2);
+      c.ncols = kTileN / 2;
       c.M = M;
       c.part = nt * 2 + half;
       c.stage = epi_stage + ew * kEpiStageBytes;

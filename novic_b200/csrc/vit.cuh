@@ -33,31 +33,36 @@ struct EpiVitBias {
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
     const int lane = lane_id();
+    const int nhalf = c.ncols / kEpiCols;              // 1 (128-column tiles) or 2 (256-column tiles): 64 columns are staged at a time
+#pragma unroll 1
+    for (int hf = 0; hf < nhalf; ++hf) {
+      const int n0 = c.n0 + hf * kEpiCols;
 #pragma unroll
-    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + ch * 32, v);
-      if (ch == kEpiCols / 32 - 1) release();
-      const int col0 = c.n0 + ch * 32;
-      if (p.bias != nullptr && col0 < p.n_valid) {
+      for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + hf * kEpiCols + ch * 32, v);
+        if (hf == nhalf - 1 && ch == kEpiCols / 32 - 1) release();
+        const int col0 = n0 + ch * 32;
+        if (p.bias != nullptr && col0 < p.n_valid) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);   // N is a multiple of 32 for every ViT GEMM
-          v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+          for (int q = 0; q < 8; ++q) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);   // N is a multiple of 32 for every ViT GEMM
+            v[q * 4] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+          }
         }
-      }
-      if (p.quick_gelu) {
+        if (p.quick_gelu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] * __fdividef(1.0f, 1.0f + __expf(-1.702f * v[j]));
+          for (int j = 0; j < 32; ++j) v[j] = v[j] * __fdividef(1.0f, 1.0f + __expf(-1.702f * v[j]));
+        }
+        stage_put32(c.stage, lane, ch * 32, v);
       }
-      stage_put32(c.stage, lane, ch * 32, v);
+      if (n0 < p.n_valid)
+        stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+          const int row = c.warp_row0 + r;
+          return row < c.M ? p.out + static_cast<size_t>(row) * p.ld + n0 : nullptr;
+        });
+      else __syncwarp();
     }
-    const int n0 = c.n0;
-    if (n0 < p.n_valid)
-      stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
-        const int row = c.warp_row0 + r;
-        return row < c.M ? p.out + static_cast<size_t>(row) * p.ld + n0 : nullptr;
-      });
   }
 };
 
@@ -74,17 +79,20 @@ struct EpiVitResid {
     const float* bias;      // [W] or nullptr
     const float* table;     // patch mode: positional embedding [T, W]
     int patches;            // patch mode: T - 1
+    int n_valid;            // W (columns >= W of a ragged last tile are not touched)
   };
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
     const int lane = lane_id();
     float* st = reinterpret_cast<float*>(c.stage);            // 32 rows x 32 fp32 = 4096 B (kEpiStageBytes)
     const int sub = lane >> 3, chunk = lane & 7;
+    const int nch = c.ncols / 32;
 #pragma unroll 1
-    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+    for (int ch = 0; ch < nch; ++ch) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + ch * 32, v);
-      if (ch == kEpiCols / 32 - 1) release();
+      if (ch == nch - 1) release();
+      if (c.n0 + ch * 32 >= p.n_valid) continue;        // warp-uniform
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q)
@@ -123,12 +131,13 @@ struct EpiVitStoreF32 {
   };
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
-#pragma unroll
-    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+    const int nch = c.ncols / 32;
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
       float v[32];
       tmem_ld_32x32(c.tmem_row + ch * 32, v);
-      if (ch == kEpiCols / 32 - 1) release();
-      if (c.row < c.M) {
+      if (ch == nch - 1) release();
+      if (c.row < c.M && c.n0 + ch * 32 < p.ld) {
         float4* d = reinterpret_cast<float4*>(p.out + static_cast<size_t>(c.row) * p.ld + c.n0 + ch * 32);
 #pragma unroll
         for (int q = 0; q < 8; ++q) d[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
