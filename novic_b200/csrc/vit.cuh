@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256) vit_layernorm_kernel(const VitLnParams p)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kVaQ = 128, kVaK = 64, kVaWarps = 8;
 constexpr int kVaPitch = kVitHeadDim + 8;                         // 88 bf16 = 176 B rows: ldmatrix rows fall into distinct bank groups
-constexpr int kVaSmemBytes = (kVaQ + 4 * kVaK) * kVaPitch * 2;    // Q + 2 x (K, V) = 67 584 B
+constexpr int kVaStages = 3;                                      // K/V ring: one CTA barrier per key tile
+constexpr int kVaSmemBytes = (kVaQ + 2 * kVaStages * kVaK) * kVaPitch * 2;    // Q + 3 x (K, V) = 90 112 B (two CTAs per SM)
 
 struct VitAttnParams {
   const __nv_bfloat16* qkv;
@@ -265,10 +266,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// 2^x on the SFU (MUFU.EX2; exp2f without fast-math expands to a dozen instructions of range handling, which made the softmax - not the
+// tensor pipe - the busiest part of the kernel); relative error 2^-22, inputs here are <= 0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kVaWarps * 32, 2) vit_attention_kernel(const VitAttnParams p) {
   extern __shared__ __align__(16) uint8_t sm_va[];
   __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sm_va);
-  __nv_bfloat16* skv = sq + kVaQ * kVaPitch;                       // [2 stages][K | V][64][pitch]
+  __nv_bfloat16* skv = sq + kVaQ * kVaPitch;                       // [kVaStages][K | V][64][pitch]
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int lm = lane >> 3, lr = lane & 7, g = lane >> 2, t = lane & 3;
   const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -293,10 +302,12 @@ __global__ void __launch_bounds__(kVaWarps * 32, 2) vit_attention_kernel(const V
       cp_async16((which ? sv : sk) + r * kVaPitch + c * 8, base + static_cast<size_t>(ok ? k0 + r : 0) * ld + (1 + which) * p.W + c * 8, ok);
     }
   };
+  const int ntiles = (T + kVaK - 1) / kVaK;
   load_kv(0, 0);
   cp_async_commit();
+  if (ntiles > 1) load_kv(1, 1);
+  cp_async_commit();
 
-  const int ntiles = (T + kVaK - 1) / kVaK;
   float o[kVitHeadDim / 8][4];
 #pragma unroll
   for (int ni = 0; ni < kVitHeadDim / 8; ++ni)
@@ -305,12 +316,15 @@ __global__ void __launch_bounds__(kVaWarps * 32, 2) vit_attention_kernel(const V
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   uint32_t aq[kVitHeadDim / 16][4];
 
+  int stage = 0;
   for (int tile = 0; tile < ntiles; ++tile) {
-    const int stage = tile & 1;
-    if (tile + 1 < ntiles) load_kv(tile + 1, stage ^ 1);          // the other stage was drained by every warp before the barrier below
-    cp_async_commit();
-    cp_async_wait<1>();                                            // this tile's (and, first time, Q's) bytes have landed
-    __syncthreads();
+    cp_async_wait<1>();                                            // everything but the newest group: this tile's (and Q's) bytes have landed
+    __syncthreads();                                               // ... for every thread; and every warp is done with tile - 1, whose stage is refilled now
+    {
+      const int nxt = stage == 0 ? kVaStages - 1 : stage - 1;      // stage of tile - 1 = stage of tile + 2
+      if (tile + 2 < ntiles) load_kv(tile + 2, nxt);
+      cp_async_commit();
+    }
     if (tile == 0) {
 #pragma unroll
       for (int ki = 0; ki < kVitHeadDim / 16; ++ki) ldsm_x4(aq[ki], sq + (warp * 16 + (lm & 1) * 8 + lr) * kVaPitch + ki * 16 + (lm >> 1) * 8);
@@ -332,41 +346,49 @@ __global__ void __launch_bounds__(kVaWarps * 32, 2) vit_attention_kernel(const V
         mma_bf16_16816(s[np * 2 + 1], aq[ki], bk[2], bk[3]);
       }
     }
-    // online softmax on this warp's 16 rows (thread: rows g and g + 8, columns ni * 8 + 2 t + {0, 1})
+    // online softmax on this warp's 16 rows (thread: rows g and g + 8, columns ni * 8 + 2 t + {0, 1}); the 1 / sqrt(80) * log2(e) factor is
+    // folded into the exponent: p = 2^(s * c - m * c) is one FFMA + one MUFU per score
     const int kbase = tile * kVaK;
     const bool ragged = kbase + kVaK > T;
+    if (ragged) {
+#pragma unroll
+      for (int ni = 0; ni < kVaK / 8; ++ni)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (kbase + ni * 8 + 2 * t + (e & 1) >= T) s[ni][e] = -INFINITY;
+    }
+    // both row halves at once, reductions as trees of independent partials (a 16-deep FMNMX / FADD chain per row costs more issue
+    // latency than the tensor work of the tile hides at four warps per scheduler)
+    float mx[2][4], sm[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mx[h][q] = fmaxf(fmaxf(s[2 * q][h * 2], s[2 * q][h * 2 + 1]), fmaxf(s[2 * q + 1][h * 2], s[2 * q + 1][h * 2 + 1]));
+    float m_new[2], corr[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float mx = -INFINITY;
+      float m = fmaxf(fmaxf(mx[h][0], mx[h][1]), fmaxf(mx[h][2], mx[h][3]));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m_new[h] = fmaxf(m_run[h], m * p.scale_log2e);               // finite: every tile holds at least one valid key (scale > 0)
+      corr[h] = ex2_approx(m_run[h] - m_new[h]);
+      m_run[h] = m_new[h];
+    }
 #pragma unroll
-      for (int ni = 0; ni < kVaK / 8; ++ni)
+    for (int ni = 0; ni < kVaK / 8; ++ni)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          float v = s[ni][h * 2 + e] * p.scale_log2e;
-          if (ragged && kbase + ni * 8 + 2 * t + e >= T) v = -INFINITY;
-          s[ni][h * 2 + e] = v;
-          mx = fmaxf(mx, v);
-        }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float m_new = fmaxf(m_run[h], mx);                     // finite: every tile holds at least one valid key
-      const float corr = exp2f(m_run[h] - m_new);
-      float sum = 0.f;
+      for (int e = 0; e < 4; ++e) s[ni][e] = ex2_approx(fmaf(s[ni][e], p.scale_log2e, -m_new[e >> 1]));
 #pragma unroll
-      for (int ni = 0; ni < kVaK / 8; ++ni)
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float ex = exp2f(s[ni][h * 2 + e] - m_new);
-          s[ni][h * 2 + e] = ex;
-          sum += ex;
-        }
+      for (int q = 0; q < 4; ++q) sm[h][q] = (s[2 * q][h * 2] + s[2 * q][h * 2 + 1]) + (s[2 * q + 1][h * 2] + s[2 * q + 1][h * 2 + 1]);
+      float sum = (sm[h][0] + sm[h][1]) + (sm[h][2] + sm[h][3]);
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      l_run[h] = l_run[h] * corr + sum;
-      m_run[h] = m_new;
-#pragma unroll
-      for (int ni = 0; ni < kVitHeadDim / 8; ++ni) { o[ni][h * 2] *= corr; o[ni][h * 2 + 1] *= corr; }
+      l_run[h] = l_run[h] * corr[h] + sum;
     }
+#pragma unroll
+    for (int ni = 0; ni < kVitHeadDim / 8; ++ni) { o[ni][0] *= corr[0]; o[ni][1] *= corr[0]; o[ni][2] *= corr[1]; o[ni][3] *= corr[1]; }
     // O += P V
 #pragma unroll
     for (int ki = 0; ki < kVaK / 16; ++ki) {
@@ -383,9 +405,9 @@ __global__ void __launch_bounds__(kVaWarps * 32, 2) vit_attention_kernel(const V
         mma_bf16_16816(o[np * 2 + 1], ap, bv[2], bv[3]);
       }
     }
-    __syncthreads();                                               // every warp is done with this stage before it is refilled
+    stage = stage + 1 == kVaStages ? 0 : stage + 1;
   }
-  // normalise, stage through the (dead) Q tile, store 16-byte chunks
+  // normalise, stage through the Q tile (each warp reads and writes only its own 16 rows of it), store 16-byte chunks
   __nv_bfloat16* so = sq + warp * 16 * kVaPitch;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
