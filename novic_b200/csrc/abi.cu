@@ -99,6 +99,18 @@ int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, i
   return 0;
 }
 
+// General 3-D bf16 map with 128-byte swizzle: dims / box innermost first, strides (bytes) of dimensions 1 and 2.
+int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3], const cuuint64_t (&strides)[2], const cuuint32_t (&box)[3]) {
+  if (load_driver_entry()) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || strides[0] % 16 != 0 || strides[1] % 16 != 0) return fail("TMA operand base / strides must be 16-byte aligned");
+  if (box[0] * 2 != 128) return fail("128-byte swizzle needs a 64-element inner box");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // GEMM launch
 // ---------------------------------------------------------------------------------------------------------

@@ -89,35 +89,49 @@ struct EpiVitResid {
     const int nch = c.ncols / 32;
 #pragma unroll 1
     for (int ch = 0; ch < nch; ++ch) {
+      const bool live = c.n0 + ch * 32 < p.n_valid;           // warp-uniform
+      const int col = c.n0 + ch * 32 + chunk * 4;
+      // the residual (or position) values of this chunk do not depend on the accumulator: all eight 16-byte loads of the thread are
+      // issued first, so that their latency overlaps the TMEM load and the staging (with the loads behind the staging the epilogue
+      // of a tile took ~6 k cycles and bound the out-proj GEMM, whose main loop needs 2.6 k)
+      float4 base[8];
+      float* dst[8];
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + sub;
+          const int row = c.warp_row0 + r;
+          dst[i] = nullptr;
+          base[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < c.M) {
+            if (p.table != nullptr) {
+              const int img = row / p.patches, pp = row - img * p.patches;
+              dst[i] = p.x + (static_cast<size_t>(img) * (p.patches + 1) + 1 + pp) * p.ld + col;
+              base[i] = __ldg(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(1 + pp) * p.ld + col));
+            } else {
+              dst[i] = p.x + static_cast<size_t>(row) * p.ld + col;
+              base[i] = *reinterpret_cast<const float4*>(dst[i]);
+            }
+          }
+        }
+      }
       float v[32];
       tmem_ld_32x32(c.tmem_row + ch * 32, v);
       if (ch == nch - 1) release();
-      if (c.n0 + ch * 32 >= p.n_valid) continue;        // warp-uniform
+      if (!live) continue;
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         *reinterpret_cast<float4*>(st + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
       __syncwarp();
-      const int col = c.n0 + ch * 32 + chunk * 4;
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll 4
+#pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + sub;
-        const int row = c.warp_row0 + r;
-        if (row >= c.M) continue;
+        if (dst[i] == nullptr) continue;
         const float4 a = *reinterpret_cast<const float4*>(st + r * 32 + ((chunk ^ (r & 7)) << 2));
-        float4 base;
-        float* dst;
-        if (p.table != nullptr) {
-          const int img = row / p.patches, pp = row - img * p.patches;
-          dst = p.x + (static_cast<size_t>(img) * (p.patches + 1) + 1 + pp) * p.ld + col;
-          base = __ldg(reinterpret_cast<const float4*>(p.table + static_cast<size_t>(1 + pp) * p.ld + col));
-        } else {
-          dst = p.x + static_cast<size_t>(row) * p.ld + col;
-          base = *reinterpret_cast<const float4*>(dst);
-        }
-        *reinterpret_cast<float4*>(dst) = make_float4(base.x + a.x + b.x, base.y + a.y + b.y, base.z + a.z + b.z, base.w + a.w + b.w);
+        *reinterpret_cast<float4*>(dst[i]) = make_float4(base[i].x + a.x + b.x, base[i].y + a.y + b.y, base[i].z + a.z + b.z, base[i].w + a.w + b.w);
       }
     }
   }
@@ -423,6 +437,290 @@ __global__ void __launch_bounds__(kVaWarps * 32, 2) vit_attention_kernel(const V
     const int row = q0 + warp * 16 + r;
     if (row < T) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(row) * p.W + c * 8) = *reinterpret_cast<const uint4*>(so + r * kVaPitch + c * 8);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same attention on the 5th-generation tensor cores (default; the mma.sync kernel above is NOVIC_VIT_ATTN=mma).
+// One CTA = 128 queries of one (image, head), keys in tiles of 128:
+//   S = Q K^T   tcgen05.mma M = 128, N = 128, five k-slices of 16 channels (the 80-wide head = one 64-channel k-block + the first slice of
+//               the next; both operands K-major with the 128-byte swizzle straight from TMA boxes of the qkv rows) -> TMEM, two S buffers
+//   softmax     eight warps, thread = query row x 64 keys: the scores leave TMEM once (two loads in flight), 2^(s c - m c) with the scale folded in, bf16
+//               probabilities written as the K-major swizzled A operand of the second product, the O accumulator (TMEM) rescaled in
+//               place when the running maximum moved
+//   O += P V    tcgen05.mma M = 128, N = 80, eight k-slices over the tile's 128 keys; B = V^T rows [channel][key] (K-major), produced once
+//               per block by vit_vt_kernel from the v columns of qkv
+// Persistent CTAs (one per SM) walk the (image, head, query tile) items.  Warp 0 = TMA producer (three-stage K / V^T ring, running ahead
+// into the next item), warp 1 = TMEM allocator + MMA issuer (Q K^T of tile t + 1 is issued before P V of tile t,
+// so the tensor core computes the next scores while the softmax warps work), warps 2..9 = softmax / correction / epilogue (two warps per
+// scheduler: with one, every dependent instruction of the exponential chain waits out its own latency - 473 us against ... for this kernel).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTaQ = 128, kTaK = 128;
+constexpr int kTaStages = 3;                              // K / V^T ring: a tile's load (~2 k cycles) overlaps two tiles of work
+constexpr int kTaQBytes = 2 * kABytes;                    // Q: two k-blocks of 128 rows x 128 B
+constexpr int kTaKBytes = 2 * kABytes;                    // K tile: the same
+constexpr int kTaVBytes = 2 * kVitHeadDim * 128;          // V^T tile: two k-blocks (64 keys each) of 80 rows x 128 B
+constexpr int kTaPBytes = 2 * kABytes;                    // P: 128 rows x 128 keys bf16
+constexpr int kTaSmemBytes = kTaQBytes + kTaStages * (kTaKBytes + kTaVBytes) + kTaPBytes + 1024 /*align*/ + 256 /*barriers*/ + 3 * 2 * 128 * 4 /*row exchange*/;   // 224.3 KB
+constexpr int kTaSoftWarps = 8;                            // two per TMEM lane quadrant: each thread owns one query row x 64 of the tile's 128 keys
+constexpr int kTaThreads = 64 + 32 * kTaSoftWarps;
+
+struct VitAttnTcParams {
+  __nv_bfloat16* out;          // [images * T, W]
+  int T, W, heads, nimg;
+  float scale_log2e;
+};
+
+// V^T per image: vt[img][c][t] = qkv[img * T + t][2 W + c] (t < T; columns T .. Tpad - 1 stay zero).  64 x 64 tiles through shared memory.
+__global__ void __launch_bounds__(256) vit_vt_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt, int T, int W, int Tpad) {
+  __shared__ __nv_bfloat16 tile[64][64 + 2];
+  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64, img = blockIdx.z;
+  const __nv_bfloat16* src = qkv + static_cast<size_t>(img) * T * 3 * W + 2 * W + c0;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {      // 64 tokens x 32 channel pairs
+    const int r = i >> 5, cp = i & 31;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (t0 + r < T) v = *reinterpret_cast<const __nv_bfloat162*>(src + static_cast<size_t>(t0 + r) * 3 * W + cp * 2);
+    tile[r][cp * 2] = v.x;
+    tile[r][cp * 2 + 1] = v.y;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = vt + (static_cast<size_t>(img) * W + c0) * Tpad + t0;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {      // 64 channels x 32 token pairs
+    const int c = i >> 5, tp = i & 31;
+    *reinterpret_cast<__nv_bfloat162*>(dst + static_cast<size_t>(c) * Tpad + tp * 2) = __halves2bfloat162(tile[tp * 2][c], tile[tp * 2 + 1][c]);
+  }
+}
+
+__global__ void __launch_bounds__(kTaThreads, 1)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_vt, const VitAttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTaQBytes;                            // [kTaStages]
+  uint8_t* sV = sK + kTaStages * kTaKBytes;                // [kTaStages]
+  uint8_t* sP = sV + kTaStages * kTaVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kTaPBytes);
+  uint64_t* q_full = bars;                                 // 1
+  uint64_t* q_empty = bars + 1;                            // 1: every Q K^T of the item has been executed
+  uint64_t* kv_full = bars + 2;                            // kTaStages
+  uint64_t* kv_empty = bars + 2 + kTaStages;               // kTaStages
+  uint64_t* s_full = bars + 2 + 2 * kTaStages;             // 2
+  uint64_t* s_empty = s_full + 2;                          // 2
+  uint64_t* p_full = s_full + 4;                           // 1
+  uint64_t* p_empty = s_full + 5;                          // 1
+  uint64_t* o_full = s_full + 6;                           // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [3][2 halves][128 rows]: row maxima (two tile parities), row sums
+
+  const int warp = threadIdx.x >> 5, lane = static_cast<int>(lane_id());
+  const int T = p.T, W = p.W;
+  const int ntiles = (T + kTaK - 1) / kTaK;                // key tiles per item
+  const int qtiles = (T + kTaQ - 1) / kTaQ;
+  const int nitems = qtiles * p.heads * p.nimg;            // item = (image, head, query tile), query tile fastest: neighbours share K / V in L2
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_vt);
+      mbar_init(q_full, 1); mbar_init(q_empty, 1);
+      for (int i = 0; i < kTaStages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], kTaSoftWarps); }
+      mbar_init(p_full, kTaSoftWarps); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+      fence_mbar_init();
+    }
+  } else if (warp == 1) {
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColS = 0, kColO = 256;
+
+  // Persistent: CTA b walks items b, b + grid, ...; `it` counts this CTA's items, `g` its key tiles over all items (ring / buffer phases).
+  if (warp == 0) {
+    if (elect_one()) {
+      int g = 0, it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const int qt = item % qtiles, head = (item / qtiles) % p.heads, img = item / (qtiles * p.heads);
+        // Q: channels [head * 80, +128) of the image's token rows (rows >= T are out of bounds: zero)
+        mbar_wait(q_empty, (it & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(q_full, kTaQBytes);
+        tma_load_3d_at(sQ, &tm_qkv, q_full, head * kVitHeadDim, qt * kTaQ, img, kEvictNormal);
+        tma_load_3d_at(sQ + kABytes, &tm_qkv, q_full, head * kVitHeadDim + 64, qt * kTaQ, img, kEvictNormal);
+        for (int t = 0; t < ntiles; ++t, ++g) {
+          const int st = g % kTaStages;
+          mbar_wait(&kv_empty[st], ((g / kTaStages) & 1) ^ 1, 1);
+          mbar_arrive_expect_tx(&kv_full[st], kTaKBytes + kTaVBytes);
+          uint8_t* k = sK + st * kTaKBytes;
+          uint8_t* v = sV + st * kTaVBytes;
+          tma_load_3d_at(k, &tm_qkv, &kv_full[st], W + head * kVitHeadDim, t * kTaK, img, kEvictLast);
+          tma_load_3d_at(k + kABytes, &tm_qkv, &kv_full[st], W + head * kVitHeadDim + 64, t * kTaK, img, kEvictLast);
+          tma_load_3d_at(v, &tm_vt, &kv_full[st], t * kTaK, head * kVitHeadDim, img, kEvictLast);
+          tma_load_3d_at(v + kVitHeadDim * 128, &tm_vt, &kv_full[st], t * kTaK + 64, head * kVitHeadDim, img, kEvictLast);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t kIdescS = umma_idesc_bf16_f32(kTaQ, kTaK);
+      constexpr uint32_t kIdescO = umma_idesc_bf16_f32(kTaQ, kVitHeadDim);
+      // Q K^T of global tile gq (scores buffer gq & 1)
+      auto issue_qk = [&](int gq) {
+        const int st = gq % kTaStages, sb = gq & 1;
+        mbar_wait(&kv_full[st], (gq / kTaStages) & 1, 2);
+        mbar_wait(&s_empty[sb], ((gq >> 1) & 1) ^ 1, 3);           // the softmax warps have read the previous scores of this buffer
+        tc_fence_after_sync();
+        const uint32_t a = smem_u32(sQ), b = smem_u32(sK + st * kTaKBytes);
+        const uint32_t d = tmem_base + kColS + sb * kTaK;
+#pragma unroll
+        for (int k = 0; k < kVitHeadDim / kUmmaK; ++k) {            // 4 slices of k-block 0, 1 of k-block 1
+          const uint32_t off = (k >> 2) * kABytes + (k & 3) * (kUmmaK * 2);
+          umma_bf16_ss(d, umma_desc_sw128_kmajor(a + off), umma_desc_sw128_kmajor(b + off), kIdescS, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[sb]);
+      };
+      int g = 0, it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        mbar_wait(q_full, it & 1, 4);
+        issue_qk(g);
+        for (int t = 0; t < ntiles; ++t, ++g) {
+          const int st = g % kTaStages;
+          if (t + 1 < ntiles) issue_qk(g + 1);
+          else umma_commit(q_empty);                                // the item's last Q K^T has been issued: Q may be replaced once they are done
+          mbar_wait(p_full, g & 1, 5);                              // P(t) is in shared memory, O has been rescaled
+          tc_fence_after_sync();
+          const uint32_t a = smem_u32(sP), b = smem_u32(sV + st * kTaVBytes);
+#pragma unroll
+          for (int k = 0; k < kTaK / kUmmaK; ++k) {
+            const uint32_t offa = (k >> 2) * kABytes + (k & 3) * (kUmmaK * 2);
+            const uint32_t offb = (k >> 2) * (kVitHeadDim * 128) + (k & 3) * (kUmmaK * 2);
+            umma_bf16_ss(tmem_base + kColO, umma_desc_sw128_kmajor(a + offa), umma_desc_sw128_kmajor(b + offb), kIdescO, (t | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[st]);
+          umma_commit(p_empty);
+          if (t + 1 == ntiles) umma_commit(o_full);
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;                                      // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                               // which 64 of the tile's 128 keys (and which part of O) this warp handles
+    const int r = quad * 32 + lane;                                 // query row inside the tile
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float c = p.scale_log2e;
+    const int oc0 = half == 0 ? 0 : 3, oc1 = half == 0 ? 3 : kVitHeadDim / 16;   // 16-column chunks of O this warp rescales / stores
+    int g = 0, it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int qt = item % qtiles, head = (item / qtiles) % p.heads, img = item / (qtiles * p.heads);
+      const int q0 = qt * kTaQ;
+      float m_run = -INFINITY, l_run = 0.f;                          // l_run: this thread's 64 columns only; the halves are added at the end
+      for (int t = 0; t < ntiles; ++t, ++g) {
+        const int sb = g & 1;
+        const int kbase = t * kTaK + half * 64;
+        mbar_wait(&s_full[sb], (g >> 1) & 1, 6);
+        tc_fence_after_sync();
+        const uint32_t srow = tlane + kColS + sb * kTaK + half * 64;
+        float v[2][32];
+        tmem_ld_32x32_nowait(srow, v[0]);
+        tmem_ld_32x32_nowait(srow + 32, v[1]);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);                   // the scores are in registers: the buffer may be overwritten
+        if (kbase + 64 > T) {                                       // ragged last tile (warp-uniform): keys past the sequence get no weight
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (kbase + ch * 32 + j >= T) v[ch][j] = -INFINITY;
+        }
+        float m8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          m8[i] = fmaxf(fmaxf(fmaxf(v[0][i], v[0][i + 8]), fmaxf(v[0][i + 16], v[0][i + 24])), fmaxf(fmaxf(v[1][i], v[1][i + 8]), fmaxf(v[1][i + 16], v[1][i + 24])));
+        float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        // row maximum over both halves (the other half's thread of this row lives in warp +- 4)
+        float* xm = xch + (g & 1) * 256;
+        xm[half * 128 + r] = mx;
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        mx = fmaxf(mx, xm[(half ^ 1) * 128 + r]);
+        const float m_new = fmaxf(m_run, mx * c);                   // finite: key 0 of every tile is valid
+        const float corr = ex2_approx(m_run - m_new);
+        m_run = m_new;
+        float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[ch][j] = ex2_approx(fmaf(v[ch][j], c, -m_new));
+            s8[j & 7] += v[ch][j];
+          }
+        // the previous P has been consumed (and, inside an item, O is complete) once the previous P V has been committed
+        if (g > 0) mbar_wait(p_empty, (g - 1) & 1, 7);
+        tc_fence_after_sync();
+        if (t > 0 && __any_sync(0xffffffffu, corr != 1.0f)) {
+#pragma unroll 1
+          for (int ch = oc0; ch < oc1; ++ch) {
+            float ov[16];
+            tmem_ld_32x16(tlane + kColO + ch * 16, ov);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ov[j] *= corr;
+            tmem_st_32x16(tlane + kColO + ch * 16, ov);
+          }
+          tmem_st_wait();
+        }
+        // bf16 -> K-major swizzled operand rows: this thread's 64 keys are exactly k-block `half` of its row
+        uint8_t* prow = sP + half * kABytes + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ch * 4 + q;
+            *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) =
+                make_uint4(pack_bf16x2(v[ch][q * 8 + 0], v[ch][q * 8 + 1]), pack_bf16x2(v[ch][q * 8 + 2], v[ch][q * 8 + 3]),
+                           pack_bf16x2(v[ch][q * 8 + 4], v[ch][q * 8 + 5]), pack_bf16x2(v[ch][q * 8 + 6], v[ch][q * 8 + 7]));
+          }
+        l_run = l_run * corr + (((s8[0] + s8[4]) + (s8[1] + s8[5])) + ((s8[2] + s8[6]) + (s8[3] + s8[7])));
+        fence_proxy_async_smem();                                   // P rows -> visible to the tensor core's shared-memory reads
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // epilogue: O / l -> bf16 -> rows staged in the (consumed) P region -> 16-byte stores
+      float* xl = xch + 512;
+      xl[half * 128 + r] = l_run;
+      mbar_wait(o_full, it & 1, 8);
+      tc_fence_after_sync();
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
+      const float inv = 1.0f / (l_run + xl[(half ^ 1) * 128 + r]);
+      __nv_bfloat16* so = reinterpret_cast<__nv_bfloat16*>(sP) + r * (kVitHeadDim + 8);
+#pragma unroll 1
+      for (int ch = oc0; ch < oc1; ++ch) {
+        float ov[16];
+        tmem_ld_32x16(tlane + kColO + ch * 16, ov);
+        *reinterpret_cast<uint4*>(so + ch * 16) = make_uint4(pack_bf16x2(ov[0] * inv, ov[1] * inv), pack_bf16x2(ov[2] * inv, ov[3] * inv),
+                                                             pack_bf16x2(ov[4] * inv, ov[5] * inv), pack_bf16x2(ov[6] * inv, ov[7] * inv));
+        *reinterpret_cast<uint4*>(so + ch * 16 + 8) = make_uint4(pack_bf16x2(ov[8] * inv, ov[9] * inv), pack_bf16x2(ov[10] * inv, ov[11] * inv),
+                                                                 pack_bf16x2(ov[12] * inv, ov[13] * inv), pack_bf16x2(ov[14] * inv, ov[15] * inv));
+      }
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");                 // both halves of every row are staged
+      // each warp copies 16 rows: 16 rows x 10 chunks of 16 B
+      constexpr int kChunks = kVitHeadDim / 8;
+      __nv_bfloat16* dst = p.out + static_cast<size_t>(img) * T * W + head * kVitHeadDim;
+      const int row0 = quad * 32 + half * 16;
+      const __nv_bfloat16* sw = reinterpret_cast<const __nv_bfloat16*>(sP) + row0 * (kVitHeadDim + 8);
+      for (int i = lane; i < 16 * kChunks; i += 32) {
+        const int rr = i / kChunks, cc = i - rr * kChunks;
+        const int row = q0 + row0 + rr;
+        if (row < T) *reinterpret_cast<uint4*>(dst + static_cast<size_t>(row) * W + cc * 8) = *reinterpret_cast<const uint4*>(sw + rr * (kVitHeadDim + 8) + cc * 8);
+      }
+      // the staging rows overlap the P rows of other warps: nobody writes the next item's P before everyone has copied
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // embed[b, :] /= ||embed[b, :]|| (fp32; embedders.py:764).  One warp per row.
