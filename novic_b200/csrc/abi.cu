@@ -116,6 +116,7 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
+bool g_fuse_qkv = false;                       // NOVIC_FUSE_QKV=1: layer l + 1's QKV projection in the tail of layer l's block kernel (bit-identical; measured 0.2-0.3 ms per decode slower than its own launch)
 bool g_attn_tf = true;                         // NOVIC_ATTN_TF=0: teacher-forced passes use the key-by-key bulk kernel instead of attention_tf_kernel
 int g_attn_hint = 1;                           // NOVIC_ATTN_HINT bit 0: evict-first L2 policy on the streamed K/V rows; bit 1: evict-last on new K/V rows
 int g_row_stages = 4;                          // NOVIC_ROW_STAGES=2|3: shallower row-kernel pipelines (tuning: co-residency with the next kernel)
@@ -124,6 +125,7 @@ bool g_early_b = true;                         // NOVIC_EARLY_B=0: no weight-til
 bool g_wide_gemm = true;                       // NOVIC_WIDE_GEMM=0: the 16 KB-request pipeline (5 stages of one k-block)
 constexpr int kWideKbs = 2, kWideStages = 3;   // decode-path QKV / logits GEMMs: 3 stages of 2 k-blocks, 32 KB TMA requests
 int g_num_sms = 148;
+int g_logits_bn = 256;                         // NOVIC_LOGITS_BN=128: the logits GEMM on 128 x 128 tiles everywhere
 int g_grid_div = 1;   // persistent grids are divided by the number of concurrent chains so that chains co-run on disjoint SMs
 constexpr int kLogitBN = kTileN;
 
@@ -205,11 +207,11 @@ int launch_ffn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tw1, co
 }
 
 // Attention output -> next LayerNorm rows in one cluster kernel (out-proj + LN2 + feed-forward + LN), decode path.
-int launch_outproj_ffn(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1q, const CUtensorMap& tw2, int M,
-                       const FusedBlockParams& ep) {
+int launch_outproj_ffn(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1q, const CUtensorMap& tw2,
+                       const CUtensorMap& twqkv, int M, const FusedBlockParams& ep) {
   static_assert(outproj_ffn_smem_bytes() <= 227 * 1024, "fused block kernel does not fit in shared memory");
   dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kBlockM)));
-  CUDA_TRY(launch_k(outproj_ffn_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1q, tw2, M, ep));
+  CUDA_TRY(launch_k(outproj_ffn_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1q, tw2, twqkv, M, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -302,6 +304,7 @@ struct WeightPtrs {
   const float *tok_f32, *pos, *final_norm, *norm1[NOVIC_MAX_LAYERS], *norm2[NOVIC_MAX_LAYERS];
   CUtensorMap tm_linear1_q[NOVIC_MAX_LAYERS];            // linear1 with a 32-row box (split-hidden feed-forward kernel)
   CUtensorMap tm_tok3, tm_in_proj3[NOVIC_MAX_LAYERS];   // 3-D maps (kWideKbs k-blocks per request) for the wide-stage decode GEMMs
+  CUtensorMap tm_tok3w;                                   // the tied matrix with 256-row boxes (128 x 256 logits tiles)
   CUtensorMap tm_embed_mlp, tm_tok, tm_in_proj[NOVIC_MAX_LAYERS], tm_out_proj[NOVIC_MAX_LAYERS], tm_linear1[NOVIC_MAX_LAYERS],
       tm_linear2[NOVIC_MAX_LAYERS];
   // transposed bf16 copies (B operands of the backward dgrad GEMMs: dX = dY * W needs W^T in K-major form)
@@ -514,30 +517,38 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   CUtensorMap tm_xn3;
   if (make_tmap3(&tm_xn3, ws.xn, M, kE, kBlockM, kWideKbs)) return 1;
   const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
-  for (int l = 0; l < L; ++l) {
+  const bool block_fused = g_fuse_block && h->fuse_ffn && c.ffn_dim == kFfnDim;
+  const bool qkv_tail = block_fused && g_fuse_qkv && g_wide_gemm;     // layer l + 1's QKV projection in the tail of layer l's block kernel
+  auto qkv_params = [&](int l) {
     __nv_bfloat16* kc = ws.kv + (static_cast<size_t>(l) * 2 + 0) * kv_layer;
     __nv_bfloat16* vc = ws.kv + (static_cast<size_t>(l) * 2 + 1) * kv_layer;
-    EpiQKV::Params pq{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S, (g_attn_hint & 2) ? 1 : 0};
-    if (g_wide_gemm) {
-      KSpan t(kKQkv, s);
-      if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
-    } else {
-      KSpan t(kKQkv, s);
-      if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+    return EpiQKV::Params{ws.q, kc, vc, pc.nq, pc.q0, pc.slot_mul, S, (g_attn_hint & 2) ? 1 : 0};
+  };
+  for (int l = 0; l < L; ++l) {
+    if (l == 0 || !qkv_tail) {
+      const EpiQKV::Params pq = qkv_params(l);
+      if (g_wide_gemm) {
+        KSpan t(kKQkv, s);
+        if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+      } else {
+        KSpan t(kKQkv, s);
+        if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+      }
     }
     if (launch_attention(h, ws, pc, l, s)) return 1;
-    if (g_fuse_block && h->fuse_ffn && c.ffn_dim == kFfnDim) {
+    if (block_fused) {
       FusedBlockParams fb{};
       fb.x = ws.x; fb.gain_mid = h->w.norm2[l]; fb.eps = c.ln_eps;
       if (l + 1 < L) {
         fb.xn = ws.xn; fb.gain_out = h->w.norm1[l + 1];
+        if (qkv_tail) { fb.qkv_tail = 1; fb.qkv = qkv_params(l + 1); }
       } else {
         fb.gain_out = h->w.final_norm;
         fb.xn = pc.remap_in > 0 ? ws.xfin : ws.xn;
         fb.remap_rows_in = pc.remap_in; fb.remap_skip = pc.remap_skip; fb.remap_rows_out = pc.remap_out;
       }
       KSpan t(kKFfn2, s);
-      if (launch_outproj_ffn(s, tm_ao, h->w.tm_out_proj[l], h->w.tm_linear1_q[l], h->w.tm_linear2[l], M, fb)) return 1;
+      if (launch_outproj_ffn(s, tm_ao, h->w.tm_out_proj[l], h->w.tm_linear1_q[l], h->w.tm_linear2[l], h->w.tm_in_proj3[l + 1 < L ? l + 1 : l], M, fb)) return 1;
       continue;
     }
     RowParams po{};
@@ -608,6 +619,13 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
   pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
   pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.allow_mod = allow_mod; pl.mask_lse = mask_lse ? 1 : 0;
   KSpan t(kKLogits, s);
+  if constexpr (HCAP == 0 && !MASKED && !BIAS) {
+    // 128 x 256 tiles (0.75 of the operand bytes per FLOP): the plain arg-max / log-sum-exp epilogue of greedy decoding and teacher forcing.
+    // Needs the same number of 64-column slices per row as the 128-column tiling the workspace was planned for, and at least a wave of tiles.
+    const int V = h->cfg.vocab_size;
+    if (g_wide_gemm && g_logits_bn == 256 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
+      return launch_gemm<EpiLogits<0, false, false>, 2, kWideKbs, 256>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b);
+  }
   if (g_wide_gemm) return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kWideStages, kWideKbs>(s, tm_a, h->w.tm_tok3, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
   return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
 }
@@ -860,7 +878,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -901,12 +919,14 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 4)));
   if (const char* e12 = getenv("NOVIC_ATTN_CFG")) h->attn_cfg = atoi(e12);
   if (const char* e14 = getenv("NOVIC_WIDE_GEMM")) g_wide_gemm = e14[0] != '0';
+  if (const char* e21 = getenv("NOVIC_LOGITS_BN")) g_logits_bn = atoi(e21);
   if (const char* e15 = getenv("NOVIC_EARLY_B")) g_early_b = e15[0] != '0';
   if (const char* e16 = getenv("NOVIC_SPLIT_FFN")) g_split_ffn = e16[0] != '0';
   if (const char* e17 = getenv("NOVIC_ROW_STAGES")) g_row_stages = atoi(e17);
   if (const char* e18 = getenv("NOVIC_ATTN_HINT")) g_attn_hint = atoi(e18);
   if (const char* e19 = getenv("NOVIC_ATTN_TF")) g_attn_tf = atoi(e19) != 0;
   if (const char* e22 = getenv("NOVIC_FUSE_BLOCK")) g_fuse_block = e22[0] != '0';
+  if (const char* e23 = getenv("NOVIC_FUSE_QKV")) g_fuse_qkv = e23[0] != '0';
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';
@@ -1051,6 +1071,7 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
   if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, kRowBN)) return 1;
   if (make_tmap(&o.tm_tok, o.tok, V, E, kLogitBN)) return 1;
   if (make_tmap3(&o.tm_tok3, o.tok, V, E, kLogitBN, kWideKbs)) return 1;
+  if (make_tmap3(&o.tm_tok3w, o.tok, V, E, 256, kWideKbs)) return 1;
   for (size_t l = 0; l < L; ++l) {
     if (make_tmap(&o.tm_in_proj[l], o.in_proj[l], 3 * E, E, 128)) return 1;
     if (make_tmap3(&o.tm_in_proj3[l], o.in_proj[l], 3 * E, E, 128, kWideKbs)) return 1;

@@ -210,8 +210,23 @@ struct EpiLogits {
     const float* bias;          // BIAS: [num_edges]
     float tau;
   };
+  // A thread owns c.ncols = 64 columns (128-column tiles) or 128 (256-column tiles): one 64-column vocabulary slice at a time, each with
+  // its own partial record; the accumulator stage is released after the last load of the last slice.
   template <class Release>
-  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
+  __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c0, Release release) {
+    const int nslices = c0.ncols / kLogitSlice;
+#pragma unroll 1
+    for (int sl = 0; sl < nslices; ++sl) {
+      EpiCtx c = c0;
+      c.tmem_row = c0.tmem_row + sl * kLogitSlice;
+      c.n0 = c0.n0 + sl * kLogitSlice;
+      c.part = c0.part + sl;
+      if (sl == nslices - 1) slice(p, c, release);
+      else slice(p, c, []() {});
+    }
+  }
+  template <class Release>
+  __device__ static __forceinline__ void slice(const Params& p, const EpiCtx& c, Release release) {
     constexpr float kLog2e = 1.4426950408889634f;
     float m = -INFINITY, s_tau = 0.f, s_one = 0.f, sum_x = 0.f, best = -INFINITY, tgt_logit = -INFINITY;
     float m_t = -INFINITY;       // MASKED: running max of the temperature softmax's support
@@ -595,7 +610,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       c.n0 = nt * kTileN + half * (kTileN / 2);
       c.ncols = kTileN / 2;
       c.M = M;
-      c.part = nt * 2 + half;
+      c.part = (nt * 2 + half) * (kTileN / 128);   // index of the thread's first 64-column slice
       c.stage = epi_stage + ew * kEpiStageBytes;
       uint64_t* rel = &tmem_empty_bar[as];
       Epi::run(ep, c, [rel, lane]() {
@@ -987,11 +1002,13 @@ struct FusedBlockParams {
   const float* gain_out;    // weight of the LayerNorm that follows the block
   int remap_rows_in, remap_skip, remap_rows_out;   // xn row remap of the last layer (0 = identity)
   float eps;
+  int qkv_tail;             // != 0: the NEXT layer's QKV projection runs in the kernel's tail (tmap_wqkv / qkv are valid; xn is not written)
+  EpiQKV::Params qkv;       // q buffer and the next layer's K / V cache pages
 };
 
 __global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kRowThreads, 1)
 outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1q,
-                   const __grid_constant__ CUtensorMap tmap_w2, int M, FusedBlockParams ep) {
+                   const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_wqkv, int M, FusedBlockParams ep) {
   constexpr int BN = kRowBN;
   constexpr int kHSplit = kFfnDim / kRowCluster;              // 32 hidden columns per CTA
   constexpr int kW1kb = kHSplit * kBlockK * 2;                // bytes of one k-block of the W1 slice: 4 KB
@@ -1015,8 +1032,13 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   uint64_t* affn_full = tmem_full0 + 5;                       // the three peers' LN2 slices have landed in this CTA's FFN1 operand
   uint64_t* hx_full = tmem_full0 + 6;                         // the three peers' hidden-column slices have landed in the h region
   uint64_t* hop_ready = tmem_full0 + 7;                       // the epilogue warps have assembled the FFN2 A operand
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 8);
-  static_assert((2 * kFbStages + 8) * 8 + 4 <= 256, "barrier area");
+  // QKV tail (the next layer's projection; ep.qkv_tail)
+  uint64_t* aq_full = tmem_full0 + 8;                         // the three peers' LayerNorm slices have landed in this CTA's QKV A operand
+  uint64_t* bq_full = tmem_full0 + 9;                         // [2] in_proj weight stages (two k-blocks of one 128-row tile each)
+  uint64_t* bq_empty = tmem_full0 + 11;                       // [2]
+  uint64_t* tmem_full_q = tmem_full0 + 13;                    // [3] one per 128-column output tile of this CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 16);
+  static_assert((2 * kFbStages + 16) * 8 + 4 <= 256, "barrier area");
   constexpr int kHSlice = kBlockM * kHSplit * 2;              // one CTA's hidden columns: 128 rows x 64 B = 8 KB
   float* s_gain_mid = reinterpret_cast<float*>(after + 256);
   float* s_gain_out = s_gain_mid + BN;
@@ -1040,12 +1062,16 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1q); tma_prefetch_desc(&tmap_w2);
+      if (ep.qkv_tail) tma_prefetch_desc(&tmap_wqkv);
       for (int st = 0; st < kFbStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
       mbar_init(tmem_full0, 1); mbar_init(w1_full, 1); mbar_init(w2_full, 1); mbar_init(tmem_full1, 1); mbar_init(tmem_full2, 1);
       mbar_init(affn_full, 1); mbar_init(hx_full, 1); mbar_init(hop_ready, kRowEpiWarps);
+      mbar_init(aq_full, 1); mbar_init(&bq_full[0], 1); mbar_init(&bq_full[1], 1); mbar_init(&bq_empty[0], 1); mbar_init(&bq_empty[1], 1);
+      mbar_init(&tmem_full_q[0], 1); mbar_init(&tmem_full_q[1], 1); mbar_init(&tmem_full_q[2], 1);
       fence_mbar_init();
       mbar_arrive_expect_tx(affn_full, (kRowCluster - 1) * 2 * kABytes);   // the peers' copies can only start after cluster barrier #1
       mbar_arrive_expect_tx(hx_full, (kRowCluster - 1) * kHSlice);
+      if (ep.qkv_tail) mbar_arrive_expect_tx(aq_full, (kRowCluster - 1) * 2 * kABytes);   // ... and these after barrier #4
       // all weights first (they do not depend on the previous kernel), then wait, then the activation tiles
       for (int kb = 0; kb < kFbStages; ++kb) {
         mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
@@ -1276,52 +1302,143 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   __syncwarp();
   cluster_sync_all();       // #4
   if (threadIdx.x == 64) trace_point(tr, 12);
-  if (is_epi) {
-    float mean = 0.f, rstd = 0.f;
-    s_stats = reinterpret_cast<float2*>(w2_smem);
-    if (row < M) gather_stats(mean, rstd);
-    uint8_t* stage = ring + ew * (32 * kRowStagePitch);      // the FFN1 operand is dead: every CTA's phase-B MMAs completed before #3
-    {
-      uint4* d = reinterpret_cast<uint4*>(stage + lane * kRowStagePitch);
+  if (!ep.qkv_tail) {
+    if (is_epi) {
+      float mean = 0.f, rstd = 0.f;
+      s_stats = reinterpret_cast<float2*>(w2_smem);
+      if (row < M) gather_stats(mean, rstd);
+      uint8_t* stage = ring + ew * (32 * kRowStagePitch);      // the FFN1 operand is dead: every CTA's phase-B MMAs completed before #3
+      {
+        uint4* d = reinterpret_cast<uint4*>(stage + lane * kRowStagePitch);
+#pragma unroll
+        for (int q = 0; q < kRowCols / 8; ++q) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain_out[half * kRowCols + q * 8 + i];
+          d[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        }
+      }
+      if (row < M) {
+#pragma unroll
+        for (int q = 0; q < kRowCols / 4; ++q)
+          *reinterpret_cast<float4*>(ep.x + xblk_off(row, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+      }
+      __syncwarp();
+      const int warp_row0 = m0 + quad * 32;
+      const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 4
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + sub;
+        const int grow = warp_row0 + rr;
+        if (grow < M) {
+          int nrow = grow;
+          bool keep = true;
+          if (ep.remap_rows_in > 0) {
+            const int seq = grow / ep.remap_rows_in;
+            const int k = grow - seq * ep.remap_rows_in;
+            keep = k >= ep.remap_skip;
+            nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+          }
+          if (keep)
+            *reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + c0 + chunk * 8) =
+                *reinterpret_cast<const uint4*>(stage + rr * kRowStagePitch + chunk * 16);
+        }
+      }
+    }
+    if (threadIdx.x == 64) trace_point(tr, 13);
+  } else {
+    // ---- QKV tail: the next layer's LayerNorm rows become the A operand of its in_proj GEMM without leaving the cluster.
+    // Same hand-over as for LN2 above: every thread writes its 128-byte row of k-block (2 * rank + half) into the local operand buffer (the
+    // ring, dead since phase B), one thread pushes the CTA's two k-block tiles to the peers.  The CTA then computes output columns
+    // [384 * rank, +384) of q | k | v: three 128-column tiles, accumulators in TMEM columns 0 / 128 / 256 (all consumed by now), weight tiles
+    // streamed as 32 KB requests (two k-blocks) through two stages that live in the dead W1 and h regions; the dead W2 region is the
+    // epilogue's staging memory.  The products are accumulated in the same order as gemm_kernel<EpiQKV> does: results are bit-identical.
+    uint8_t* bstage[2] = {w1_smem, h_smem};
+    if (is_epi) {
+      float mean = 0.f, rstd = 0.f;
+      s_stats = reinterpret_cast<float2*>(w2_smem);
+      if (row < M) gather_stats(mean, rstd);
+      const int kb = static_cast<int>(crank) * 2 + half;
+      uint8_t* arow = ring + kb * kABytes + row_in_tile * 128;
 #pragma unroll
       for (int q = 0; q < kRowCols / 8; ++q) {
         float y[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain_out[half * kRowCols + q * 8 + i];
-        d[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+        *reinterpret_cast<uint4*>(arow + ((q ^ (row_in_tile & 7)) << 4)) =
+            make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+      fence_proxy_async_smem();
+      if (row < M) {
+#pragma unroll
+        for (int q = 0; q < kRowCols / 4; ++q)
+          *reinterpret_cast<float4*>(ep.x + xblk_off(row, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
       }
     }
-    if (row < M) {
+    __syncthreads();
+    if (threadIdx.x == 64) trace_point(tr, 13);
+    constexpr int kQTiles = 3 * kE / (kRowCluster * kTileN);    // 3 output tiles per CTA
+    constexpr int kQLoads = kQTiles * (kNkb / 2);               // 12 weight requests of two k-blocks
+    if (warp == 0) {
+      if (elect_one()) {
+        const uint8_t* src = ring + static_cast<int>(crank) * 2 * kABytes;
 #pragma unroll
-      for (int q = 0; q < kRowCols / 4; ++q)
-        *reinterpret_cast<float4*>(ep.x + xblk_off(row, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        for (uint32_t d = 1; d < kRowCluster; ++d) {
+          const uint32_t pr = (crank + d) % kRowCluster;
+          dsmem_bulk_copy(dsmem_addr(src, pr), src, 2 * kABytes, dsmem_addr(aq_full, pr));
+        }
+        for (int i = 0; i < kQLoads; ++i) {
+          const int st = i & 1;
+          mbar_wait(&bq_empty[st], ((i >> 1) & 1) ^ 1, 1);
+          mbar_arrive_expect_tx(&bq_full[st], 2 * kBBytes);
+          tma_load_3d(bstage[st], &tmap_wqkv, &bq_full[st], static_cast<int>(crank) * (kQTiles * kTileN) + (i / (kNkb / 2)) * kTileN, (i % (kNkb / 2)) * 2, kEvictLast);
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        mbar_wait(aq_full, 0, 5);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(ring);
+        for (int nt = 0; nt < kQTiles; ++nt) {
+          for (int kp = 0; kp < kNkb / 2; ++kp) {
+            const int i = nt * (kNkb / 2) + kp, st = i & 1;
+            mbar_wait(&bq_full[st], (i >> 1) & 1, 2);
+            tc_fence_after_sync();
+            const uint32_t sb = smem_u32(bstage[st]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16_ss(tmem_base + nt * kTileN, umma_desc_sw128_kmajor(sa + (kp * 2 + j) * kABytes + k * (kUmmaK * 2)),
+                             umma_desc_sw128_kmajor(sb + j * kBBytes + k * (kUmmaK * 2)), kIdesc, (kp | j | k) != 0 ? 1u : 0u);
+            umma_commit(&bq_empty[st]);
+          }
+          umma_commit(&tmem_full_q[nt]);
+        }
+      }
     }
     __syncwarp();
-    const int warp_row0 = m0 + quad * 32;
-    const int sub = lane >> 3, chunk = lane & 7;
-#pragma unroll 4
-    for (int i = 0; i < 8; ++i) {
-      const int rr = i * 4 + sub;
-      const int grow = warp_row0 + rr;
-      if (grow < M) {
-        int nrow = grow;
-        bool keep = true;
-        if (ep.remap_rows_in > 0) {
-          const int seq = grow / ep.remap_rows_in;
-          const int k = grow - seq * ep.remap_rows_in;
-          keep = k >= ep.remap_skip;
-          nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
-        }
-        if (keep)
-          *reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + c0 + chunk * 8) =
-              *reinterpret_cast<const uint4*>(stage + rr * kRowStagePitch + chunk * 16);
+    if (is_epi) {
+      for (int nt = 0; nt < kQTiles; ++nt) {
+        mbar_wait(&tmem_full_q[nt], 0, 9);
+        tc_fence_after_sync();
+        EpiCtx c;
+        c.tmem_row = tmem_lane + nt * kTileN + half * kEpiCols;
+        c.warp_row0 = m0 + quad * 32;
+        c.row = c.warp_row0 + lane;
+        c.n0 = static_cast<int>(crank) * (kQTiles * kTileN) + nt * kTileN + half * kEpiCols;
+        c.ncols = kEpiCols;
+        c.M = M;
+        c.part = 0;
+        c.stage = w2_smem + ew * kEpiStageBytes;
+        EpiQKV::run(ep.qkv, c, []() {});
       }
     }
+    if (threadIdx.x == 64) trace_point(tr, 15);
   }
-  if (threadIdx.x == 64) trace_point(tr, 13);
   tc_fence_before_sync();
   __syncwarp();
-  cluster_sync_relaxed();   // peers may still be reading this CTA's statistics
+  cluster_sync_relaxed();   // peers may still be reading this CTA's statistics / operand tiles
   if (threadIdx.x == 0) trace_point(tr, 14);
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }

@@ -418,7 +418,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attention_stream_kernel_t(const
     }
   };
 
-  // chunks other than an item's last hold only rows written by earlier decode steps: safe to request before the wait
+  // chunks other than an item's last hold only rows written by earlier decode steps: safe to request before the wait, because
+  // select_greedy_kernel releases its dependents only after its own wait (no kernel of this step started before the previous step,
+  // and with it the prefix pass, had completed)
   int issued = 0;
   if (p.early_loads == 1 && contiguous && nchunks >= 2) {
     const int early = min(min(nloads, kAsSlots), nchunks >= 3 ? 3 : 2);
@@ -694,8 +696,12 @@ select_greedy_kernel(const LogitPartial* __restrict__ part, int ntiles, int B, i
                      float inv_tau, float label_smoothing, GreedyState st, const float* __restrict__ wtok,
                      const float* __restrict__ pos_next, const float* __restrict__ gain0, float* __restrict__ x,
                      __nv_bfloat16* __restrict__ xn, float eps, GuideTrie guide, int* __restrict__ guide_node) {
-  pdl_trigger();
+  // Wait BEFORE releasing the dependents: this kernel is the fence of a decode step.  Every other kernel releases its dependent at
+  // entry, so with small grids a chain of prologues can run many launches ahead of the kernel that is actually executing; the
+  // attention kernel's early K/V requests (rows written by earlier decode steps, issued before its own wait) are only safe because no
+  // kernel of step t + 1 starts before this wait has passed, i.e. before every kernel of step t has completed.
   pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (b >= B) return;
   const bool guided = guide_node != nullptr;

@@ -344,3 +344,34 @@ def test_forward_without_targets_is_the_first_step(models):
     assert lg.shape == (12, 1, cfg.vocab_size) and pad is None and ls is None and lb is None and cor is None
     assert (lg.cpu() - o).abs().max().item() <= 0.06
     assert (lg[:, 0] - g[2][:, 0]).abs().max().item() <= 1e-3          # same kernels, prefill path vs decode path
+
+
+@pytest.mark.gpu
+def test_qkv_tail_of_the_block_kernel_is_bit_identical(monkeypatch):
+    """The next layer's QKV projection in the tail of the fused block kernel (opt-in, NOVIC_FUSE_QKV=1: measured slower than the
+    stand-alone launches) against the stand-alone QKV GEMM launches (default): same operands, same accumulation
+    order -> bit-identical ids, scores, logits, for greedy (ragged batch: the last 128-row block is partial), beam search and the
+    teacher-forced forward.  The small graph-replayed batches are the regression case of the decode step's launch fence: with a
+    few CTAs per kernel a whole step's prologues fit on the GPU at once, and the attention kernel's early K/V requests read rows of
+    the prefix pass before it had finished until select_greedy_kernel was made to wait before releasing its dependents."""
+    dims = synth.DecoderDims()
+    sd = weight_case("eos")
+    embed = synth.synth_embeddings(300, seed=5).to(DEV)
+    tgt, pad = synth.synth_targets(40, dims, seed=3)
+    outs = []
+    for flag in ("0", "1"):                      # the switch is read when a handle is created
+        monkeypatch.setenv("NOVIC_FUSE_QKV", flag)
+        m = default_decoder(dims, sd).to(DEV)
+        with torch.inference_mode():
+            g = m.generate(embed, True, True, 0.9, 0.2, None, None, False)
+            b = m.generate_beam(embed[:64], 3, 1.0, 0.0, None, False, 0.0, None, False)
+            f = m(embed[:40], tgt.to(DEV), pad.to(DEV), None, True, True, False, None)
+            small = [m.generate(embed[:n], False, True, 1.0, 0.0, None, None, False) for n in (1, 2, 5, 31, 33) for _ in range(2)]
+        outs.append((g, b, f, small))
+        del m
+    (g0, b0, f0, s0), (g1, b1, f1, s1) = outs
+    for a, c in zip(s0, s1):
+        assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[5], c[5])
+    assert torch.equal(g0[0], g1[0]) and torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2]) and torch.equal(g0[5], g1[5])
+    assert torch.equal(b0[0], b1[0]) and torch.equal(b0[2], b1[2])
+    assert torch.equal(f0[0], f1[0]) and f0[2].item() == f1[2].item() and torch.equal(f0[4], f1[4])
