@@ -467,7 +467,10 @@ def main():
             sampler.wait_started()
             sampler.mark()
         total_ms, launches, out, dev_steps = timed(step_device, args.steps)
-        e2e_ms, out_host = run_e2e(args.steps)
+        # three passes of exactly K steps each; the median pass is reported (all three are in e2e.runs_ms): one host hiccup in a 60 ms
+        # loop (page-in after the previous process, a scheduler tick) otherwise decides the headline
+        e2e_runs = [run_e2e(args.steps) for _ in range(3)]
+        e2e_ms, out_host = sorted(e2e_runs, key=lambda r: r[0])[1]
         clocks = sampler.stop() if sampler else None
         tok = out[0]
         assert tok.shape[0] == B * world and tok.shape[-1] == G
@@ -624,7 +627,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "runs_ms": [round(r[0], 3) for r in e2e_runs],
                     "h2d_bytes_per_step": B * dims.embed_dim * 4, "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in out_host)),
                     "api": "novic_b200.serve.GenerationPipeline.run (double-buffered H2D / D2H around PrefixedIterDecoder.generate; per-rank H2D, rank 0 reads the gathered result)"},
             "gpu_launches": int(launches), "roofline": roofline,

@@ -116,6 +116,10 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
+int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
+int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 = 64-row tiles in the fused block kernel up to kBlock64MaxRows rows, 128-row tiles above; 64 / 128 = always
+constexpr int kBlock64MaxRows = 1536;
+int g_qkv_bn = 128;                            // NOVIC_QKV_BN=256: 128 x 256 tiles in the QKV GEMM when they fill a wave
 bool g_fuse_qkv = false;                       // NOVIC_FUSE_QKV=1: layer l + 1's QKV projection in the tail of layer l's block kernel (bit-identical; measured 0.2-0.3 ms per decode slower than its own launch)
 bool g_attn_tf = true;                         // NOVIC_ATTN_TF=0: teacher-forced passes use the key-by-key bulk kernel instead of attention_tf_kernel
 int g_attn_hint = 1;                           // NOVIC_ATTN_HINT bit 0: evict-first L2 policy on the streamed K/V rows; bit 1: evict-last on new K/V rows
@@ -173,6 +177,8 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn_smem_bytes()));
+  CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn64_smem_bytes() + 16384));
+  CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM need all of it
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
@@ -212,6 +218,16 @@ int launch_outproj_ffn(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap
   static_assert(outproj_ffn_smem_bytes() <= 227 * 1024, "fused block kernel does not fit in shared memory");
   dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kBlockM)));
   CUDA_TRY(launch_k(outproj_ffn_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1q, tw2, twqkv, M, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// The same block on 64-row tiles, two CTAs per SM (outproj_ffn64_kernel); all four maps are 3-D (tao: 64 rows x 2 k-blocks).
+int launch_outproj_ffn64(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1q, const CUtensorMap& tw2, int M,
+                         const FusedBlockParams& ep) {
+  dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kHbRows)));
+  CUDA_TRY(launch_k(outproj_ffn64_kernel, grid, dim3(kHbThreads), outproj_ffn64_smem_bytes() + g_block64_pad, s, tao, two, tw1q, tw2, M, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -303,8 +319,12 @@ struct WeightPtrs {
   const __nv_bfloat16 *in_proj[NOVIC_MAX_LAYERS], *out_proj[NOVIC_MAX_LAYERS], *linear1[NOVIC_MAX_LAYERS], *linear2[NOVIC_MAX_LAYERS];
   const float *tok_f32, *pos, *final_norm, *norm1[NOVIC_MAX_LAYERS], *norm2[NOVIC_MAX_LAYERS];
   CUtensorMap tm_linear1_q[NOVIC_MAX_LAYERS];            // linear1 with a 32-row box (split-hidden feed-forward kernel)
+  // 3-D maps of the 64-row block kernel: out_proj (128 rows x 2 k-blocks = 32 KB per request), linear1 (32 rows x 8 k-blocks: the CTA's whole
+  // slice in one request), linear2 (128 rows x 2 k-blocks: the CTA's whole slice in one request)
+  CUtensorMap tm_out_proj3[NOVIC_MAX_LAYERS], tm_linear1_q3[NOVIC_MAX_LAYERS], tm_linear2_3[NOVIC_MAX_LAYERS];
   CUtensorMap tm_tok3, tm_in_proj3[NOVIC_MAX_LAYERS];   // 3-D maps (kWideKbs k-blocks per request) for the wide-stage decode GEMMs
   CUtensorMap tm_tok3w;                                   // the tied matrix with 256-row boxes (128 x 256 logits tiles)
+  CUtensorMap tm_in_proj3w[NOVIC_MAX_LAYERS];             // in_proj with 256-row boxes (NOVIC_QKV_BN=256)
   CUtensorMap tm_embed_mlp, tm_tok, tm_in_proj[NOVIC_MAX_LAYERS], tm_out_proj[NOVIC_MAX_LAYERS], tm_linear1[NOVIC_MAX_LAYERS],
       tm_linear2[NOVIC_MAX_LAYERS];
   // transposed bf16 copies (B operands of the backward dgrad GEMMs: dX = dY * W needs W^T in K-major form)
@@ -514,8 +534,9 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   if (make_tmap(&tm_xn, ws.xn, M, kE, kBlockM)) return 1;
   if (make_tmap(&tm_ao, ws.ao, M, kE, kBlockM)) return 1;
   if (make_tmap(&tm_hb, ws.hb, M, c.ffn_dim, kBlockM)) return 1;
-  CUtensorMap tm_xn3;
+  CUtensorMap tm_xn3, tm_ao64;
   if (make_tmap3(&tm_xn3, ws.xn, M, kE, kBlockM, kWideKbs)) return 1;
+  if (make_tmap3(&tm_ao64, ws.ao, M, kE, kHbRows, 2)) return 1;
   const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
   const bool block_fused = g_fuse_block && h->fuse_ffn && c.ffn_dim == kFfnDim;
   const bool qkv_tail = block_fused && g_fuse_qkv && g_wide_gemm;     // layer l + 1's QKV projection in the tail of layer l's block kernel
@@ -529,7 +550,9 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       const EpiQKV::Params pq = qkv_params(l);
       if (g_wide_gemm) {
         KSpan t(kKQkv, s);
-        if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+        if (g_qkv_bn == 256 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {
+          if (launch_gemm<EpiQKV, 2, kWideKbs, 256>(s, tm_xn3, h->w.tm_in_proj3w[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
+        } else if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
       } else {
         KSpan t(kKQkv, s);
         if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
@@ -548,6 +571,10 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
         fb.remap_rows_in = pc.remap_in; fb.remap_skip = pc.remap_skip; fb.remap_rows_out = pc.remap_out;
       }
       KSpan t(kKFfn2, s);
+      if ((g_block_rows == 64 || (g_block_rows == 0 && M <= kBlock64MaxRows)) && !fb.qkv_tail) {
+        if (launch_outproj_ffn64(s, tm_ao64, h->w.tm_out_proj3[l], h->w.tm_linear1_q3[l], h->w.tm_linear2_3[l], M, fb)) return 1;
+        continue;
+      }
       if (launch_outproj_ffn(s, tm_ao, h->w.tm_out_proj[l], h->w.tm_linear1_q[l], h->w.tm_linear2[l], h->w.tm_in_proj3[l + 1 < L ? l + 1 : l], M, fb)) return 1;
       continue;
     }
@@ -878,7 +905,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -927,6 +954,9 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e19 = getenv("NOVIC_ATTN_TF")) g_attn_tf = atoi(e19) != 0;
   if (const char* e22 = getenv("NOVIC_FUSE_BLOCK")) g_fuse_block = e22[0] != '0';
   if (const char* e23 = getenv("NOVIC_FUSE_QKV")) g_fuse_qkv = e23[0] != '0';
+  if (const char* e24 = getenv("NOVIC_QKV_BN")) g_qkv_bn = atoi(e24);
+  if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
+  if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';
@@ -1075,10 +1105,16 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
   for (size_t l = 0; l < L; ++l) {
     if (make_tmap(&o.tm_in_proj[l], o.in_proj[l], 3 * E, E, 128)) return 1;
     if (make_tmap3(&o.tm_in_proj3[l], o.in_proj[l], 3 * E, E, 128, kWideKbs)) return 1;
+    if (make_tmap3(&o.tm_in_proj3w[l], o.in_proj[l], 3 * E, E, 256, kWideKbs)) return 1;
     if (make_tmap(&o.tm_out_proj[l], o.out_proj[l], E, E, kRowBN)) return 1;
     if (make_tmap(&o.tm_linear1[l], o.linear1[l], K, E, 128)) return 1;
     if (make_tmap(&o.tm_linear1_q[l], o.linear1[l], K, E, kFfnDim / kRowCluster)) return 1;
     if (make_tmap(&o.tm_linear2[l], o.linear2[l], E, K, kRowBN)) return 1;
+    if (K == kFfnDim) {
+      if (make_tmap3(&o.tm_out_proj3[l], o.out_proj[l], E, E, kRowBN, 2)) return 1;
+      if (make_tmap3(&o.tm_linear1_q3[l], o.linear1[l], K, E, kFfnDim / kRowCluster, E / kBlockK)) return 1;
+      if (make_tmap3(&o.tm_linear2_3[l], o.linear2[l], E, K, kRowBN, K / kBlockK)) return 1;
+    }
   }
   // the weight pointers are baked into captured graphs (the training step's graphs only bake addresses inside wbuf, which a
   // re-pack into the same buffer leaves valid: they are dropped only when the buffer moved)

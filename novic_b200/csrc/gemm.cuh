@@ -106,26 +106,31 @@ struct EpiQKV {
     int rows_per_seq, pos0, slot_mul, smax;
     int kv_hint;            // K/V rows are stored with an evict-last L2 policy (decode steps: the next step reads them back)
   };
+  // A thread owns c.ncols = 64 columns (128-column tiles) or 128 (256-column tiles; a 256-column tile lies inside one of q / K / V):
+  // 64 columns are staged and written at a time.
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
     const int lane = lane_id();
+    const int nparts = c.ncols / kEpiCols;
+    for (int part = 0; part < nparts; ++part) {
 #pragma unroll
-    for (int ch = 0; ch < kEpiCols / 32; ++ch) {
-      float v[32];
-      tmem_ld_32x32(c.tmem_row + ch * 32, v);
-      if (ch == kEpiCols / 32 - 1) release();
-      stage_put32(c.stage, lane, ch * 32, v);
+      for (int ch = 0; ch < kEpiCols / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32(c.tmem_row + part * kEpiCols + ch * 32, v);
+        if (part == nparts - 1 && ch == kEpiCols / 32 - 1) release();
+        stage_put32(c.stage, lane, ch * 32, v);
+      }
+      const int n0 = c.n0 + part * kEpiCols;
+      stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
+        const int row = c.warp_row0 + r;
+        if (row >= c.M) return nullptr;
+        if (n0 < kE) return p.q + static_cast<size_t>(row) * kE + n0;
+        const int seq = row / p.rows_per_seq;
+        const int pos = p.pos0 + (row - seq * p.rows_per_seq);
+        const size_t page = (static_cast<size_t>(seq) * p.slot_mul * p.smax + pos) * kE;
+        return (n0 < 2 * kE) ? p.kcache + page + (n0 - kE) : p.vcache + page + (n0 - 2 * kE);
+      }, (n0 >= kE && p.kv_hint) ? kEvictLast : 0ull);   // new K/V rows: keep them in L2 for the next step's attention
     }
-    const int n0 = c.n0;
-    stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
-      const int row = c.warp_row0 + r;
-      if (row >= c.M) return nullptr;
-      if (n0 < kE) return p.q + static_cast<size_t>(row) * kE + n0;
-      const int seq = row / p.rows_per_seq;
-      const int pos = p.pos0 + (row - seq * p.rows_per_seq);
-      const size_t page = (static_cast<size_t>(seq) * p.slot_mul * p.smax + pos) * kE;
-      return (n0 < 2 * kE) ? p.kcache + page + (n0 - kE) : p.vcache + page + (n0 - 2 * kE);
-    }, (n0 >= kE && p.kv_hint) ? kEvictLast : 0ull);   // new K/V rows: keep them in L2 for the next step's attention
   }
 };
 
@@ -1441,6 +1446,369 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
   cluster_sync_relaxed();   // peers may still be reading this CTA's statistics / operand tiles
   if (threadIdx.x == 0) trace_point(tr, 14);
   if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same block on 64-ROW tiles with TWO CTAs resident per SM (decode path, default; NOVIC_BLOCK_ROWS=128 restores the kernel above).
+// The kernel above is one serial chain per CTA - loads -> MMA -> statistics -> hand-over -> MMA -> GELU -> hand-over -> MMA ->
+// statistics -> stores, about 30 k cycles of which the tensor core works 3 k - and at 4096 rows there is exactly one 128-row tile per
+// cluster, so nothing overlaps anything.  Halving the tile doubles the clusters (256 CTAs for 4096 rows) and fits two CTAs on an SM
+// (<= 113 KB of shared memory, 256 TMEM columns, <= 170 registers x 192 threads each): one CTA's waits are the other's work.
+//   * UMMA keeps M = 128: rows 64..127 of every A operand are whatever follows the 64-row tile in shared memory (always inside the
+//     allocation); their accumulator lanes 64..127 are never read.  Rows 0..63 <-> TMEM lanes 0..63, so the four epilogue warps
+//     are the ones whose (warp % 4) is 0 or 1: warps 0, 1, 4, 5; warp 2 issues the loads and bulk copies, warp 3 the MMAs.
+//   * every operand arrives through 3-D tensor maps, two or more k-block tiles per request (the TMA unit serves ~2 requests at a time
+//     whatever their size, and two CTAs share it): 4 x 16 KB of rows + 4 x 32 KB of Wo + W1 and W2 in one 32 KB request each
+//   * shared memory: [X 64 KB | HS 16 KB | W1 32 KB].  X + HS + the first half of W1 are the two 48 KB stages (2 x (A 8 KB) + 2 x (Wo 16 KB)) of
+//     the out-proj pipeline (W1 is requested when its MMAs have completed), then X is the FFN1 A operand (8 k-block tiles of 64 rows: own two written locally, six by the peers' bulk
+//     copies), then - once this CTA's FFN1 MMAs have completed - W2 (32 KB, loaded late: it lands while GELU and the hidden-column
+//     exchange run), the second round of LayerNorm partials and the bf16 output staging.  HS receives the four 4 KB hidden slices
+//     (its first KB holds the first round of partials before that); W1 becomes the FFN2 A operand.  Accumulators: out-proj and FFN2
+//     share TMEM columns 0..127, FFN1 uses 128..159.  The LayerNorm gains are read with warp-uniform loads (no shared copy).
+// Same operands and accumulation order as the 128-row kernel: results are bit-identical.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kHbRows = 64;
+constexpr int kHbThreads = 192;
+constexpr int kHbABytes = kHbRows * kBlockK * 2;                 // 8 KB: one k-block of a 64-row A tile
+constexpr int kHbKbs = 2;                                        // k-blocks per request and stage (3-D tensor maps)
+constexpr int kHbStageBytes = kHbKbs * (kHbABytes + kBBytes);    // 48 KB: [A: 2 x 8 KB][Wo: 2 x 16 KB]
+constexpr int kHbStages = 2;
+constexpr int kHbXBytes = (kE / kBlockK) * kHbABytes;            // 64 KB
+constexpr int kHbHsBytes = kRowCluster * kHbRows * 64;           // 16 KB
+constexpr int kHbW1Bytes = (kFfnDim / kRowCluster) * kE * 2;     // 32 KB
+constexpr int kHbBarBytes = 256;
+__host__ __device__ constexpr int outproj_ffn64_smem_bytes() { return kHbXBytes + kHbHsBytes + kHbW1Bytes + kHbBarBytes + 768 /*alignment slack*/; }
+static_assert(outproj_ffn64_smem_bytes() <= 113 * 1024, "two CTAs of the 64-row block kernel must fit on an SM");
+static_assert(kHbStages * kHbStageBytes <= kHbXBytes + kHbHsBytes + kHbW1Bytes, "the out-proj stages fill X, HS and half of the W1 region");
+
+__global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kHbThreads, 2)
+outproj_ffn64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1q,
+                     const __grid_constant__ CUtensorMap tmap_w2, int M, FusedBlockParams ep) {
+  constexpr int BN = kRowBN;
+  constexpr int kHSplit = kFfnDim / kRowCluster;              // 32 hidden columns per CTA
+  constexpr int kW1kb = kHSplit * kBlockK * 2;                // 4 KB
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
+  constexpr uint32_t kIdescH = umma_idesc_bf16_f32(kBlockM, kHSplit);
+  constexpr int kNkb = kE / kBlockK;                          // 8
+  constexpr int kHSlice = kHbRows * kHSplit * 2;              // one CTA's hidden columns: 64 rows x 64 B = 4 KB
+  constexpr uint32_t kTmem = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xop = smem;
+  uint8_t* hs = xop + kHbXBytes;
+  uint8_t* w1_smem = hs + kHbHsBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(w1_smem + kHbW1Bytes);
+  uint64_t* empty_bar = full_bar + kHbStages;
+  uint64_t* tmem_full0 = empty_bar + kHbStages;
+  uint64_t* w1_full = tmem_full0 + 1;
+  uint64_t* w2_full = tmem_full0 + 2;
+  uint64_t* tmem_full1 = tmem_full0 + 3;
+  uint64_t* tmem_full2 = tmem_full0 + 4;
+  uint64_t* affn_full = tmem_full0 + 5;
+  uint64_t* hx_full = tmem_full0 + 6;
+  uint64_t* hop_ready = tmem_full0 + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 8);
+  static_assert((2 * kHbStages + 8) * 8 + 4 <= kHbBarBytes, "barrier area");
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = static_cast<int>(lane_id());
+  const int m0 = blockIdx.y * kHbRows;
+  const uint32_t crank = cluster_ctarank();
+  const int coff = static_cast<int>(crank) * BN;
+  const int n0 = coff;
+  pdl_trigger();
+  if (threadIdx.x == 0 && static_cast<int>(smem - smem_raw) > 768) {   // the slack covers a base that is not 1 KB aligned by at most this much
+    printf("outproj_ffn64_kernel: dynamic shared memory base %u leaves no room for the 1 KB alignment\n", smem_u32(smem_raw));
+    __trap();
+  }
+
+  if (warp == 2) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1q); tma_prefetch_desc(&tmap_w2);
+      for (int st = 0; st < kHbStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
+      mbar_init(tmem_full0, 1); mbar_init(w1_full, 1); mbar_init(w2_full, 1); mbar_init(tmem_full1, 1); mbar_init(tmem_full2, 1);
+      mbar_init(affn_full, 1); mbar_init(hx_full, 1); mbar_init(hop_ready, 4);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(affn_full, (kRowCluster - 1) * 2 * kHbABytes);   // the peers' copies can only start after cluster barrier #1
+      mbar_arrive_expect_tx(hx_full, (kRowCluster - 1) * kHSlice);
+      // the weights do not depend on the previous kernel: the first Wo tiles before the wait, the activation tiles after it
+      for (int i = 0; i < kHbStages; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], kHbStageBytes);
+        tma_load_3d(xop + i * kHbStageBytes + kHbKbs * kHbABytes, &tmap_wo, &full_bar[i], n0, i * kHbKbs, kEvictLast);
+      }
+      pdl_wait();
+      for (int i = 0; i < kHbStages; ++i)
+        tma_load_3d(xop + i * kHbStageBytes, &tmap_ao, &full_bar[i], m0, i * kHbKbs, kEvictNormal);
+    }
+  } else if (warp == 3) {
+    tmem_alloc<kTmem>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 2) {
+    if (elect_one()) {
+      for (int i = kHbStages; i < kNkb / kHbKbs; ++i) {
+        const int st = i % kHbStages;
+        mbar_wait(&empty_bar[st], ((i / kHbStages) & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(&full_bar[st], kHbStageBytes);
+        tma_load_3d(xop + st * kHbStageBytes, &tmap_ao, &full_bar[st], m0, i * kHbKbs, kEvictNormal);
+        tma_load_3d(xop + st * kHbStageBytes + kHbKbs * kHbABytes, &tmap_wo, &full_bar[st], n0, i * kHbKbs, kEvictLast);
+      }
+      // the W1 slice (one request) goes into its region once the out-proj MMAs have read the stage that overlaps it
+      mbar_wait(tmem_full0, 0, 1);
+      mbar_arrive_expect_tx(w1_full, kNkb * kW1kb);
+      tma_load_3d(w1_smem, &tmap_w1q, w1_full, static_cast<int>(crank) * kHSplit, 0, kEvictLast);
+    }
+  } else if (warp == 3) {
+    if (elect_one()) {
+      for (int i = 0; i < kNkb / kHbKbs; ++i) {
+        const int st = i % kHbStages;
+        mbar_wait(&full_bar[st], (i / kHbStages) & 1, 2);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(xop + st * kHbStageBytes), sb = sa + kHbKbs * kHbABytes;
+#pragma unroll
+        for (int j = 0; j < kHbKbs; ++j)
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(sa + j * kHbABytes + k * (kUmmaK * 2)),
+                         umma_desc_sw128_kmajor(sb + j * kBBytes + k * (kUmmaK * 2)), kIdesc, (i | j | k) != 0 ? 1u : 0u);
+        umma_commit(&empty_bar[st]);
+      }
+      umma_commit(tmem_full0);                                  // acc0 -> TMEM columns [0, 128)
+    }
+  }
+  __syncwarp();
+
+  // ---- phase A epilogue: residual + accumulator, LN2 statistics
+  const bool is_epi = (warp & 2) == 0;                          // warps 0, 1, 4, 5: TMEM lane quadrants 0 and 1
+  const int quad = warp & 3;
+  const int half = warp >> 2;
+  const int row_in_tile = quad * 32 + lane;
+  const int row = m0 + row_in_tile;
+  const int c0 = coff + half * kRowCols;
+  const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  float2* s_stats = reinterpret_cast<float2*>(hs);              // [2 halves][64 rows]
+  float r[kRowCols];
+  auto add_acc_and_stats = [&]() {
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRowCols / 16; ++c) {
+      float v[16];
+      tmem_ld_32x16(tmem_lane + half * kRowCols + c * 16, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float t = r[c * 16 + j] + v[j];
+        r[c * 16 + j] = t;
+        sum += t;
+        sumsq = fmaf(t, t, sumsq);
+      }
+    }
+    s_stats[half * kHbRows + row_in_tile] = make_float2(sum, sumsq);
+  };
+  auto gather_stats = [&](float& mean, float& rstd) {
+    float2 part[kRowCluster * 2];
+#pragma unroll
+    for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) part[pr * 2 + hh] = dsmem_ld_f32x2_addr(dsmem_addr(&s_stats[hh * kHbRows + row_in_tile], pr));
+    }
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowCluster * 2; ++i) { sum += part[i].x; sumsq += part[i].y; }
+    mean = sum * (1.0f / kE);
+    rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
+  };
+  if (is_epi) {
+    if (row < M) {
+#pragma unroll
+      for (int q = 0; q < kRowCols / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (c0 >> 2) + q));
+        r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRowCols; ++i) r[i] = 0.f;
+    }
+    mbar_wait(tmem_full0, 0, 3);
+    tc_fence_after_sync();
+    add_acc_and_stats();
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  cluster_sync_all();       // #1: LN2 partials visible; every CTA's out-proj MMAs have completed (their accumulators were read)
+
+  // ---- hand-over: LN2 rows -> FFN1 operand of all four CTAs (local write of the CTA's two k-block tiles, one bulk copy per peer)
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    if (row < M) gather_stats(mean, rstd);
+    const int kb = static_cast<int>(crank) * 2 + half;
+    uint8_t* arow = xop + kb * kHbABytes + row_in_tile * 128;
+    const float* gm = ep.gain_mid + c0;
+#pragma unroll
+    for (int q = 0; q < kRowCols / 8; ++q) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * __ldg(gm + q * 8 + i);
+      *reinterpret_cast<uint4*>(arow + ((q ^ (row_in_tile & 7)) << 4)) =
+          make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    }
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    if (elect_one()) {
+      const uint8_t* src = xop + static_cast<int>(crank) * 2 * kHbABytes;
+#pragma unroll
+      for (uint32_t d = 1; d < kRowCluster; ++d) {
+        const uint32_t pr = (crank + d) % kRowCluster;
+        dsmem_bulk_copy(dsmem_addr(src, pr), src, 2 * kHbABytes, dsmem_addr(affn_full, pr));
+      }
+      // W2 goes where the FFN1 operand lies, as soon as this CTA's FFN1 MMAs have read it
+      mbar_wait(tmem_full1, 0, 6);
+      mbar_arrive_expect_tx(w2_full, 2 * kBBytes);
+      tma_load_3d(xop, &tmap_w2, w2_full, n0, 0, kEvictLast);
+    }
+  } else if (warp == 3) {
+    // ---- phase B: this CTA's 32 hidden columns
+    if (elect_one()) {
+      mbar_wait(affn_full, 0, 5);
+      mbar_wait(w1_full, 0, 6);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(xop), sb = smem_u32(w1_smem);
+#pragma unroll
+      for (int kb = 0; kb < kNkb; ++kb)
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base + 128, umma_desc_sw128_kmajor(sa + kb * kHbABytes + k * (kUmmaK * 2)),
+                       umma_desc_sw128_kmajor(sb + kb * kW1kb + k * (kUmmaK * 2)), kIdescH, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full1);
+    }
+  }
+  __syncwarp();
+  if (is_epi) {
+    mbar_wait(tmem_full1, 0, 7);
+    tc_fence_after_sync();
+    float v[16];
+    tmem_ld_32x16(tmem_lane + 128 + half * 16, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+    // hidden-column exchange: HS holds four 4 KB slices [source CTA][64 rows][64 B]; the local one is written here and pushed to the peers
+    uint4* mine = reinterpret_cast<uint4*>(hs + static_cast<int>(crank) * kHSlice + row_in_tile * 64 + half * 32);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      mine[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    if (elect_one()) {
+      const uint8_t* src = hs + static_cast<int>(crank) * kHSlice;
+#pragma unroll
+      for (uint32_t d = 1; d < kRowCluster; ++d) {
+        const uint32_t pr = (crank + d) % kRowCluster;
+        dsmem_bulk_copy(dsmem_addr(src, pr), src, kHSlice, dsmem_addr(hx_full, pr));
+      }
+    }
+  }
+  __syncwarp();
+  if (is_epi) {
+    // assemble the K-major swizzled A operand of FFN2 in the (dead) W1 region: this thread's row, k-block `half` = the slices of source
+    // CTAs 2 * half and 2 * half + 1
+    mbar_wait(hx_full, 0, 10);
+    uint8_t* hrow = w1_smem + half * kHbABytes + row_in_tile * 128;
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const uint4* src = reinterpret_cast<const uint4*>(hs + (2 * half + sidx) * kHSlice + row_in_tile * 64);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int chunk = sidx * 4 + c;
+        *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row_in_tile & 7)) << 4)) = src[c];
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(hop_ready);
+  }
+
+  // ---- phase C: second feed-forward GEMM (accumulator columns 0..127 again), residual, LayerNorm
+  if (warp == 3) {
+    if (elect_one()) {
+      mbar_wait(hop_ready, 0, 11);
+      mbar_wait(w2_full, 0, 8);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(w1_smem), sb = smem_u32(xop);
+#pragma unroll
+      for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base, umma_desc_sw128_kmajor(sa + kb * kHbABytes + k * (kUmmaK * 2)),
+                       umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full2);
+    }
+  }
+  __syncwarp();
+  s_stats = reinterpret_cast<float2*>(xop + 2 * kBBytes);      // second round of partials: behind W2 (the FFN1 operand is dead)
+  if (is_epi) {
+    mbar_wait(tmem_full2, 0, 9);
+    tc_fence_after_sync();
+    add_acc_and_stats();
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  cluster_sync_all();       // #2
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    if (row < M) gather_stats(mean, rstd);
+    const int ew = half * 2 + quad;
+    uint8_t* stage = xop + 2 * kBBytes + 2048 + ew * (32 * kRowStagePitch);
+    {
+      uint4* d = reinterpret_cast<uint4*>(stage + lane * kRowStagePitch);
+      const float* go = ep.gain_out + c0;
+#pragma unroll
+      for (int q = 0; q < kRowCols / 8; ++q) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * __ldg(go + q * 8 + i);
+        d[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+    }
+    if (row < M) {
+#pragma unroll
+      for (int q = 0; q < kRowCols / 4; ++q)
+        *reinterpret_cast<float4*>(ep.x + xblk_off(row, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+    }
+    __syncwarp();
+    const int warp_row0 = m0 + quad * 32;
+    const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 4
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + sub;
+      const int grow = warp_row0 + rr;
+      if (grow < M) {
+        int nrow = grow;
+        bool keep = true;
+        if (ep.remap_rows_in > 0) {
+          const int seq = grow / ep.remap_rows_in;
+          const int k = grow - seq * ep.remap_rows_in;
+          keep = k >= ep.remap_skip;
+          nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+        }
+        if (keep)
+          *reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + c0 + chunk * 8) =
+              *reinterpret_cast<const uint4*>(stage + rr * kRowStagePitch + chunk * 16);
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncwarp();
+  cluster_sync_relaxed();   // peers may still be reading this CTA's partials
+  if (warp == 3) tmem_dealloc<kTmem>(tmem_base);
 }
 
 }  // namespace novic

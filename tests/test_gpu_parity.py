@@ -375,3 +375,33 @@ def test_qkv_tail_of_the_block_kernel_is_bit_identical(monkeypatch):
     assert torch.equal(g0[0], g1[0]) and torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2]) and torch.equal(g0[5], g1[5])
     assert torch.equal(b0[0], b1[0]) and torch.equal(b0[2], b1[2])
     assert torch.equal(f0[0], f1[0]) and f0[2].item() == f1[2].item() and torch.equal(f0[4], f1[4])
+
+
+def test_block_kernel_on_64_row_tiles_is_bit_identical(monkeypatch):
+    """The fused out-proj + feed-forward block kernel on 64-row tiles (outproj_ffn64_kernel: what small row counts use, NOVIC_BLOCK_ROWS=64
+    forces it everywhere) against the 128-row kernel (NOVIC_BLOCK_ROWS=128): same operands and accumulation order -> bit-identical ids,
+    scores and logits for greedy (ragged: 300 = 4 x 64 + 44 rows per decode step, 1200 prefix rows), beam search and the
+    teacher-forced forward; and with two CTAs resident per SM (NOVIC_BLOCK64_PAD=0) as well."""
+    dims = synth.DecoderDims()
+    sd = weight_case("eos")
+    embed = synth.synth_embeddings(300, seed=5).to(DEV)
+    tgt, pad = synth.synth_targets(40, dims, seed=3)
+    outs = []
+    for rows, extra in (("128", "16384"), ("64", "16384"), ("64", "0")):     # the switches are read when a handle is created
+        monkeypatch.setenv("NOVIC_BLOCK_ROWS", rows)
+        monkeypatch.setenv("NOVIC_BLOCK64_PAD", extra)
+        m = default_decoder(dims, sd).to(DEV)
+        with torch.inference_mode():
+            g = m.generate(embed, True, True, 0.9, 0.2, None, None, False)
+            b = m.generate_beam(embed[:64], 3, 1.0, 0.0, None, False, 0.0, None, False)
+            f = m(embed[:40], tgt.to(DEV), pad.to(DEV), None, True, True, False, None)
+            small = [m.generate(embed[:n], False, True, 1.0, 0.0, None, None, False) for n in (1, 63, 65)]
+        outs.append((g, b, f, small))
+        del m
+    g0, b0, f0, s0 = outs[0]
+    for g1, b1, f1, s1 in outs[1:]:
+        assert torch.equal(g0[0], g1[0]) and torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2]) and torch.equal(g0[5], g1[5])
+        assert torch.equal(b0[0], b1[0]) and torch.equal(b0[2], b1[2])
+        assert torch.equal(f0[0], f1[0]) and f0[2].item() == f1[2].item() and torch.equal(f0[4], f1[4])
+        for a, c in zip(s0, s1):
+            assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[5], c[5])
