@@ -172,6 +172,25 @@ int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, in
   return 0;
 }
 
+// CTA-pair GEMM (gemm2_kernel): ta / tb are 3-D maps with 128-row boxes and kWideKbs k-blocks per request; K a multiple of 128.
+template <class Epi, int STAGES>
+int set_gemm2_attr() {
+  static_assert(gemm2_smem_bytes(STAGES) <= 227 * 1024, "pair GEMM pipeline does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<Epi, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(STAGES)));
+  return 0;
+}
+template <class Epi, int STAGES>
+int launch_gemm2(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const typename Epi::Params& ep, bool b_is_static = false) {
+  const int n_tiles = static_cast<int>(ceil_div(N, kPairTileN));
+  const int64_t total = n_tiles * ceil_div(M, 2 * kBlockM);
+  if (K % (kBlockK * kPairKbs) != 0) return fail("pair GEMM needs K %% %d == 0", kBlockK * kPairKbs);
+  const unsigned pairs = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div / 2)));
+  CUDA_TRY(launch_k(gemm2_kernel<Epi, STAGES>, dim3(2 * pairs), dim3(kGemmThreads), gemm2_smem_bytes(STAGES), s, ta, tb, M, n_tiles, static_cast<int>(K / kBlockK), b_is_static ? 1 : 0, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
@@ -550,7 +569,9 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       const EpiQKV::Params pq = qkv_params(l);
       if (g_wide_gemm) {
         KSpan t(kKQkv, s);
-        if (g_qkv_bn == 256 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {
+        if (g_qkv_bn == 512 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {
+          if (launch_gemm2<EpiQKV, 3>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, g_early_b)) return 1;
+        } else if (g_qkv_bn == 256 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {
           if (launch_gemm<EpiQKV, 2, kWideKbs, 256>(s, tm_xn3, h->w.tm_in_proj3w[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
         } else if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
       } else {
@@ -650,7 +671,9 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
     // 128 x 256 tiles (0.75 of the operand bytes per FLOP): the plain arg-max / log-sum-exp epilogue of greedy decoding and teacher forcing.
     // Needs the same number of 64-column slices per row as the 128-column tiling the workspace was planned for, and at least a wave of tiles.
     const int V = h->cfg.vocab_size;
-    if (g_wide_gemm && g_logits_bn == 256 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
+    if (g_wide_gemm && g_logits_bn == 512 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
+      return launch_gemm2<EpiLogits<0, false, false>, 3>(s, tm_a, h->w.tm_tok3, M, V, kE, pl, g_early_b);      // CTA pairs, 256 x 256 tiles
+    if (g_wide_gemm && g_logits_bn >= 256 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
       return launch_gemm<EpiLogits<0, false, false>, 2, kWideKbs, 256>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b);
   }
   if (g_wide_gemm) return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kWideStages, kWideKbs>(s, tm_a, h->w.tm_tok3, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
@@ -905,7 +928,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -1661,9 +1684,27 @@ int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs
 int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,
                      int32_t block_n, void* stream) {
   if (M < 1 || N < 1 || K < 64 || K % 64 != 0) return fail("bad GEMM shape");
-  if (block_n != 128) return fail("debug GEMM supports block_n = 128");
-  if (set_gemm_attr<EpiLogits<0>, kStagesLogits>()) return 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (block_n == 256 || block_n == 512) {     // 256: 128 x 256 tiles of one CTA; 512: 256 x 256 tiles of a CTA pair (cta_group::2)
+    if (K % (kBlockK * kWideKbs) != 0) return fail("wide debug GEMM needs K %% 128 == 0");
+    CUtensorMap ta3, tb3;
+    if (make_tmap3(&ta3, a_bf16, M, K, kBlockM, kWideKbs)) return 1;
+    if (make_tmap3(&tb3, w_bf16, N, K, block_n == 256 ? 256 : 128, kWideKbs)) return 1;
+    const int np = 4 * static_cast<int>(ceil_div(N, 256));
+    LogitPartial* pt = nullptr;
+    CUDA_TRY(cudaMallocAsync(&pt, sizeof(LogitPartial) * static_cast<size_t>(M) * np, s));
+    EpiLogits<0>::Params q;
+    q.logits = out; q.ld_logits = N; q.part = pt; q.topv = nullptr; q.topi = nullptr; q.target = nullptr;
+    q.n_valid = N; q.nparts = np; q.inv_tau = 1.0f; q.ban_eos = 0; q.want_sumx = 0;
+    q.allow = nullptr; q.allow_ld = 0; q.allow_mod = 0; q.mask_lse = 0;
+    int rc2;
+    if (block_n == 256) rc2 = set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || launch_gemm<EpiLogits<0>, 2, kWideKbs, 256>(s, ta3, tb3, M, N, K, q);
+    else rc2 = set_gemm2_attr<EpiLogits<0>, 3>() || launch_gemm2<EpiLogits<0>, 3>(s, ta3, tb3, M, N, K, q);
+    CUDA_TRY(cudaFreeAsync(pt, s));
+    return rc2;
+  }
+  if (block_n != 128) return fail("debug GEMM supports block_n = 128, 256 (128 x 256 tiles) and 512 (CTA pairs)");
+  if (set_gemm_attr<EpiLogits<0>, kStagesLogits>()) return 1;
   CUtensorMap ta, tb;
   if (make_tmap(&ta, a_bf16, M, K, kBlockM)) return 1;
   if (make_tmap(&tb, w_bf16, N, K, 128)) return 1;

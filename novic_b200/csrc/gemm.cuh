@@ -1811,4 +1811,160 @@ outproj_ffn64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_c
   if (warp == 3) tmem_dealloc<kTmem>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The persistent GEMM on CTA PAIRS: 256 x 256 output tiles, one tcgen05.mma.cta_group::2 of M = 256, N = 256 per k-slice.
+// Why: the 128 x 128 single-CTA tile takes in 256 KB of operands per 33.5 MFLOP - 4.4 k cycles per tile at the ~58 B/clk per SM that the L2
+// delivers when all 148 SMs pull (phase trace of the QKV GEMM; the chip-wide L2 output cap is ~6300 B/clk), against 2.1 k cycles of
+// MMA.  A pair moves HALF the bytes per FLOP: each CTA loads its own 128 rows of A and 128 of the tile's 256 rows of B (the tensor
+// cores of both SMs read both shared memories), and owns the 128 x 256 accumulator rows of its half in its own TMEM.
+//   * cluster (2, 1, 1); rank 0 = leader: its MMA warp waits on ITS full barrier - both CTAs' TMA loads count their bytes there
+//     (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address) - and issues the MMAs; tcgen05.commit multicasts the
+//     "stage free" and "accumulator ready" arrivals to the barriers of both CTAs
+//   * both CTAs run the 8 epilogue warps on their own accumulator half (any epilogue that honours EpiCtx::ncols = 128); the leader's
+//     "accumulator drained" barrier counts the warps of both CTAs (the peer arrives through the cluster address)
+//   * stages: KBS = 2 k-blocks of [A 128 x 64 | B-half 128 x 64] = 64 KB per CTA, 3-D tensor maps with 128-row boxes (the same maps as
+//     gemm_kernel<.., KBS = 2>), two accumulator stages of 256 columns = all 512 TMEM columns.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPairKbs = 2;
+constexpr int kPairTileN = 256;
+constexpr int kPairStageBytes = kPairKbs * (kABytes + kBBytes);   // 64 KB per CTA: [A: 2 x 16 KB][B half: 2 x 16 KB]
+__host__ __device__ constexpr int gemm2_smem_bytes(int stages) { return stages * kPairStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256; }
+
+template <class Epi, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles /* of 256 columns */,
+             int num_k_blocks, int b_is_static, typename Epi::Params ep) {
+  constexpr int KBS = kPairKbs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  uint8_t* epi_stage = smem + STAGES * kPairStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;        // [kAccStages]
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;   // used in the leader only: 2 x kEpiWarps arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int total_tiles = m_tiles * n_tiles;
+  const int loads_per_tile = num_k_blocks / KBS;
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 2 * kEpiWarps); }
+      fence_mbar_init();
+    }
+  } else if (warp == 1) {
+    tmem_alloc2<kAccStages * kPairTileN>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();       // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t leader_full0 = dsmem_addr(&full_bar[0], 0);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // weight halves of the first pipeline fill before griddepcontrol.wait (they do not depend on the previous kernel)
+      const int early_b = (b_is_static && pair < total_tiles) ? min(STAGES, loads_per_tile) : 0;
+      if (early_b > 0) {
+        const int n0 = (pair % n_tiles) * kPairTileN + static_cast<int>(rank) * kTileN;
+        for (int i = 0; i < early_b; ++i) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[i], 2 * kPairStageBytes);
+          tma_load_3d_2sm(stages + i * kPairStageBytes + KBS * kABytes, &tmap_b, leader_full0 + i * 8, n0, i * KBS, kEvictLast);
+        }
+      }
+      pdl_wait();
+      int stage = 0; uint32_t phase = 0;
+      int nload = 0;
+      for (int t = pair; t < total_tiles; t += npairs) {
+        const int m0 = (t / n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+        const int n0 = (t % n_tiles) * kPairTileN + static_cast<int>(rank) * kTileN;
+        for (int kb = 0; kb < num_k_blocks; kb += KBS, ++nload) {
+          uint8_t* sa = stages + stage * kPairStageBytes;
+          if (nload >= early_b) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          }
+          tma_load_3d_2sm(sa, &tmap_a, leader_full0 + stage * 8, m0, kb, kEvictNormal);
+          if (nload >= early_b) tma_load_3d_2sm(sa + KBS * kABytes, &tmap_b, leader_full0 + stage * 8, n0, kb, kEvictLast);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    pdl_wait();
+    if (leader && elect_one()) {
+      constexpr uint32_t kIdesc = umma_idesc_bf16_f32(2 * kBlockM, kPairTileN);
+      int stage = 0; uint32_t phase = 0;
+      int i = 0;
+      for (int t = pair; t < total_tiles; t += npairs, ++i) {
+        const int as = i & 1;
+        mbar_wait(&tmem_empty_bar[as], ((i >> 1) & 1) ^ 1, 9);   // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + as * kPairTileN;
+        for (int kb = 0; kb < num_k_blocks; kb += KBS) {
+          mbar_wait(&full_bar[stage], phase, 2);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(stages + stage * kPairStageBytes);
+          const uint32_t sb = sa + KBS * kABytes;
+#pragma unroll
+          for (int j = 0; j < KBS; ++j)
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma2_bf16_ss(acc, umma_desc_sw128_kmajor(sa + j * kABytes + k * (kUmmaK * 2)),
+                            umma_desc_sw128_kmajor(sb + j * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb > 0 || (j | k) != 0) ? 1u : 0u);
+          umma2_commit_mc(&empty_bar[stage], 0x3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_mc(&tmem_full_bar[as], 0x3);
+      }
+    }
+    __syncwarp();
+  } else {
+    pdl_wait();
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;            // which 128 of the tile's 256 columns
+    const int lane = static_cast<int>(lane_id());
+    const uint32_t leader_tmem_empty0 = dsmem_addr(&tmem_empty_bar[0], 0);
+    int i = 0;
+    for (int t = pair; t < total_tiles; t += npairs, ++i) {
+      const int as = i & 1;
+      const int m0 = (t / n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM, nt = t % n_tiles;
+      mbar_wait(&tmem_full_bar[as], (i >> 1) & 1, 3);
+      tc_fence_after_sync();
+      EpiCtx c;
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kPairTileN + half * (kPairTileN / 2);
+      c.warp_row0 = m0 + quad * 32;
+      c.row = c.warp_row0 + lane;
+      c.n0 = nt * kPairTileN + half * (kPairTileN / 2);
+      c.ncols = kPairTileN / 2;
+      c.M = M;
+      c.part = (nt * 2 + half) * (kPairTileN / 128);
+      c.stage = epi_stage + ew * kEpiStageBytes;
+      const uint32_t rel = leader_tmem_empty0 + as * 8;
+      Epi::run(ep, c, [rel, lane]() {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(rel);
+      });
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();       // the leader's MMAs have read the peer's shared memory; the peer's arrivals have landed in the leader
+  if (warp == 1) tmem_dealloc2<kAccStages * kPairTileN>(tmem_base);
+}
+
 }  // namespace novic

@@ -253,6 +253,51 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a cluster (ranks 2i, 2i + 1, same TPC) run ONE MMA of M = 256.  Each CTA holds its own 128 rows
+// of A, HALF of the B tile (N / 2 rows) and the 128 x N accumulator rows of its half in its own TMEM; the even ("leader") CTA issues
+// the instruction, the tensor cores of both SMs read both shared memories.  Per FLOP each SM takes in half the operand bytes of a
+// 128 x 128 single-CTA tile, which is what the L2 -> SM path can sustain next to the MMA rate (gemm.cuh, gemm2_kernel).
+// ------------------------------------------------------------------------------------------------
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst) {   // by one full warp of EACH CTA of the pair, same smem offset
+  static_assert(kCols >= 32 && kCols <= 512 && (kCols & (kCols - 1)) == 0, "TMEM columns: power of two in [32,512]");
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256 rows (128 per CTA); issued by ONE thread of the leader CTA.
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once the pair's previously issued MMAs have completed.
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+// 3-D tiled load into THIS CTA's shared memory whose bytes are counted on an mbarrier given by its cluster address (the leader's).
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int32_t c1, int32_t c2,
+                                                uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(0), "r"(c1), "r"(c2), "l"(cache_hint)
+      : "memory");
+}
+// Arrive on an mbarrier of any CTA of the cluster (address from dsmem_addr); release at cluster scope.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread t receives lane/row
 // (warp_id % 4) * 32 + t, columns [col, col + 32)).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {

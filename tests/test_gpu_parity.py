@@ -47,13 +47,18 @@ def test_library_is_the_cuda_path(built_lib):
     assert built_lib.novic_launch_count() - before > 100  # kernels were really launched through the library
 
 
+@pytest.mark.parametrize("block_n", [128, 256, 512])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 512), (100, 200, 128), (1, 6912, 512), (4096, 1536, 512), (777, 2048, 1024)])
-def test_tcgen05_gemm_building_block(built_lib, M, N, K):
+def test_tcgen05_gemm_building_block(built_lib, M, N, K, block_n):
+    """The persistent tcgen05 GEMM against an fp64 matmul of the same bf16 operands: 128 x 128 tiles (block_n 128), 128 x 256 tiles (256) and
+    256 x 256 tiles computed by CTA pairs with tcgen05.mma.cta_group::2 (512; ragged M / N exercise the pair whose second CTA has no rows)."""
+    if block_n != 128 and K % 128 != 0:
+        pytest.skip("the wide-stage kernels take two k-blocks per request")
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
     a = (torch.randn(M, K, generator=g) * 0.5).bfloat16().to(DEV)
     w = (torch.randn(N, K, generator=g) * 0.5).bfloat16().to(DEV)
     out = torch.full((M, N), float("nan"), device=DEV)
-    _abi.check(built_lib.novic_debug_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, 128, torch.cuda.current_stream().cuda_stream))
+    _abi.check(built_lib.novic_debug_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), M, N, K, block_n, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = a.double() @ w.double().t()
     assert (out.double() - ref).abs().max().item() < 1e-3
