@@ -119,6 +119,7 @@ bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj +
 int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
 int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 = 64-row tiles in the fused block kernel up to kBlock64MaxRows rows, 128-row tiles above; 64 / 128 = always
 constexpr int kBlock64MaxRows = 1536;
+int g_qkv_ws = 1;                              // NOVIC_QKV_WS=0: the QKV projection on the generic persistent kernel (else weight-stationary when every CTA gets >= 2 row blocks)
 int g_qkv_bn = 128;                            // NOVIC_QKV_BN=256: 128 x 256 tiles in the QKV GEMM when they fill a wave
 bool g_fuse_qkv = false;                       // NOVIC_FUSE_QKV=1: layer l + 1's QKV projection in the tail of layer l's block kernel (bit-identical; measured 0.2-0.3 ms per decode slower than its own launch)
 bool g_attn_tf = true;                         // NOVIC_ATTN_TF=0: teacher-forced passes use the key-by-key bulk kernel instead of attention_tf_kernel
@@ -172,20 +173,37 @@ int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, in
   return 0;
 }
 
-// CTA-pair GEMM (gemm2_kernel): ta / tb are 3-D maps with 128-row boxes and kWideKbs k-blocks per request; K a multiple of 128.
-template <class Epi, int STAGES>
-int set_gemm2_attr() {
-  static_assert(gemm2_smem_bytes(STAGES) <= 227 * 1024, "pair GEMM pipeline does not fit in shared memory");
-  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<Epi, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(STAGES)));
+// Weight-stationary GEMM (gemm_ws_kernel): K = 512, ta / tb 3-D maps with 128-row boxes and 2 k-blocks per request.
+template <class Epi, int WS_STAGES>
+int set_gemm_ws_attr() {
+  static_assert(gemm_ws_smem_bytes(WS_STAGES) <= 227 * 1024, "weight-stationary GEMM does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm_ws_kernel<Epi, WS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws_smem_bytes(WS_STAGES)));
   return 0;
 }
-template <class Epi, int STAGES>
+template <class Epi, int WS_STAGES>
+int launch_gemm_ws(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, const typename Epi::Params& ep, bool b_is_static) {
+  const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
+  const int per_tile = std::max(1, std::min<int>(g_num_sms / g_grid_div / n_tiles, static_cast<int>(ceil_div(M, kBlockM))));
+  CUDA_TRY(launch_k(gemm_ws_kernel<Epi, WS_STAGES>, dim3(static_cast<unsigned>(n_tiles * per_tile)), dim3(kGemmThreads), gemm_ws_smem_bytes(WS_STAGES), s, ta, tb, M, n_tiles, b_is_static ? 1 : 0, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// CTA-pair GEMM (gemm2_kernel): ta / tb are 3-D maps (kWideKbs k-blocks per request) with 128-row (A) and PN / 2-row (B) boxes; K a multiple of 128.
+template <class Epi, int STAGES, int PN = 256>
+int set_gemm2_attr() {
+  static_assert(gemm2_smem_bytes(STAGES, PN) <= 227 * 1024, "pair GEMM pipeline does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm2_kernel<Epi, STAGES, PN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm2_smem_bytes(STAGES, PN)));
+  return 0;
+}
+template <class Epi, int STAGES, int PN = 256>
 int launch_gemm2(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const typename Epi::Params& ep, bool b_is_static = false) {
-  const int n_tiles = static_cast<int>(ceil_div(N, kPairTileN));
+  const int n_tiles = static_cast<int>(ceil_div(N, PN));
   const int64_t total = n_tiles * ceil_div(M, 2 * kBlockM);
   if (K % (kBlockK * kPairKbs) != 0) return fail("pair GEMM needs K %% %d == 0", kBlockK * kPairKbs);
   const unsigned pairs = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div / 2)));
-  CUDA_TRY(launch_k(gemm2_kernel<Epi, STAGES>, dim3(2 * pairs), dim3(kGemmThreads), gemm2_smem_bytes(STAGES), s, ta, tb, M, n_tiles, static_cast<int>(K / kBlockK), b_is_static ? 1 : 0, ep));
+  CUDA_TRY(launch_k(gemm2_kernel<Epi, STAGES, PN>, dim3(2 * pairs), dim3(kGemmThreads), gemm2_smem_bytes(STAGES, PN), s, ta, tb, M, n_tiles, static_cast<int>(K / kBlockK), b_is_static ? 1 : 0, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -344,6 +362,7 @@ struct WeightPtrs {
   CUtensorMap tm_tok3, tm_in_proj3[NOVIC_MAX_LAYERS];   // 3-D maps (kWideKbs k-blocks per request) for the wide-stage decode GEMMs
   CUtensorMap tm_tok3w;                                   // the tied matrix with 256-row boxes (128 x 256 logits tiles)
   CUtensorMap tm_in_proj3w[NOVIC_MAX_LAYERS];             // in_proj with 256-row boxes (NOVIC_QKV_BN=256)
+  CUtensorMap tm_in_proj3h[NOVIC_MAX_LAYERS];             // in_proj with 64-row boxes (CTA pairs on 256 x 128 tiles: each CTA loads half of the tile's weight rows)
   CUtensorMap tm_embed_mlp, tm_tok, tm_in_proj[NOVIC_MAX_LAYERS], tm_out_proj[NOVIC_MAX_LAYERS], tm_linear1[NOVIC_MAX_LAYERS],
       tm_linear2[NOVIC_MAX_LAYERS];
   // transposed bf16 copies (B operands of the backward dgrad GEMMs: dX = dY * W needs W^T in K-major form)
@@ -569,8 +588,12 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       const EpiQKV::Params pq = qkv_params(l);
       if (g_wide_gemm) {
         KSpan t(kKQkv, s);
-        if (g_qkv_bn == 512 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {
+        if (g_qkv_ws && kE == kWsKb * kBlockK && ceil_div(M, kBlockM) >= 2 * (g_num_sms / g_grid_div / (3 * kE / kTileN))) {   // weight-stationary: >= 2 row blocks per CTA
+          if (launch_gemm_ws<EpiQKV, 2>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, pq, g_early_b)) return 1;
+        } else if (g_qkv_bn == 512 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {            // CTA pairs, 256 x 256 tiles
           if (launch_gemm2<EpiQKV, 3>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, g_early_b)) return 1;
+        } else if (g_qkv_bn == 384 && ceil_div(M, 2 * kBlockM) * (3 * kE / 128) >= g_num_sms / 2) {   // CTA pairs, 256 x 128 tiles
+          if (launch_gemm2<EpiQKV, 4, 128>(s, tm_xn3, h->w.tm_in_proj3h[l], M, 3 * kE, kE, pq, g_early_b)) return 1;
         } else if (g_qkv_bn == 256 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {
           if (launch_gemm<EpiQKV, 2, kWideKbs, 256>(s, tm_xn3, h->w.tm_in_proj3w[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
         } else if (launch_gemm<EpiQKV, kWideStages, kWideKbs>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
@@ -928,7 +951,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -978,6 +1001,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e22 = getenv("NOVIC_FUSE_BLOCK")) g_fuse_block = e22[0] != '0';
   if (const char* e23 = getenv("NOVIC_FUSE_QKV")) g_fuse_qkv = e23[0] != '0';
   if (const char* e24 = getenv("NOVIC_QKV_BN")) g_qkv_bn = atoi(e24);
+  if (const char* e27 = getenv("NOVIC_QKV_WS")) g_qkv_ws = atoi(e27);
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
@@ -1129,6 +1153,7 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
     if (make_tmap(&o.tm_in_proj[l], o.in_proj[l], 3 * E, E, 128)) return 1;
     if (make_tmap3(&o.tm_in_proj3[l], o.in_proj[l], 3 * E, E, 128, kWideKbs)) return 1;
     if (make_tmap3(&o.tm_in_proj3w[l], o.in_proj[l], 3 * E, E, 256, kWideKbs)) return 1;
+    if (make_tmap3(&o.tm_in_proj3h[l], o.in_proj[l], 3 * E, E, 64, kWideKbs)) return 1;
     if (make_tmap(&o.tm_out_proj[l], o.out_proj[l], E, E, kRowBN)) return 1;
     if (make_tmap(&o.tm_linear1[l], o.linear1[l], K, E, 128)) return 1;
     if (make_tmap(&o.tm_linear1_q[l], o.linear1[l], K, E, kFfnDim / kRowCluster)) return 1;

@@ -635,6 +635,156 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Weight-stationary variant of the persistent kernel for GEMMs with few column tiles and K = 512 (the decoder's QKV projection: 12 column
+// tiles, 32+ row blocks).  The generic kernel moves 256 KB of operands per 128 x 128 x 512 tile - 4.4 k cycles at what the L2 delivers when all
+// SMs pull, against 2.1 k cycles of MMA - and half of those bytes are the same 128 KB weight tile every time.  Here CTA b owns ONE column
+// tile (b % n_tiles) for the whole launch: its weight tile (8 k-blocks, 128 KB) is loaded once - before griddepcontrol.wait, i.e. under the
+// previous kernel's tail, since weights do not depend on it - and stays in shared memory; the CTA then walks the row blocks
+// b / n_tiles, + gridDim.x / n_tiles, ... streaming only the activation tiles through two or three 32 KB stages.  Grid = n_tiles x floor(#SMs / n_tiles).
+// Same accumulation order as gemm_kernel: results are bit-identical.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWsKb = 8;                                   // k-blocks of the stationary weight tile (K = 512)
+constexpr int kWsABytes = 2 * kABytes;                     // activation stage: two k-blocks (32 KB)
+// WS_STAGES = 2 (with the epilogue's 32 KB staging tile; a third stage only fits without it, and storing q / K / V straight from registers
+// - half-sector writes - costs more than the stage gains: 5.5 k instead of 4.5 k cycles per tile)
+__host__ __device__ constexpr int gemm_ws_smem_bytes(int stages) { return kWsKb * kBBytes + stages * kWsABytes + (stages == 2 ? kEpiWarps * kEpiStageBytes : 0) + 1024 + 256; }
+
+template <class Epi, int WS_STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles, int b_is_static,
+               typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_smem = smem;                                   // [8 k-blocks][128 rows x 128 B]
+  uint8_t* a_ring = b_smem + kWsKb * kBBytes;
+  uint8_t* epi_stage = a_ring + WS_STAGES * kWsABytes;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(epi_stage + (WS_STAGES == 2 ? kEpiWarps * kEpiStageBytes : 0));   // [4] one per pair of k-blocks
+  uint64_t* a_full = b_full + kWsKb / 2;
+  uint64_t* a_empty = a_full + WS_STAGES;
+  uint64_t* tmem_full_bar = a_empty + WS_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+  __shared__ int s_trace;
+
+  const int warp = threadIdx.x >> 5;
+  const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  const int nt = blockIdx.x % n_tiles, g0 = blockIdx.x / n_tiles, gstep = gridDim.x / n_tiles;
+  const int n0 = nt * kTileN;
+  pdl_trigger();
+  if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+      for (int j = 0; j < kWsKb / 2; ++j) mbar_init(&b_full[j], 1);
+      for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+      for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
+      fence_mbar_init();
+      if (b_is_static && g0 < m_blocks) {
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          mbar_arrive_expect_tx(&b_full[j], 2 * kBBytes);
+          tma_load_3d(b_smem + j * 2 * kBBytes, &tmap_b, &b_full[j], n0, 2 * j, kEvictLast);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    tmem_alloc<kAccStages * kTileN>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool tr = s_trace != 0;
+  pdl_wait();
+  if (threadIdx.x == 0) trace_point(tr, 1);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      if (!b_is_static && g0 < m_blocks) {
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          mbar_arrive_expect_tx(&b_full[j], 2 * kBBytes);
+          tma_load_3d(b_smem + j * 2 * kBBytes, &tmap_b, &b_full[j], n0, 2 * j, kEvictLast);
+        }
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int mb = g0; mb < m_blocks; mb += gstep) {
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          mbar_wait(&a_empty[stage], phase ^ 1, 1);
+          mbar_arrive_expect_tx(&a_full[stage], kWsABytes);
+          tma_load_3d(a_ring + stage * kWsABytes, &tmap_a, &a_full[stage], mb * kBlockM, 2 * j, kEvictNormal);
+          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      trace_point(tr, 3);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, kTileN);
+      int stage = 0; uint32_t phase = 0;
+      int i = 0;
+      for (int mb = g0; mb < m_blocks; mb += gstep, ++i) {
+        const int as = i & 1;
+        mbar_wait(&tmem_empty_bar[as], ((i >> 1) & 1) ^ 1, 9);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + as * kTileN;
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          if (i == 0) mbar_wait(&b_full[j], 0, 4);
+          mbar_wait(&a_full[stage], phase, 2);
+          if (i == 0 && j == 0) trace_point(tr, 4);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(a_ring + stage * kWsABytes);
+          const uint32_t sb = smem_u32(b_smem + j * 2 * kBBytes);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + jj * kABytes + k * (kUmmaK * 2)),
+                           umma_desc_sw128_kmajor(sb + jj * kBBytes + k * (kUmmaK * 2)), kIdesc, (j | jj | k) != 0 ? 1u : 0u);
+          umma_commit(&a_empty[stage]);
+          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[as]);
+        if (i == 0) trace_point(tr, 5);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const int lane = static_cast<int>(lane_id());
+    int i = 0;
+    for (int mb = g0; mb < m_blocks; mb += gstep, ++i) {
+      const int as = i & 1;
+      mbar_wait(&tmem_full_bar[as], (i >> 1) & 1, 3);
+      if (i < 8 && threadIdx.x == 64) trace_point(tr, 16 + 2 * i);
+      tc_fence_after_sync();
+      EpiCtx c;
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * (kTileN / 2);
+      c.warp_row0 = mb * kBlockM + quad * 32;
+      c.row = c.warp_row0 + lane;
+      c.n0 = n0 + half * (kTileN / 2);
+      c.ncols = kTileN / 2;
+      c.M = M;
+      c.part = nt * 2 + half;
+      c.stage = epi_stage + ew * kEpiStageBytes;
+      uint64_t* rel = &tmem_empty_bar[as];
+      Epi::run(ep, c, [rel, lane]() {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rel);
+      });
+      if (i < 8 && threadIdx.x == 64) trace_point(tr, 17 + 2 * i);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) trace_point(tr, 10);
+  if (warp == 1) tmem_dealloc<kAccStages * kTileN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Full-row GEMM + residual + LayerNorm, split over a 4-CTA cluster.
 //
 // The 512-wide output row of a 128-row tile is split across the 4 CTAs of a cluster (128 columns each), so a
@@ -1826,15 +1976,21 @@ outproj_ffn64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_c
 //     gemm_kernel<.., KBS = 2>), two accumulator stages of 256 columns = all 512 TMEM columns.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kPairKbs = 2;
-constexpr int kPairTileN = 256;
-constexpr int kPairStageBytes = kPairKbs * (kABytes + kBBytes);   // 64 KB per CTA: [A: 2 x 16 KB][B half: 2 x 16 KB]
-__host__ __device__ constexpr int gemm2_smem_bytes(int stages) { return stages * kPairStageBytes + kEpiWarps * kEpiStageBytes + 1024 + 256; }
+// PN = columns of the pair's tile: 256 (64 KB stages, the big GEMMs of the image encoder) or 128 (48 KB stages; keeps the 128 x 128 tile count
+// per CTA - and with it the wave quantisation - of the single-CTA kernel at 0.75 of its operand bytes: the decoder's QKV projection).
+__host__ __device__ constexpr int pair_stage_bytes(int pn) { return kPairKbs * (kABytes + (pn / 2) * kBlockK * 2); }
+__host__ __device__ constexpr int gemm2_smem_bytes(int stages, int pn = 256) { return stages * pair_stage_bytes(pn) + kEpiWarps * kEpiStageBytes + 1024 + 256; }
 
-template <class Epi, int STAGES>
+template <class Epi, int STAGES, int PN = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles /* of 256 columns */,
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles /* of PN columns */,
              int num_k_blocks, int b_is_static, typename Epi::Params ep) {
+  static_assert(PN == 256 || PN == 128, "pair tile width");
   constexpr int KBS = kPairKbs;
+  constexpr int kPairTileN = PN;
+  constexpr int kHalfN = PN / 2;                              // rows of B (= output columns) this CTA loads
+  constexpr int kBBytes = kHalfN * kBlockK * 2;               // shadows the namespace constant: one k-block of this CTA's B half
+  constexpr int kPairStageBytes = pair_stage_bytes(PN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -1877,7 +2033,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       // weight halves of the first pipeline fill before griddepcontrol.wait (they do not depend on the previous kernel)
       const int early_b = (b_is_static && pair < total_tiles) ? min(STAGES, loads_per_tile) : 0;
       if (early_b > 0) {
-        const int n0 = (pair % n_tiles) * kPairTileN + static_cast<int>(rank) * kTileN;
+        const int n0 = (pair % n_tiles) * kPairTileN + static_cast<int>(rank) * kHalfN;
         for (int i = 0; i < early_b; ++i) {
           if (leader) mbar_arrive_expect_tx(&full_bar[i], 2 * kPairStageBytes);
           tma_load_3d_2sm(stages + i * kPairStageBytes + KBS * kABytes, &tmap_b, leader_full0 + i * 8, n0, i * KBS, kEvictLast);
@@ -1888,7 +2044,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int nload = 0;
       for (int t = pair; t < total_tiles; t += npairs) {
         const int m0 = (t / n_tiles) * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
-        const int n0 = (t % n_tiles) * kPairTileN + static_cast<int>(rank) * kTileN;
+        const int n0 = (t % n_tiles) * kPairTileN + static_cast<int>(rank) * kHalfN;
         for (int kb = 0; kb < num_k_blocks; kb += KBS, ++nload) {
           uint8_t* sa = stages + stage * kPairStageBytes;
           if (nload >= early_b) {
@@ -1934,7 +2090,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     pdl_wait();
     const int ew = warp - 2;
     const int quad = warp & 3;
-    const int half = ew >> 2;            // which 128 of the tile's 256 columns
+    const int half = ew >> 2;            // which half of the tile's columns
     const int lane = static_cast<int>(lane_id());
     const uint32_t leader_tmem_empty0 = dsmem_addr(&tmem_empty_bar[0], 0);
     int i = 0;
