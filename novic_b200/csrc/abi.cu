@@ -759,7 +759,7 @@ int enqueue_greedy(NovicHandle* h, const Workspace& ws, float tau, float alpha, 
     const float* pos_next = step < G ? h->w.pos + static_cast<size_t>(P + step - 1) * kE : nullptr;
     {
       KSpan t(kKSelect, s);
-      CUDA_TRY(launch_k(select_greedy_kernel, dim3(static_cast<unsigned>(ceil_div(B, kWarpsPerBlock))), dim3(kWarpsPerBlock * 32), 0, s,
+      CUDA_TRY(launch_k(select_greedy_kernel, dim3(static_cast<unsigned>(ceil_div(B, kSelRows))), dim3(kSelRows * 32), kSelSmemBytes, s,
                         ws.part, ws.ntiles, B, G, step, V, inv_tau, c.label_smoothing, st, h->w.tok_f32, pos_next, h->w.norm1[0], ws.x,
                         ws.xn, c.ln_eps, guide.trie, guide.on ? ws.g_node : static_cast<int*>(nullptr)));
       ++g_launches;
@@ -981,6 +981,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   g_num_sms = prop.multiProcessorCount;
   h->attn_smem_budget = std::min<int>(200 * 1024, static_cast<int>(prop.sharedMemPerBlockOptin) - 8 * 1024);
   CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
+  CUDA_TRY(cudaFuncSetAttribute(select_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 3, 4)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<12, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(12, 2, 8)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));

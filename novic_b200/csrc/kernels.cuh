@@ -44,9 +44,12 @@ embed_prep_kernel(const float* __restrict__ embed, __nv_bfloat16* __restrict__ o
 // One residual-stream row from a token id: x = W_tied[tok] + pos[p]; xn = LayerNorm(x) * gain -> bf16.
 // Executed by a full warp; lane owns columns [16*lane, 16*lane + 16).
 // ---------------------------------------------------------------------------------------------------------
+// xs != nullptr: the fp32 values go to a shared-memory image of the row's 32-row block of the blocked layout instead of to x -
+// float4 unit (col4, r) at xs[col4 * 32 + (r ^ ((col4 >> 2) & 31))] (the XOR keeps both the row-wise writes here and the block-wise
+// read-out of select_greedy_kernel free of bank conflicts) - and the caller writes the whole 64 KB block with coalesced stores.
 __device__ __forceinline__ void embed_token_row(const float* __restrict__ wtok, const float* __restrict__ pos_row,
                                                 const float* __restrict__ gain, long long tok, int out_row,
-                                                float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps) {
+                                                float* __restrict__ x, __nv_bfloat16* __restrict__ xn, float eps, float4* xs = nullptr) {
   const int lane = lane_id();
   const float4* w4 = reinterpret_cast<const float4*>(wtok + static_cast<size_t>(tok) * kE) + lane * 4;
   const float4* p4 = reinterpret_cast<const float4*>(pos_row) + lane * 4;
@@ -64,10 +67,16 @@ __device__ __forceinline__ void embed_token_row(const float* __restrict__ wtok, 
   sumsq = warp_sum(sumsq);
   const float mean = sum * (1.0f / kE);
   const float rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + eps);
+  if (xs != nullptr) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<float4*>(x + xblk_off(out_row, lane * 4 + q)) =
-        make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    for (int q = 0; q < 4; ++q)
+      xs[(lane * 4 + q) * 32 + ((out_row & 31) ^ lane)] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(x + xblk_off(out_row, lane * 4 + q)) =
+          make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+  }
   const float4* g4 = reinterpret_cast<const float4*>(gain) + lane * 4;
   uint32_t o[8];
 #pragma unroll
@@ -691,39 +700,57 @@ struct GreedyState {
   int* alldone;          // [G + 1] per-step "every row finished" flags (host resets to 1)
 };
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// One CTA = 32 warps = the 32 consecutive rows of one block of the blocked fp32 layout of x: the warps stage their rows' values in a 64 KB
+// shared-memory image of the block and the CTA writes it out as one contiguous run (the warp-per-row version wrote every row as 128
+// scattered 16-byte pieces, half a sector each).
+constexpr int kSelRows = 32;
+constexpr int kSelSmemBytes = kSelRows * kE * 4;
+__global__ void __launch_bounds__(kSelRows * 32, 1)
 select_greedy_kernel(const LogitPartial* __restrict__ part, int ntiles, int B, int G, int step /*1-based*/, int V,
                      float inv_tau, float label_smoothing, GreedyState st, const float* __restrict__ wtok,
                      const float* __restrict__ pos_next, const float* __restrict__ gain0, float* __restrict__ x,
                      __nv_bfloat16* __restrict__ xn, float eps, GuideTrie guide, int* __restrict__ guide_node) {
+  extern __shared__ __align__(16) uint8_t sel_smem[];
+  float4* xs = reinterpret_cast<float4*>(sel_smem);
   // Wait BEFORE releasing the dependents: this kernel is the fence of a decode step.  Every other kernel releases its dependent at
   // entry, so with small grids a chain of prologues can run many launches ahead of the kernel that is actually executing; the
   // attention kernel's early K/V requests (rows written by earlier decode steps, issued before its own wait) are only safe because no
   // kernel of step t + 1 starts before this wait has passed, i.e. before every kernel of step t has completed.
   pdl_wait();
   pdl_trigger();
-  const int b = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (b >= B) return;
-  const bool guided = guide_node != nullptr;
-  const RowStats r = merge_partials(part + static_cast<size_t>(b) * ntiles, ntiles, inv_tau, guided);
-  const bool was_done = st.done[b] != 0;
-  const long long tok = r.best_idx < V ? r.best_idx : 0;   // no allowed id left: arg-max over all -inf = id 0 (the end token)
-  if (guided && lane_id() == 0) guide_node[b] = guide_child(guide, guide_node[b], static_cast<int>(tok));
-  if (lane_id() == 0) {
-    st.pad[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 1 : 0;
-    st.tok[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 0 : tok;
-    if (!was_done) {
-      st.score[b] += r.best_val * inv_tau - r.lse_tau;
-      float nll = r.lse_one - r.best_val;
-      if (label_smoothing != 0.f) nll = (1.f - label_smoothing) * nll + label_smoothing * (r.lse_one - r.sum_x / V);
-      st.nll[b] += nll;
-      st.len[b] += 1.f;
+  const int b0 = blockIdx.x * kSelRows;
+  const int b = b0 + (threadIdx.x >> 5);
+  if (b < B) {
+    const bool guided = guide_node != nullptr;
+    const RowStats r = merge_partials(part + static_cast<size_t>(b) * ntiles, ntiles, inv_tau, guided);
+    const bool was_done = st.done[b] != 0;
+    const long long tok = r.best_idx < V ? r.best_idx : 0;   // no allowed id left: arg-max over all -inf = id 0 (the end token)
+    if (guided && lane_id() == 0) guide_node[b] = guide_child(guide, guide_node[b], static_cast<int>(tok));
+    if (lane_id() == 0) {
+      st.pad[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 1 : 0;
+      st.tok[static_cast<size_t>(b) * G + (step - 1)] = was_done ? 0 : tok;
+      if (!was_done) {
+        st.score[b] += r.best_val * inv_tau - r.lse_tau;
+        float nll = r.lse_one - r.best_val;
+        if (label_smoothing != 0.f) nll = (1.f - label_smoothing) * nll + label_smoothing * (r.lse_one - r.sum_x / V);
+        st.nll[b] += nll;
+        st.len[b] += 1.f;
+      }
+      const bool now_done = was_done || tok == 0;
+      st.done[b] = now_done ? 1 : 0;
+      if (!now_done) st.alldone[step] = 0;
     }
-    const bool now_done = was_done || tok == 0;
-    st.done[b] = now_done ? 1 : 0;
-    if (!now_done) st.alldone[step] = 0;
+    if (pos_next != nullptr) embed_token_row(wtok, pos_next, gain0, tok, b, x, xn, eps, xs);
   }
-  if (pos_next != nullptr) embed_token_row(wtok, pos_next, gain0, tok, b, x, xn, eps);
+  if (pos_next == nullptr) return;
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(x + xblk_off(b0, 0));
+#pragma unroll
+  for (int i = 0; i < kSelRows * kE / 4 / (kSelRows * 32); ++i) {
+    const int e = i * (kSelRows * 32) + threadIdx.x;     // float4 unit of the block: col4 = e / 32, row = e % 32
+    const int col4 = e >> 5, r = e & 31;
+    if (b0 + r < B) dst[e] = xs[col4 * 32 + (r ^ ((col4 >> 2) & 31))];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
