@@ -130,6 +130,7 @@ bool g_early_b = true;                         // NOVIC_EARLY_B=0: no weight-til
 bool g_wide_gemm = true;                       // NOVIC_WIDE_GEMM=0: the 16 KB-request pipeline (5 stages of one k-block)
 constexpr int kWideKbs = 2, kWideStages = 3;   // decode-path QKV / logits GEMMs: 3 stages of 2 k-blocks, 32 KB TMA requests
 int g_num_sms = 148;
+int g_logits_ew = 16;                          // NOVIC_LOGITS_EW=8: eight epilogue warps in the 128 x 256 logits kernel (else 16)
 int g_logits_bn = 256;                         // NOVIC_LOGITS_BN=128: the logits GEMM on 128 x 128 tiles everywhere
 int g_grid_div = 1;   // persistent grids are divided by the number of concurrent chains so that chains co-run on disjoint SMs
 constexpr int kLogitBN = kTileN;
@@ -152,22 +153,22 @@ cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-template <class Epi, int STAGES, int KBS = 1, int BN = kTileN>
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN, int EW = kEpiWarps>
 int set_gemm_attr() {
-  static_assert(gemm_persistent_smem_bytes(STAGES, KBS, BN) <= 227 * 1024, "GEMM pipeline does not fit in shared memory");
-  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES, KBS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES, KBS, BN)));
+  static_assert(gemm_persistent_smem_bytes(STAGES, KBS, BN, EW) <= 227 * 1024, "GEMM pipeline does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES, KBS, BN, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES, KBS, BN, EW)));
   return 0;
 }
 
 // KBS > 1: ta / tb are 3-D maps (make_tmap3 with kbs = KBS), K a multiple of 64 * KBS, no split-K.
-template <class Epi, int STAGES, int KBS = 1, int BN = kTileN>
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN, int EW = kEpiWarps>
 int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K,
                 const typename Epi::Params& ep, int k_splits = 1, bool b_is_static = false) {
   const int n_tiles = static_cast<int>(ceil_div(N, BN));
   const int64_t total = n_tiles * ceil_div(M, kBlockM) * k_splits;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
   if (KBS > 1 && (k_splits != 1 || K % (kBlockK * KBS) != 0)) return fail("wide-stage GEMM needs K %% %d == 0 and no split-K", kBlockK * KBS);
-  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, KBS, BN>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES, KBS, BN), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, b_is_static ? 1 : 0, ep));
+  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, KBS, BN, EW>, dim3(grid), dim3(64 + 32 * EW), gemm_persistent_smem_bytes(STAGES, KBS, BN, EW), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, b_is_static ? 1 : 0, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -697,7 +698,8 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
     if (g_wide_gemm && g_logits_bn == 512 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
       return launch_gemm2<EpiLogits<0, false, false>, 3>(s, tm_a, h->w.tm_tok3, M, V, kE, pl, g_early_b);      // CTA pairs, 256 x 256 tiles
     if (g_wide_gemm && g_logits_bn >= 256 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
-      return launch_gemm<EpiLogits<0, false, false>, 2, kWideKbs, 256>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b);
+      return g_logits_ew == 16 ? launch_gemm<EpiLogits<0, false, false>, 2, kWideKbs, 256, 16>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b)
+                               : launch_gemm<EpiLogits<0, false, false>, 2, kWideKbs, 256>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b);
   }
   if (g_wide_gemm) return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kWideStages, kWideKbs>(s, tm_a, h->w.tm_tok3, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
   return launch_gemm<EpiLogits<HCAP, MASKED, BIAS>, kStagesLogits>(s, tm_a, h->w.tm_tok, M, h->cfg.vocab_size, kE, pl, 1, g_early_b);
@@ -951,7 +953,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -994,6 +996,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e12 = getenv("NOVIC_ATTN_CFG")) h->attn_cfg = atoi(e12);
   if (const char* e14 = getenv("NOVIC_WIDE_GEMM")) g_wide_gemm = e14[0] != '0';
   if (const char* e21 = getenv("NOVIC_LOGITS_BN")) g_logits_bn = atoi(e21);
+  if (const char* e28 = getenv("NOVIC_LOGITS_EW")) g_logits_ew = atoi(e28);
   if (const char* e15 = getenv("NOVIC_EARLY_B")) g_early_b = e15[0] != '0';
   if (const char* e16 = getenv("NOVIC_SPLIT_FFN")) g_split_ffn = e16[0] != '0';
   if (const char* e17 = getenv("NOVIC_ROW_STAGES")) g_row_stages = atoi(e17);
@@ -1724,7 +1727,7 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
     q.n_valid = N; q.nparts = np; q.inv_tau = 1.0f; q.ban_eos = 0; q.want_sumx = 0;
     q.allow = nullptr; q.allow_ld = 0; q.allow_mod = 0; q.mask_lse = 0;
     int rc2;
-    if (block_n == 256) rc2 = set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || launch_gemm<EpiLogits<0>, 2, kWideKbs, 256>(s, ta3, tb3, M, N, K, q);
+    if (block_n == 256) rc2 = set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() || launch_gemm<EpiLogits<0>, 2, kWideKbs, 256>(s, ta3, tb3, M, N, K, q);
     else rc2 = set_gemm2_attr<EpiLogits<0>, 3>() || launch_gemm2<EpiLogits<0>, 3>(s, ta3, tb3, M, N, K, q);
     CUDA_TRY(cudaFreeAsync(pt, s));
     return rc2;

@@ -464,8 +464,9 @@ __device__ __forceinline__ void mma_mainloop(const GemmSmemView& sv, uint32_t tm
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // 320
 constexpr int kAccStages = 2;                       // TMEM accumulator double buffering: 2 x 128 columns
 
-__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs = 1, int bn = kTileN) {
-  return stages * kbs * (kABytes + bn * kBlockK * 2) + kEpiWarps * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+// ew = epilogue warps: 8 (with their 4 KB staging tiles) or 16 (no staging memory: only for epilogues that do not use EpiCtx::stage)
+__host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs = 1, int bn = kTileN, int ew = kEpiWarps) {
+  return stages * kbs * (kABytes + bn * kBlockK * 2) + (ew == kEpiWarps ? kEpiWarps * kEpiStageBytes : 0) + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 // Persistent: grid = min(#tiles, #SMs); CTA b walks tiles b, b + grid, ... (n fastest, so neighbouring CTAs share A).
@@ -478,11 +479,17 @@ __host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs
 // two 128 x 128 ones, i.e. 0.75 of the L2 -> SM traffic per FLOP - the large GEMMs of the image encoder are bound by exactly that; the
 // two accumulator stages then fill all 512 TMEM columns and every epilogue thread owns 128 columns).  Only epilogues that honour
 // EpiCtx::ncols may be instantiated with BN = 256.
-template <class Epi, int STAGES, int KBS = 1, int BN = kTileN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// EW = epilogue warps: 8, or 16 (BN = 256 only: four warps per TMEM lane quadrant, 64 columns per thread).  The logits epilogue is bound by
+// issue latency - 32 k exponentials, compares and FMAs per tile on two warps per scheduler take 1.6 x the tile's MMA time - so twice the
+// warps make the kernel MMA-bound.  Such epilogues get no staging memory (EpiCtx::stage is null).
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN, int EW = kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles,
             int num_k_blocks, int k_splits, int b_is_static, typename Epi::Params ep) {
   static_assert(BN == 128 || BN == 256, "tile width");
+  static_assert(EW == kEpiWarps || (EW == 16 && BN == 256), "epilogue warps");
+  constexpr int kSubs = EW / 4;                            // column groups of the tile: 2 or 4
+  constexpr int kColsPerThread = BN / kSubs;
   constexpr int kTileN = BN;                               // shadows the namespace constant inside this kernel
   constexpr int kBBytes = BN * kBlockK * 2;
   constexpr int kStageBytes = KBS * (kABytes + kBBytes);   // this kernel's stage: [A: KBS k-blocks][B: KBS k-blocks]
@@ -490,7 +497,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
   uint8_t* epi_stage = smem + STAGES * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + (EW == kEpiWarps ? kEpiWarps * kEpiStageBytes : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;        // [kAccStages]
   uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
@@ -513,7 +520,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
+      for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], EW); }
       fence_mbar_init();
       if (early_b > 0) {
         const int tt = blockIdx.x % mn_tiles, sp = blockIdx.x / mn_tiles;
@@ -597,7 +604,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else {
     const int ew = warp - 2;
     const int quad = warp & 3;           // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;            // which 64 of the tile's 128 columns
+    const int half = ew >> 2;            // which column group of the tile
     const int lane = static_cast<int>(lane_id());
     int i = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
@@ -609,14 +616,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       if (i < 8 && threadIdx.x == 64) trace_point(tr, 16 + 2 * i);   // per-tile: accumulator ready / epilogue done
       tc_fence_after_sync();
       EpiCtx c;
-      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * (kTileN / 2);
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * kColsPerThread;
       c.warp_row0 = m0 + quad * 32;
       c.row = c.warp_row0 + lane;
-      c.n0 = nt * kTileN + half * (kTileN / 2);
-      c.ncols = kTileN / 2;
+      c.n0 = nt * kTileN + half * kColsPerThread;
+      c.ncols = kColsPerThread;
       c.M = M;
-      c.part = (nt * 2 + half) * (kTileN / 128);   // index of the thread's first 64-column slice
-      c.stage = epi_stage + ew * kEpiStageBytes;
+      c.part = nt * (kTileN / 64) + half * (kColsPerThread / 64);   // index of the thread's first 64-column slice
+      c.stage = EW == kEpiWarps ? epi_stage + ew * kEpiStageBytes : nullptr;
       uint64_t* rel = &tmem_empty_bar[as];
       Epi::run(ep, c, [rel, lane]() {
         tc_fence_before_sync();
