@@ -116,6 +116,7 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
+bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
 int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
 int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 = 64-row tiles in the fused block kernel up to kBlock64MaxRows rows, 128-row tiles above; 64 / 128 = always
 constexpr int kBlock64MaxRows = 1536;
@@ -215,6 +216,7 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, true)));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn_smem_bytes()));
+  CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn64_smem_bytes() + 16384));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM need all of it
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
@@ -256,6 +258,16 @@ int launch_outproj_ffn(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap
   static_assert(outproj_ffn_smem_bytes() <= 227 * 1024, "fused block kernel does not fit in shared memory");
   dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kBlockM)));
   CUDA_TRY(launch_k(outproj_ffn_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1q, tw2, twqkv, M, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// The block kernel with FFN1 split over K (outproj_ffn_ks_kernel); tw1 = linear1 with a 128-row box.
+int launch_outproj_ffn_ks(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1, const CUtensorMap& tw2, int M,
+                          const FusedBlockParams& ep) {
+  dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kBlockM)));
+  CUDA_TRY(launch_k(outproj_ffn_ks_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1, tw2, M, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -618,6 +630,10 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       KSpan t(kKFfn2, s);
       if ((g_block_rows == 64 || (g_block_rows == 0 && M <= kBlock64MaxRows)) && !fb.qkv_tail) {
         if (launch_outproj_ffn64(s, tm_ao64, h->w.tm_out_proj3[l], h->w.tm_linear1_q3[l], h->w.tm_linear2_3[l], M, fb)) return 1;
+        continue;
+      }
+      if (g_ffn1_ksplit && !fb.qkv_tail) {
+        if (launch_outproj_ffn_ks(s, tm_ao, h->w.tm_out_proj[l], h->w.tm_linear1[l], h->w.tm_linear2[l], M, fb)) return 1;
         continue;
       }
       if (launch_outproj_ffn(s, tm_ao, h->w.tm_out_proj[l], h->w.tm_linear1_q[l], h->w.tm_linear2[l], h->w.tm_in_proj3[l + 1 < L ? l + 1 : l], M, fb)) return 1;
@@ -1008,6 +1024,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e27 = getenv("NOVIC_QKV_WS")) g_qkv_ws = atoi(e27);
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
+  if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));
   if (const char* e1 = getenv("NOVIC_ATTN_V1")) h->attn_v1 = e1[0] == '1';
   if (const char* e7 = getenv("NOVIC_ATTN_STREAM")) h->attn_stream = e7[0] != '0';

@@ -1606,6 +1606,390 @@ outproj_ffn_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The block kernel with the first feed-forward GEMM split over K instead of over the hidden columns (default; NOVIC_FFN1_KSPLIT=0 restores
+// outproj_ffn_kernel).  The phase trace of outproj_ffn_kernel shows its largest single wait - 5.6 k of 29 k cycles - between the local LN2
+// rows and FFN1: every CTA needs the whole 512-wide LN2 row, i.e. 96 KB from its three peers at the ~17 B/clk a CTA receives over DSMEM.
+// Here a CTA multiplies only ITS OWN 128 LN2 columns (resident, nothing to wait for) with W1[:, own 128 columns]: a partial 128 x 128 hidden
+// tile in fp32.  The partial sums are then reduce-scattered - each CTA receives the three 128 x 32 fp32 blocks for the hidden columns it owns,
+// 48 KB instead of 96 KB - added in the order of the source rank, passed through GELU, and from there the kernel continues as before
+// (hidden-column exchange, FFN2, LayerNorm).  The hidden pre-activations are sums of four K = 128 partial products instead of one K = 512
+// accumulation: equal to fp32 rounding, not bit-identical to the other variants (tests compare with a tolerance of 1e-5 relative).
+// Shared memory after the out-proj phase: ring slot 0-1 = own LN2 tiles, 2-4 = outgoing blocks, 5-7 = incoming blocks (16 KB each).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(kRowCluster, 1, 1) __launch_bounds__(kRowThreads, 1)
+outproj_ffn_ks_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1,
+                      const __grid_constant__ CUtensorMap tmap_w2, int M, FusedBlockParams ep) {
+  constexpr int BN = kRowBN;
+  constexpr int kHSplit = kFfnDim / kRowCluster;              // 32 hidden columns per CTA
+  constexpr int kW1kb = kHSplit * kBlockK * 2;                // bytes of one k-block of the W1 slice: 4 KB
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, BN);
+  constexpr int kNkb = kE / kBlockK;                          // 8
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;                                       // phase A pipeline; afterwards the 8 k-block tiles of LN2(x_mid)
+  uint8_t* w1_smem = ring + kFbRing * kStageBytes;
+  uint8_t* w2_smem = w1_smem + kNkb * kW1kb;
+  uint8_t* h_smem = w2_smem + 2 * kBBytes;
+  uint8_t* after = h_smem + 2 * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
+  uint64_t* empty_bar = full_bar + kFbStages;
+  uint64_t* tmem_full0 = empty_bar + kFbStages;
+  uint64_t* w1_full = tmem_full0 + 1;
+  uint64_t* w2_full = tmem_full0 + 2;
+  uint64_t* tmem_full1 = tmem_full0 + 3;
+  uint64_t* tmem_full2 = tmem_full0 + 4;
+  uint64_t* pq_full = tmem_full0 + 5;                         // the three peers' partial FFN1 sums for this CTA's hidden columns have landed
+  uint64_t* hx_full = tmem_full0 + 6;                         // the three peers' hidden-column slices have landed in the h region
+  uint64_t* hop_ready = tmem_full0 + 7;                       // the epilogue warps have assembled the FFN2 A operand
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full0 + 8);
+  static_assert((2 * kFbStages + 8) * 8 + 4 <= 256, "barrier area");
+  constexpr int kPartBytes = kBlockM * kHSplit * 4;           // one peer's block of partial sums: 128 rows x 32 floats = 16 KB
+  constexpr int kHSlice = kBlockM * kHSplit * 2;              // one CTA's hidden columns: 128 rows x 64 B = 8 KB
+  float* s_gain_mid = reinterpret_cast<float*>(after + 256);
+  float* s_gain_out = s_gain_mid + BN;
+  // LayerNorm partials [2 halves][128 rows]: the first exchange uses the start of the h region (no hidden slice exists yet), the second
+  // the start of the W2 region (FFN2 has read it; the h region may still be the source of this CTA's outgoing slice copies)
+  float2* s_stats = reinterpret_cast<float2*>(h_smem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = static_cast<int>(lane_id());
+  const int m0 = blockIdx.y * kBlockM;
+  const uint32_t crank = cluster_ctarank();
+  const int coff = static_cast<int>(crank) * BN;
+  const int n0 = coff;
+  __shared__ int s_trace;
+  pdl_trigger();
+  if (threadIdx.x == 0) { s_trace = trace_begin() ? 1 : 0; trace_point(s_trace != 0, 0); }
+
+  GemmSmemView sv;
+  sv.stages = ring; sv.full_bar = full_bar; sv.empty_bar = empty_bar; sv.tmem_full_bar = tmem_full0; sv.tmem_slot = tmem_slot; sv.scratch = nullptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1); tma_prefetch_desc(&tmap_w2);
+      for (int st = 0; st < kFbStages; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
+      mbar_init(tmem_full0, 1); mbar_init(w1_full, 1); mbar_init(w2_full, 1); mbar_init(tmem_full1, 1); mbar_init(tmem_full2, 1);
+      mbar_init(pq_full, 1); mbar_init(hx_full, 1); mbar_init(hop_ready, kRowEpiWarps);
+      fence_mbar_init();
+      mbar_arrive_expect_tx(pq_full, (kRowCluster - 1) * kPartBytes);     // the peers' copies can only start after cluster barrier #1
+      mbar_arrive_expect_tx(hx_full, (kRowCluster - 1) * kHSlice);
+      // all weights first (they do not depend on the previous kernel), then wait, then the activation tiles
+      for (int kb = 0; kb < kFbStages; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], kStageBytes);
+        tma_load_2d(ring + kb * kStageBytes + kABytes, &tmap_wo, &full_bar[kb], kb * kBlockK, n0, kEvictLast);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < kFbStages; ++kb)
+        tma_load_2d(ring + kb * kStageBytes, &tmap_ao, &full_bar[kb], kb * kBlockK, m0, kEvictNormal);
+    }
+  } else if (warp == 1) {
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool tr = s_trace != 0;
+  pdl_wait();
+  if (threadIdx.x == 0) trace_point(tr, 1);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      producer_rest<kFbStages>(sv, &tmap_ao, &tmap_wo, kNkb, m0, n0);
+      // stages 4 and 5 are the W1 / W2 regions: load the feed-forward weights as soon as the out-proj MMAs have read them
+      mbar_wait(&empty_bar[kFbRing], 0, 1);
+      mbar_arrive_expect_tx(w1_full, 2 * kBBytes);
+      for (int j = 0; j < 2; ++j) tma_load_2d(w1_smem + j * kBBytes, &tmap_w1, w1_full, (static_cast<int>(crank) * 2 + j) * kBlockK, 0, kEvictLast);
+      mbar_wait(&empty_bar[kFbRing + 1], 0, 1);
+      mbar_arrive_expect_tx(w2_full, 2 * kBBytes);
+      tma_load_2d(w2_smem, &tmap_w2, w2_full, 0, n0, kEvictLast);
+      tma_load_2d(w2_smem + kBBytes, &tmap_w2, w2_full, kBlockK, n0, kEvictLast);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) mma_mainloop<kFbStages>(sv, tmem_base, kNkb, false);      // acc0 -> TMEM columns [0, 128)
+  }
+
+  // ---- phase A epilogue: residual + accumulator, LN2 statistics
+  const bool is_epi = warp >= 2;
+  const int ew = warp - 2;
+  const int quad = warp & 3;
+  const int half = ew >> 2;
+  const int row_in_tile = quad * 32 + lane;
+  const int row = m0 + row_in_tile;
+  const int c0 = coff + half * kRowCols;
+  const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  float r[kRowCols];
+  auto add_acc_and_stats = [&](uint32_t acc_col) {
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int c = 0; c < kRowCols / 16; ++c) {
+      float v[16];
+      tmem_ld_32x16(tmem_lane + acc_col + half * kRowCols + c * 16, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float t = r[c * 16 + j] + v[j];
+        r[c * 16 + j] = t;
+        sum += t;
+        sumsq = fmaf(t, t, sumsq);
+      }
+    }
+    s_stats[half * 128 + row_in_tile] = make_float2(sum, sumsq);
+  };
+  auto gather_stats = [&](float& mean, float& rstd) {
+    float2 part[kRowCluster * 2];
+#pragma unroll
+    for (uint32_t pr = 0; pr < kRowCluster; ++pr) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) part[pr * 2 + hh] = dsmem_ld_f32x2_addr(dsmem_addr(&s_stats[hh * 128 + row_in_tile], pr));
+    }
+    float sum = 0.f, sumsq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowCluster * 2; ++i) { sum += part[i].x; sumsq += part[i].y; }
+    mean = sum * (1.0f / kE);
+    rstd = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
+  };
+  if (is_epi) {
+    if (ew < 4) {
+      s_gain_mid[threadIdx.x - 64] = __ldg(ep.gain_mid + coff + (threadIdx.x - 64));
+      s_gain_out[threadIdx.x - 64] = __ldg(ep.gain_out + coff + (threadIdx.x - 64));
+    }
+    if (row < M) {
+#pragma unroll
+      for (int q = 0; q < kRowCols / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(ep.x + xblk_off(row, (c0 >> 2) + q));
+        r[q * 4] = t.x; r[q * 4 + 1] = t.y; r[q * 4 + 2] = t.z; r[q * 4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRowCols; ++i) r[i] = 0.f;
+    }
+    mbar_wait(tmem_full0, 0, 3);
+    if (threadIdx.x == 64) trace_point(tr, 2);
+    tc_fence_after_sync();
+    add_acc_and_stats(0);
+    if (threadIdx.x == 64) trace_point(tr, 3);
+  }
+  __syncthreads();          // s_gain visible to all epilogue warps
+  cluster_sync_all();       // #1: LN2 partials visible; every CTA's phase-A MMAs have completed (their accumulators were read)
+  if (threadIdx.x == 64) trace_point(tr, 4);
+
+  // ---- LN2 rows of this CTA's 128 columns -> the two k-block tiles of ITS FFN1 operand (ring slots 0 and 1); nothing leaves the CTA
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    if (row < M) gather_stats(mean, rstd);
+    const int kb = half;                                                     // this thread's 64 columns = one row of that k-block
+    uint8_t* arow = ring + kb * kABytes + row_in_tile * 128;
+#pragma unroll
+    for (int q = 0; q < kRowCols / 8; ++q) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain_mid[half * kRowCols + q * 8 + i];
+      *reinterpret_cast<uint4*>(arow + ((q ^ (row_in_tile & 7)) << 4)) =
+          make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    }
+    fence_proxy_async_smem();      // generic-proxy writes -> visible to the async proxy (the bulk copies and this CTA's own MMAs)
+    if (threadIdx.x == 64) trace_point(tr, 5);
+  }
+  __syncthreads();
+  if (threadIdx.x == 64) trace_point(tr, 6);
+
+  // ---- phase B: partial products of ALL 128 hidden columns over this CTA's 128 columns of K (acc1 -> TMEM columns [128, 256))
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(w1_full, 0, 6);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(ring), sb = smem_u32(w1_smem);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base + 128, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
+                       umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full1);
+    }
+  }
+  __syncwarp();
+  // reduce-scatter of the partial sums: the 32 hidden columns that CTA p owns go to p (16 KB per peer: [128 rows][32 floats], 16-byte units
+  // XOR-swizzled by the row); a thread stages the columns of destinations 2 * half and 2 * half + 1
+  uint8_t* send_buf = ring + 2 * kABytes;                       // [3][16 KB]: slot d - 1 holds the block for peer (rank + d) % 4
+  uint8_t* recv_buf = ring + 5 * kABytes;                       // [3][16 KB]: slot d - 1 receives the block of source (rank - d) % 4
+  if (is_epi) {
+    mbar_wait(tmem_full1, 0, 7);
+    if (threadIdx.x == 64) trace_point(tr, 7);
+    tc_fence_after_sync();
+#pragma unroll
+    for (int dd = 0; dd < 2; ++dd) {
+      const uint32_t dest = 2 * half + dd;
+      if (dest != crank) {
+        float pv[32];
+        tmem_ld_32x32(tmem_lane + 128 + dest * kHSplit, pv);
+        uint8_t* prow = send_buf + (((dest - crank) & 3u) - 1u) * kPartBytes + row_in_tile * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(prow + ((q ^ (row_in_tile & 7)) << 4)) = make_float4(pv[q * 4], pv[q * 4 + 1], pv[q * 4 + 2], pv[q * 4 + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+#pragma unroll
+      for (uint32_t d = 1; d < kRowCluster; ++d) {
+        const uint32_t pr = (crank + d) % kRowCluster;
+        dsmem_bulk_copy(dsmem_addr(recv_buf + (d - 1) * kPartBytes, pr), send_buf + (d - 1) * kPartBytes, kPartBytes, dsmem_addr(pq_full, pr));
+      }
+    }
+  }
+  __syncwarp();
+  if (threadIdx.x == 64) trace_point(tr, 15);
+  if (is_epi) {
+    // this thread's 16 hidden columns: the four partial sums added in the order of the source rank (the same in every kernel variant)
+    float own[16], v[16];
+    tmem_ld_32x16(tmem_lane + 128 + crank * kHSplit + half * 16, own);
+    mbar_wait(pq_full, 0, 5);
+#pragma unroll
+    for (uint32_t src = 0; src < kRowCluster; ++src) {
+      float t[16];
+      if (src == crank) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t[j] = own[j];
+      } else {
+        const uint8_t* prow = recv_buf + (((crank - src) & 3u) - 1u) * kPartBytes + row_in_tile * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 f = *reinterpret_cast<const float4*>(prow + (((half * 4 + q) ^ (row_in_tile & 7)) << 4));
+          t[q * 4] = f.x; t[q * 4 + 1] = f.y; t[q * 4 + 2] = f.z; t[q * 4 + 3] = f.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = src == 0 ? t[j] : v[j] + t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+    // hidden-column exchange: the h region holds four 8 KB slices [source CTA][128 rows][64 B]; this thread's 16 columns go into the
+    // local slice, which one thread then pushes to the peers with bulk copies (per-thread st.shared::cluster stores: 4.2 k cycles)
+    uint4* mine = reinterpret_cast<uint4*>(h_smem + static_cast<int>(crank) * kHSlice + row_in_tile * 64 + half * 32);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      mine[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                           pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint8_t* src = h_smem + static_cast<int>(crank) * kHSlice;
+#pragma unroll
+      for (uint32_t d = 1; d < kRowCluster; ++d) {
+        const uint32_t pr = (crank + d) % kRowCluster;
+        dsmem_bulk_copy(dsmem_addr(src, pr), src, kHSlice, dsmem_addr(hx_full, pr));
+      }
+    }
+  }
+  __syncwarp();
+  if (threadIdx.x == 64) trace_point(tr, 8);
+  if (is_epi) {
+    // assemble the K-major swizzled A operand of FFN2 in the (now dead) W1 region: this thread's row, k-block `half` = the slices of
+    // source CTAs 2 * half and 2 * half + 1
+    mbar_wait(hx_full, 0, 10);
+    uint8_t* hrow = w1_smem + half * kABytes + row_in_tile * 128;
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const uint4* src = reinterpret_cast<const uint4*>(h_smem + (2 * half + sidx) * kHSlice + row_in_tile * 64);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int chunk = sidx * 4 + c;
+        *reinterpret_cast<uint4*>(hrow + ((chunk ^ (row_in_tile & 7)) << 4)) = src[c];
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(hop_ready);
+  }
+  if (threadIdx.x == 64) trace_point(tr, 9);
+
+  // ---- phase C: second feed-forward GEMM, residual, LayerNorm
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(hop_ready, 0, 11);
+      mbar_wait(w2_full, 0, 8);
+      tc_fence_after_sync();
+      const uint32_t sa = smem_u32(w1_smem), sb = smem_u32(w2_smem);
+#pragma unroll
+      for (int kb = 0; kb < kFfnDim / kBlockK; ++kb)
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16_ss(tmem_base + 256, umma_desc_sw128_kmajor(sa + kb * kABytes + k * (kUmmaK * 2)),
+                       umma_desc_sw128_kmajor(sb + kb * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb | k) != 0 ? 1u : 0u);
+      umma_commit(tmem_full2);
+    }
+  }
+  __syncwarp();
+  if (is_epi) {
+    mbar_wait(tmem_full2, 0, 9);     // FFN2 has read W2: its first 2 KB hold the second round of statistics
+    if (threadIdx.x == 64) trace_point(tr, 10);
+    tc_fence_after_sync();
+    s_stats = reinterpret_cast<float2*>(w2_smem);
+    add_acc_and_stats(256);
+    if (threadIdx.x == 64) trace_point(tr, 11);
+  }
+  __syncwarp();
+  cluster_sync_all();       // #4
+  if (threadIdx.x == 64) trace_point(tr, 12);
+  if (is_epi) {
+    float mean = 0.f, rstd = 0.f;
+    s_stats = reinterpret_cast<float2*>(w2_smem);
+    if (row < M) gather_stats(mean, rstd);
+    uint8_t* stage = ring + ew * (32 * kRowStagePitch);      // the FFN1 operand is dead: every CTA's phase-B MMAs completed before #3
+    {
+      uint4* d = reinterpret_cast<uint4*>(stage + lane * kRowStagePitch);
+#pragma unroll
+      for (int q = 0; q < kRowCols / 8; ++q) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = (r[q * 8 + i] - mean) * rstd * s_gain_out[half * kRowCols + q * 8 + i];
+        d[q] = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+      }
+    }
+    if (row < M) {
+#pragma unroll
+      for (int q = 0; q < kRowCols / 4; ++q)
+        *reinterpret_cast<float4*>(ep.x + xblk_off(row, (c0 >> 2) + q)) = make_float4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+    }
+    __syncwarp();
+    const int warp_row0 = m0 + quad * 32;
+    const int sub = lane >> 3, chunk = lane & 7;
+#pragma unroll 4
+    for (int i = 0; i < 8; ++i) {
+      const int rr = i * 4 + sub;
+      const int grow = warp_row0 + rr;
+      if (grow < M) {
+        int nrow = grow;
+        bool keep = true;
+        if (ep.remap_rows_in > 0) {
+          const int seq = grow / ep.remap_rows_in;
+          const int k = grow - seq * ep.remap_rows_in;
+          keep = k >= ep.remap_skip;
+          nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+        }
+        if (keep)
+          *reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE + c0 + chunk * 8) =
+              *reinterpret_cast<const uint4*>(stage + rr * kRowStagePitch + chunk * 16);
+      }
+    }
+  }
+  if (threadIdx.x == 64) trace_point(tr, 13);
+  tc_fence_before_sync();
+  __syncwarp();
+  cluster_sync_relaxed();   // peers may still be reading this CTA's statistics / operand tiles
+  if (threadIdx.x == 0) trace_point(tr, 14);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
 // The same block on 64-ROW tiles with TWO CTAs resident per SM (decode path, default; NOVIC_BLOCK_ROWS=128 restores the kernel above).
 // The kernel above is one serial chain per CTA - loads -> MMA -> statistics -> hand-over -> MMA -> GELU -> hand-over -> MMA ->
 // statistics -> stores, about 30 k cycles of which the tensor core works 3 k - and at 4096 rows there is exactly one 128-row tile per
