@@ -298,6 +298,16 @@ int novic_debug_trace(int64_t* out16, int32_t enable);
 int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_per_seq,
                           const char* name, size_t* offset_out);
 
+/* The test-suite's own memory checker (compute-sanitizer is not available on the target pool).  novic_debug_redzone(bytes) makes every
+ * buffer that the library carves out of a caller-owned workspace (novic_workspace_bytes / novic_train_workspace_bytes / weight buffers;
+ * call it before those) be followed by `bytes` (a multiple of 256) that no kernel may touch; 0 restores the packed layout.
+ * novic_debug_zones lists the untouchable (offset, length) ranges - guard bands plus alignment gaps - of a workspace: kind 0 = the
+ * decode / teacher-forced workspace for the arguments of novic_workspace_bytes, kind 1 = the training workspace for the arguments
+ * (B, M, C) of novic_train_workspace_bytes.  Returns the number of ranges (pairs_out: room for `cap` pairs, may be NULL) or -1. */
+int novic_debug_redzone(size_t bytes);
+int64_t novic_debug_zones(const NovicHandle* h, int32_t kind, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_or_cols,
+                          uint64_t* pairs_out, int64_t cap);
+
 /* Kernel launches issued by this process through the library since load (bench.py's gpu_launches). */
 int64_t novic_launch_count(void);
 /* Device-side watchdog word (non-zero after a kernel trapped on a stuck mbarrier). */

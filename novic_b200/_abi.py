@@ -110,6 +110,8 @@ SIGNATURES = {
     "novic_debug_trace": (C.c_int, [C.POINTER(C.c_int64), C.c_int32]),
     "novic_debug_ws_offset": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_size_t)]),
     "novic_debug_keep_classes": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "novic_debug_redzone": (C.c_int, [C.c_size_t]),
+    "novic_debug_zones": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int64]),
     "novic_debug_transpose_bf16": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_int32, _FP, C.c_int32, C.c_void_p]),
     "novic_debug_wgrad": (C.c_int, [_FP, C.c_int32, _FP, C.c_int32, C.c_int64, C.c_int32, _FP, C.c_void_p]),
     "novic_debug_wgrad_splits": (C.c_int32, [C.c_int64, C.c_int64, C.c_int32]),

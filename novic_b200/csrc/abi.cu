@@ -350,11 +350,20 @@ struct KSpan {
   }
 };
 
+// Guard bands (novic_debug_redzone; compute-sanitizer is not available on the target pool, so the test-suite brings its own memcheck):
+// every buffer carved out of a caller-owned workspace is followed by g_redzone untouched bytes.  The tests fill a whole workspace with
+// 0xFF (bf16 / fp32 NaN patterns: a read of a byte no kernel wrote poisons the results), run a pass, and verify that the guard bands and
+// the alignment gaps - their (offset, length) list comes from novic_debug_zones - still hold the fill.
+size_t g_redzone = 0;
+std::vector<std::pair<size_t, size_t>>* g_zone_log = nullptr;
+
 struct Bump {
   size_t off = 0;
   size_t take(size_t bytes) {
     size_t o = off;
-    off = align_up(off + bytes, 256);
+    const size_t end = off + bytes;
+    off = align_up(end, 256) + g_redzone;
+    if (g_zone_log != nullptr && off > end) g_zone_log->emplace_back(end, off - end);
     return o;
   }
 };
@@ -1725,6 +1734,37 @@ int novic_debug_ws_offset(const NovicHandle* h, int64_t num_embeds, int32_t seqs
   else return fail("unknown workspace buffer '%s'", name);
   *offset_out = static_cast<size_t>(p - static_cast<const char*>(nullptr));
   return 0;
+}
+
+int novic_debug_redzone(size_t bytes) {
+  if (bytes % 256 != 0 || bytes > (1u << 20)) return fail("guard bands are multiples of 256 bytes, at most 1 MiB");
+  g_redzone = bytes;
+  return 0;
+}
+
+int64_t novic_debug_zones(const NovicHandle* h, int32_t kind, int64_t num_embeds, int32_t seqs_per_embed, int32_t rows_or_cols,
+                          uint64_t* pairs_out, int64_t cap) {
+  if (h == nullptr) { fail("null handle"); return -1; }
+  std::vector<std::pair<size_t, size_t>> zones;
+  g_zone_log = &zones;
+  if (kind == 0) {
+    ChainPlan cp;
+    plan_chains(h, num_embeds, seqs_per_embed, rows_or_cols, nullptr, &cp);
+    if (cp.n != 1) { g_zone_log = nullptr; fail("guard-band listing supports one chain"); return -1; }
+  } else if (kind == 1) {
+    TrainPlan t;
+    plan_train(h, num_embeds, seqs_per_embed, rows_or_cols, nullptr, &t);
+  } else {
+    g_zone_log = nullptr;
+    fail("kind: 0 = decode / teacher-forced workspace, 1 = training workspace");
+    return -1;
+  }
+  g_zone_log = nullptr;
+  for (size_t i = 0; i < zones.size() && static_cast<int64_t>(i) < cap && pairs_out != nullptr; ++i) {
+    pairs_out[2 * i] = zones[i].first;
+    pairs_out[2 * i + 1] = zones[i].second;
+  }
+  return static_cast<int64_t>(zones.size());
 }
 
 int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t M, int32_t N, int32_t K,
