@@ -121,6 +121,8 @@ int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra 
 int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 = 64-row tiles in the fused block kernel up to kBlock64MaxRows rows, 128-row tiles above; 64 / 128 = always
 constexpr int kBlock64MaxRows = 1536;
 int g_qkv_ws = 1;                              // NOVIC_QKV_WS=0: the QKV projection on the generic persistent kernel (else weight-stationary when every CTA gets >= 2 row blocks)
+int g_qkv_per_tile = 0;                        // NOVIC_QKV_PER_TILE: cap on the CTAs per column tile of the weight-stationary QKV kernel (tuning)
+int g_qkv_mc = 0;                              // NOVIC_QKV_MC=0: the weight-stationary QKV kernel without the cluster multicast of its activation stages
 int g_qkv_bn = 128;                            // NOVIC_QKV_BN=256: 128 x 256 tiles in the QKV GEMM when they fill a wave
 bool g_fuse_qkv = false;                       // NOVIC_FUSE_QKV=1: layer l + 1's QKV projection in the tail of layer l's block kernel (bit-identical; measured 0.2-0.3 ms per decode slower than its own launch)
 bool g_attn_tf = true;                         // NOVIC_ATTN_TF=0: teacher-forced passes use the key-by-key bulk kernel instead of attention_tf_kernel
@@ -180,13 +182,52 @@ template <class Epi, int WS_STAGES>
 int set_gemm_ws_attr() {
   static_assert(gemm_ws_smem_bytes(WS_STAGES) <= 227 * 1024, "weight-stationary GEMM does not fit in shared memory");
   CUDA_TRY(cudaFuncSetAttribute(gemm_ws_kernel<Epi, WS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws_smem_bytes(WS_STAGES)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_wsmc_kernel<Epi, WS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws_smem_bytes(WS_STAGES)));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_wsmc2_kernel<Epi, WS_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws_smem_bytes(WS_STAGES)));
   return 0;
 }
 template <class Epi, int WS_STAGES>
-int launch_gemm_ws(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, const typename Epi::Params& ep, bool b_is_static) {
+int launch_gemm_ws(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, const typename Epi::Params& ep, bool b_is_static,
+                   const CUtensorMap* ta2 = nullptr) {   // ta2: 2-D map of the activations (one k-block per request) for the multicast variant
   const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
-  const int per_tile = std::max(1, std::min<int>(g_num_sms / g_grid_div / n_tiles, static_cast<int>(ceil_div(M, kBlockM))));
-  CUDA_TRY(launch_k(gemm_ws_kernel<Epi, WS_STAGES>, dim3(static_cast<unsigned>(n_tiles * per_tile)), dim3(kGemmThreads), gemm_ws_smem_bytes(WS_STAGES), s, ta, tb, M, n_tiles, b_is_static ? 1 : 0, ep));
+  int per_tile = std::max(1, std::min<int>(g_num_sms / g_grid_div / n_tiles, static_cast<int>(ceil_div(M, kBlockM))));
+  if (g_qkv_per_tile > 0) per_tile = std::min(per_tile, g_qkv_per_tile);
+  if (getenv("NOVIC_DEBUG_CLUSTERS")) {
+    static bool once = false;
+    if (!once) {
+      once = true;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(144); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = gemm_ws_smem_bytes(WS_STAGES);
+      int n4 = -1, n2 = -1;
+      cudaOccupancyMaxActiveClusters(&n4, gemm_wsmc_kernel<Epi, WS_STAGES>, &cfg);
+      cudaOccupancyMaxActiveClusters(&n2, gemm_wsmc2_kernel<Epi, WS_STAGES>, &cfg);
+      fprintf(stderr, "max active clusters: of 4 CTAs %d, of 2 CTAs %d\n", n4, n2);
+    }
+  }
+  if (g_qkv_mc == 2 && ta2 != nullptr && n_tiles % 2 == 0)
+    CUDA_TRY(launch_k(gemm_wsmc2_kernel<Epi, WS_STAGES>, dim3(static_cast<unsigned>(n_tiles * per_tile)), dim3(kGemmThreads), gemm_ws_smem_bytes(WS_STAGES), s, *ta2, tb, M, n_tiles, b_is_static ? 1 : 0, ep));
+  else if (g_qkv_mc == 4 && ta2 != nullptr && n_tiles % 4 == 0)
+    CUDA_TRY(launch_k(gemm_wsmc_kernel<Epi, WS_STAGES>, dim3(static_cast<unsigned>(n_tiles * per_tile)), dim3(kGemmThreads), gemm_ws_smem_bytes(WS_STAGES), s, *ta2, tb, M, n_tiles, b_is_static ? 1 : 0, ep));
+  else
+    CUDA_TRY(launch_k(gemm_ws_kernel<Epi, WS_STAGES>, dim3(static_cast<unsigned>(n_tiles * per_tile)), dim3(kGemmThreads), gemm_ws_smem_bytes(WS_STAGES), s, ta, tb, M, n_tiles, b_is_static ? 1 : 0, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Weight-stationary GEMM on CTA pairs (gemm_ws2_kernel): K = 512; ta 3-D map with 128-row boxes, tb 3-D map with 64-row boxes (2 k-blocks per request).
+template <class Epi>
+int set_gemm_ws2_attr() {
+  static_assert(gemm_ws2_smem_bytes() <= 227 * 1024, "pair weight-stationary GEMM does not fit in shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(gemm_ws2_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_ws2_smem_bytes()));
+  return 0;
+}
+template <class Epi>
+int launch_gemm_ws2(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tbh, int M, int N, const typename Epi::Params& ep, bool b_is_static) {
+  const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
+  int per_tile = std::max(1, std::min<int>(g_num_sms / g_grid_div / 2 / n_tiles, static_cast<int>(ceil_div(M, 2 * kBlockM))));
+  if (g_qkv_per_tile > 0) per_tile = std::min(per_tile, g_qkv_per_tile);
+  CUDA_TRY(launch_k(gemm_ws2_kernel<Epi>, dim3(static_cast<unsigned>(2 * n_tiles * per_tile)), dim3(kGemmThreads), gemm_ws2_smem_bytes(), s, ta, tbh, M, n_tiles, b_is_static ? 1 : 0, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -611,7 +652,9 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       if (g_wide_gemm) {
         KSpan t(kKQkv, s);
         if (g_qkv_ws && kE == kWsKb * kBlockK && ceil_div(M, kBlockM) >= 2 * (g_num_sms / g_grid_div / (3 * kE / kTileN))) {   // weight-stationary: >= 2 row blocks per CTA
-          if (launch_gemm_ws<EpiQKV, 2>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, pq, g_early_b)) return 1;
+          if (g_qkv_ws == 2) {
+            if (launch_gemm_ws2<EpiQKV>(s, tm_xn3, h->w.tm_in_proj3h[l], M, 3 * kE, pq, g_early_b)) return 1;
+          } else if (launch_gemm_ws<EpiQKV, 2>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, pq, g_early_b, &tm_xn)) return 1;
         } else if (g_qkv_bn == 512 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {            // CTA pairs, 256 x 256 tiles
           if (launch_gemm2<EpiQKV, 3>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, g_early_b)) return 1;
         } else if (g_qkv_bn == 384 && ceil_div(M, 2 * kBlockM) * (3 * kE / 128) >= g_num_sms / 2) {   // CTA pairs, 256 x 128 tiles
@@ -978,7 +1021,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm_ws2_attr<EpiQKV>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -1031,6 +1074,8 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e23 = getenv("NOVIC_FUSE_QKV")) g_fuse_qkv = e23[0] != '0';
   if (const char* e24 = getenv("NOVIC_QKV_BN")) g_qkv_bn = atoi(e24);
   if (const char* e27 = getenv("NOVIC_QKV_WS")) g_qkv_ws = atoi(e27);
+  if (const char* e27b = getenv("NOVIC_QKV_MC")) g_qkv_mc = atoi(e27b);
+  if (const char* e27c = getenv("NOVIC_QKV_PER_TILE")) g_qkv_per_tile = atoi(e27c);
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';

@@ -656,10 +656,22 @@ constexpr int kWsABytes = 2 * kABytes;                     // activation stage: 
 // - half-sector writes - costs more than the stage gains: 5.5 k instead of 4.5 k cycles per tile)
 __host__ __device__ constexpr int gemm_ws_smem_bytes(int stages) { return kWsKb * kBBytes + stages * kWsABytes + (stages == 2 ? kEpiWarps * kEpiStageBytes : 0) + 1024 + 256; }
 
-template <class Epi, int WS_STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles, int b_is_static,
-               typename Epi::Params ep) {
+// MC (gemm_wsmc_kernel): the four CTAs of a cluster own four neighbouring column tiles and walk the SAME row blocks, so every activation
+// stage is requested once per cluster and multicast - stage-load n by the CTA of rank n % 4, which first waits until all four CTAs'
+// MMAs have released the stage (their commits arrive on every peer's `a_empty`, count 4).  A quarter of the L2 -> SM activation
+// traffic and of the TMA requests per SM (the limiter of the non-multicast kernel: two 32 KB requests in flight per SM, ~1.7 k cycles
+// each when 144 SMs pull at once).  Same operands, same accumulation order: bit-identical.
+// MC runs WS_STAGES * 2 stages of ONE k-block (16 KB, 2-D map tmap_a2): the same 64 KB of ring, but four requests in flight per cluster,
+// one per SM's TMA unit (with two 32 KB stages the cross-CTA release -> request -> multicast round trip was the cadence: measured
+// 6.2 instead of 5.3 ms per decode).
+template <class Epi, int WS_STAGES, int CL>     // CL = cluster size: 1 (no multicast), 2 or 4
+__device__ __forceinline__ void gemm_ws_body(const CUtensorMap& tmap_a, const CUtensorMap& tmap_a2, const CUtensorMap& tmap_b, int M, int n_tiles, int b_is_static,
+                                             const typename Epi::Params& ep) {
+  constexpr bool MC = CL > 1;
+  constexpr int kWsCluster = CL;
+  constexpr int KBS = MC ? 1 : 2;                           // k-blocks per activation stage
+  constexpr int NST = WS_STAGES * 2 / KBS;                  // activation stages
+  constexpr int kStBytes = KBS * kABytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_smem = smem;                                   // [8 k-blocks][128 rows x 128 B]
@@ -667,8 +679,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* epi_stage = a_ring + WS_STAGES * kWsABytes;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(epi_stage + (WS_STAGES == 2 ? kEpiWarps * kEpiStageBytes : 0));   // [4] one per pair of k-blocks
   uint64_t* a_full = b_full + kWsKb / 2;
-  uint64_t* a_empty = a_full + WS_STAGES;
-  uint64_t* tmem_full_bar = a_empty + WS_STAGES;
+  uint64_t* a_empty = a_full + NST;
+  uint64_t* tmem_full_bar = a_empty + NST;
   uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
   __shared__ int s_trace;
@@ -685,7 +697,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tma_prefetch_desc(&tmap_a);
       tma_prefetch_desc(&tmap_b);
       for (int j = 0; j < kWsKb / 2; ++j) mbar_init(&b_full[j], 1);
-      for (int s = 0; s < WS_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+      for (int s = 0; s < NST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], MC ? kWsCluster : 1); }
       for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kEpiWarps); }
       fence_mbar_init();
       if (b_is_static && g0 < m_blocks) {
@@ -700,9 +712,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (MC) cluster_sync_all();     // every CTA's barriers exist before a peer's multicast load or commit can reach them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const bool tr = s_trace != 0;
+  const uint32_t crank = MC ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMcMask = (1u << kWsCluster) - 1u;
   pdl_wait();
   if (threadIdx.x == 0) trace_point(tr, 1);
 
@@ -715,12 +730,14 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
       int stage = 0; uint32_t phase = 0;
+      uint32_t nload = 0;
       for (int mb = g0; mb < m_blocks; mb += gstep) {
-        for (int j = 0; j < kWsKb / 2; ++j) {
+        for (int j = 0; j < kWsKb / KBS; ++j, ++nload) {
           mbar_wait(&a_empty[stage], phase ^ 1, 1);
-          mbar_arrive_expect_tx(&a_full[stage], kWsABytes);
-          tma_load_3d(a_ring + stage * kWsABytes, &tmap_a, &a_full[stage], mb * kBlockM, 2 * j, kEvictNormal);
-          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+          mbar_arrive_expect_tx(&a_full[stage], kStBytes);
+          if (!MC) tma_load_3d(a_ring + stage * kStBytes, &tmap_a, &a_full[stage], mb * kBlockM, 2 * j, kEvictNormal);
+          else if ((nload % kWsCluster) == crank) tma_load_2d_mc(a_ring + stage * kStBytes, &tmap_a2, &a_full[stage], j * kBlockK, mb * kBlockM, kMcMask, kEvictNormal);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
       trace_point(tr, 3);
@@ -735,21 +752,21 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&tmem_empty_bar[as], ((i >> 1) & 1) ^ 1, 9);
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + as * kTileN;
-        for (int j = 0; j < kWsKb / 2; ++j) {
-          if (i == 0) mbar_wait(&b_full[j], 0, 4);
+        for (int j = 0; j < kWsKb / KBS; ++j) {
+          if (i == 0 && (j * KBS) % 2 == 0) mbar_wait(&b_full[j * KBS / 2], 0, 4);
           mbar_wait(&a_full[stage], phase, 2);
           if (i == 0 && j == 0) trace_point(tr, 4);
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(a_ring + stage * kWsABytes);
-          const uint32_t sb = smem_u32(b_smem + j * 2 * kBBytes);
+          const uint32_t sa = smem_u32(a_ring + stage * kStBytes);
+          const uint32_t sb = smem_u32(b_smem + j * KBS * kBBytes);
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj)
+          for (int jj = 0; jj < KBS; ++jj)
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + jj * kABytes + k * (kUmmaK * 2)),
                            umma_desc_sw128_kmajor(sb + jj * kBBytes + k * (kUmmaK * 2)), kIdesc, (j | jj | k) != 0 ? 1u : 0u);
-          umma_commit(&a_empty[stage]);
-          if (++stage == WS_STAGES) { stage = 0; phase ^= 1; }
+          if (MC) umma_commit_mc(&a_empty[stage], kMcMask); else umma_commit(&a_empty[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full_bar[as]);
         if (i == 0) trace_point(tr, 5);
@@ -787,8 +804,28 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before_sync();
   __syncthreads();
+  if (MC) cluster_sync_relaxed();   // a peer's last commits still arrive on this CTA's barriers: shared memory must outlive them
   if (threadIdx.x == 0) trace_point(tr, 10);
   if (warp == 1) tmem_dealloc<kAccStages * kTileN>(tmem_base);
+}
+
+template <class Epi, int WS_STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles, int b_is_static,
+               typename Epi::Params ep) {
+  gemm_ws_body<Epi, WS_STAGES, 1>(tmap_a, tmap_a, tmap_b, M, n_tiles, b_is_static, ep);
+}
+template <class Epi, int WS_STAGES>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_wsmc_kernel(const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles, int b_is_static,
+                 typename Epi::Params ep) {
+  gemm_ws_body<Epi, WS_STAGES, 4>(tmap_a2, tmap_a2, tmap_b, M, n_tiles, b_is_static, ep);
+}
+template <class Epi, int WS_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_wsmc2_kernel(const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles, int b_is_static,
+                  typename Epi::Params ep) {
+  gemm_ws_body<Epi, WS_STAGES, 2>(tmap_a2, tmap_a2, tmap_b, M, n_tiles, b_is_static, ep);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2513,5 +2550,168 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   cluster_sync_all();       // the leader's MMAs have read the peer's shared memory; the peer's arrivals have landed in the leader
   if (warp == 1) tmem_dealloc2<kAccStages * kPairTileN>(tmem_base);
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight-stationary GEMM on CTA pairs (the decoder's QKV projection at large batch; NOVIC_QKV_WS=2).  The phase traces of gemm_ws_kernel
+// and of its multicast variants show the same cadence - a 128 x 128 x 512 tile every ~4.5 k cycles against 2.1 k cycles of MMA - whatever
+// the request size or the L2 traffic: a TMA request takes ~2.2 k cycles from "stage released" to "landed" when every SM pulls, so the
+// tile rate is (bytes in flight) / (round trip), and with the 128 KB weight tile resident only 64 KB of activations fit in flight.
+// A CTA pair (tcgen05.mma.cta_group::2, M = 256) needs only HALF of the weight tile per CTA (64 of its 128 rows: 64 KB), which leaves
+// room for FOUR 32 KB activation stages - twice the bytes in flight for the same 128 x 128 x 512 of MMA work per CTA and tile.
+//   pair p owns column tile p % n_tiles for the whole launch and walks the 256-row blocks p / n_tiles, + npairs / n_tiles, ...;
+//   CTA r of the pair loads rows [64 r, 64 r + 64) of the weight tile once (before griddepcontrol.wait) and streams its own 128 rows
+//   of every block; barrier protocol as in gemm2_kernel (byte counts on the leader's barriers, multicast commits, the peer's epilogue
+//   warps arrive on the leader's "drained" barrier through its cluster address).  Same accumulation order: bit-identical.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWs2AStages = 4;
+constexpr int kWs2BKb = (kTileN / 2) * kBlockK * 2;        // one k-block of a CTA's weight half: 64 rows x 128 B = 8 KB
+__host__ __device__ constexpr int gemm_ws2_smem_bytes() { return kWsKb * kWs2BKb + kWs2AStages * kWsABytes + kEpiWarps * kEpiStageBytes + 1024 + 256; }
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_ws2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b /* 64-row boxes */, int M, int n_tiles, int b_is_static,
+                typename Epi::Params ep) {
+  constexpr int NST = kWs2AStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_smem = smem;                                   // [8 k-blocks][64 rows x 128 B]
+  uint8_t* a_ring = b_smem + kWsKb * kWs2BKb;
+  uint8_t* epi_stage = a_ring + NST * kWsABytes;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(epi_stage + kEpiWarps * kEpiStageBytes);   // [4] used in the leader only
+  uint64_t* a_full = b_full + kWsKb / 2;                    // used in the leader only
+  uint64_t* a_empty = a_full + NST;
+  uint64_t* tmem_full_bar = a_empty + NST;
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;    // used in the leader only: 2 x kEpiWarps arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
+  static_assert((kWsKb / 2 + 2 * NST + 2 * kAccStages) * 8 + 4 <= 256, "barrier area");
+  __shared__ int s_trace;
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int nt = pair % n_tiles, g0 = pair / n_tiles, gstep = npairs / n_tiles;
+  const int n0 = nt * kTileN;
+  pdl_trigger();
+  if (threadIdx.x == 0) { s_trace = (leader && trace_begin()) ? 1 : 0; trace_point(s_trace != 0, 0); }
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+      for (int j = 0; j < kWsKb / 2; ++j) mbar_init(&b_full[j], 1);
+      for (int s = 0; s < NST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+      for (int a = 0; a < kAccStages; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 2 * kEpiWarps); }
+      fence_mbar_init();
+    }
+  } else if (warp == 1) {
+    tmem_alloc2<kAccStages * kTileN>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();       // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const bool tr = s_trace != 0;
+  const uint32_t leader_bfull0 = dsmem_addr(&b_full[0], 0);
+  const uint32_t leader_afull0 = dsmem_addr(&a_full[0], 0);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      auto load_b = [&]() {
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          if (leader) mbar_arrive_expect_tx(&b_full[j], 2 * 2 * kWs2BKb);
+          tma_load_3d_2sm(b_smem + j * 2 * kWs2BKb, &tmap_b, leader_bfull0 + j * 8, n0 + static_cast<int>(rank) * (kTileN / 2), 2 * j, kEvictLast);
+        }
+      };
+      if (b_is_static && g0 < m_tiles) load_b();
+      pdl_wait();
+      if (threadIdx.x == 0) trace_point(tr, 1);
+      if (!b_is_static && g0 < m_tiles) load_b();
+      int stage = 0; uint32_t phase = 0;
+      for (int rp = g0; rp < m_tiles; rp += gstep) {
+        const int m0 = rp * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          mbar_wait(&a_empty[stage], phase ^ 1, 1);
+          if (leader) mbar_arrive_expect_tx(&a_full[stage], 2 * kWsABytes);
+          tma_load_3d_2sm(a_ring + stage * kWsABytes, &tmap_a, leader_afull0 + stage * 8, m0, 2 * j, kEvictNormal);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+      }
+      trace_point(tr, 3);
+    }
+  } else if (warp == 1) {
+    pdl_wait();
+    if (leader && elect_one()) {
+      constexpr uint32_t kIdesc = umma_idesc_bf16_f32(2 * kBlockM, kTileN);
+      int stage = 0; uint32_t phase = 0;
+      int i = 0;
+      for (int rp = g0; rp < m_tiles; rp += gstep, ++i) {
+        const int as = i & 1;
+        mbar_wait(&tmem_empty_bar[as], ((i >> 1) & 1) ^ 1, 9);   // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + as * kTileN;
+        for (int j = 0; j < kWsKb / 2; ++j) {
+          if (i == 0) mbar_wait(&b_full[j], 0, 4);
+          mbar_wait(&a_full[stage], phase, 2);
+          if (i == 0 && j == 0) trace_point(tr, 4);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(a_ring + stage * kWsABytes);
+          const uint32_t sb = smem_u32(b_smem + j * 2 * kWs2BKb);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma2_bf16_ss(acc, umma_desc_sw128_kmajor(sa + jj * kABytes + k * (kUmmaK * 2)),
+                            umma_desc_sw128_kmajor(sb + jj * kWs2BKb + k * (kUmmaK * 2)), kIdesc, (j | jj | k) != 0 ? 1u : 0u);
+          umma2_commit_mc(&a_empty[stage], 0x3);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+        umma2_commit_mc(&tmem_full_bar[as], 0x3);
+        if (i == 0) trace_point(tr, 5);
+      }
+    }
+    __syncwarp();
+  } else {
+    pdl_wait();
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int half = ew >> 2;
+    const int lane = static_cast<int>(lane_id());
+    const uint32_t leader_tmem_empty0 = dsmem_addr(&tmem_empty_bar[0], 0);
+    int i = 0;
+    for (int rp = g0; rp < m_tiles; rp += gstep, ++i) {
+      const int as = i & 1;
+      const int m0 = rp * (2 * kBlockM) + static_cast<int>(rank) * kBlockM;
+      mbar_wait(&tmem_full_bar[as], (i >> 1) & 1, 3);
+      if (i < 8 && threadIdx.x == 64) trace_point(tr, 16 + 2 * i);
+      tc_fence_after_sync();
+      EpiCtx c;
+      c.tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * kTileN + half * (kTileN / 2);
+      c.warp_row0 = m0 + quad * 32;
+      c.row = c.warp_row0 + lane;
+      c.n0 = n0 + half * (kTileN / 2);
+      c.ncols = kTileN / 2;
+      c.M = M;
+      c.part = nt * 2 + half;
+      c.stage = epi_stage + ew * kEpiStageBytes;
+      const uint32_t rel = leader_tmem_empty0 + as * 8;
+      Epi::run(ep, c, [rel, lane]() {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(rel);
+      });
+      if (i < 8 && threadIdx.x == 64) trace_point(tr, 17 + 2 * i);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();       // the leader's MMAs have read the peer's shared memory; the peer's arrivals have landed in the leader
+  if (threadIdx.x == 0) trace_point(tr, 10);
+  if (warp == 1) tmem_dealloc2<kAccStages * kTileN>(tmem_base);
+}
+
 
 }  // namespace novic

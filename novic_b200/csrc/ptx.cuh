@@ -159,6 +159,25 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// The same request delivered to the same shared-memory offset of EVERY CTA of `cta_mask` (bit r = cluster rank r); each destination's
+// mbarrier at the offset of `bar` receives the complete_tx of the bytes that landed there.
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c1, int32_t c2, uint16_t cta_mask,
+                                               uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6, %7;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(0), "r"(c1), "r"(c2), "h"(cta_mask), "l"(cache_hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, uint16_t cta_mask,
+                                               uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask), "l"(cache_hint)
+      : "memory");
+}
+
 // 3-D tiled load with all three coordinates (c0 innermost)
 __device__ __forceinline__ void tma_load_3d_at(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2,
                                                uint64_t cache_hint) {
@@ -277,6 +296,13 @@ __device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Single-CTA MMAs, arrival multicast: once this CTA's previously issued MMAs have completed, arrive on the mbarrier at this shared-memory
+// offset in every CTA of `cta_mask` (the peers whose multicast loads refill the operand stage those MMAs were reading).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 // Arrive on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once the pair's previously issued MMAs have completed.
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t cta_mask) {

@@ -442,3 +442,25 @@ def test_block_kernel_with_k_split_ffn1_agrees_to_rounding(monkeypatch):
     same = (g0[:, :n] == g1[:, :n]).all(dim=1).float().mean().item()
     print(f"rows with identical greedy ids: {same:.4f}")
     assert same >= 0.98
+
+
+def test_qkv_projection_variants_are_bit_identical(monkeypatch):
+    """The QKV projection of a large decode step (>= 24 row blocks) has five implementations with the same operands and accumulation order:
+    the generic persistent kernel (NOVIC_QKV_WS=0), the weight-stationary kernel (default), its cluster-multicast variants
+    (NOVIC_QKV_MC=2 / 4: activation stages requested once per cluster) and the weight-stationary CTA-pair kernel (NOVIC_QKV_WS=2,
+    tcgen05.mma.cta_group::2).  3100 embeddings = 24 full row blocks + a ragged one of 28 rows (the pair kernel's last pair has an empty
+    second CTA).  Ids, padding and scores must be bit-identical."""
+    dims = synth.DecoderDims()
+    sd = weight_case("lively")
+    embed = synth.synth_embeddings(3100, seed=8).to(DEV)
+    outs = []
+    for ws, mc in (("0", "0"), ("1", "0"), ("1", "2"), ("1", "4"), ("2", "0")):     # the switches are read when a handle is created
+        monkeypatch.setenv("NOVIC_QKV_WS", ws)
+        monkeypatch.setenv("NOVIC_QKV_MC", mc)
+        m = default_decoder(dims, sd).to(DEV)
+        with torch.inference_mode():
+            g = m.generate(embed, False, True, 0.9, 0.2, None, None, False)
+        outs.append((g[0].clone(), g[1].clone(), g[5].clone()))
+        del m
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) and torch.equal(outs[0][2], o[2])
