@@ -273,6 +273,10 @@ int novic_debug_gemm(const void* a_bf16, const void* w_bf16, float* out, int32_t
  *     CTAs (pure host arithmetic; -1 on bad arguments). */
 int novic_debug_transpose_bf16(const void* src, int64_t rows, int32_t cols, int32_t ld_src, void* dst, int32_t ld_dst, void* stream);
 int novic_debug_wgrad(const void* a_t, int32_t Mo, const void* b_t, int32_t No, int64_t K, int32_t ld, float* dw, void* stream);
+/*   novic_debug_wgrad_mn: the same product from the UN-transposed operands, dw[Mo, No] += a[K, Mo]^T * b[K, No] (row-major bf16, leading
+ *     dimensions ld_a / ld_b: multiples of 8, at least the column count rounded up to 64) - MN-major tcgen05 operand descriptors; what the
+ *     training step uses (NOVIC_WGRAD_MN=0 restores the transposed copies). */
+int novic_debug_wgrad_mn(const void* a, int32_t Mo, int32_t ld_a, const void* b, int32_t No, int32_t ld_b, int64_t K, float* dw, void* stream);
 int32_t novic_debug_wgrad_splits(int64_t tiles, int64_t kblocks, int32_t sms);
 
 /* Per-kernel-class device timing for roofline reports.  novic_kernel_timing(1) makes every subsequent direct

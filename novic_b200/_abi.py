@@ -114,6 +114,7 @@ SIGNATURES = {
     "novic_debug_zones": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_int64]),
     "novic_debug_transpose_bf16": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_int32, _FP, C.c_int32, C.c_void_p]),
     "novic_debug_wgrad": (C.c_int, [_FP, C.c_int32, _FP, C.c_int32, C.c_int64, C.c_int32, _FP, C.c_void_p]),
+    "novic_debug_wgrad_mn": (C.c_int, [_FP, C.c_int32, C.c_int32, _FP, C.c_int32, C.c_int32, C.c_int64, _FP, C.c_void_p]),
     "novic_debug_wgrad_splits": (C.c_int32, [C.c_int64, C.c_int64, C.c_int32]),
     "novic_kernel_timing": (C.c_int, [C.c_int32]),
     "novic_kernel_times": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),

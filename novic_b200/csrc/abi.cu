@@ -99,6 +99,22 @@ int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, i
   return 0;
 }
 
+// Row-major bf16 matrix [k_rows, cols] (leading dimension ld elements, ld >= cols rounded up to 64) as an MN-major GEMM operand: dims
+// (64 columns, k_rows, column blocks), box [64, 64, 2] = the two 64-column blocks of a 128-wide tile for one k-block of 64 rows.
+int make_tmap_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t cols, int64_t ld) {
+  if (load_driver_entry()) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ld % 8 != 0 || ld < static_cast<int64_t>(align_up(static_cast<size_t>(cols), 64)))
+    return fail("MN-major TMA operand: base must be 16-byte aligned, ld (%lld) a multiple of 8 and >= cols (%lld) rounded up to 64", (long long)ld, (long long)cols);
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(k_rows), static_cast<cuuint64_t>(ceil_div(cols, 64))};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(kBlockK), 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (MN-major) failed with CUresult %d (k_rows=%lld cols=%lld ld=%lld)", (int)r, (long long)k_rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
 // General 3-D bf16 map with 128-byte swizzle: dims / box innermost first, strides (bytes) of dimensions 1 and 2.
 int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3], const cuuint64_t (&strides)[2], const cuuint32_t (&box)[3]) {
   if (load_driver_entry()) return 1;
@@ -121,6 +137,7 @@ int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra 
 int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 = 64-row tiles in the fused block kernel up to kBlock64MaxRows rows, 128-row tiles above; 64 / 128 = always
 constexpr int kBlock64MaxRows = 1536;
 int g_qkv_ws = 1;                              // NOVIC_QKV_WS=0: the QKV projection on the generic persistent kernel (else weight-stationary when every CTA gets >= 2 row blocks)
+bool g_wgrad_mn = true;                        // NOVIC_WGRAD_MN=0: the training step's weight-gradient GEMMs on transposed bf16 copies of their operands (K-major descriptors)
 int g_qkv_per_tile = 0;                        // NOVIC_QKV_PER_TILE: cap on the CTAs per column tile of the weight-stationary QKV kernel (tuning)
 int g_qkv_mc = 0;                              // NOVIC_QKV_MC=0: the weight-stationary QKV kernel without the cluster multicast of its activation stages
 int g_qkv_bn = 128;                            // NOVIC_QKV_BN=256: 128 x 256 tiles in the QKV GEMM when they fill a wave
@@ -172,6 +189,25 @@ int launch_gemm(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, in
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
   if (KBS > 1 && (k_splits != 1 || K % (kBlockK * KBS) != 0)) return fail("wide-stage GEMM needs K %% %d == 0 and no split-K", kBlockK * KBS);
   CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, KBS, BN, EW>, dim3(grid), dim3(64 + 32 * EW), gemm_persistent_smem_bytes(STAGES, KBS, BN, EW), s, ta, tb, M, n_tiles, static_cast<int>(ceil_div(K, kBlockK)), k_splits, b_is_static ? 1 : 0, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// out[M, N] (+)= A[K, M]^T * B[K, N] with row-major operands (make_tmap_mn), split over K.
+template <class Epi, int STAGES, int MN = 3>
+int set_gemm_mn_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(gemm_kernel<Epi, STAGES, 1, kTileN, kEpiWarps, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_persistent_smem_bytes(STAGES, 1, kTileN, kEpiWarps)));
+  return 0;
+}
+// MN = 3: ta / tb from make_tmap_mn; MN = 2: ta an ordinary 2-D K-major map (make_tmap), tb from make_tmap_mn
+template <class Epi, int STAGES, int MN = 3>
+int launch_gemm_mn(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int64_t K, const typename Epi::Params& ep, int k_splits = 1) {
+  const int n_tiles = static_cast<int>(ceil_div(N, kTileN));
+  const int64_t total = n_tiles * ceil_div(M, kBlockM) * k_splits;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(total, std::max(1, g_num_sms / g_grid_div)));
+  CUDA_TRY(launch_k(gemm_kernel<Epi, STAGES, 1, kTileN, kEpiWarps, MN>, dim3(grid), dim3(kGemmThreads), gemm_persistent_smem_bytes(STAGES, 1, kTileN, kEpiWarps), s, ta, tb, M, n_tiles,
+                    static_cast<int>(ceil_div(K, kBlockK)), k_splits, 0, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -1029,7 +1065,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<0, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<4, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<16, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<16, true, true>, kWideStages, kWideKbs>() || set_gemm_attr<EpiStoreBF16, kStagesQKV>() || set_gemm_attr<EpiGeluTrain, kStagesGelu>() ||
-      set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
+      set_gemm_attr<EpiGradBlocked, kStagesQKV>() || set_gemm_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_mn_attr<EpiAtomicF32, kStagesQKV>() || set_gemm_mn_attr<EpiGradBlocked, kStagesQKV, 2>() || set_gemm_mn_attr<EpiStoreBF16, kStagesQKV, 2>() || set_gemm_attr<EpiDLogits, kStagesLogits>())
     return 1;
   CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_bwd_smem_bytes(kAttnBwdMaxS)));
   if (g_wd_host == nullptr) {
@@ -1076,6 +1112,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e27 = getenv("NOVIC_QKV_WS")) g_qkv_ws = atoi(e27);
   if (const char* e27b = getenv("NOVIC_QKV_MC")) g_qkv_mc = atoi(e27b);
   if (const char* e27c = getenv("NOVIC_QKV_PER_TILE")) g_qkv_per_tile = atoi(e27c);
+  if (const char* e27d = getenv("NOVIC_WGRAD_MN")) g_wgrad_mn = atoi(e27d) != 0;
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';
@@ -1205,20 +1242,33 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
     ++g_launches;
     return dst;
   };
-  o.tok_t = tr(o.tok, V, E, Vp);
-  for (size_t l = 0; l < L; ++l) {
-    o.in_proj_t[l] = tr(o.in_proj[l], 3 * E, E, 3 * E);
-    o.out_proj_t[l] = tr(o.out_proj[l], E, E, E);
-    o.linear1_t[l] = tr(o.linear1[l], K, E, K);
-    o.linear2_t[l] = tr(o.linear2[l], E, K, E);
-  }
-  CUDA_TRY(cudaGetLastError());
-  if (make_tmap(&o.tm_tok_t, o.tok_t, E, Vp, kTileN)) return 1;
-  for (size_t l = 0; l < L; ++l) {
-    if (make_tmap(&o.tm_in_proj_t[l], o.in_proj_t[l], E, 3 * E, kTileN)) return 1;
-    if (make_tmap(&o.tm_out_proj_t[l], o.out_proj_t[l], E, E, kTileN)) return 1;
-    if (make_tmap(&o.tm_linear1_t[l], o.linear1_t[l], E, K, kTileN)) return 1;
-    if (make_tmap(&o.tm_linear2_t[l], o.linear2_t[l], K, E, kTileN)) return 1;
+  if (g_wgrad_mn) {
+    // the data-gradient GEMMs dX = dY W read W[N_out, K_in] itself as an MN-major B operand (rows = contraction index; the rows beyond a
+    // ragged vocabulary are zero-filled by TMA): no transposed copies, nothing to refresh after an optimizer step but the bf16 casts
+    CUDA_TRY(cudaGetLastError());
+    if (make_tmap_mn(&o.tm_tok_t, o.tok, V, E, E)) return 1;
+    for (size_t l = 0; l < L; ++l) {
+      if (make_tmap_mn(&o.tm_in_proj_t[l], o.in_proj[l], 3 * E, E, E)) return 1;
+      if (make_tmap_mn(&o.tm_out_proj_t[l], o.out_proj[l], E, E, E)) return 1;
+      if (make_tmap_mn(&o.tm_linear1_t[l], o.linear1[l], K, E, E)) return 1;
+      if (make_tmap_mn(&o.tm_linear2_t[l], o.linear2[l], E, K, K)) return 1;
+    }
+  } else {
+    o.tok_t = tr(o.tok, V, E, Vp);
+    for (size_t l = 0; l < L; ++l) {
+      o.in_proj_t[l] = tr(o.in_proj[l], 3 * E, E, 3 * E);
+      o.out_proj_t[l] = tr(o.out_proj[l], E, E, E);
+      o.linear1_t[l] = tr(o.linear1[l], K, E, K);
+      o.linear2_t[l] = tr(o.linear2[l], E, K, E);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (make_tmap(&o.tm_tok_t, o.tok_t, E, Vp, kTileN)) return 1;
+    for (size_t l = 0; l < L; ++l) {
+      if (make_tmap(&o.tm_in_proj_t[l], o.in_proj_t[l], E, 3 * E, kTileN)) return 1;
+      if (make_tmap(&o.tm_out_proj_t[l], o.out_proj_t[l], E, E, kTileN)) return 1;
+      if (make_tmap(&o.tm_linear1_t[l], o.linear1_t[l], E, K, kTileN)) return 1;
+      if (make_tmap(&o.tm_linear2_t[l], o.linear2_t[l], K, E, kTileN)) return 1;
+    }
   }
   if (make_tmap(&o.tm_embed_mlp, o.embed_mlp, P * E, F, kRowBN)) return 1;
   if (make_tmap(&o.tm_tok, o.tok, V, E, kLogitBN)) return 1;
@@ -1860,6 +1910,12 @@ int novic_debug_transpose_bf16(const void* src, int64_t rows, int32_t cols, int3
   if (rows < 1 || cols < 1 || ld_src < cols || ld_dst < rows) return fail("bad transpose shape");
   return launch_transpose(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(src), rows, cols, ld_src,
                           static_cast<__nv_bfloat16*>(dst), ld_dst);
+}
+
+int novic_debug_wgrad_mn(const void* a, int32_t Mo, int32_t ld_a, const void* b, int32_t No, int32_t ld_b, int64_t K, float* dw, void* stream) {
+  if (Mo < 1 || No < 1 || K < 1) return fail("bad wgrad shape");
+  if (set_gemm_mn_attr<EpiAtomicF32, kStagesQKV>()) return 1;
+  return launch_wgrad_mn(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a), Mo, ld_a, static_cast<const __nv_bfloat16*>(b), No, ld_b, K, dw);
 }
 
 int novic_debug_wgrad(const void* a_t, int32_t Mo, const void* b_t, int32_t No, int64_t K, int32_t ld, float* dw, void* stream) {

@@ -482,11 +482,17 @@ __host__ __device__ constexpr int gemm_persistent_smem_bytes(int stages, int kbs
 // EW = epilogue warps: 8, or 16 (BN = 256 only: four warps per TMEM lane quadrant, 64 columns per thread).  The logits epilogue is bound by
 // issue latency - 32 k exponentials, compares and FMAs per tile on two warps per scheduler take 1.6 x the tile's MMA time - so twice the
 // warps make the kernel MMA-bound.  Such epilogues get no staging memory (EpiCtx::stage is null).
-template <class Epi, int STAGES, int KBS = 1, int BN = kTileN, int EW = kEpiWarps>
+// MN (bit 0: operand A, bit 1: operand B): that operand is a ROW-major matrix whose rows are the contraction index - A[K, M] or
+// B[K, N] - given as a 3-D map (64 columns, K rows, column blocks) with boxes of [64, 64, 2]: one request per k-block lands as two
+// [64 K rows][128 B] blocks, which the MMAs read through MN-major descriptors.  MN = 3: the weight-gradient GEMMs, out[M, N] =
+// A[K, M]^T * B[K, N], straight from the activations; MN = 2: the data-gradient GEMMs, out[M, N] = A[M, K] * B[K, N], straight from the
+// forward weights.  No transposed copies.
+template <class Epi, int STAGES, int KBS = 1, int BN = kTileN, int EW = kEpiWarps, int MN = 0>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int n_tiles,
             int num_k_blocks, int k_splits, int b_is_static, typename Epi::Params ep) {
   static_assert(BN == 128 || BN == 256, "tile width");
+  static_assert(!MN || (KBS == 1 && BN == 128), "MN-major operands: one k-block per stage, 128-wide tiles");
   static_assert(EW == kEpiWarps || (EW == 16 && BN == 256), "epilogue warps");
   constexpr int kSubs = EW / 4;                            // column groups of the tile: 2 or 4
   constexpr int kColsPerThread = BN / kSubs;
@@ -558,7 +564,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           }
-          if (KBS == 1) {
+          if (MN) {
+            if (MN & 1) tma_load_3d_at(sa, &tmap_a, &full_bar[stage], 0, kb * kBlockK, m0 / 64, kEvictNormal);
+            else tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
+            if (MN & 2) tma_load_3d_at(sa + kABytes, &tmap_b, &full_bar[stage], 0, kb * kBlockK, n0 / 64, (MN & 1) ? kEvictNormal : kEvictLast);
+            else tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
+          } else if (KBS == 1) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0, kEvictNormal);
             if (nload >= early_b) tma_load_2d(sa + kABytes, &tmap_b, &full_bar[stage], kb * kBlockK, n0, kEvictLast);
           } else {
@@ -572,7 +583,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t kIdesc = umma_idesc_bf16_f32(kBlockM, kTileN);
+      constexpr uint32_t kIdesc = MN ? umma_idesc_bf16_f32_mn(kBlockM, kTileN, (MN & 1) != 0, (MN & 2) != 0) : umma_idesc_bf16_f32(kBlockM, kTileN);
       int stage = 0; uint32_t phase = 0;
       int i = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
@@ -588,12 +599,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(stages + stage * kStageBytes);
           const uint32_t sb = sa + KBS * kABytes;
+          if (MN) {
 #pragma unroll
-          for (int j = 0; j < KBS; ++j)
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)     // 16 K rows = two 1024-byte groups of every 64-element block
+              umma_bf16_ss(acc, (MN & 1) ? umma_desc_sw128_mnmajor(sa + k * (kUmmaK * 128), kBlockK * 128) : umma_desc_sw128_kmajor(sa + k * (kUmmaK * 2)),
+                           (MN & 2) ? umma_desc_sw128_mnmajor(sb + k * (kUmmaK * 128), kBlockK * 128) : umma_desc_sw128_kmajor(sb + k * (kUmmaK * 2)),
+                           kIdesc, (kb > kb0 || k != 0) ? 1u : 0u);
+          } else {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + j * kABytes + k * (kUmmaK * 2)),
-                           umma_desc_sw128_kmajor(sb + j * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb > kb0 || (j | k) != 0) ? 1u : 0u);
+            for (int j = 0; j < KBS; ++j)
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16_ss(acc, umma_desc_sw128_kmajor(sa + j * kABytes + k * (kUmmaK * 2)),
+                             umma_desc_sw128_kmajor(sb + j * kBBytes + k * (kUmmaK * 2)), kIdesc, (kb > kb0 || (j | k) != 0) ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

@@ -244,6 +244,26 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr_by
   return d;
 }
 
+// MN-major operand (the weight-gradient GEMMs contract over the ROWS of two row-major activation matrices, so the contraction index is
+// the strided one): the tile is stored as blocks of 64 M/N-elements - each block [K rows][128 B], written by one TMA box with the
+// 128-byte swizzle - LBO apart; inside a block the 8-row groups along K are 1024 B apart (SBO).  One MMA (K = 16) reads two such
+// groups, so the start address advances by 2048 B per K step.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr_bytes & 0x3FFFFu) >> 4);  // [0,14)  start address >> 4
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;               // [16,30) leading byte offset >> 4: between 64-element blocks along M/N
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                    // [32,46) stride byte offset >> 4: between 8-row groups along K
+  d |= static_cast<uint64_t>(1) << 46;                            // [46,48) descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                            // [61,64) layout: SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_mn(uint32_t M, uint32_t N, bool a_mn = true, bool b_mn = true) {
+  return (1u << 4) | (1u << 7) | (1u << 10)
+         | ((a_mn ? 1u : 0u) << 15)       // [15]    A major: M
+         | ((b_mn ? 1u : 0u) << 16)       // [16]    B major: N
+         | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B (both K-major) and fp32 accumulation.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t M, uint32_t N) {
   return (1u << 4)          // [4,6)   D format: f32

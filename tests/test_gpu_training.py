@@ -177,6 +177,49 @@ def test_transpose_kernel_on_ragged_and_strided_shapes(R, Cc, ld_src, ld_dst, of
     assert bool((dst[:, R:] == 7.0).all())                # nothing written past the valid rows
 
 
+def test_gradients_with_transposed_operand_copies(monkeypatch):
+    """NOVIC_WGRAD_MN=0 - weight- and data-gradient GEMMs on transposed bf16 copies (K-major descriptors), the path before the MN-major
+    descriptors - gives the same gradients as the default path up to fp32 atomic order."""
+    dims = synth.DecoderDims()
+    sd = weight_case("eos")
+    embed = synth.synth_embeddings(24, seed=21).to(DEV)
+    tgt, pad = synth.synth_targets(24, dims, seed=5)
+    grads = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NOVIC_WGRAD_MN", flag)       # read when a handle is created
+        model = default_decoder(dims, sd, input_dropout=0.0, layer_dropout=0.0).to(DEV).train()
+        _, _, loss_sum, loss_basis, _ = model(embed, tgt.to(DEV), pad.to(DEV), None, True, True, False, None)
+        (loss_sum / loss_basis).backward()
+        grads.append({k: p.grad.detach().double().cpu() for k, p in model.named_parameters()})
+        del model
+    monkeypatch.setenv("NOVIC_WGRAD_MN", "1")
+    default_decoder(dims, sd).to(DEV)._state(torch.device(DEV))      # restore the process-wide switch
+    for k, g in grads[0].items():
+        rel = (grads[1][k] - g).norm().item() / max(g.norm().item(), 1e-30)
+        assert rel <= 1e-5, (k, rel)
+
+
+@pytest.mark.parametrize("Mo,No,K", [(128, 512, 19456), (512, 128, 456), (1536, 512, 95), (200, 72, 1000), (6907, 512, 360), (128, 128, 64), (512, 1024, 7)])
+def test_wgrad_gemm_from_row_major_operands(Mo, No, K):
+    """dw += a^T b straight from the row-major activations (MN-major tcgen05 descriptors; what the training step runs): against an fp64
+    product of the same bf16 operands, on top of a non-zero dw.  The columns between Mo / No and the leading dimension hold NaN: they
+    may be loaded (a 64-column block is the unit) but must never reach a stored element; rows beyond K do not exist (TMA zero fill)."""
+    from novic_b200 import _abi
+    lib = _abi.lib()
+    lda, ldb = (Mo + 63) // 64 * 64, (No + 63) // 64 * 64 + 64
+    g = torch.Generator().manual_seed(Mo + No + K)
+    a = torch.full((K, lda), float("nan"), dtype=torch.bfloat16); a[:, :Mo] = (torch.randn(K, Mo, generator=g) * 0.5).to(torch.bfloat16)
+    b = torch.full((K, ldb), float("nan"), dtype=torch.bfloat16); b[:, :No] = (torch.randn(K, No, generator=g) * 0.5).to(torch.bfloat16)
+    dw0 = torch.randn(Mo, No, generator=g)
+    dw = dw0.clone().to(DEV)
+    ad, bd = a.to(DEV), b.to(DEV)
+    _abi.check(lib.novic_debug_wgrad_mn(ad.data_ptr(), Mo, lda, bd.data_ptr(), No, ldb, K, dw.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = dw0.double() + a[:, :Mo].double().t() @ b[:, :No].double()
+    err = (dw.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, K ** 0.5), err
+
+
 @pytest.mark.parametrize("Mo,No,K", [(128, 512, 19456), (512, 128, 456), (1536, 512, 95), (200, 72, 1000), (6912, 512, 360)])
 def test_wgrad_gemm_accumulates_into_fp32(Mo, No, K):
     """dw += a_t b_t^T with split-K vector reductions: against an fp64 product of the same bf16 operands, on top of a non-zero dw."""
