@@ -9,7 +9,7 @@ CMD="python tools/ncu_target.py"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 340 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"
-for spec in "attention_stream_kernel_t:234:attention" "EpiQKV:252:qkv_gemm" "outproj_ffn_kernel:252:block_outproj_ffn" "EpiLogits:41:logits_gemm" "select_greedy_kernel:41:select"; do
+for spec in "attention_stream_kernel_t:234:attention" "EpiQKV:252:qkv_gemm" "outproj_ffn_ks_kernel:252:block_outproj_ffn" "EpiLogits:41:logits_gemm" "select_greedy_kernel:41:select"; do
   IFS=: read k skip name <<< "$spec"
   ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:$k --launch-skip $skip -c 1 -o gpurun_out/prof_${TAG}_$name $CMD > gpurun_out/ncu_${TAG}_$name.log 2>&1
   echo "ncu $name rc=$?"
