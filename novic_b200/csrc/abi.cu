@@ -14,6 +14,7 @@
 #include "train.cuh"
 #include "optim.cuh"
 #include "vit.cuh"
+#include "blockrows.cuh"
 
 using namespace novic;
 
@@ -99,6 +100,50 @@ int make_tmap3(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, i
   return 0;
 }
 
+// Weight matrix [rows, cols] with the row index split as 4 i + t (row-owner block kernel, blockrows.cuh): dims (64 columns, i, t, k-blocks);
+// a box of [64, 128, box_t, kbs] is box_t tiles "rows {4 i + t}" x kbs k-blocks, each tile in the K-major 128B-swizzled operand layout.
+int make_tmap4_perm(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_t, int kbs) {
+  if (load_driver_entry()) return 1;
+  if (rows != 512 || cols % (kBlockK * kbs) != 0) return fail("4-D TMA operand: rows = %lld (need 512), K = %lld", (long long)rows, (long long)cols);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail("TMA operand base is not 16-byte aligned");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(kBlockK), static_cast<cuuint64_t>(rows / 4), 4, static_cast<cuuint64_t>(cols / kBlockK)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(cols) * 2 * 4, static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(kBlockK) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBlockK), 128, static_cast<cuuint32_t>(box_t), static_cast<cuuint32_t>(kbs)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (4-D) failed with CUresult %d (rows=%lld cols=%lld box_t=%d kbs=%d)", (int)r,
+                                     (long long)rows, (long long)cols, box_t, kbs);
+  return 0;
+}
+
+// Store maps of the row-owner block kernel.  x: the 32-row blocked fp32 residual layout as (32 floats = 8 rows x 4 features, col4 index, 8-row
+// group, 32-row block); one box = one block's 64 KB, staged as [group][col4][128 B] with the 128-byte swizzle.
+int make_tmap_xblk(CUtensorMap* map, float* x, int64_t rows32) {
+  if (load_driver_entry()) return 1;
+  cuuint64_t dims[4] = {32, static_cast<cuuint64_t>(kE / 4), 4, static_cast<cuuint64_t>(rows32 / 32)};
+  cuuint64_t strides[3] = {32 * 4 * 4, 8 * 4 * 4, static_cast<cuuint64_t>(kE) * 32 * 4};
+  cuuint32_t box[4] = {32, static_cast<cuuint32_t>(kE / 4), 4, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (blocked residual) failed with CUresult %d (rows32=%lld)", (int)r, (long long)rows32);
+  return 0;
+}
+// xn [rows, 512] bf16 row-major, boxes of 32 rows x 256 columns, no swizzle (rows at or beyond `rows` are clipped by the store)
+int make_tmap_rows_store(CUtensorMap* map, __nv_bfloat16* base, int64_t rows) {
+  if (load_driver_entry()) return 1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(kE), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kE) * 2};
+  cuuint32_t box[2] = {256, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (row store) failed with CUresult %d (rows=%lld)", (int)r, (long long)rows);
+  return 0;
+}
+
 // Row-major bf16 matrix [k_rows, cols] (leading dimension ld elements, ld >= cols rounded up to 64) as an MN-major GEMM operand: dims
 // (64 columns, k_rows, column blocks), box [64, 64, 2] = the two 64-column blocks of a 128-wide tile for one k-block of 64 rows.
 int make_tmap_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t cols, int64_t ld) {
@@ -134,7 +179,7 @@ constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
 int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
-int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 = 64-row tiles in the fused block kernel up to kBlock64MaxRows rows, 128-row tiles above; 64 / 128 = always
+int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 / 32 = the row-owner block kernel (blockrows.cuh, one CTA per 32 rows); 64 / 128 = the cluster kernels on 64- / 128-row tiles; -1 = the round-2 policy (64-row tiles up to kBlock64MaxRows rows, 128-row tiles above)
 constexpr int kBlock64MaxRows = 1536;
 int g_qkv_ws = 1;                              // NOVIC_QKV_WS=0: the QKV projection on the generic persistent kernel (else weight-stationary when every CTA gets >= 2 row blocks)
 bool g_wgrad_mn = true;                        // NOVIC_WGRAD_MN=0: the training step's weight-gradient GEMMs on transposed bf16 copies of their operands (K-major descriptors)
@@ -296,6 +341,7 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn64_smem_bytes() + 16384));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM need all of it
+  CUDA_TRY(cudaFuncSetAttribute(block_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
@@ -345,6 +391,17 @@ int launch_outproj_ffn_ks(cudaStream_t s, const CUtensorMap& tao, const CUtensor
                           const FusedBlockParams& ep) {
   dim3 grid(static_cast<unsigned>(kRowCluster), static_cast<unsigned>(ceil_div(M, kBlockM)));
   CUDA_TRY(launch_k(outproj_ffn_ks_kernel, grid, dim3(kRowThreads), outproj_ffn_smem_bytes(), s, tao, two, tw1, tw2, M, ep));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// The same block with one CTA per 32 rows and the weights streamed as the M operand (block_rows_kernel, blockrows.cuh); tao: 3-D, 32 rows x 8
+// k-blocks; two / tw2: 4-D row-permuted maps (make_tmap4_perm); tw1: 3-D, 128 rows x 4 k-blocks.
+int launch_block_rows(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
+                      const CUtensorMap& txn, int M, const FusedBlockParams& ep) {
+  CUDA_TRY(launch_k(block_rows_kernel, dim3(static_cast<unsigned>(ceil_div(M, kBrRows))), dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn,
+                    M, ep));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -458,6 +515,8 @@ struct WeightPtrs {
   // 3-D maps of the 64-row block kernel: out_proj (128 rows x 2 k-blocks = 32 KB per request), linear1 (32 rows x 8 k-blocks: the CTA's whole
   // slice in one request), linear2 (128 rows x 2 k-blocks: the CTA's whole slice in one request)
   CUtensorMap tm_out_proj3[NOVIC_MAX_LAYERS], tm_linear1_q3[NOVIC_MAX_LAYERS], tm_linear2_3[NOVIC_MAX_LAYERS];
+  // maps of the row-owner block kernel: out_proj / linear2 with rows split as 4 i + t (64 KB requests), linear1 as 128 rows x 4 k-blocks
+  CUtensorMap tm_out_proj4[NOVIC_MAX_LAYERS], tm_linear1_r3[NOVIC_MAX_LAYERS], tm_linear2_4[NOVIC_MAX_LAYERS];
   CUtensorMap tm_tok3, tm_in_proj3[NOVIC_MAX_LAYERS];   // 3-D maps (kWideKbs k-blocks per request) for the wide-stage decode GEMMs
   CUtensorMap tm_tok3w;                                   // the tied matrix with 256-row boxes (128 x 256 logits tiles)
   CUtensorMap tm_in_proj3w[NOVIC_MAX_LAYERS];             // in_proj with 256-row boxes (NOVIC_QKV_BN=256)
@@ -674,6 +733,11 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   CUtensorMap tm_xn3, tm_ao64;
   if (make_tmap3(&tm_xn3, ws.xn, M, kE, kBlockM, kWideKbs)) return 1;
   if (make_tmap3(&tm_ao64, ws.ao, M, kE, kHbRows, 2)) return 1;
+  CUtensorMap tm_ao32;
+  if (make_tmap3(&tm_ao32, ws.ao, M, kE, kBrRows, kE / kBlockK)) return 1;
+  CUtensorMap tm_x_st, tm_xn_st;
+  if (make_tmap_xblk(&tm_x_st, ws.x, static_cast<int64_t>(ceil_div(M, 32)) * 32)) return 1;
+  if (make_tmap_rows_store(&tm_xn_st, ws.xn, M)) return 1;
   const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
   const bool block_fused = g_fuse_block && h->fuse_ffn && c.ffn_dim == kFfnDim;
   const bool qkv_tail = block_fused && g_fuse_qkv && g_wide_gemm;     // layer l + 1's QKV projection in the tail of layer l's block kernel
@@ -716,7 +780,11 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
         fb.remap_rows_in = pc.remap_in; fb.remap_skip = pc.remap_skip; fb.remap_rows_out = pc.remap_out;
       }
       KSpan t(kKFfn2, s);
-      if ((g_block_rows == 64 || (g_block_rows == 0 && M <= kBlock64MaxRows)) && !fb.qkv_tail) {
+      if ((g_block_rows == 32 || g_block_rows == 0) && !fb.qkv_tail) {
+        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, tm_xn_st, M, fb)) return 1;
+        continue;
+      }
+      if ((g_block_rows == 64 || (g_block_rows <= 0 && M <= kBlock64MaxRows)) && !fb.qkv_tail) {
         if (launch_outproj_ffn64(s, tm_ao64, h->w.tm_out_proj3[l], h->w.tm_linear1_q3[l], h->w.tm_linear2_3[l], M, fb)) return 1;
         continue;
       }
@@ -1287,6 +1355,9 @@ int novic_set_weights(NovicHandle* h, const NovicWeights* w, void* wbuf, size_t 
       if (make_tmap3(&o.tm_out_proj3[l], o.out_proj[l], E, E, kRowBN, 2)) return 1;
       if (make_tmap3(&o.tm_linear1_q3[l], o.linear1[l], K, E, kFfnDim / kRowCluster, E / kBlockK)) return 1;
       if (make_tmap3(&o.tm_linear2_3[l], o.linear2[l], E, K, kRowBN, K / kBlockK)) return 1;
+      if (make_tmap4_perm(&o.tm_out_proj4[l], o.out_proj[l], E, E, 1, 4)) return 1;
+      if (make_tmap3(&o.tm_linear1_r3[l], o.linear1[l], K, E, 128, 4)) return 1;
+      if (make_tmap4_perm(&o.tm_linear2_4[l], o.linear2[l], E, K, 2, 2)) return 1;
     }
   }
   // the weight pointers are baked into captured graphs (the training step's graphs only bake addresses inside wbuf, which a

@@ -1,5 +1,6 @@
 """Per-phase clock64 trace of the fused out-proj + feed-forward cluster kernel (CTA (0,1), decode step, 1-layer model)."""
 import ctypes as C, os, sys
+os.environ.setdefault("NOVIC_BLOCK_ROWS", "128")   # this tool traces the 128-row cluster kernel (the default block kernel has tools/trace_blockrows.py)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from novic_b200 import synth, default_decoder, _abi
