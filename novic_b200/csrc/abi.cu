@@ -177,6 +177,7 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
+bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
 int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
 int g_block_rows = 0;                          // NOVIC_BLOCK_ROWS: 0 / 32 = the row-owner block kernel (blockrows.cuh, one CTA per 32 rows); 64 / 128 = the cluster kernels on 64- / 128-row tiles; -1 = the round-2 policy (64-row tiles up to kBlock64MaxRows rows, 128-row tiles above)
@@ -341,7 +342,8 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, outproj_ffn64_smem_bytes() + 16384));
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM need all of it
-  CUDA_TRY(cudaFuncSetAttribute(block_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows_smem_bytes()));
+  CUDA_TRY(cudaFuncSetAttribute(block_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows_smem_bytes()));
+  CUDA_TRY(cudaFuncSetAttribute(block_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
@@ -398,10 +400,12 @@ int launch_outproj_ffn_ks(cudaStream_t s, const CUtensorMap& tao, const CUtensor
 
 // The same block with one CTA per 32 rows and the weights streamed as the M operand (block_rows_kernel, blockrows.cuh); tao: 3-D, 32 rows x 8
 // k-blocks; two / tw2: 4-D row-permuted maps (make_tmap4_perm); tw1: 3-D, 128 rows x 4 k-blocks.
+// pa != nullptr: the decode-step attention of the same rows runs inside the kernel (block_rows_kernel<true>: no attention launch, no ao round trip).
 int launch_block_rows(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
-                      const CUtensorMap& txn, int M, const FusedBlockParams& ep) {
-  CUDA_TRY(launch_k(block_rows_kernel, dim3(static_cast<unsigned>(ceil_div(M, kBrRows))), dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn,
-                    M, ep));
+                      const CUtensorMap& txn, int M, const FusedBlockParams& ep, const AttnParams* pa) {
+  const dim3 grid(static_cast<unsigned>(ceil_div(M, kBrRows)));
+  if (pa != nullptr) CUDA_TRY(launch_k(block_rows_kernel<true>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn, M, ep, *pa));
+  else CUDA_TRY(launch_k(block_rows_kernel<false>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn, M, ep, AttnParams{}));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -670,7 +674,7 @@ struct PassCfg {
   int remap_in, remap_skip, remap_out;
 };
 
-int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int l, cudaStream_t s) {
+AttnParams attention_params(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int l) {
   const NovicCfg& c = h->cfg;
   const int S = h->S();
   const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
@@ -684,6 +688,12 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   pa.early_loads = h->attn_early;
   pa.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHeadDim));
   pa.stream_hint = g_attn_hint;
+  return pa;
+}
+
+int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int l, cudaStream_t s) {
+  const NovicCfg& c = h->cfg;
+  const AttnParams pa = attention_params(h, ws, pc, l);
   KSpan t(kKAttn, s);
   if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
     auto go = [&](auto kernel, int warps, int slots, int chunk) {
@@ -767,7 +777,10 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
         if (launch_gemm<EpiQKV, kStagesQKV>(s, tm_xn, h->w.tm_in_proj[l], M, 3 * kE, kE, pq, 1, g_early_b)) return 1;
       }
     }
-    if (launch_attention(h, ws, pc, l, s)) return 1;
+    // decode steps (one query per sequence, no key padding) with the row-owner block kernel: the attention runs inside it
+    const bool attn_in_block = block_fused && !qkv_tail && (g_block_rows == 32 || g_block_rows == 0) && g_fuse_attn && h->attn_stream && pc.nq == 1 &&
+                               pc.keypad == nullptr;
+    if (!attn_in_block && launch_attention(h, ws, pc, l, s)) return 1;
     if (block_fused) {
       FusedBlockParams fb{};
       fb.x = ws.x; fb.gain_mid = h->w.norm2[l]; fb.eps = c.ln_eps;
@@ -781,7 +794,8 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       }
       KSpan t(kKFfn2, s);
       if ((g_block_rows == 32 || g_block_rows == 0) && !fb.qkv_tail) {
-        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, tm_xn_st, M, fb)) return 1;
+        const AttnParams pa = attention_params(h, ws, pc, l);
+        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, tm_xn_st, M, fb, attn_in_block ? &pa : nullptr)) return 1;
         continue;
       }
       if ((g_block_rows == 64 || (g_block_rows <= 0 && M <= kBlock64MaxRows)) && !fb.qkv_tail) {
@@ -1182,6 +1196,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e27c = getenv("NOVIC_QKV_PER_TILE")) g_qkv_per_tile = atoi(e27c);
   if (const char* e27d = getenv("NOVIC_WGRAD_MN")) g_wgrad_mn = atoi(e27d) != 0;
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
+  if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));

@@ -479,6 +479,32 @@ def test_row_owner_block_kernel_agrees_with_the_cluster_kernel_to_rounding(monke
         assert torch.equal(t0[:, 0], t1[:, 0]) or (l0[:, 0].topk(2, dim=-1).values.diff(dim=-1).abs().min().item() <= 0.02)
 
 
+def test_attention_inside_the_block_kernel_is_bit_identical(monkeypatch):
+    """NOVIC_FUSE_ATTN=1: the decode-step attention of a CTA's 32 sequences runs on the epilogue warps of the row-owner block kernel
+    (block_rows_kernel<true>, K / V staged in two slots of the weight ring, the attention row written straight into the resident MMA
+    operand) instead of as a launch of its own.  Same arithmetic in the same order -> bit-identical ids, padding, scores and step
+    logits for greedy (ragged: 301 rows = 9 blocks + 13 rows, so some warps own one sequence and some none), beam search (ancestry
+    tables, per-row K / V requests) and guided decoding keeps working on the unfused kernels of its masked passes."""
+    dims = synth.DecoderDims()
+    sd = weight_case("eos")
+    embed = synth.synth_embeddings(301, seed=5).to(DEV)
+    outs = []
+    for flag in ("0", "1"):                      # the switch is read when a handle is created
+        monkeypatch.setenv("NOVIC_FUSE_ATTN", flag)
+        m = default_decoder(dims, sd).to(DEV)
+        with torch.inference_mode():
+            g = m.generate(embed, True, True, 0.9, 0.2, None, None, False)
+            b = m.generate_beam(embed[:70], 3, 1.0, 0.0, None, False, 0.0, None, False)
+            small = [m.generate(embed[:n], False, True, 1.0, 0.0, None, None, False) for n in (1, 17, 33)]
+        outs.append((g, b, small))
+        del m
+    (g0, b0, s0), (g1, b1, s1) = outs
+    assert torch.equal(g0[0], g1[0]) and torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2]) and torch.equal(g0[5], g1[5])
+    assert torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1]) and torch.equal(b0[2], b1[2])
+    for a, c in zip(s0, s1):
+        assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[5], c[5])
+
+
 def test_qkv_projection_variants_are_bit_identical(monkeypatch):
     """The QKV projection of a large decode step (>= 24 row blocks) has five implementations with the same operands and accumulation order:
     the generic persistent kernel (NOVIC_QKV_WS=0), the weight-stationary kernel (default), its cluster-multicast variants

@@ -39,7 +39,9 @@ def to_bytes(v, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-res = {"_comment": "per kernel class: DRAM traffic of ONE launch from an ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum; decode step with 16 visible keys, B = 4096, cold L2, serialised) beside that launch's algorithmic bytes; written by tools/ncu_traffic.py"}
+out_path = os.path.join(ROOT, "profiles", "traffic.json")
+res = json.load(open(out_path)) if os.path.isfile(out_path) else {}      # classes without a capture under this tag keep their entry
+res["_comment"] =  "per kernel class: DRAM traffic of ONE launch from an ncu --set full capture (dram__bytes_read.sum + dram__bytes_write.sum; decode step with 16 visible keys, B = 4096, cold L2, serialised) beside that launch's algorithmic bytes; written by tools/ncu_traffic.py"
 for name, algo in ALGO.items():
     path = os.path.join(src, f"{tag}_ncu_{name}_raw.csv")
     if not os.path.isfile(path):
@@ -53,4 +55,4 @@ for name, algo in ALGO.items():
                  "dram_pct": m["dram_pct"], "tensor_pipe_pct": m["tensor_pct"], "warps_active_pct": m["warps_pct"],
                  "duration": m["duration"], "duration_unit": m["duration_unit"], "kernel": m["kernel"], "capture": f"profiles/{tag}_ncu_{name}_raw.csv"}
     print(name, json.dumps(res[name]))
-json.dump(res, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+json.dump(res, open(out_path, "w"), indent=1)
