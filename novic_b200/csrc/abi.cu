@@ -177,6 +177,7 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
+int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes of at least this many rows run the row-owner block kernel on 64 rows per CTA (block_rows64_kernel); 0 = never
 bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
 int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
@@ -344,6 +345,7 @@ int set_rowln_attr() {
   CUDA_TRY(cudaFuncSetAttribute(outproj_ffn64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // two CTAs per SM need all of it
   CUDA_TRY(cudaFuncSetAttribute(block_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(block_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows_smem_bytes()));
+  CUDA_TRY(cudaFuncSetAttribute(block_rows64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_rows64_smem_bytes()));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<kStagesRow, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(kStagesRow, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, false)));
   CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rowln_smem_bytes(2, true)));
@@ -402,8 +404,14 @@ int launch_outproj_ffn_ks(cudaStream_t s, const CUtensorMap& tao, const CUtensor
 // k-blocks; two / tw2: 4-D row-permuted maps (make_tmap4_perm); tw1: 3-D, 128 rows x 4 k-blocks.
 // pa != nullptr: the decode-step attention of the same rows runs inside the kernel (block_rows_kernel<true>: no attention launch, no ao round trip).
 int launch_block_rows(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
-                      const CUtensorMap& txn, int M, const FusedBlockParams& ep, const AttnParams* pa) {
+                      const CUtensorMap& txn, int M, const FusedBlockParams& ep, const AttnParams* pa, const CUtensorMap* ta64 = nullptr) {
   const dim3 grid(static_cast<unsigned>(ceil_div(M, kBrRows)));
+  if (pa == nullptr && ta64 != nullptr) {
+    CUDA_TRY(launch_k(block_rows64_kernel, dim3(static_cast<unsigned>(ceil_div(M, kB64Rows))), dim3(kBrThreads), block_rows64_smem_bytes(), s, *ta64, two, tw1, tw2, tx, txn, M, ep));
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   if (pa != nullptr) CUDA_TRY(launch_k(block_rows_kernel<true>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn, M, ep, *pa));
   else CUDA_TRY(launch_k(block_rows_kernel<false>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn, M, ep, AttnParams{}));
   ++g_launches;
@@ -745,6 +753,10 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   if (make_tmap3(&tm_ao64, ws.ao, M, kE, kHbRows, 2)) return 1;
   CUtensorMap tm_ao32;
   if (make_tmap3(&tm_ao32, ws.ao, M, kE, kBrRows, kE / kBlockK)) return 1;
+  CUtensorMap tm_ao64r;
+  if (make_tmap3(&tm_ao64r, ws.ao, M, kE, kB64Rows, kE / kBlockK)) return 1;
+  // 64 rows per CTA once 32-row CTAs need more than one wave (g_block_rows64_min, NOVIC_BLOCK_ROWS64_MIN; 0 = never)
+  const bool rows64 = g_block_rows64_min > 0 && M >= g_block_rows64_min;
   CUtensorMap tm_x_st, tm_xn_st;
   if (make_tmap_xblk(&tm_x_st, ws.x, static_cast<int64_t>(ceil_div(M, 32)) * 32)) return 1;
   if (make_tmap_rows_store(&tm_xn_st, ws.xn, M)) return 1;
@@ -795,7 +807,8 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       KSpan t(kKFfn2, s);
       if ((g_block_rows == 32 || g_block_rows == 0) && !fb.qkv_tail) {
         const AttnParams pa = attention_params(h, ws, pc, l);
-        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, tm_xn_st, M, fb, attn_in_block ? &pa : nullptr)) return 1;
+        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, tm_xn_st, M, fb, attn_in_block ? &pa : nullptr,
+                              (rows64 && !attn_in_block) ? &tm_ao64r : nullptr)) return 1;
         continue;
       }
       if ((g_block_rows == 64 || (g_block_rows <= 0 && M <= kBlock64MaxRows)) && !fb.qkv_tail) {
@@ -1197,6 +1210,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e27d = getenv("NOVIC_WGRAD_MN")) g_wgrad_mn = atoi(e27d) != 0;
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
+  if (const char* e25c = getenv("NOVIC_BLOCK_ROWS64_MIN")) g_block_rows64_min = atoi(e25c);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';
   if (const char* e13 = getenv("NOVIC_SKIP_CLASSES")) g_skip_classes = static_cast<unsigned>(strtoul(e13, nullptr, 0));

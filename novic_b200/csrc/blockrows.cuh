@@ -606,4 +606,340 @@ block_rows_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_cons
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same kernel on 64 rows per CTA, for passes of more rows than one wave of 32-row CTAs covers (beam search, prefix / teacher-forced
+// passes, 8192-embedding batches).  A tcgen05.mma costs the same 60 cycles for N = 64 as for N = 32 and the weight stream per CTA is the
+// same 768 KB, so a CTA handles twice the rows in the same stream time: half the waves.  What changes: two 64 KB weight slots (the resident
+// operand takes 64 KB), and the fp32 residual rows live in TMEM instead of registers - the x tile is written into the out-proj accumulator
+// columns before the first MMA (tcgen05.st), every out-proj and FFN2 MMA accumulates onto it, and the epilogue reads it back once for
+// the LayerNorm statistics and once to normalise (64 values per thread would not fit beside the statistics in 112 registers).
+// TMEM columns: [0, 256) residual rows (4 tiles x 64 rows), [256, 320) hidden.  Thread = (TMEM lane i = features 4 i .. 4 i + 3,
+// rows 32 h + 8 rg .. + 7 for h = 0, 1).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kB64Rows = 64;
+constexpr int kB64Slots = 2;
+constexpr int kB64ActBytes = kB64Rows * kE * 2;      // 64 KB
+constexpr int kB64KbBytes = kB64Rows * kBlockK * 2;  // 8 KB
+constexpr int kB64StatsBytes = kB64Rows * 4 * 8;
+__host__ __device__ constexpr int block_rows64_smem_bytes() { return 1024 + kB64Slots * kBrSlotBytes + kB64ActBytes + 256 + kB64StatsBytes; }
+static_assert(block_rows64_smem_bytes() <= 227 * 1024, "64-row row-owner block kernel does not fit in shared memory");
+
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kBrThreads, 1)
+block_rows64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1,
+                    const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xn, int M,
+                    FusedBlockParams ep) {
+  constexpr uint32_t kIdesc = umma_idesc_bf16_f32(128, kB64Rows);
+  constexpr uint32_t kColHidden = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* act = ring + kB64Slots * kBrSlotBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(act + kB64ActBytes);  // [2]
+  uint64_t* empty_bar = full_bar + kB64Slots;                            // [2]
+  uint64_t* act_full = empty_bar + kB64Slots;
+  uint64_t* x_ready = act_full + 1;                                      // the residual rows are in TMEM (16 warp arrivals)
+  uint64_t* acc0_full = x_ready + 1;                                     // [4]
+  uint64_t* ln2_ready = acc0_full + 4;
+  uint64_t* acc1_full = ln2_ready + 1;
+  uint64_t* h_ready = acc1_full + 1;
+  uint64_t* acc2_full = h_ready + 1;                                     // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 4);
+  static_assert((2 * kB64Slots + 2 + 4 + 3 + 4) * 8 + 4 <= 256, "barrier area");
+  float2* s_stats = reinterpret_cast<float2*>(act + kB64ActBytes + 256);  // [64 rows][4 quadrants]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = static_cast<int>(lane_id());
+  const int m0 = blockIdx.x * kB64Rows;
+  pdl_trigger();
+
+  auto issue = [&](int i) {
+    const int slot = i % kB64Slots;
+    mbar_arrive_expect_tx(&full_bar[slot], kBrSlotBytes);
+    uint8_t* dst = ring + slot * kBrSlotBytes;
+    if (i < 8) tma_load_4d(dst, &tmap_wo, &full_bar[slot], 0, 0, i >> 1, (i & 1) * 4, kEvictLast);
+    else if (i < 10) tma_load_3d(dst, &tmap_w1, &full_bar[slot], 0, (i - 8) * 4, kEvictLast);
+    else tma_load_4d(dst, &tmap_w2, &full_bar[slot], 0, 0, (i - 10) * 2, 0, kEvictLast);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1); tma_prefetch_desc(&tmap_w2);
+      tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_xn);
+      for (int st = 0; st < kB64Slots; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
+      mbar_init(act_full, 1); mbar_init(x_ready, kBrEpiWarps);
+      for (int t = 0; t < 4; ++t) { mbar_init(&acc0_full[t], 1); mbar_init(&acc2_full[t], 1); }
+      mbar_init(ln2_ready, kBrEpiWarps); mbar_init(acc1_full, 1); mbar_init(h_ready, kBrEpiWarps);
+      fence_mbar_init();
+      for (int i = 0; i < kB64Slots; ++i) issue(i);
+      pdl_wait();
+      mbar_arrive_expect_tx(act_full, kB64ActBytes);
+      tma_load_3d(act, &tmap_ao, act_full, m0, 0, kEvictFirst);
+    }
+  } else if (warp == 1) {
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = kB64Slots; i < kBrRequests; ++i) {
+        mbar_wait(&empty_bar[i % kB64Slots], ((i / kB64Slots) - 1) & 1, 1);
+        issue(i);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t lb = (smem_u32(act) & 0x3FFFFu) >> 4;
+      auto lo = [](const void* p) { return (smem_u32(p) & 0x3FFFFu) >> 4; };
+      constexpr uint32_t kKs = (kUmmaK * 2) >> 4, kAo = kABytes >> 4, kBo = kB64KbBytes >> 4;
+      mbar_wait(act_full, 0, 2);
+      mbar_wait(x_ready, 0, 2);
+      tc_fence_after_sync();
+      for (int i = 0; i < 8; ++i) {                      // out-proj, accumulated onto the residual rows
+        const int slot = i % kB64Slots;
+        mbar_wait(&full_bar[slot], (i / kB64Slots) & 1, 3);
+        tc_fence_after_sync();
+        const uint32_t la = lo(ring + slot * kBrSlotBytes);
+        const uint32_t lbi = lb + (i & 1) * 4 * kBo;
+        const uint32_t d = tmem_base + (i >> 1) * kB64Rows;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) umma_lo<true>(d, la + (q >> 2) * kAo + (q & 3) * kKs, lbi + (q >> 2) * kBo + (q & 3) * kKs, kIdesc);
+        umma_commit(&empty_bar[slot]);
+        if (i & 1) umma_commit(&acc0_full[i >> 1]);
+      }
+      mbar_wait(ln2_ready, 0, 4);
+      tc_fence_after_sync();
+      for (int i = 8; i < 10; ++i) {                     // FFN1
+        const int slot = i % kB64Slots;
+        mbar_wait(&full_bar[slot], (i / kB64Slots) & 1, 5);
+        tc_fence_after_sync();
+        const uint32_t la = lo(ring + slot * kBrSlotBytes);
+        const uint32_t lbi = lb + (i - 8) * 4 * kBo;
+        const uint32_t d = tmem_base + kColHidden;
+        if (i == 8) {
+          umma_lo<false>(d, la, lbi, kIdesc);
+#pragma unroll
+          for (int q = 1; q < 16; ++q) umma_lo<true>(d, la + (q >> 2) * kAo + (q & 3) * kKs, lbi + (q >> 2) * kBo + (q & 3) * kKs, kIdesc);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) umma_lo<true>(d, la + (q >> 2) * kAo + (q & 3) * kKs, lbi + (q >> 2) * kBo + (q & 3) * kKs, kIdesc);
+        }
+        umma_commit(&empty_bar[slot]);
+      }
+      umma_commit(acc1_full);
+      mbar_wait(h_ready, 0, 6);
+      tc_fence_after_sync();
+      for (int i = 10; i < 12; ++i) {                    // FFN2, accumulated onto the residual rows
+        const int slot = i % kB64Slots;
+        mbar_wait(&full_bar[slot], (i / kB64Slots) & 1, 7);
+        tc_fence_after_sync();
+        const uint32_t la = lo(ring + slot * kBrSlotBytes);
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+          const uint32_t d = tmem_base + ((i - 10) * 2 + tt) * kB64Rows;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) umma_lo<true>(d, la + (q >> 2) * (2 * kAo) + tt * kAo + (q & 3) * kKs, lb + (q >> 2) * kBo + (q & 3) * kKs, kIdesc);
+          umma_commit(&acc2_full[(i - 10) * 2 + tt]);
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int rg = ew >> 2;
+    const int fi = quad * 32 + lane;
+    const int r0 = rg * 8;
+    const uint32_t tl = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(r0);
+    const float4 g_mid = __ldg(reinterpret_cast<const float4*>(ep.gain_mid) + fi);
+    const float4 g_out = __ldg(reinterpret_cast<const float4*>(ep.gain_out) + fi);
+    pdl_wait();
+    // ---- residual rows -> TMEM (column 64 t + 32 h + row of tile t = feature 4 fi + t)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[4][8];
+      if (m0 + 32 * h < M) {
+        const float* xrow = ep.x + (static_cast<size_t>(blockIdx.x * 2 + h) * (kE / 4) + fi) * (32 * 4) + r0 * 4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) ld_global_v8(xrow + p * 8, v[p]);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[p][c] = 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = v[j >> 1][(j & 1) * 4 + t];
+        tmem_st_32x8(tl + t * kB64Rows + 32 * h, c);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(x_ready);
+
+    float val[32];      // [h][0..7 sums, 8..15 sums of squares] of rows 32 h + r0 + j
+    auto stat_tiles = [&](uint64_t* bars) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        mbar_wait(&bars[t], 0, 8);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[8];
+          tmem_ld_32x8(tl + t * kB64Rows + 32 * h, v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            val[h * 16 + j] = t == 0 ? v[j] : val[h * 16 + j] + v[j];
+            val[h * 16 + 8 + j] = t == 0 ? v[j] * v[j] : fmaf(v[j], v[j], val[h * 16 + 8 + j]);
+          }
+        }
+      }
+    };
+    float ca[2][8], cb[2][8];
+    auto row_stats = [&]() {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float part[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) part[k] = val[h * 16 + k];
+        const float tot = br_warp_reduce16(part, lane);
+        if ((lane & 1) == 0) {
+          const int k = lane >> 1;
+          reinterpret_cast<float*>(&s_stats[(32 * h + r0 + (k & 7)) * 4 + quad])[k >> 3] = tot;
+        }
+      }
+      br_epi_sync();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float ra = 0.f, rb = 0.f;
+        if (lane < 8) {
+          const float4 p = *reinterpret_cast<const float4*>(&s_stats[(32 * h + r0 + lane) * 4]);
+          const float4 q = *reinterpret_cast<const float4*>(&s_stats[(32 * h + r0 + lane) * 4 + 2]);
+          const float sum = (p.x + p.z) + (q.x + q.z), sumsq = (p.y + p.w) + (q.y + q.w);
+          const float mean = sum * (1.0f / kE);
+          ra = rsqrtf(fmaxf(sumsq * (1.0f / kE) - mean * mean, 0.f) + ep.eps);
+          rb = -mean * ra;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ca[h][j] = __shfl_sync(0xffffffffu, ra, j); cb[h][j] = __shfl_sync(0xffffffffu, rb, j); }
+      }
+    };
+    // this thread's residual values of half h: r[j][t]
+    auto load_rows = [&](int h, float (&r)[8][4]) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float v[8];
+        tmem_ld_32x8(tl + t * kB64Rows + 32 * h, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j][t] = v[j];
+      }
+    };
+
+    // ---- phase A: statistics of x + out-proj, LN2 rows -> resident operand
+    stat_tiles(acc0_full);
+    row_stats();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float r[8][4];
+      load_rows(h, r);
+      uint8_t* dst = act + (fi >> 4) * kB64KbBytes + (32 * h + r0) * 128 + (fi & 1) * 8;
+      const int chunk = (fi >> 1) & 7;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y0 = fmaf(r[j][0], ca[h][j], cb[h][j]) * g_mid.x, y1 = fmaf(r[j][1], ca[h][j], cb[h][j]) * g_mid.y;
+        const float y2 = fmaf(r[j][2], ca[h][j], cb[h][j]) * g_mid.z, y3 = fmaf(r[j][3], ca[h][j], cb[h][j]) * g_mid.w;
+        *reinterpret_cast<uint2*>(dst + j * 128 + ((chunk ^ j) << 4)) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ln2_ready);
+
+    // ---- phase B: GELU -> hidden rows in the resident operand (k-blocks 0, 1)
+    mbar_wait(acc1_full, 0, 9);
+    tc_fence_after_sync();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[8];
+      tmem_ld_32x8(tl + kColHidden + 32 * h, v);
+      uint8_t* dst = act + (fi >> 6) * kB64KbBytes + (32 * h + r0) * 128 + (fi & 7) * 2;
+      const int chunk = (fi >> 3) & 7;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<__nv_bfloat16*>(dst + j * 128 + ((chunk ^ j) << 4)) = __float2bfloat16_rn(gelu_fast(v[j]));
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(h_ready);
+
+    // ---- phase C: statistics of the block's output rows, x / xn tiles out through the TMA unit
+    stat_tiles(acc2_full);
+    row_stats();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float r[8][4];
+      load_rows(h, r);
+      uint8_t* line = ring + h * kBrSlotBytes + (rg * 128 + fi) * 128;                 // x tile of 32-row block h: [rg][col4][8 rows x 16 B], swizzled
+      uint8_t* dst = act + h * (kBrRows * 1024) + (fi >> 6) * (kBrRows * 512) + r0 * 512 + (fi & 63) * 8;   // xn: [block][column half][32 rows][512 B]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<float4*>(line + ((j ^ (fi & 7)) << 4)) = make_float4(r[j][0], r[j][1], r[j][2], r[j][3]);
+        const float y0 = fmaf(r[j][0], ca[h][j], cb[h][j]) * g_out.x, y1 = fmaf(r[j][1], ca[h][j], cb[h][j]) * g_out.y;
+        const float y2 = fmaf(r[j][2], ca[h][j], cb[h][j]) * g_out.z, y3 = fmaf(r[j][3], ca[h][j], cb[h][j]) * g_out.w;
+        *reinterpret_cast<uint2*>(dst + j * 512) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+      }
+    }
+    fence_proxy_async_smem();
+    br_epi_sync();
+    if (threadIdx.x == 64) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        tma_store_4d(&tmap_x, ring + h * kBrSlotBytes, 0, 0, 0, static_cast<int>(blockIdx.x) * 2 + h);   // a block beyond the allocation is clipped
+        if (ep.remap_rows_in == 0) {
+          tma_store_2d(&tmap_xn, act + h * (kBrRows * 1024), 0, m0 + 32 * h);
+          tma_store_2d(&tmap_xn, act + h * (kBrRows * 1024) + kBrRows * 512, 256, m0 + 32 * h);
+        }
+      }
+      bulk_commit_group();
+    }
+    if (ep.remap_rows_in > 0) {
+      const int e = threadIdx.x - 64;                        // 0..511: row e >> 3, 16-byte chunks (e & 7) + 8 c
+      const int rr = e >> 3;
+      const int grow = m0 + rr;
+      if (grow < M) {
+        const int seq = grow / ep.remap_rows_in;
+        const int k = grow - seq * ep.remap_rows_in;
+        if (k >= ep.remap_skip) {
+          const int nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+          uint4* dstg = reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE);
+          const uint8_t* srow = act + (rr >> 5) * (kBrRows * 1024) + (rr & 31) * 512;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int ch = (e & 7) + 8 * c;
+            dstg[ch] = *reinterpret_cast<const uint4*>(srow + (ch >> 5) * (kBrRows * 512) + (ch & 31) * 16);
+          }
+        }
+      }
+    }
+    if (threadIdx.x == 64) bulk_wait_group_read0();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace novic

@@ -452,15 +452,18 @@ def test_row_owner_block_kernel_agrees_with_the_cluster_kernel_to_rounding(monke
     summed in a different order, so the two agree to fp32 rounding before the bf16 casts and to a few bf16 flips after six layers:
     teacher-forced logits within 0.01 (tolerance against the reference: 0.06), greedy ids identical on >= 98 % of the rows.  Ragged row
     counts: 2049 rows per decode step (64 full 32-row blocks + one row), 8196 prefix rows, 160 x 16 teacher-forced rows with the row
-    remap of the last layer, and single-block passes of 1 / 31 / 33 rows."""
+    remap of the last layer, and single-block passes of 1 / 31 / 33 rows.  The third leg runs the same kernel on 64 rows per CTA
+    (block_rows64_kernel, what passes of more than 4736 rows use: the residual rows live in TMEM and the out-proj / FFN2 MMAs accumulate
+    onto them; NOVIC_BLOCK_ROWS64_MIN=1 forces it for every pass - a last CTA with one row, a last 32-row block that does not exist)."""
     dims = synth.DecoderDims()
     sd = weight_case("lively")
     embed = synth.synth_embeddings(2049, seed=5).to(DEV)
     tgt, pad = synth.synth_targets(160, dims, seed=3)
     outs = []
-    for rows in ("128", "32"):
+    for rows, min64 in (("128", "0"), ("32", "0"), ("32", "1")):     # cluster kernel; 32 rows per CTA everywhere; 64 rows per CTA everywhere
         monkeypatch.setenv("NOVIC_FFN1_KSPLIT", "0")
         monkeypatch.setenv("NOVIC_BLOCK_ROWS", rows)
+        monkeypatch.setenv("NOVIC_BLOCK_ROWS64_MIN", min64)
         m = default_decoder(dims, sd).to(DEV)
         with torch.inference_mode():
             f = m(embed[:160], tgt.to(DEV), pad.to(DEV), None, True, True, False, None)
@@ -468,15 +471,18 @@ def test_row_owner_block_kernel_agrees_with_the_cluster_kernel_to_rounding(monke
             small = [m.generate(embed[:n], True, True, 1.0, 0.0, None, None, False) for n in (1, 31, 33)]
         outs.append((f[0].float().cpu(), g[0].cpu(), [(s[0].cpu(), s[2].float().cpu()) for s in small]))
         del m
-    (f0, g0, s0), (f1, g1, s1) = outs
-    assert (f0 - f1)[~pad].abs().max().item() <= 0.01
-    n = min(g0.shape[1], g1.shape[1])
-    same = (g0[:, :n] == g1[:, :n]).all(dim=1).float().mean().item()
-    print(f"rows with identical greedy ids: {same:.4f}")
-    assert same >= 0.98
-    for (t0, l0), (t1, l1) in zip(s0, s1):
-        assert (l0[:, 0] - l1[:, 0]).abs().max().item() <= 0.01          # first step: same inputs, no trajectory effects
-        assert torch.equal(t0[:, 0], t1[:, 0]) or (l0[:, 0].topk(2, dim=-1).values.diff(dim=-1).abs().min().item() <= 0.02)
+    f0, g0, s0 = outs[0]
+    for (f1, g1, s1), floor in zip(outs[1:], (0.98, 0.965)):
+        d = (f0 - f1)[~pad].abs()
+        assert d.max().item() <= 0.01
+        n = min(g0.shape[1], g1.shape[1])
+        same = (g0[:, :n] == g1[:, :n]).all(dim=1).float().mean().item()
+        print(f"teacher-forced logits: max |d| {d.max().item():.2e}, mean {d.mean().item():.2e}; rows with identical greedy ids: {same:.4f}")
+        # measured: 0.9966 (32 rows per CTA), 0.9800 (64 rows: the residual is also summed in another order - inside the tensor core)
+        assert same >= floor
+        for (t0, l0), (t1, l1) in zip(s0, s1):
+            assert (l0[:, 0] - l1[:, 0]).abs().max().item() <= 0.01          # first step: same inputs, no trajectory effects
+            assert torch.equal(t0[:, 0], t1[:, 0]) or (l0[:, 0].topk(2, dim=-1).values.diff(dim=-1).abs().min().item() <= 0.02)
 
 
 def test_attention_inside_the_block_kernel_is_bit_identical(monkeypatch):
