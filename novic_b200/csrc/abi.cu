@@ -178,6 +178,7 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
 int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes of at least this many rows run the row-owner block kernel on 64 rows per CTA (block_rows64_kernel); 0 = never
+bool g_attn_split = true;                      // NOVIC_ATTN_SPLIT=0: the stream attention kernel (one warp per sequence) for small batches too
 bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
 int g_block64_pad = 16384;                     // NOVIC_BLOCK64_PAD=0: no extra shared memory per CTA of the 64-row block kernel -> two CTAs per SM (measured slower)
@@ -703,7 +704,12 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   const NovicCfg& c = h->cfg;
   const AttnParams pa = attention_params(h, ws, pc, l);
   KSpan t(kKAttn, s);
-  if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
+  const int nkeys_step = (pa.prefix_bidir && pc.q0 < pa.P) ? pa.P : pc.q0 + 1;
+  if (h->attn_stream && g_attn_split && pc.nq == 1 && pc.keypad == nullptr && nkeys_step <= kSpMaxKeys &&
+      ceil_div(pc.nseq, kSpSeqs) <= std::max(1, h->num_sms / g_grid_div)) {
+    // small batches: four warps per sequence, one HBM round trip (attention_split_kernel)
+    CUDA_TRY(launch_k(attention_split_kernel, dim3(static_cast<unsigned>(ceil_div(pc.nseq, kSpSeqs))), dim3(kSpWarps * 32), kSpSmemBytes, s, pa));
+  } else if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
     auto go = [&](auto kernel, int warps, int slots, int chunk) {
       const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, warps)));
       return launch_k(kernel, dim3(grid), dim3(warps * 32), as_smem_bytes(warps, slots, chunk), s, pa);
@@ -1184,6 +1190,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   CUDA_TRY(cudaFuncSetAttribute(attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->attn_smem_budget + 1024));
   CUDA_TRY(cudaFuncSetAttribute(select_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 3, 4)));
+  CUDA_TRY(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<12, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(12, 2, 8)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<8, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(8, 3, 8)));
@@ -1210,6 +1217,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e27d = getenv("NOVIC_WGRAD_MN")) g_wgrad_mn = atoi(e27d) != 0;
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
+  if (const char* e25d = getenv("NOVIC_ATTN_SPLIT")) g_attn_split = e25d[0] != '0';
   if (const char* e25c = getenv("NOVIC_BLOCK_ROWS64_MIN")) g_block_rows64_min = atoi(e25c);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';

@@ -533,6 +533,167 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attention_stream_kernel_t(const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Attention, decode-step version for SMALL batches (at most 4 x #SMs sequences, at most 24 keys): the stream kernel above gives every
+// sequence one warp, so 512 sequences occupy 32 CTAs and every warp walks its sequence's 2-5 chunks as a chain of HBM round trips (9 us
+// per launch for 17 MB at 512 sequences).  Here a CTA takes four sequences and FOUR warps share a sequence's keys: each warp requests all
+// its K rows and all its V rows at once (one round trip), computes a partial softmax (max, sum, weighted V) over its at most 6 keys, and
+// the four partials are merged through shared memory (each warp's K slot, free by then, holds its partial).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSpWarps = 16, kSpParts = 4, kSpSeqs = kSpWarps / kSpParts, kSpMaxRows = 6;
+constexpr int kSpMaxKeys = kSpParts * kSpMaxRows;                       // 24
+constexpr int kSpSlotBytes = kSpMaxRows * 1024;                         // K rows (later: the warp's partial), V rows
+constexpr int kSpSmemBytes = kSpWarps * 2 * kSpSlotBytes + kSpWarps * 2 * 8 + 128;
+
+__global__ void __launch_bounds__(kSpWarps * 32, 1) attention_split_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t sp_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  const int sq = warp / kSpParts, part = warp % kSpParts;
+  uint8_t* kslot = sp_smem + static_cast<size_t>(warp) * (2 * kSpSlotBytes);
+  uint8_t* vslot = kslot + kSpSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sp_smem + kSpWarps * 2 * kSpSlotBytes) + warp * 2;
+  pdl_trigger();
+
+  const int a = blockIdx.x * kSpSeqs + sq;
+  const bool valid = a < p.nseq;
+  const int qpos = p.q0;
+  const int nkeys = (p.prefix_bidir && qpos < p.P) ? p.P : qpos + 1;
+  const int j0 = part * nkeys / kSpParts, rows = valid ? (part + 1) * nkeys / kSpParts - j0 : 0;
+  const bool contiguous = p.beams == 1;
+  const int own_slot = a * p.slot_mul;
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+  __syncwarp();
+
+  auto request = [&](int kv) {
+    const __nv_bfloat16* base = kv ? p.vcache : p.kcache;
+    uint8_t* dst = kv ? vslot : kslot;
+    if (lane == 0) mbar_arrive_expect_tx(&bars[kv], static_cast<uint32_t>(rows) * 1024u);
+    if (contiguous) {
+      if (lane == 0) {
+        const void* src = base + (static_cast<size_t>(own_slot) * p.smax + j0) * kE;
+        if (p.stream_hint) bulk_load_1d_hint(dst, src, static_cast<uint32_t>(rows) * 1024u, &bars[kv], 0x12F0000000000000ull /* evict first */);
+        else bulk_load_1d(dst, src, static_cast<uint32_t>(rows) * 1024u, &bars[kv]);
+      }
+    } else {
+      __syncwarp();
+      if (lane < rows) {
+        const int j = j0 + lane;
+        const int group0 = (own_slot / p.beams) * p.beams;
+        int slot;
+        if (j < p.P) slot = group0;
+        else if (p.anc != nullptr && j < qpos) slot = group0 + p.anc[static_cast<size_t>(a) * p.anc_ld + (j - p.P)];
+        else slot = own_slot;
+        bulk_load_1d(dst + lane * 1024, base + (static_cast<size_t>(slot) * p.smax + j) * kE, 1024u, &bars[kv]);
+      }
+    }
+  };
+  // rows written by earlier decode steps (every part but the one that holds the newest key) may be requested before the wait - see
+  // attention_stream_kernel_t
+  const bool early = p.early_loads == 1 && contiguous && rows > 0 && j0 + rows <= qpos;
+  if (early) { request(0); request(1); }
+  pdl_wait();
+  if (!early && rows > 0) { request(0); request(1); }
+
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  if (rows > 0) {
+    float qf[16];
+    {
+      const uint4* q4 = reinterpret_cast<const uint4*>(p.q + static_cast<size_t>(a) * kE) + lane * 2;
+      const uint4 qa = __ldg(q4), qb = __ldg(q4 + 1);
+      bf16x8_to_f32(qa, qf);
+      bf16x8_to_f32(qb, qf + 8);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) qf[k] *= p.scale_log2e;
+    }
+    float s[kSpMaxRows];
+    mbar_wait(&bars[0], 0, 5);
+#pragma unroll
+    for (int u = 0; u < kSpMaxRows; ++u) {
+      s[u] = -INFINITY;
+      if (u < rows) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(kslot + u * 1024 + lane * 32);
+        float kf[16];
+        bf16x8_to_f32(k4[0], kf);
+        bf16x8_to_f32(k4[1], kf + 8);
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { d0 = fmaf(qf[k], kf[k], d0); d1 = fmaf(qf[8 + k], kf[8 + k], d1); }
+        s[u] = d0 + d1;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSpMaxRows; ++u) {
+      if (u < rows) {
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 1);
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kSpMaxRows; ++u) m = fmaxf(m, s[u]);
+    float pj[kSpMaxRows];
+#pragma unroll
+    for (int u = 0; u < kSpMaxRows; ++u) { pj[u] = exp2f(s[u] - m); l += pj[u]; }
+    mbar_wait(&bars[1], 0, 5);
+#pragma unroll
+    for (int u = 0; u < kSpMaxRows; ++u) {
+      if (u < rows) {
+        const uint4* v4 = reinterpret_cast<const uint4*>(vslot + u * 1024 + lane * 32);
+        float vf[16];
+        bf16x8_to_f32(v4[0], vf);
+        bf16x8_to_f32(v4[1], vf + 8);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = fmaf(pj[u], vf[k], acc[k]);
+      }
+    }
+  }
+  // partial of this warp -> its K slot (every lane has read its K rows: the scores are complete): acc at lane * 64 B, (m, l) of head h at 2048 + 8 h
+  __syncwarp();
+  {
+    float4* d = reinterpret_cast<float4*>(kslot + lane * 64);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+    if ((lane & 3) == 0) *reinterpret_cast<float2*>(kslot + 2048 + (lane >> 2) * 8) = make_float2(m, l);
+  }
+  __syncthreads();
+  if (part == 0 && valid) {
+    float mp[kSpParts], lp[kSpParts];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < kSpParts; ++q) {
+      const float2 t = *reinterpret_cast<const float2*>(sp_smem + static_cast<size_t>(sq * kSpParts + q) * (2 * kSpSlotBytes) + 2048 + (lane >> 2) * 8);
+      mp[q] = t.x; lp[q] = t.y;
+      mx = fmaxf(mx, t.x);
+    }
+    float out[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) out[k] = 0.f;
+    float L = 0.f;
+#pragma unroll
+    for (int q = 0; q < kSpParts; ++q) {
+      const float w = lp[q] > 0.f ? exp2f(mp[q] - mx) : 0.f;
+      L = fmaf(lp[q], w, L);
+      const float4* src = reinterpret_cast<const float4*>(sp_smem + static_cast<size_t>(sq * kSpParts + q) * (2 * kSpSlotBytes) + lane * 64);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = src[k];
+        out[4 * k] = fmaf(t.x, w, out[4 * k]); out[4 * k + 1] = fmaf(t.y, w, out[4 * k + 1]);
+        out[4 * k + 2] = fmaf(t.z, w, out[4 * k + 2]); out[4 * k + 3] = fmaf(t.w, w, out[4 * k + 3]);
+      }
+    }
+    const float inv = 1.0f / L;
+    uint32_t o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = pack_bf16x2(out[2 * k] * inv, out[2 * k + 1] * inv);
+    uint4* d = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(a) * kE) + lane * 2;
+    d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Merging the per-tile logits statistics of one row (executed by a full warp)
 // ---------------------------------------------------------------------------------------------------------
 struct RowStats {
