@@ -178,6 +178,7 @@ int make_tmap_3d(CUtensorMap* map, const void* base, const cuuint64_t (&dims)[3]
 constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5;
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
 int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes of at least this many rows run the row-owner block kernel on 64 rows per CTA (block_rows64_kernel); 0 = never
+int g_attn_split_max = 0;                      // NOVIC_ATTN_SPLIT_MAX: largest decode batch (sequences) of the split-key attention kernel; 0 = two waves of CTAs (8 x #SMs = 1184: measured 0.75 against 0.84 ms at 1024 sequences, 1.37 against 0.94 ms at 2048)
 bool g_attn_split = true;                      // NOVIC_ATTN_SPLIT=0: the stream attention kernel (one warp per sequence) for small batches too
 bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
@@ -706,7 +707,7 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
   KSpan t(kKAttn, s);
   const int nkeys_step = (pa.prefix_bidir && pc.q0 < pa.P) ? pa.P : pc.q0 + 1;
   if (h->attn_stream && g_attn_split && pc.nq == 1 && pc.keypad == nullptr && nkeys_step <= kSpMaxKeys &&
-      ceil_div(pc.nseq, kSpSeqs) <= std::max(1, h->num_sms / g_grid_div)) {
+      pc.nseq <= (g_attn_split_max > 0 ? g_attn_split_max : 2 * kSpSeqs * std::max(1, h->num_sms / g_grid_div))) {
     // small batches: four warps per sequence, one HBM round trip (attention_split_kernel)
     CUDA_TRY(launch_k(attention_split_kernel, dim3(static_cast<unsigned>(ceil_div(pc.nseq, kSpSeqs))), dim3(kSpWarps * 32), kSpSmemBytes, s, pa));
   } else if (h->attn_stream && pc.nq == 1 && pc.keypad == nullptr) {
@@ -1218,6 +1219,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
   if (const char* e25d = getenv("NOVIC_ATTN_SPLIT")) g_attn_split = e25d[0] != '0';
+  if (const char* e25e = getenv("NOVIC_ATTN_SPLIT_MAX")) g_attn_split_max = atoi(e25e);
   if (const char* e25c = getenv("NOVIC_BLOCK_ROWS64_MIN")) g_block_rows64_min = atoi(e25c);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);
   if (const char* e29 = getenv("NOVIC_FFN1_KSPLIT")) g_ffn1_ksplit = e29[0] != '0';
