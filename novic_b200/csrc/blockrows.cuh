@@ -546,7 +546,7 @@ block_rows_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_cons
     if (lane == 0) mbar_arrive(h_ready);
     tp(5);
 
-    // ---- phase C: residual + FFN2, final LayerNorm; both result tiles leave through the TMA unit
+    // ---- phase C: residual + FFN2, final LayerNorm; the x tile leaves through the TMA unit, the xn rows straight from the registers
     add_tiles(acc2_full, kColFfn2);
     tp(6);
     // x tile, staged in ring slot 0 (every MMA has completed: acc2_full[3]) as [rg][col4 fi][8 rows x 16 B], 16-byte chunks XOR-swizzled by
@@ -560,44 +560,28 @@ block_rows_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_cons
     tp(27);
     row_stats(ca, cb, true);
     tp(28);
-    // xn tile, staged in the resident operand as [half = fi >> 6][32 rows][256 features] bf16 (the box of tmap_xn, no swizzle)
+    // xn rows straight from the registers: a thread's four features are 8 contiguous bytes and a warp's 32 threads hold consecutive
+    // feature quadruples - one 256-byte run per row and store instruction (no staging tile, no barrier, nothing for the exit to wait for)
     {
-      uint8_t* dst = act + (fi >> 6) * (kBrRows * 512) + r0 * 512 + (fi & 63) * 8;
+      const bool remap = ep.remap_rows_in > 0;      // last layer of a prefix / teacher-forced pass: rows are renumbered, leading rows of a sequence dropped
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float y0 = fmaf(r[j][0], ca[j], cb[j]) * g_out.x, y1 = fmaf(r[j][1], ca[j], cb[j]) * g_out.y;
         const float y2 = fmaf(r[j][2], ca[j], cb[j]) * g_out.z, y3 = fmaf(r[j][3], ca[j], cb[j]) * g_out.w;
-        *reinterpret_cast<uint2*>(dst + j * 512) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-      }
-    }
-    fence_proxy_async_smem();
-    br_epi_sync();
-    tp(29);
-    if (threadIdx.x == 64 && ep.remap_rows_in == 0) {
-      tma_store_2d(&tmap_xn, act, 0, m0);
-      tma_store_2d(&tmap_xn, act + kBrRows * 512, 256, m0);
-      bulk_commit_group();
-    }
-    if (ep.remap_rows_in > 0) {
-      // last layer of a prefix / teacher-forced pass: rows are renumbered (and the leading rows of a sequence dropped) on the way out
-      const int e = threadIdx.x - 64;                        // 0..511: row e >> 4, 16-byte chunks (e & 15) + 16 c
-      const int rr = e >> 4;
-      const int grow = m0 + rr;
-      if (grow < M) {
-        const int seq = grow / ep.remap_rows_in;
-        const int k = grow - seq * ep.remap_rows_in;
-        if (k >= ep.remap_skip) {
-          const int nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
-          uint4* dst = reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int ch = (e & 15) + 16 * c;                // 16-byte chunk of the 1 KB row: half ch >> 5
-            dst[ch] = *reinterpret_cast<const uint4*>(act + (ch >> 5) * (kBrRows * 512) + rr * 512 + (ch & 31) * 16);
-          }
+        const int grow = m0 + r0 + j;
+        int nrow = grow;
+        bool keep = grow < M;
+        if (remap) {
+          const int seq = grow / ep.remap_rows_in;
+          const int k = grow - seq * ep.remap_rows_in;
+          keep = keep && k >= ep.remap_skip;
+          nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
         }
+        if (keep) *reinterpret_cast<uint2*>(ep.xn + static_cast<size_t>(nrow) * kE + fi * 4) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
       }
     }
-    if (threadIdx.x == 64) bulk_wait_group_read0();          // the staged tiles must stay in place until the TMA unit has read them
+    tp(29);
+    if (threadIdx.x == 64) bulk_wait_group_read0();          // the staged x tile must stay in place until the TMA unit has read it
     tp(7);
   }
   tc_fence_before_sync();
@@ -886,7 +870,7 @@ block_rows64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_co
     __syncwarp();
     if (lane == 0) mbar_arrive(h_ready);
 
-    // ---- phase C: statistics of the block's output rows, x / xn tiles out through the TMA unit
+    // ---- phase C: statistics of the block's output rows; the x tiles leave through the TMA unit, the xn rows straight from the registers
     stat_tiles(acc2_full);
     row_stats();
 #pragma unroll
@@ -894,46 +878,31 @@ block_rows64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_co
       float r[8][4];
       load_rows(h, r);
       uint8_t* line = ring + h * kBrSlotBytes + (rg * 128 + fi) * 128;                 // x tile of 32-row block h: [rg][col4][8 rows x 16 B], swizzled
-      uint8_t* dst = act + h * (kBrRows * 1024) + (fi >> 6) * (kBrRows * 512) + r0 * 512 + (fi & 63) * 8;   // xn: [block][column half][32 rows][512 B]
+      const bool remap = ep.remap_rows_in > 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         *reinterpret_cast<float4*>(line + ((j ^ (fi & 7)) << 4)) = make_float4(r[j][0], r[j][1], r[j][2], r[j][3]);
         const float y0 = fmaf(r[j][0], ca[h][j], cb[h][j]) * g_out.x, y1 = fmaf(r[j][1], ca[h][j], cb[h][j]) * g_out.y;
         const float y2 = fmaf(r[j][2], ca[h][j], cb[h][j]) * g_out.z, y3 = fmaf(r[j][3], ca[h][j], cb[h][j]) * g_out.w;
-        *reinterpret_cast<uint2*>(dst + j * 512) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+        // xn rows straight from the registers (8 contiguous bytes per thread, 256 per warp and row), renumbered in a pass's last layer
+        const int grow = m0 + 32 * h + r0 + j;
+        int nrow = grow;
+        bool keep = grow < M;
+        if (remap) {
+          const int seq = grow / ep.remap_rows_in;
+          const int k = grow - seq * ep.remap_rows_in;
+          keep = keep && k >= ep.remap_skip;
+          nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
+        }
+        if (keep) *reinterpret_cast<uint2*>(ep.xn + static_cast<size_t>(nrow) * kE + fi * 4) = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
       }
     }
     fence_proxy_async_smem();
     br_epi_sync();
     if (threadIdx.x == 64) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tma_store_4d(&tmap_x, ring + h * kBrSlotBytes, 0, 0, 0, static_cast<int>(blockIdx.x) * 2 + h);   // a block beyond the allocation is clipped
-        if (ep.remap_rows_in == 0) {
-          tma_store_2d(&tmap_xn, act + h * (kBrRows * 1024), 0, m0 + 32 * h);
-          tma_store_2d(&tmap_xn, act + h * (kBrRows * 1024) + kBrRows * 512, 256, m0 + 32 * h);
-        }
-      }
+      for (int h = 0; h < 2; ++h) tma_store_4d(&tmap_x, ring + h * kBrSlotBytes, 0, 0, 0, static_cast<int>(blockIdx.x) * 2 + h);   // a block beyond the allocation is clipped
       bulk_commit_group();
-    }
-    if (ep.remap_rows_in > 0) {
-      const int e = threadIdx.x - 64;                        // 0..511: row e >> 3, 16-byte chunks (e & 7) + 8 c
-      const int rr = e >> 3;
-      const int grow = m0 + rr;
-      if (grow < M) {
-        const int seq = grow / ep.remap_rows_in;
-        const int k = grow - seq * ep.remap_rows_in;
-        if (k >= ep.remap_skip) {
-          const int nrow = seq * ep.remap_rows_out + (k - ep.remap_skip);
-          uint4* dstg = reinterpret_cast<uint4*>(ep.xn + static_cast<size_t>(nrow) * kE);
-          const uint8_t* srow = act + (rr >> 5) * (kBrRows * 1024) + (rr & 31) * 512;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int ch = (e & 7) + 8 * c;
-            dstg[ch] = *reinterpret_cast<const uint4*>(srow + (ch >> 5) * (kBrRows * 512) + (ch & 31) * 16);
-          }
-        }
-      }
     }
     if (threadIdx.x == 64) bulk_wait_group_read0();
   }
