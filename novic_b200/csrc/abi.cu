@@ -179,6 +179,7 @@ constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
 int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes of at least this many rows run the row-owner block kernel on 64 rows per CTA (block_rows64_kernel); 0 = never
 int g_attn_split_max = 0;                      // NOVIC_ATTN_SPLIT_MAX: largest decode batch (sequences) of the split-key attention kernel; 0 = two waves of CTAs (8 x #SMs = 1184: measured 0.75 against 0.84 ms at 1024 sequences, 1.37 against 0.94 ms at 2048)
+int g_qkv_ws_stages = 3;                       // NOVIC_QKV_WS_STAGES: 3 = three 32 KB activation stages in the weight-stationary QKV kernel, q / K / V stored from registers with 256-bit stores (default: QKV class 1.10 -> 0.99 ms per decode); 2 = two stages + the epilogue's 32 KB staging tile
 bool g_attn_split = true;                      // NOVIC_ATTN_SPLIT=0: the stream attention kernel (one warp per sequence) for small batches too
 bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
@@ -783,6 +784,8 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
         if (g_qkv_ws && kE == kWsKb * kBlockK && ceil_div(M, kBlockM) >= 2 * (g_num_sms / g_grid_div / (3 * kE / kTileN))) {   // weight-stationary: >= 2 row blocks per CTA
           if (g_qkv_ws == 2) {
             if (launch_gemm_ws2<EpiQKV>(s, tm_xn3, h->w.tm_in_proj3h[l], M, 3 * kE, pq, g_early_b)) return 1;
+          } else if (g_qkv_ws_stages == 3) {
+            if (launch_gemm_ws<EpiQKV, 3>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, pq, g_early_b, &tm_xn)) return 1;
           } else if (launch_gemm_ws<EpiQKV, 2>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, pq, g_early_b, &tm_xn)) return 1;
         } else if (g_qkv_bn == 512 && ceil_div(M, kBlockM) * (3 * kE / 256) >= g_num_sms) {            // CTA pairs, 256 x 256 tiles
           if (launch_gemm2<EpiQKV, 3>(s, tm_xn3, h->w.tm_in_proj3[l], M, 3 * kE, kE, pq, g_early_b)) return 1;
@@ -1159,7 +1162,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm_ws2_attr<EpiQKV>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm_ws_attr<EpiQKV, 3>() || set_gemm_ws2_attr<EpiQKV>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||
@@ -1219,6 +1222,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
   if (const char* e25d = getenv("NOVIC_ATTN_SPLIT")) g_attn_split = e25d[0] != '0';
+  if (const char* e25g = getenv("NOVIC_QKV_WS_STAGES")) g_qkv_ws_stages = atoi(e25g) == 2 ? 2 : 3;
   if (const char* e25e = getenv("NOVIC_ATTN_SPLIT_MAX")) g_attn_split_max = atoi(e25e);
   if (const char* e25c = getenv("NOVIC_BLOCK_ROWS64_MIN")) g_block_rows64_min = atoi(e25c);
   if (const char* e26 = getenv("NOVIC_BLOCK64_PAD")) g_block64_pad = atoi(e26);

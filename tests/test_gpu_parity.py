@@ -522,9 +522,10 @@ def test_qkv_projection_variants_are_bit_identical(monkeypatch):
     sd = weight_case("lively")
     embed = synth.synth_embeddings(3100, seed=8).to(DEV)
     outs = []
-    for ws, mc in (("0", "0"), ("1", "0"), ("1", "2"), ("1", "4"), ("2", "0")):     # the switches are read when a handle is created
+    for ws, mc, st in (("0", "0", "2"), ("1", "0", "2"), ("1", "2", "2"), ("1", "4", "2"), ("2", "0", "2"), ("1", "0", "3")):     # the switches are read when a handle is created
         monkeypatch.setenv("NOVIC_QKV_WS", ws)
         monkeypatch.setenv("NOVIC_QKV_MC", mc)
+        monkeypatch.setenv("NOVIC_QKV_WS_STAGES", st)     # 3: a third activation stage instead of the staging tile, q / K / V stored with 256-bit stores
         m = default_decoder(dims, sd).to(DEV)
         with torch.inference_mode():
             g = m.generate(embed, False, True, 0.9, 0.2, None, None, False)
