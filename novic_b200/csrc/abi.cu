@@ -180,6 +180,7 @@ bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj +
 int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes of at least this many rows run the row-owner block kernel on 64 rows per CTA (block_rows64_kernel); 0 = never
 int g_attn_split_max = 0;                      // NOVIC_ATTN_SPLIT_MAX: largest decode batch (sequences) of the split-key attention kernel; 0 = two waves of CTAs (8 x #SMs = 1184: measured 0.75 against 0.84 ms at 1024 sequences, 1.37 against 0.94 ms at 2048)
 int g_qkv_ws_stages = 3;                       // NOVIC_QKV_WS_STAGES: 3 = three 32 KB activation stages in the weight-stationary QKV kernel, q / K / V stored from registers with 256-bit stores (default: QKV class 1.10 -> 0.99 ms per decode); 2 = two stages + the epilogue's 32 KB staging tile
+bool g_attn_prefix = true;                     // NOVIC_ATTN_PREFIX=0: the prefix pass on attention_bulk_kernel instead of attention_prefix_kernel
 bool g_attn_split = true;                      // NOVIC_ATTN_SPLIT=0: the stream attention kernel (one warp per sequence) for small batches too
 bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
 bool g_ffn1_ksplit = true;                     // NOVIC_FFN1_KSPLIT=0: the 128-row block kernel gathers the whole LN2 row in every CTA (outproj_ffn_kernel) instead of reduce-scattering partial FFN1 sums
@@ -727,6 +728,10 @@ int launch_attention(NovicHandle* h, const Workspace& ws, const PassCfg& pc, int
       case 8: CUDA_TRY(go(attention_stream_kernel_t<16, 2, 4>, 16, 2, 4)); break;   // 128 KB: can share an SM with a 2-stage row kernel
       default: CUDA_TRY(go(attention_stream_kernel_t<16, 3, 4>, 16, 3, 4)); break;
     }
+  } else if (g_attn_prefix && pc.q0 == 0 && pc.nq == c.prefix_len && pc.nq <= kApMaxP && pc.keypad == nullptr && pc.anc == nullptr) {
+    // prefix pass: a warp per sequence, all P queries against the P prefix keys (attention_prefix_kernel)
+    const int grid = static_cast<int>(std::min<int64_t>(std::max(1, h->num_sms / g_grid_div), ceil_div(pc.nseq, kApWarps)));
+    CUDA_TRY(launch_k(attention_prefix_kernel, dim3(grid), dim3(kApWarps * 32), kApSmemBytes, s, pa));
   } else if (g_attn_tf && pc.q0 == 0 && pc.nq > c.prefix_len && pc.nq <= kAttnBwdMaxS && pc.beams == 1 && pc.slot_mul == 1 && pc.anc == nullptr) {
     // teacher-forced passes (forward, score_targets): all positions of a sequence at once on tensor-core tiles
     const unsigned grid = static_cast<unsigned>(ceil_div(static_cast<int64_t>(pc.nseq) * kHeads, kAttnTfWarps));
@@ -1195,6 +1200,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   CUDA_TRY(cudaFuncSetAttribute(select_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 3, 4)));
   CUDA_TRY(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kApSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<12, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(12, 2, 8)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<16, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(16, 2, 6)));
   CUDA_TRY(cudaFuncSetAttribute(attention_stream_kernel_t<8, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, as_smem_bytes(8, 3, 8)));
@@ -1222,6 +1228,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e25 = getenv("NOVIC_BLOCK_ROWS")) g_block_rows = atoi(e25);
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
   if (const char* e25d = getenv("NOVIC_ATTN_SPLIT")) g_attn_split = e25d[0] != '0';
+  if (const char* e25h = getenv("NOVIC_ATTN_PREFIX")) g_attn_prefix = e25h[0] != '0';
   if (const char* e25g = getenv("NOVIC_QKV_WS_STAGES")) g_qkv_ws_stages = atoi(e25g) == 2 ? 2 : 3;
   if (const char* e25e = getenv("NOVIC_ATTN_SPLIT_MAX")) g_attn_split_max = atoi(e25e);
   if (const char* e25c = getenv("NOVIC_BLOCK_ROWS64_MIN")) g_block_rows64_min = atoi(e25c);
