@@ -118,7 +118,7 @@ int make_tmap4_perm(CUtensorMap* map, const void* base, int64_t rows, int64_t co
   return 0;
 }
 
-// Store maps of the row-owner block kernel.  x: the 32-row blocked fp32 residual layout as (32 floats = 8 rows x 4 features, col4 index, 8-row
+// Store map of the row-owner block kernels.  x: the 32-row blocked fp32 residual layout as (32 floats = 8 rows x 4 features, col4 index, 8-row
 // group, 32-row block); one box = one block's 64 KB, staged as [group][col4][128 B] with the 128-byte swizzle.
 int make_tmap_xblk(CUtensorMap* map, float* x, int64_t rows32) {
   if (load_driver_entry()) return 1;
@@ -131,19 +131,6 @@ int make_tmap_xblk(CUtensorMap* map, float* x, int64_t rows32) {
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (blocked residual) failed with CUresult %d (rows32=%lld)", (int)r, (long long)rows32);
   return 0;
 }
-// xn [rows, 512] bf16 row-major, boxes of 32 rows x 256 columns, no swizzle (rows at or beyond `rows` are clipped by the store)
-int make_tmap_rows_store(CUtensorMap* map, __nv_bfloat16* base, int64_t rows) {
-  if (load_driver_entry()) return 1;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(kE), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(kE) * 2};
-  cuuint32_t box[2] = {256, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (row store) failed with CUresult %d (rows=%lld)", (int)r, (long long)rows);
-  return 0;
-}
-
 // Row-major bf16 matrix [k_rows, cols] (leading dimension ld elements, ld >= cols rounded up to 64) as an MN-major GEMM operand: dims
 // (64 columns, k_rows, column blocks), box [64, 64, 2] = the two 64-column blocks of a 128-wide tile for one k-block of 64 rows.
 int make_tmap_mn(CUtensorMap* map, const void* base, int64_t k_rows, int64_t cols, int64_t ld) {
@@ -408,16 +395,16 @@ int launch_outproj_ffn_ks(cudaStream_t s, const CUtensorMap& tao, const CUtensor
 // k-blocks; two / tw2: 4-D row-permuted maps (make_tmap4_perm); tw1: 3-D, 128 rows x 4 k-blocks.
 // pa != nullptr: the decode-step attention of the same rows runs inside the kernel (block_rows_kernel<true>: no attention launch, no ao round trip).
 int launch_block_rows(cudaStream_t s, const CUtensorMap& tao, const CUtensorMap& two, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tx,
-                      const CUtensorMap& txn, int M, const FusedBlockParams& ep, const AttnParams* pa, const CUtensorMap* ta64 = nullptr) {
+                      int M, const FusedBlockParams& ep, const AttnParams* pa, const CUtensorMap* ta64 = nullptr) {
   const dim3 grid(static_cast<unsigned>(ceil_div(M, kBrRows)));
   if (pa == nullptr && ta64 != nullptr) {
-    CUDA_TRY(launch_k(block_rows64_kernel, dim3(static_cast<unsigned>(ceil_div(M, kB64Rows))), dim3(kBrThreads), block_rows64_smem_bytes(), s, *ta64, two, tw1, tw2, tx, txn, M, ep));
+    CUDA_TRY(launch_k(block_rows64_kernel, dim3(static_cast<unsigned>(ceil_div(M, kB64Rows))), dim3(kBrThreads), block_rows64_smem_bytes(), s, *ta64, two, tw1, tw2, tx, M, ep));
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
-  if (pa != nullptr) CUDA_TRY(launch_k(block_rows_kernel<true>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn, M, ep, *pa));
-  else CUDA_TRY(launch_k(block_rows_kernel<false>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, txn, M, ep, AttnParams{}));
+  if (pa != nullptr) CUDA_TRY(launch_k(block_rows_kernel<true>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, M, ep, *pa));
+  else CUDA_TRY(launch_k(block_rows_kernel<false>, grid, dim3(kBrThreads), block_rows_smem_bytes(), s, tao, two, tw1, tw2, tx, M, ep, AttnParams{}));
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -770,9 +757,8 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
   if (make_tmap3(&tm_ao64r, ws.ao, M, kE, kB64Rows, kE / kBlockK)) return 1;
   // 64 rows per CTA once 32-row CTAs need more than one wave (g_block_rows64_min, NOVIC_BLOCK_ROWS64_MIN; 0 = never)
   const bool rows64 = g_block_rows64_min > 0 && M >= g_block_rows64_min;
-  CUtensorMap tm_x_st, tm_xn_st;
+  CUtensorMap tm_x_st;
   if (make_tmap_xblk(&tm_x_st, ws.x, static_cast<int64_t>(ceil_div(M, 32)) * 32)) return 1;
-  if (make_tmap_rows_store(&tm_xn_st, ws.xn, M)) return 1;
   const size_t kv_layer = static_cast<size_t>(ws.nseq) * S * kE;
   const bool block_fused = g_fuse_block && h->fuse_ffn && c.ffn_dim == kFfnDim;
   const bool qkv_tail = block_fused && g_fuse_qkv && g_wide_gemm;     // layer l + 1's QKV projection in the tail of layer l's block kernel
@@ -822,7 +808,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       KSpan t(kKFfn2, s);
       if ((g_block_rows == 32 || g_block_rows == 0) && !fb.qkv_tail) {
         const AttnParams pa = attention_params(h, ws, pc, l);
-        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, tm_xn_st, M, fb, attn_in_block ? &pa : nullptr,
+        if (launch_block_rows(s, tm_ao32, h->w.tm_out_proj4[l], h->w.tm_linear1_r3[l], h->w.tm_linear2_4[l], tm_x_st, M, fb, attn_in_block ? &pa : nullptr,
                               (rows64 && !attn_in_block) ? &tm_ao64r : nullptr)) return 1;
         continue;
       }

@@ -9,7 +9,8 @@
 //
 // Feature permutation: tile t of Wo / W2 holds weight rows {4 i + t, i = 0..127} (a 4-D tensor map with the row index split into
 // (i, t)), so the thread that reads TMEM lane i owns features 4 i .. 4 i + 3 after the four tiles - one float4 of the 32-row blocked
-// residual layout per row, and 8 contiguous bytes of the K-major LN2 operand.  No shuffles, no staging transposes.
+// residual layout per row, 8 contiguous bytes of the K-major LN2 operand and 8 contiguous bytes of the row-major xn row (a warp writes one
+// 256-byte run per row and store).  No shuffles, no staging transposes.  The fp32 x tile leaves through one TMA tensor store.
 //
 // Warps: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..17 = epilogue (warp & 3 = TMEM lane quadrant, (warp - 2) >> 2 = which 8
 // of the 32 rows).  TMEM columns: [0,128) out-proj (4 tiles x 32 rows), [128,160) hidden, [160,288) FFN2.
@@ -85,15 +86,10 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
                : "memory");
 }
 
-// Tiled stores shared -> global (bulk async-group completion): the tile leaves through the TMA unit instead of 64 KB of scattered per-thread stores
+// Tiled store shared -> global (bulk async-group completion): the x tile leaves through the TMA unit instead of 64 KB of scattered per-thread stores
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(map)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
@@ -275,7 +271,7 @@ __device__ __forceinline__ void br_attention_phase(const AttnParams& p, int m0, 
 template <bool ATTN>
 __global__ void __launch_bounds__(kBrThreads, 1)
 block_rows_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1,
-                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xn, int M,
+                  const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, int M,
                   FusedBlockParams ep, AttnParams pa) {
   // ATTN: the decode-step attention of the CTA's 32 sequences runs first, on the epilogue warps (br_attention_phase): pa is valid, tmap_ao is
   // not used.  The weight ring is rotated by two slots so that request 0 (prefetched at launch) lands in slot 2 while slots 0 and 1 stage K / V.
@@ -321,7 +317,7 @@ block_rows_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_cons
     if (elect_one()) {
       if (!ATTN) tma_prefetch_desc(&tmap_ao);
       tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1); tma_prefetch_desc(&tmap_w2);
-      tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_xn);
+      tma_prefetch_desc(&tmap_x);
       for (int st = 0; st < kBrSlots; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
       mbar_init(act_full, ATTN ? kBrEpiWarps : 1);
       for (int t = 0; t < 4; ++t) { mbar_init(&acc0_full[t], 1); mbar_init(&acc2_full[t], 1); }
@@ -617,7 +613,7 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const float (&v)[8]
 
 __global__ void __launch_bounds__(kBrThreads, 1)
 block_rows64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_constant__ CUtensorMap tmap_wo, const __grid_constant__ CUtensorMap tmap_w1,
-                    const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_xn, int M,
+                    const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_x, int M,
                     FusedBlockParams ep) {
   constexpr uint32_t kIdesc = umma_idesc_bf16_f32(128, kB64Rows);
   constexpr uint32_t kColHidden = 256;
@@ -655,7 +651,7 @@ block_rows64_kernel(const __grid_constant__ CUtensorMap tmap_ao, const __grid_co
   if (warp == 0) {
     if (elect_one()) {
       tma_prefetch_desc(&tmap_ao); tma_prefetch_desc(&tmap_wo); tma_prefetch_desc(&tmap_w1); tma_prefetch_desc(&tmap_w2);
-      tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_xn);
+      tma_prefetch_desc(&tmap_x);
       for (int st = 0; st < kB64Slots; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], 1); }
       mbar_init(act_full, 1); mbar_init(x_ready, kBrEpiWarps);
       for (int t = 0; t < 4; ++t) { mbar_init(&acc0_full[t], 1); mbar_init(&acc2_full[t], 1); }
