@@ -166,6 +166,7 @@ constexpr int kStagesQKV = 5, kStagesGelu = 5, kStagesRow = 4, kStagesLogits = 5
 bool g_fuse_block = true;                      // NOVIC_FUSE_BLOCK=0: out-proj + LN2 and the feed-forward block as two row kernels
 int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes of at least this many rows run the row-owner block kernel on 64 rows per CTA (block_rows64_kernel); 0 = never
 int g_attn_split_max = 0;                      // NOVIC_ATTN_SPLIT_MAX: largest decode batch (sequences) of the split-key attention kernel; 0 = two waves of CTAs (8 x #SMs = 1184: measured 0.75 against 0.84 ms at 1024 sequences, 1.37 against 0.94 ms at 2048)
+int g_qkv_ws_div = 24;                         // NOVIC_QKV_WS_DIV: the weight-stationary QKV kernel from 24 / div row blocks per pass on (24 = every pass - with three activation stages and 256-bit stores it beats the generic persistent kernel at every size measured: QKV class 0.52 -> 0.42 ms at 128 rows, 0.55 -> 0.45 at 512, 0.58 -> 0.47 at 1024, 0.82 -> 0.69 at 2048; 1 = the round-2 rule, at least two row blocks per CTA)
 int g_qkv_ws_stages = 3;                       // NOVIC_QKV_WS_STAGES: 3 = three 32 KB activation stages in the weight-stationary QKV kernel, q / K / V stored from registers with 256-bit stores (default: QKV class 1.10 -> 0.99 ms per decode); 2 = two stages + the epilogue's 32 KB staging tile
 bool g_attn_prefix = true;                     // NOVIC_ATTN_PREFIX=0: the prefix pass on attention_bulk_kernel instead of attention_prefix_kernel
 bool g_attn_split = true;                      // NOVIC_ATTN_SPLIT=0: the stream attention kernel (one warp per sequence) for small batches too
@@ -772,7 +773,7 @@ int run_layers(NovicHandle* h, const Workspace& ws, const PassCfg& pc, cudaStrea
       const EpiQKV::Params pq = qkv_params(l);
       if (g_wide_gemm) {
         KSpan t(kKQkv, s);
-        if (g_qkv_ws && kE == kWsKb * kBlockK && ceil_div(M, kBlockM) >= 2 * (g_num_sms / g_grid_div / (3 * kE / kTileN))) {   // weight-stationary: >= 2 row blocks per CTA
+        if (g_qkv_ws && kE == kWsKb * kBlockK && ceil_div(M, kBlockM) * g_qkv_ws_div >= 2 * (g_num_sms / g_grid_div / (3 * kE / kTileN))) {   // weight-stationary: >= 2 (NOVIC_QKV_WS_DIV: 2 / div) row blocks per CTA
           if (g_qkv_ws == 2) {
             if (launch_gemm_ws2<EpiQKV>(s, tm_xn3, h->w.tm_in_proj3h[l], M, 3 * kE, pq, g_early_b)) return 1;
           } else if (g_qkv_ws_stages == 3) {
@@ -1215,6 +1216,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
   if (const char* e25d = getenv("NOVIC_ATTN_SPLIT")) g_attn_split = e25d[0] != '0';
   if (const char* e25h = getenv("NOVIC_ATTN_PREFIX")) g_attn_prefix = e25h[0] != '0';
+  if (const char* e25i = getenv("NOVIC_QKV_WS_DIV")) g_qkv_ws_div = std::max(1, atoi(e25i));
   if (const char* e25g = getenv("NOVIC_QKV_WS_STAGES")) g_qkv_ws_stages = atoi(e25g) == 2 ? 2 : 3;
   if (const char* e25e = getenv("NOVIC_ATTN_SPLIT_MAX")) g_attn_split_max = atoi(e25e);
   if (const char* e25c = getenv("NOVIC_BLOCK_ROWS64_MIN")) g_block_rows64_min = atoi(e25c);
