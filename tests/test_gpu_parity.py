@@ -512,6 +512,27 @@ def test_attention_inside_the_block_kernel_is_bit_identical(monkeypatch):
         assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[5], c[5])
 
 
+def test_beam_logits_on_wide_tiles_are_bit_identical(monkeypatch):
+    """Beam search with up to three beams ranks four candidates per 64-column vocabulary slice in the logits epilogue (EpiLogits<4>).  From
+    ~700 candidate rows per step on, that GEMM runs on 128 x 256 tiles with 16 epilogue warps like the greedy one (NOVIC_LOGITS_BN=128
+    restores the 128 x 128 tiles with 8 warps): the same products in the same order and the same per-slice records -> bit-identical
+    tokens, padding and scores.  300 embeddings x 3 beams = 900 rows per step (a ragged eighth row block)."""
+    dims = synth.DecoderDims()
+    sd = weight_case("lively")
+    embed = synth.synth_embeddings(300, seed=11).to(DEV)
+    outs = []
+    for bn in ("128", "256"):                    # the switch is read when a handle is created
+        monkeypatch.setenv("NOVIC_LOGITS_BN", bn)
+        m = default_decoder(dims, sd).to(DEV)
+        with torch.inference_mode():
+            b = m.generate_beam(embed, 3, 1.0, 0.0, None, False, 0.0, None, False)
+            b2 = m.generate_beam(embed, 3, 1.3, 0.6, None, False, 0.0, None, False)
+        outs.append((b, b2))
+        del m
+    for x, y in zip(outs[0], outs[1]):
+        assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
+
+
 def test_qkv_projection_variants_are_bit_identical(monkeypatch):
     """The QKV projection of a large decode step (>= 24 row blocks) has five implementations with the same operands and accumulation order:
     the generic persistent kernel (NOVIC_QKV_WS=0), the weight-stationary kernel (default), its cluster-multicast variants
