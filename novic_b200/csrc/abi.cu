@@ -892,12 +892,13 @@ int launch_logits(NovicHandle* h, const Workspace& ws, const __nv_bfloat16* a, i
   pl.want_sumx = h->cfg.label_smoothing != 0.f ? 1 : 0;
   pl.allow = MASKED ? ws.allow : nullptr; pl.allow_ld = ws.allow_words; pl.allow_mod = allow_mod; pl.mask_lse = mask_lse ? 1 : 0;
   KSpan t(kKLogits, s);
-  if constexpr (HCAP == 4 && !MASKED && !BIAS) {
-    // beam search with up to 3 beams (HCAP = 4 candidates per 64-column slice): the same 128 x 256 tiles with 16 epilogue warps - the top-k
-    // epilogue on two warps per scheduler ran at 0.27 of the tensor roof (7.1 of the 29.8 ms of BASELINE config #3)
+  if constexpr ((HCAP == 4 || HCAP == 12) && !BIAS) {
+    // beam search with up to 3 / up to 11 beams (HCAP = 4 / 12 candidates per 64-column slice), guided or not: the same 128 x 256 tiles with 16
+    // epilogue warps as the greedy GEMM - the top-k epilogue on two warps per scheduler ran at 0.27 of the tensor roof (7.1 of the 29.8 ms
+    // of BASELINE config #3)
     const int V = h->cfg.vocab_size;
     if (g_wide_gemm && g_logits_bn >= 256 && g_logits_ew == 16 && 4 * ceil_div(V, 256) == ws.ntiles && ceil_div(M, kBlockM) * ceil_div(V, 256) >= g_num_sms)
-      return launch_gemm<EpiLogits<4, false, false>, 2, kWideKbs, 256, 16>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b);
+      return launch_gemm<EpiLogits<HCAP, MASKED, false>, 2, kWideKbs, 256, 16>(s, tm_a, h->w.tm_tok3w, M, V, kE, pl, 1, g_early_b);
   }
   if constexpr (HCAP == 0 && !MASKED && !BIAS) {
     // 128 x 256 tiles (0.75 of the operand bytes per FLOP): the plain arg-max / log-sum-exp epilogue of greedy decoding and teacher forcing.
@@ -1161,7 +1162,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
       set_gemm_attr<EpiLogits<16>, kStagesLogits>() || set_gemm_attr<EpiLogits<0, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<4, true, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<16, true, true>, kStagesLogits>() ||
-      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm_ws_attr<EpiQKV, 3>() || set_gemm_ws2_attr<EpiQKV>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() || set_gemm_attr<EpiLogits<4>, 2, kWideKbs, 256, 16>() ||
+      set_gemm_attr<EpiQKV, kWideStages, kWideKbs>() || set_gemm_attr<EpiQKV, 2, kWideKbs, 256>() || set_gemm2_attr<EpiQKV, 3>() || set_gemm2_attr<EpiQKV, 4, 128>() || set_gemm_ws_attr<EpiQKV, 2>() || set_gemm_ws_attr<EpiQKV, 3>() || set_gemm_ws2_attr<EpiQKV>() || set_gemm2_attr<EpiLogits<0>, 3>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256>() || set_gemm_attr<EpiLogits<0>, 2, kWideKbs, 256, 16>() || set_gemm_attr<EpiLogits<4>, 2, kWideKbs, 256, 16>() || set_gemm_attr<EpiLogits<12>, 2, kWideKbs, 256, 16>() || set_gemm_attr<EpiLogits<4, true>, 2, kWideKbs, 256, 16>() || set_gemm_attr<EpiLogits<12, true>, 2, kWideKbs, 256, 16>() ||
       set_gemm_attr<EpiLogits<12>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true>, kStagesLogits>() || set_gemm_attr<EpiLogits<12, true, true>, kStagesLogits>() ||
       set_gemm_attr<EpiLogits<12>, kWideStages, kWideKbs>() || set_gemm_attr<EpiLogits<12, true>, kWideStages, kWideKbs>() ||
       set_gemm_attr<EpiLogits<12, true, true>, kWideStages, kWideKbs>() ||

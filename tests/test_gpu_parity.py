@@ -516,18 +516,23 @@ def test_beam_logits_on_wide_tiles_are_bit_identical(monkeypatch):
     """Beam search with up to three beams ranks four candidates per 64-column vocabulary slice in the logits epilogue (EpiLogits<4>).  From
     ~700 candidate rows per step on, that GEMM runs on 128 x 256 tiles with 16 epilogue warps like the greedy one (NOVIC_LOGITS_BN=128
     restores the 128 x 128 tiles with 8 warps): the same products in the same order and the same per-slice records -> bit-identical
-    tokens, padding and scores.  300 embeddings x 3 beams = 900 rows per step (a ragged eighth row block)."""
+    tokens, padding and scores.  300 embeddings x 3 beams = 900 rows per step (a ragged eighth row block); also ten beams (EpiLogits<12>)
+    and guided decoding (the masked epilogue), with and without guide_renorm."""
     dims = synth.DecoderDims()
     sd = weight_case("lively")
     embed = synth.synth_embeddings(300, seed=11).to(DEV)
+    guide = synth.synth_guide_targets(400, dims, seed=33, first_pool=200).to(DEV)
     outs = []
     for bn in ("128", "256"):                    # the switch is read when a handle is created
         monkeypatch.setenv("NOVIC_LOGITS_BN", bn)
         m = default_decoder(dims, sd).to(DEV)
         with torch.inference_mode():
-            b = m.generate_beam(embed, 3, 1.0, 0.0, None, False, 0.0, None, False)
-            b2 = m.generate_beam(embed, 3, 1.3, 0.6, None, False, 0.0, None, False)
-        outs.append((b, b2))
+            runs = [m.generate_beam(embed, 3, 1.0, 0.0, None, False, 0.0, None, False),
+                    m.generate_beam(embed, 3, 1.3, 0.6, None, False, 0.0, None, False),
+                    m.generate_beam(embed[:90], 10, 1.0, 0.0, None, False, 0.0, None, False),          # 12 candidates per slice, 900 rows
+                    m.generate_beam(embed, 3, 1.0, 0.0, None, False, 0.0, guide, False),             # guided: masked epilogue
+                    m.generate_beam(embed[:90], 10, 1.0, 0.0, None, False, 0.0, guide, True)]        # the reference's default configuration
+        outs.append(runs)
         del m
     for x, y in zip(outs[0], outs[1]):
         assert torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2])
