@@ -168,6 +168,7 @@ int g_block_rows64_min = 148 * 32 + 1;         // NOVIC_BLOCK_ROWS64_MIN: passes
 int g_attn_split_max = 0;                      // NOVIC_ATTN_SPLIT_MAX: largest decode batch (sequences) of the split-key attention kernel; 0 = two waves of CTAs (8 x #SMs = 1184: measured 0.75 against 0.84 ms at 1024 sequences, 1.37 against 0.94 ms at 2048)
 int g_qkv_ws_div = 24;                         // NOVIC_QKV_WS_DIV: the weight-stationary QKV kernel from 24 / div row blocks per pass on (24 = every pass - with three activation stages and 256-bit stores it beats the generic persistent kernel at every size measured: QKV class 0.52 -> 0.42 ms at 128 rows, 0.55 -> 0.45 at 512, 0.58 -> 0.47 at 1024, 0.82 -> 0.69 at 2048; 1 = the round-2 rule, at least two row blocks per CTA)
 int g_qkv_ws_stages = 3;                       // NOVIC_QKV_WS_STAGES: 3 = three 32 KB activation stages in the weight-stationary QKV kernel, q / K / V stored from registers with 256-bit stores (default: QKV class 1.10 -> 0.99 ms per decode); 2 = two stages + the epilogue's 32 KB staging tile
+int g_vit_direct = 1;                          // NOVIC_VIT_DIRECT=0: the image encoder's bias / QuickGELU epilogues store their bf16 rows through the staging tile instead of with 256-bit stores from the registers (measured: 848 -> 855 images/s)
 bool g_attn_prefix = true;                     // NOVIC_ATTN_PREFIX=0: the prefix pass on attention_bulk_kernel instead of attention_prefix_kernel
 bool g_attn_split = true;                      // NOVIC_ATTN_SPLIT=0: the stream attention kernel (one warp per sequence) for small batches too
 bool g_fuse_attn = false;                      // NOVIC_FUSE_ATTN=1: the decode-step attention runs inside the row-owner block kernel (block_rows_kernel<true>; bit-identical, one launch and the ao round trip less per layer; measured 5.05 vs 5.09 ms per decode - kept as a switch so that the attention stays a launch of its own with its own HBM roofline record)
@@ -1224,6 +1225,7 @@ int novic_create(const NovicCfg* cfg, NovicHandle** out) {
   if (const char* e25b = getenv("NOVIC_FUSE_ATTN")) g_fuse_attn = e25b[0] != '0';
   if (const char* e25d = getenv("NOVIC_ATTN_SPLIT")) g_attn_split = e25d[0] != '0';
   if (const char* e25h = getenv("NOVIC_ATTN_PREFIX")) g_attn_prefix = e25h[0] != '0';
+  if (const char* e25j = getenv("NOVIC_VIT_DIRECT")) g_vit_direct = atoi(e25j) != 0 ? 1 : 0;
   if (const char* e25i = getenv("NOVIC_QKV_WS_DIV")) g_qkv_ws_div = std::max(1, atoi(e25i));
   if (const char* e25g = getenv("NOVIC_QKV_WS_STAGES")) g_qkv_ws_stages = atoi(e25g) == 2 ? 2 : 3;
   if (const char* e25e = getenv("NOVIC_ATTN_SPLIT_MAX")) g_attn_split_max = atoi(e25e);

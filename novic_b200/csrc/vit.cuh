@@ -29,6 +29,7 @@ struct EpiVitBias {
     const float* bias;      // [N] or nullptr
     int n_valid;            // N (columns >= N of the last tile are not stored)
     int quick_gelu;
+    int direct;             // != 0: rows stored straight from the registers with 256-bit stores (ld must be a multiple of 16 elements)
   };
   template <class Release>
   __device__ static __forceinline__ void run(const Params& p, const EpiCtx& c, Release release) {
@@ -54,8 +55,25 @@ struct EpiVitBias {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = v[j] * __fdividef(1.0f, 1.0f + __expf(-1.702f * v[j]));
         }
-        stage_put32(c.stage, lane, ch * 32, v);
+        if (p.direct) {
+          // thread = row: 32 columns are 64 contiguous bytes of the row = two full 32-byte sectors (st.global.v8.b32); no staging tile
+          if (c.row < c.M && col0 < p.n_valid) {
+            __nv_bfloat16* dst = p.out + static_cast<size_t>(c.row) * p.ld + col0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t w[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[h * 16 + 2 * i], v[h * 16 + 2 * i + 1]);
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(dst + h * 16), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                           "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                           : "memory");
+            }
+          }
+        } else {
+          stage_put32(c.stage, lane, ch * 32, v);
+        }
       }
+      if (p.direct) continue;
       if (n0 < p.n_valid)
         stage_copy_out(c.stage, lane, [&](int r) -> __nv_bfloat16* {
           const int row = c.warp_row0 + r;
