@@ -1,6 +1,7 @@
 """Per-phase clock64 trace of the row-owner block kernel (blockrows.cuh; CTA 0, decode step, 1-layer model)."""
 import ctypes as C, os, sys
 os.environ.setdefault("NOVIC_BLOCK_ROWS", "32")
+os.environ.setdefault("NOVIC_BLOCK_ROWS64_MIN", "0")   # the prefix pass on the traced kernel too, so that the launch ordinals below hold
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 from novic_b200 import synth, default_decoder, _abi
